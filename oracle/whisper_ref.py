@@ -1,0 +1,397 @@
+"""
+oracle/whisper_ref.py — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+PyTorch fp32 CPU restatement of the encoder/decoder arithmetic the reference exports to CoreML
+(/root/reference/whisper_to_cml.py:6-8,10-23,25-43: `whisper.load_model("small")`, `model.encoder` traced on
+(1,80,3000), `model.decoder` traced on (tokens(1,1), audio(1,1500,768))) and of the language-ID decode the
+reference's Swift performs on it (/root/reference/Whisper/Whisper/Whisper.swift:33-40).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this module.
+
+PARITY UNPINNED. The arithmetic itself lives in the PyPI package `openai-whisper` (whisper/model.py,
+whisper/decoding.py), which is imported by whisper_to_cml.py:1 but is neither vendored in /root/reference nor
+version-pinned there (no requirements file; the Swift headers are dated 2022-09-26, i.e. the first public release),
+and is not installed in this image. The reference holds no test or golden output for any encoder/decoder value.
+This file therefore restates the *published* upstream algorithm:
+  sinusoids()                  sin/cos table, log-timescale increment ln(10000)/(d/2-1)
+  AudioEncoder.forward         gelu(conv1 k3 p1) -> gelu(conv2 k3 s2 p1) -> +sinusoids -> L pre-LN blocks -> ln_post
+  MultiHeadAttention           query/value/out with bias, key without; q and k each scaled by d_head**-0.25;
+                               softmax in fp32; additive -inf causal mask for decoder self-attention
+  ResidualAttentionBlock       x += attn(attn_ln(x)); [x += cross_attn(cross_attn_ln(x), xa)]; x += mlp(mlp_ln(x))
+  TextDecoder.forward          token_embedding[x] + positional_embedding[offset:offset+t]; blocks; ln;
+                               logits = x @ token_embedding.T  (fp32)
+  DecodingTask (greedy, t=0)   SuppressBlank at the first sampled position, SuppressTokens, argmax, EOT forcing,
+                               sum_logprobs += logprob * (last != eot), stop when every sequence ended or after
+                               sample_len steps
+  detect_language              argmax over the language-token logits after one decoder call on [sot]
+and is cross-checked, on identical seeded weights, against the independent implementation that IS in this image,
+`transformers.WhisperForConditionalGeneration` (tests/test_oracle_whisper.py, tools/gen_golden.py): encoder
+output, teacher-forced logits and greedy tokens agree to fp32 round-off. Token-ID layout for the language-ID path
+is pinned by the reference itself: sot = 50258, language logits 50259...50357 (Whisper.swift:35,37).
+
+State-dict keys follow upstream openai-whisper names (encoder.blocks.N.attn.query.weight, decoder.ln.weight, ...).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+@dataclass(frozen=True)
+class ModelDims:
+    """Upstream `ModelDimensions`. n_audio_ctx=1500 and n_mels=80 are pinned by whisper_to_cml.py:13,29."""
+    n_mels: int = 80
+    n_audio_ctx: int = 1500
+    n_audio_state: int = 384
+    n_audio_head: int = 6
+    n_audio_layer: int = 4
+    n_vocab: int = 51864
+    n_text_ctx: int = 448
+    n_text_state: int = 384
+    n_text_head: int = 6
+    n_text_layer: int = 4
+
+    @property
+    def is_multilingual(self) -> bool:
+        return self.n_vocab == 51865
+
+
+DIMS = {
+    "tiny.en": ModelDims(80, 1500, 384, 6, 4, 51864, 448, 384, 6, 4),
+    "tiny": ModelDims(80, 1500, 384, 6, 4, 51865, 448, 384, 6, 4),
+    "base.en": ModelDims(80, 1500, 512, 8, 6, 51864, 448, 512, 8, 6),
+    "base": ModelDims(80, 1500, 512, 8, 6, 51865, 448, 512, 8, 6),
+    "small.en": ModelDims(80, 1500, 768, 12, 12, 51864, 448, 768, 12, 12),
+    "small": ModelDims(80, 1500, 768, 12, 12, 51865, 448, 768, 12, 12),
+    "medium": ModelDims(80, 1500, 1024, 16, 24, 51865, 448, 1024, 16, 24),
+    "large-v2": ModelDims(80, 1500, 1280, 20, 32, 51865, 448, 1280, 20, 32),
+}
+
+
+@dataclass(frozen=True)
+class Vocab:
+    """Special-token layout (upstream tokenizer.py). Multilingual values match Whisper.swift:35,37."""
+    eot: int
+    sot: int
+    lang0: int          # first language token; 99 languages follow
+    translate: int
+    transcribe: int
+    sot_lm: int
+    sot_prev: int
+    no_speech: int
+    no_timestamps: int
+    timestamp_begin: int
+
+    @staticmethod
+    def for_dims(dims: ModelDims) -> "Vocab":
+        if dims.is_multilingual:
+            return Vocab(50257, 50258, 50259, 50358, 50359, 50360, 50361, 50362, 50363, 50364)
+        return Vocab(50256, 50257, 50258, 50357, 50358, 50359, 50360, 50361, 50362, 50363)
+
+
+def sinusoids(length: int, channels: int, max_timescale: float = 10000.0) -> torch.Tensor:
+    assert channels % 2 == 0
+    inc = math.log(max_timescale) / (channels // 2 - 1)
+    inv = torch.exp(-inc * torch.arange(channels // 2, dtype=torch.float32))
+    t = torch.arange(length, dtype=torch.float32)[:, None] * inv[None, :]
+    return torch.cat([torch.sin(t), torch.cos(t)], dim=1)
+
+
+def weight_shapes(dims: ModelDims) -> Dict[str, tuple]:
+    """Every tensor of the upstream state dict, in a fixed order (also the order of the packed weight file)."""
+    d, dt = dims.n_audio_state, dims.n_text_state
+    s: Dict[str, tuple] = {}
+    s["encoder.conv1.weight"] = (d, dims.n_mels, 3)
+    s["encoder.conv1.bias"] = (d,)
+    s["encoder.conv2.weight"] = (d, d, 3)
+    s["encoder.conv2.bias"] = (d,)
+    s["encoder.positional_embedding"] = (dims.n_audio_ctx, d)
+
+    def block(prefix: str, n: int, cross: bool):
+        for nm in (["attn"] + (["cross_attn"] if cross else [])):
+            s[f"{prefix}.{nm}.query.weight"] = (n, n)
+            s[f"{prefix}.{nm}.query.bias"] = (n,)
+            s[f"{prefix}.{nm}.key.weight"] = (n, n)
+            s[f"{prefix}.{nm}.value.weight"] = (n, n)
+            s[f"{prefix}.{nm}.value.bias"] = (n,)
+            s[f"{prefix}.{nm}.out.weight"] = (n, n)
+            s[f"{prefix}.{nm}.out.bias"] = (n,)
+            s[f"{prefix}.{nm}_ln.weight"] = (n,)
+            s[f"{prefix}.{nm}_ln.bias"] = (n,)
+        s[f"{prefix}.mlp.0.weight"] = (4 * n, n)
+        s[f"{prefix}.mlp.0.bias"] = (4 * n,)
+        s[f"{prefix}.mlp.2.weight"] = (n, 4 * n)
+        s[f"{prefix}.mlp.2.bias"] = (n,)
+        s[f"{prefix}.mlp_ln.weight"] = (n,)
+        s[f"{prefix}.mlp_ln.bias"] = (n,)
+
+    for i in range(dims.n_audio_layer):
+        block(f"encoder.blocks.{i}", d, False)
+    s["encoder.ln_post.weight"] = (d,)
+    s["encoder.ln_post.bias"] = (d,)
+    s["decoder.token_embedding.weight"] = (dims.n_vocab, dt)
+    s["decoder.positional_embedding"] = (dims.n_text_ctx, dt)
+    for i in range(dims.n_text_layer):
+        block(f"decoder.blocks.{i}", dt, True)
+    s["decoder.ln.weight"] = (dt,)
+    s["decoder.ln.bias"] = (dt,)
+    return s
+
+
+def random_weights(dims: ModelDims, seed: int = 0, fp16_round: bool = True) -> Dict[str, torch.Tensor]:
+    """Seeded synthetic checkpoint (no real checkpoints exist offline). Non-trivial biases and LN affine
+    parameters so that every term of the arithmetic is exercised. With fp16_round=True every value is exactly
+    representable in fp16, so an fp16-weight implementation and this fp32 oracle hold identical weights."""
+    g = torch.Generator().manual_seed(seed)
+    w: Dict[str, torch.Tensor] = {}
+    for name, shape in weight_shapes(dims).items():
+        if name == "encoder.positional_embedding":
+            t = sinusoids(*shape)
+        elif name.endswith("_ln.weight") or name.endswith("ln_post.weight") or name == "decoder.ln.weight":
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif name.endswith("_ln.bias") or name.endswith("ln_post.bias") or name == "decoder.ln.bias":
+            t = 0.05 * torch.randn(shape, generator=g)
+        elif name.endswith(".bias"):
+            t = 0.02 * torch.randn(shape, generator=g)
+        elif name == "decoder.token_embedding.weight":
+            t = 0.05 * torch.randn(shape, generator=g)
+        elif name == "decoder.positional_embedding":
+            t = 0.1 * torch.randn(shape, generator=g)
+        elif "conv" in name:
+            fan_in = shape[1] * shape[2]
+            t = torch.randn(shape, generator=g) * (1.0 / math.sqrt(fan_in))
+        elif ".query." in name or ".key." in name:
+            t = torch.randn(shape, generator=g) * (2.0 / math.sqrt(shape[1]))     # peaked (trained-like) attention
+        else:
+            fan_in = shape[1]
+            t = torch.randn(shape, generator=g) * (0.7 / math.sqrt(fan_in))
+        if fp16_round:
+            t = t.to(torch.float16).to(torch.float32)
+        w[name] = t.contiguous()
+    return w
+
+
+def _ln(x, w, b):
+    return F.layer_norm(x.float(), (x.shape[-1],), w, b, 1e-5)
+
+
+class WhisperRef:
+    """fp32 restatement of upstream `Whisper` (encoder + decoder) over a plain state dict."""
+
+    def __init__(self, dims: ModelDims, weights: Dict[str, torch.Tensor]):
+        self.dims = dims
+        self.w = {k: v.float() for k, v in weights.items()}
+        missing = set(weight_shapes(dims)) - set(self.w)
+        assert not missing, f"missing weights: {sorted(missing)[:4]}"
+        n = dims.n_text_ctx
+        self.mask = torch.full((n, n), float("-inf")).triu_(1)
+        self.vocab = Vocab.for_dims(dims)
+
+    # ---- attention ------------------------------------------------------------------------------------------
+    def _proj_kv(self, p: str, src: torch.Tensor):
+        k = F.linear(src, self.w[f"{p}.key.weight"])
+        v = F.linear(src, self.w[f"{p}.value.weight"], self.w[f"{p}.value.bias"])
+        return k, v
+
+    def _attend(self, p: str, n_head: int, q_in, k, v, mask=None):
+        q = F.linear(q_in, self.w[f"{p}.query.weight"], self.w[f"{p}.query.bias"])
+        B, T, D = q.shape
+        scale = (D // n_head) ** -0.25
+        qh = q.view(B, T, n_head, -1).permute(0, 2, 1, 3) * scale
+        kh = k.view(B, k.shape[1], n_head, -1).permute(0, 2, 3, 1) * scale
+        vh = v.view(B, v.shape[1], n_head, -1).permute(0, 2, 1, 3)
+        qk = qh @ kh
+        if mask is not None:
+            qk = qk + mask
+        a = F.softmax(qk.float(), dim=-1)
+        o = (a @ vh).permute(0, 2, 1, 3).flatten(start_dim=2)
+        return F.linear(o, self.w[f"{p}.out.weight"], self.w[f"{p}.out.bias"])
+
+    def _mlp(self, p: str, x):
+        h = F.gelu(F.linear(x, self.w[f"{p}.mlp.0.weight"], self.w[f"{p}.mlp.0.bias"]))
+        return F.linear(h, self.w[f"{p}.mlp.2.weight"], self.w[f"{p}.mlp.2.bias"])
+
+    # ---- encoder (AudioEncoder.forward; exported at whisper_to_cml.py:10-23) -------------------------------------
+    @torch.no_grad()
+    def encode(self, mel: torch.Tensor) -> torch.Tensor:
+        """mel [B,80,3000] (already normalised log-mel, Whisper.swift:25-29) -> xa [B,1500,d]."""
+        w, dims = self.w, self.dims
+        x = F.gelu(F.conv1d(mel.float(), w["encoder.conv1.weight"], w["encoder.conv1.bias"], padding=1))
+        x = F.gelu(F.conv1d(x, w["encoder.conv2.weight"], w["encoder.conv2.bias"], stride=2, padding=1))
+        x = x.permute(0, 2, 1)
+        x = x + w["encoder.positional_embedding"]
+        for i in range(dims.n_audio_layer):
+            p = f"encoder.blocks.{i}"
+            h = _ln(x, w[f"{p}.attn_ln.weight"], w[f"{p}.attn_ln.bias"])
+            k, v = self._proj_kv(f"{p}.attn", h)
+            x = x + self._attend(f"{p}.attn", dims.n_audio_head, h, k, v)
+            x = x + self._mlp(p, _ln(x, w[f"{p}.mlp_ln.weight"], w[f"{p}.mlp_ln.bias"]))
+        return _ln(x, w["encoder.ln_post.weight"], w["encoder.ln_post.bias"])
+
+    # ---- decoder (TextDecoder.forward; exported at whisper_to_cml.py:25-43) ------------------------------------
+    @torch.no_grad()
+    def cross_kv(self, xa: torch.Tensor):
+        return [self._proj_kv(f"decoder.blocks.{i}.cross_attn", xa.float()) for i in range(self.dims.n_text_layer)]
+
+    @torch.no_grad()
+    def decoder_logits(self, tokens: torch.Tensor, xa: torch.Tensor, cross=None, self_cache=None) -> torch.Tensor:
+        """tokens [B,t] int64, xa [B,1500,d] -> logits [B,t,V] fp32. With `self_cache` (list of [k,v] per layer,
+        mutated in place) only the new tokens are fed and the cache supplies the history (upstream kv_cache hooks)."""
+        w, dims = self.w, self.dims
+        offset = 0 if not self_cache or self_cache[0] is None else self_cache[0][0].shape[1]
+        t = tokens.shape[-1]
+        x = w["decoder.token_embedding.weight"][tokens] + w["decoder.positional_embedding"][offset:offset + t]
+        if cross is None:
+            cross = self.cross_kv(xa)
+        for i in range(dims.n_text_layer):
+            p = f"decoder.blocks.{i}"
+            h = _ln(x, w[f"{p}.attn_ln.weight"], w[f"{p}.attn_ln.bias"])
+            k, v = self._proj_kv(f"{p}.attn", h)
+            if self_cache is not None:
+                if self_cache[i] is not None:
+                    k = torch.cat([self_cache[i][0], k], dim=1)
+                    v = torch.cat([self_cache[i][1], v], dim=1)
+                self_cache[i] = (k, v)
+            n = k.shape[1]
+            mask = self.mask[n - t:n, :n]
+            x = x + self._attend(f"{p}.attn", dims.n_text_head, h, k, v, mask)
+            h = _ln(x, w[f"{p}.cross_attn_ln.weight"], w[f"{p}.cross_attn_ln.bias"])
+            x = x + self._attend(f"{p}.cross_attn", dims.n_text_head, h, cross[i][0], cross[i][1])
+            x = x + self._mlp(p, _ln(x, w[f"{p}.mlp_ln.weight"], w[f"{p}.mlp_ln.bias"]))
+        x = _ln(x, w["decoder.ln.weight"], w["decoder.ln.bias"])
+        return (x @ w["decoder.token_embedding.weight"].t()).float()
+
+    # ---- Whisper.decode (Whisper.swift:33-40): language ID ------------------------------------------------------
+    @torch.no_grad()
+    def detect_language(self, xa: torch.Tensor) -> torch.Tensor:
+        """One decoder call on the single token `sot`; argmax over the 99 language logits. Returns [B] in 0..98."""
+        v = self.vocab
+        B = xa.shape[0]
+        logits = self.decoder_logits(torch.full((B, 1), v.sot, dtype=torch.long), xa)[:, 0]
+        return language_argmax(logits, v.lang0)
+
+    # ---- greedy transcribe (upstream DecodingTask with temperature 0) ---------------------------------------------
+    @torch.no_grad()
+    def greedy(self, xa: torch.Tensor, opts: "DecodeOptions"):
+        B = xa.shape[0]
+        v = self.vocab
+        init = list(opts.initial_tokens)
+        tokens = torch.tensor([init] * B, dtype=torch.long)
+        sample_begin = len(init)
+        sum_logprobs = torch.zeros(B)
+        cross = self.cross_kv(xa)
+        cache: List[Optional[tuple]] = [None] * self.dims.n_text_layer
+        all_logits = []
+        for i in range(opts.sample_len):
+            feed = tokens if i == 0 else tokens[:, -1:]
+            logits = self.decoder_logits(feed, xa, cross, cache)[:, -1].clone()
+            if tokens.shape[1] == sample_begin and len(opts.suppress_begin):
+                logits[:, list(opts.suppress_begin)] = float("-inf")
+            if len(opts.suppress):
+                logits[:, list(opts.suppress)] = float("-inf")
+            all_logits.append(logits)
+            nxt = logits.argmax(dim=-1)
+            logprobs = F.log_softmax(logits.float(), dim=-1)
+            cur = logprobs[torch.arange(B), nxt]
+            sum_logprobs += cur * (tokens[:, -1] != v.eot)
+            nxt[tokens[:, -1] == v.eot] = v.eot
+            tokens = torch.cat([tokens, nxt[:, None]], dim=-1)
+            if (tokens[:, -1] == v.eot).all() or tokens.shape[-1] > self.dims.n_text_ctx:
+                break
+        return tokens, sum_logprobs, torch.stack(all_logits, dim=1)
+
+
+def language_argmax(logits: torch.Tensor, lang0: int = 50259) -> torch.Tensor:
+    """Whisper.swift:37-38: `(50259...50357).map{...}.enumerated().max{ $0.element < $1.element }`.
+    Swift's `max(by:)` returns the LAST maximal element on ties."""
+    conf = logits[..., lang0:lang0 + 99].float()
+    rev = torch.flip(conf, dims=[-1])
+    return 98 - rev.argmax(dim=-1)
+
+
+@dataclass
+class DecodeOptions:
+    initial_tokens: Sequence[int]
+    sample_len: int = 224                      # upstream default n_text_ctx // 2
+    suppress: Sequence[int] = field(default_factory=list)         # SuppressTokens (every step)
+    suppress_begin: Sequence[int] = field(default_factory=list)   # SuppressBlank (first sampled position only)
+
+    @staticmethod
+    def default_for(dims: ModelDims, sample_len: int = 224, language: int = 0) -> "DecodeOptions":
+        """Upstream defaults with `without_timestamps=True`. The non-speech symbol list needs the tokenizer vocab,
+        which is not available offline; the special tokens upstream always suppresses are included."""
+        v = Vocab.for_dims(dims)
+        if dims.is_multilingual:
+            init = [v.sot, v.lang0 + language, v.transcribe, v.no_timestamps]
+        else:
+            init = [v.sot, v.no_timestamps]
+        suppress = sorted({v.sot, v.sot_prev, v.sot_lm, v.translate, v.transcribe, v.no_speech})
+        return DecodeOptions(init, sample_len, suppress, [220, v.eot])
+
+
+# ---- independent cross-check: map these weights into transformers' Whisper ------------------------------------------
+def to_hf(dims: ModelDims, weights: Dict[str, torch.Tensor]):
+    """Build transformers.WhisperForConditionalGeneration holding exactly `weights` (upstream->HF name map)."""
+    from transformers import WhisperConfig, WhisperForConditionalGeneration
+
+    cfg = WhisperConfig(
+        vocab_size=dims.n_vocab, num_mel_bins=dims.n_mels, d_model=dims.n_audio_state,
+        encoder_layers=dims.n_audio_layer, encoder_attention_heads=dims.n_audio_head,
+        decoder_layers=dims.n_text_layer, decoder_attention_heads=dims.n_text_head,
+        encoder_ffn_dim=4 * dims.n_audio_state, decoder_ffn_dim=4 * dims.n_text_state,
+        max_source_positions=dims.n_audio_ctx, max_target_positions=dims.n_text_ctx,
+        activation_function="gelu", dropout=0.0, attention_dropout=0.0, activation_dropout=0.0,
+        pad_token_id=0, bos_token_id=0, eos_token_id=0, decoder_start_token_id=0,
+        suppress_tokens=None, begin_suppress_tokens=None,
+    )
+    cfg._attn_implementation = "eager"
+    model = WhisperForConditionalGeneration(cfg).eval().float()
+
+    def ren(k: str) -> str:
+        k = k.replace("blocks.", "layers.")
+        for a, b in ((".cross_attn_ln.", ".encoder_attn_layer_norm."), (".attn_ln.", ".self_attn_layer_norm."),
+                     (".mlp_ln.", ".final_layer_norm."), (".cross_attn.", ".encoder_attn."), (".attn.", ".self_attn."),
+                     (".query.", ".q_proj."), (".key.", ".k_proj."), (".value.", ".v_proj."), (".out.", ".out_proj."),
+                     (".mlp.0.", ".fc1."), (".mlp.2.", ".fc2.")):
+            k = k.replace(a, b)
+        k = k.replace("encoder.ln_post.", "encoder.layer_norm.").replace("decoder.ln.", "decoder.layer_norm.")
+        k = k.replace("encoder.positional_embedding", "encoder.embed_positions.weight")
+        k = k.replace("decoder.positional_embedding", "decoder.embed_positions.weight")
+        k = k.replace("decoder.token_embedding.", "decoder.embed_tokens.")
+        return "model." + k
+
+    sd = {ren(k): v.clone() for k, v in weights.items()}
+    sd["proj_out.weight"] = sd["model.decoder.embed_tokens.weight"]
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all("k_proj.bias" in m for m in missing) or not missing, missing
+    return model
+
+
+def synth_audio(seed: int, kind: str = "noise", n: int = 480000) -> np.ndarray:
+    """The synthetic clips SURVEY.md §8(d) config 1 names. float64, 16 kHz, 30 s."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / 16000.0
+    if kind == "noise":
+        return rng.standard_normal(n) * 0.1
+    if kind == "zeros":
+        return np.zeros(n)
+    if kind == "sine":
+        return 0.5 * np.sin(2 * np.pi * 440.0 * t)
+    if kind == "chirp":
+        return 0.5 * np.sin(2 * np.pi * (7000.0 / 60.0) * t * t)
+    if kind == "noise_then_zeros":
+        a = np.zeros(n)
+        a[:160000] = rng.standard_normal(160000) * 0.1
+        return a
+    if kind == "int16":
+        a = rng.standard_normal(n) * 0.1 * (0.5 + 0.5 * np.sin(2 * np.pi * 3.0 * t))
+        return np.round(a * 32768.0) / 32768.0
+    if kind == "fullscale":
+        return rng.uniform(-1.0, 1.0, n)
+    raise ValueError(kind)
