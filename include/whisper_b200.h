@@ -1,0 +1,159 @@
+/*
+ * whisper_b200.h — C ABI of libwhisper_b200.so: the B200 (sm_100a) replacement for the hot path of
+ * tanmayb123/OpenAI-Whisper-CoreML:  audio -> log-mel -> encoder -> decoder -> token IDs.
+ *
+ * Every entry point cites the reference interface it replaces. Plain pointers and sizes only; no C++ or torch
+ * types. Functions return 0 on success and a negative wb_status on failure (never throw, never abort);
+ * wb_last_error() returns a thread-local message for the last failure. A handle owns all device memory of one
+ * model instance on one GPU; distinct handles may be used from distinct threads, one handle may not.
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry point returns WB_ERR_CUDA.
+ */
+#ifndef WHISPER_B200_H
+#define WHISPER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WB_N_SAMPLES_PER_CHUNK 480000 /* 16000 * 30           stft/src/lib.rs:37,112 ; ContentView.swift:57-60 */
+#define WB_N_SAMPLES_PADDED 480400    /* + 200 + 200          stft.swift:10-11 ; lib.rs:112                    */
+#define WB_N_MELS_C 80                /*                      lib.rs:60 ; whisper_to_cml.py:13                 */
+#define WB_N_FRAMES_C 3000            /*                      lib.rs:52,62 ; whisper_to_cml.py:13              */
+
+typedef enum wb_status {
+  WB_OK = 0,
+  WB_ERR_ARG = -1,     /* bad argument (null pointer, size out of range, unknown weight name, ...) */
+  WB_ERR_CUDA = -2,    /* CUDA runtime / driver error, or no device                                  */
+  WB_ERR_STATE = -3,   /* call sequence error (weights not loaded, encode not run before decode ...) */
+  WB_ERR_NOMEM = -4
+} wb_status;
+
+/* Upstream `ModelDimensions`; the reference fixes n_mels=80, n_audio_ctx=1500 (whisper_to_cml.py:13,29) and exports
+ * "small" (d=768, :7). d_head is 64 for every Whisper size and is required here (state % head == 0, state/head == 64). */
+typedef struct wb_dims {
+  int32_t n_mels, n_audio_ctx, n_audio_state, n_audio_head, n_audio_layer;
+  int32_t n_vocab, n_text_ctx, n_text_state, n_text_head, n_text_layer;
+} wb_dims;
+
+/* Greedy / beam decoding options (north-star extension; semantics of upstream whisper/decoding.py DecodingTask,
+ * see SURVEY.md §8c). Token lists are passed as data because the tokenizer vocabulary is not part of the model. */
+typedef struct wb_decode_opts {
+  const int32_t* initial_tokens; /* sot sequence, e.g. {50257,50362} (.en) or {50258,50259,50359,50363}           */
+  int32_t n_initial;
+  int32_t sample_len;            /* max sampled tokens; upstream default n_text_ctx/2 = 224                         */
+  int32_t eot;                   /* 50256 (.en) / 50257 (multilingual)                                              */
+  const int32_t* suppress;       /* SuppressTokens: -inf at every step                                              */
+  int32_t n_suppress;
+  const int32_t* suppress_begin; /* SuppressBlank: -inf at the first sampled position only                          */
+  int32_t n_suppress_begin;
+  int32_t beam_size;             /* 0 or 1 = greedy; >1 = beam search with patience 1                               */
+  int32_t eot_check_interval;    /* how often (in steps) the host polls "all sequences ended"; 0 = default (8)      */
+} wb_decode_opts;
+
+typedef struct wb_handle wb_handle;
+
+/* ---- legacy symbol -----------------------------------------------------------------------------------------------
+ * Replaces `#[no_mangle] pub extern fn generate_spectrogram(audio: *mut f64, output: *mut f64)`
+ * (stft/src/lib.rs:110-122), declared to Swift at Whisper/Whisper/bridge.h:11 and called at stft.swift:15.
+ * Same contract: audio[480400] in/out — the two 200-sample pads are overwritten with the torch-style reflection
+ * (lib.rs:34-40); output[240000] = [80][3000] normalised log-mel, out[i*3000+j]. Computed in f64 on GPU 0 (device
+ * overridable with env WB_DEVICE) by the templated fused kernel. On a CUDA failure the process aborts with a
+ * message, mirroring the Rust panic-across-FFI behaviour of the reference (there is no status to return). */
+void generate_spectrogram(double* audio, double* output);
+
+/* Same computation with a status code instead of abort, B clips at once: audio [B][480400] f64 in/out, output
+ * [B][80][3000] f64. Host pointers. */
+int wb_generate_spectrogram_f64(double* audio, int32_t B, double* output);
+
+const char* wb_last_error(void);
+int wb_version(void);
+
+/* ---- model instance -----------------------------------------------------------------------------------------------
+ * Replaces `Whisper.init()` (Whisper/Whisper/Whisper.swift:17-21: loads encoder.mlpackage and decoder.mlpackage).
+ * `stream` is a cudaStream_t (NULL = a private non-blocking stream created by the handle); all work of the handle is
+ * enqueued there. max_batch = maximum number of 30 s chunks per call; max_beams >= 1. */
+int wb_create(const wb_dims* dims, int32_t max_batch, int32_t max_beams, int32_t device, void* stream, wb_handle** out);
+int wb_destroy(wb_handle* h);
+int wb_get_dims(const wb_handle* h, wb_dims* out);
+
+/* Weights. Replaces `whisper.load_model("small")` + the two ct.convert exports (whisper_to_cml.py:6-8,10-43) which
+ * bake the checkpoint into the .mlpackages. Tensors are addressed by their upstream openai-whisper state-dict names
+ * ("encoder.blocks.0.attn.query.weight", "decoder.token_embedding.weight", ...), passed as host fp32 and stored on
+ * the device as fp16 (matrices, embeddings) or fp32 (biases, LayerNorm, encoder positional table) in the layouts the
+ * kernels want. wb_weights_commit() checks that every tensor was set. */
+int wb_set_weight(wb_handle* h, const char* name, const float* data, size_t numel);
+int wb_weights_commit(wb_handle* h);
+/* Seeded synthetic weights generated on the device (benchmarks without a checkpoint). */
+int wb_init_random_weights(wb_handle* h, uint64_t seed);
+/* The packed device arena holding every weight (for a load-time NCCL broadcast from rank 0). */
+int wb_weight_arena(wb_handle* h, void** device_ptr, size_t* bytes);
+/* Mark weights as present after the arena was filled externally (e.g. by the broadcast). */
+int wb_weights_mark_loaded(wb_handle* h);
+
+/* ---- log-mel ------------------------------------------------------------------------------------------------------
+ * Replaces `generateSpectrogram(audio:)` (Whisper/Whisper/stft.swift:8-19) for B clips of f32 PCM: audio [B][480000]
+ * (the unpadded clip; the wrapper's 200+200 zero pad and the crate's reflection are folded into the kernel's index
+ * map), out [B][80][3000] f32. `*_dev` variants take device pointers and only enqueue work on the handle's stream. */
+int wb_logmel(wb_handle* h, const float* audio, int32_t B, float* out);
+int wb_logmel_dev(wb_handle* h, const float* audio_dev, int32_t B, float* out_dev);
+
+/* ---- encoder ------------------------------------------------------------------------------------------------------
+ * wb_encode replaces `Whisper.encode(audio:)` (Whisper.swift:23-31): log-mel, then the encoder forward
+ * (`encoderModel.prediction(x_1:).var_1385`, exported at whisper_to_cml.py:10-23). audio [B][480000] f32 host;
+ * xa_out [B][1500][d] f32 host, or NULL to keep the features on the device only. The features and the
+ * cross-attention K/V derived from them stay resident in the handle for the decode calls that follow.
+ * wb_encode_mel replaces `encoderModel.prediction(x_1:)` alone: mel [B][80][3000] f32 host (already normalised). */
+int wb_encode(wb_handle* h, const float* audio, int32_t B, float* xa_out);
+int wb_encode_mel(wb_handle* h, const float* mel, int32_t B, float* xa_out);
+int wb_encode_dev(wb_handle* h, const float* audio_dev, int32_t B);
+/* Load externally computed audio features (decoder.prediction's `xa` argument, Whisper.swift:36): xa [B][1500][d]. */
+int wb_set_audio_features(wb_handle* h, const float* xa, int32_t B);
+
+/* ---- decoder ------------------------------------------------------------------------------------------------------
+ * wb_decoder_logits replaces `decoderModel.prediction(x_1: tokens, xa: audioFeatures).var_2217`
+ * (Whisper.swift:36; exported at whisper_to_cml.py:25-43 with tokens (1,1)): teacher-forced logits of tokens [B][t]
+ * against the resident audio features; logits [B][t][n_vocab] f32 host. (The reference passes the token as a float32
+ * MLMultiArray, Whisper.swift:34-35; wb_decoder_logits_f32tok accepts that form.) */
+int wb_decoder_logits(wb_handle* h, const int32_t* tokens, int32_t B, int32_t t, float* logits);
+int wb_decoder_logits_f32tok(wb_handle* h, const float* tokens, int32_t B, int32_t t, float* logits);
+
+/* Replaces `Whisper.decode(audioFeatures:)` (Whisper.swift:33-40): one decoder call on [sot], arg-max over the 99
+ * language logits [lang0, lang0+99) with Swift `max(by:)` tie-breaking (last maximal element). sot/lang0 default to
+ * 50258/50259 (Whisper.swift:35,37) when passed as 0. lang_idx [B] in 0..98. */
+int wb_detect_language(wb_handle* h, int32_t B, int32_t sot, int32_t lang0, int32_t* lang_idx);
+
+/* Greedy / beam decode of the resident features. tokens_out [B][n_initial + sample_len] (padded with eot), lens [B]
+ * (initial tokens included, first eot included), sum_logprob [B]. */
+int wb_decode(wb_handle* h, int32_t B, const wb_decode_opts* opts, int32_t* tokens_out, int32_t* lens, float* sum_logprob);
+/* audio -> tokens in one call (= wb_encode + wb_decode). Host pointers. */
+int wb_transcribe(wb_handle* h, const float* audio, int32_t B, const wb_decode_opts* opts, int32_t* tokens_out,
+                  int32_t* lens, float* sum_logprob);
+/* Same with the audio already on the device (throughput path; device pointer, results to host). */
+int wb_transcribe_dev(wb_handle* h, const float* audio_dev, int32_t B, const wb_decode_opts* opts, int32_t* tokens_out,
+                      int32_t* lens, float* sum_logprob);
+
+/* ---- introspection for tests / benchmarks ----------------------------------------------------------------------------- */
+/* Number of kernels this library launched on the handle since creation (graph replays count their nodes). */
+int64_t wb_launch_count(const wb_handle* h);
+/* Device time (ms) of the last call's phases, measured with CUDA events on the handle's stream:
+ * out[0]=logmel, out[1]=encoder (incl. cross K/V), out[2]=decode loop, out[3]=number of decode steps run. */
+int wb_last_timings(const wb_handle* h, float out[4]);
+int wb_sync(wb_handle* h);
+
+/* Low-level operator entry points used by the parity tests (device pointers, enqueue on the handle's stream).
+ * C[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual); A,W fp16; fp32 accumulate; C fp16 or fp32. */
+int wb_op_gemm(wb_handle* h, const void* A_f16, const void* W_f16, const float* bias, const float* residual, int32_t M,
+               int32_t N, int32_t K, int32_t gelu, void* C, int32_t c_is_f32);
+int wb_op_layernorm(wb_handle* h, const float* x, const float* gamma, const float* beta, int32_t M, int32_t d,
+                    void* out_f16);
+/* Encoder self-attention on fused qkv [B*T][3d] fp16 -> out [B*T][d] fp16 (non-causal). */
+int wb_op_attention(wb_handle* h, const void* qkv_f16, int32_t B, int32_t T, int32_t n_head, void* out_f16);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WHISPER_B200_H */

@@ -1,0 +1,363 @@
+// Encoder-side GEMM: C = act(A * W^T + bias) (+ residual), fp16 operands, fp32 accumulation in TMEM.
+//
+// Replaces the dense layers of the reference's CoreML encoder (exported at whisper_to_cml.py:10-23 from upstream
+// AudioEncoder): conv1/conv2 (as implicit GEMMs over overlapping-row tensor maps), the fused QKV / out / MLP linears,
+// and the decoder's cross-attention K/V projection of the audio features.
+//
+// Kernel (gemm_tc_kernel), one CTA per 128 x BN output tile, 192 threads:
+//   warp 0   TMA producer: cp.async.bulk.tensor (128B swizzle) of a 128x64 A tile and a BNx64 W tile per stage
+//   warp 1   TMEM allocator + MMA issuer: 4 x tcgen05.mma (M=128, N=BN, K=16) per stage, tcgen05.commit frees the stage
+//   warps 2-5 epilogue: tcgen05.ld the fp32 accumulator (one TMEM lane = one output row per thread), bias / exact-erf
+//            GELU / residual in registers, fp16 and/or fp32 stores
+// A second kernel (gemm_mma_kernel, mma.sync) computes the same contract without TMA/tcgen05. It exists for bring-up
+// and as the in-GPU cross-check of the tcgen05 path (env WB_GEMM_IMPL=mma selects it); the product path is tcgen05.
+#include <cuda.h>
+
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "ops.cuh"
+#include "ptx.cuh"
+
+namespace wb {
+
+constexpr int kBM = 128, kBK = 64, kStages = 3;
+constexpr int kGemmThreads = 192;
+
+struct GemmEpi {
+  const float* bias;
+  const float* res;
+  __half* c16;
+  float* c32;
+  int N, K, rows, gelu, res_mode, ldc, c_row_off;
+  long long c_batch_rows;
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOff = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOff + 256 + 1024;   // barriers + slack for the 1024-byte alignment
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB, GemmEpi ep) {
+  using S = GemmSmem<BN>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
+  uint64_t* empty = full + kStages;
+  uint64_t* tmem_full = empty + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, t0 = blockIdx.y * kBM, b = blockIdx.z;
+  const int nkb = (ep.K + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    ptx::mbar_init(tmem_full, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, BN);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+        ptx::mbar_wait(&empty[s], ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(&full[s], S::kStageBytes);
+        unsigned char* sa = smem + s * S::kStageBytes;
+        ptx::tma_load_3d(sa, &tmA, &full[s], kb * kBK, t0, b);
+        ptx::tma_load_2d(sa + S::kABytes, &tmB, &full[s], kb * kBK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(kBM, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+        ptx::mbar_wait(&full[s], ph);
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(smem + s * S::kStageBytes);
+        const uint64_t adesc = ptx::umma_desc_sw128_kmajor(sa);
+        const uint64_t bdesc = ptx::umma_desc_sw128_kmajor(sa + S::kABytes);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom: +2 in 16-byte units
+          ptx::umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+        }
+        ptx::umma_commit(&empty[s]);
+      }
+      ptx::umma_commit(tmem_full);
+    }
+  } else {
+    // epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int t = t0 + row;
+    const bool row_ok = t < ep.rows;
+    const long long crow = (long long)b * ep.c_batch_rows + ep.c_row_off + t;
+    ptx::mbar_wait(tmem_full, 0);
+    ptx::tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      ptx::tmem_ld_wait();
+      const int nb = n0 + c * 32;
+      if (row_ok) {
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (ep.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bb = *reinterpret_cast<const float4*>(ep.bias + nb + j);
+            f[j] += bb.x, f[j + 1] += bb.y, f[j + 2] += bb.z, f[j + 3] += bb.w;
+          }
+        }
+        if (ep.gelu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+        }
+        if (ep.res_mode) {
+          const float* rp = ep.res + (ep.res_mode == 1 ? crow * ep.ldc : (long long)t * ep.N) + nb;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 rr = *reinterpret_cast<const float4*>(rp + j);
+            f[j] += rr.x, f[j + 1] += rr.y, f[j + 2] += rr.z, f[j + 3] += rr.w;
+          }
+        }
+        if (ep.c32) {
+          float* cp = ep.c32 + crow * ep.ldc + nb;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        }
+        if (ep.c16) {
+          __half* cp = ep.c16 + crow * ep.ldc + nb;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            __half2 h0 = __floats2half2_rn(f[j], f[j + 1]), h1 = __floats2half2_rn(f[j + 2], f[j + 3]);
+            __half2 h2 = __floats2half2_rn(f[j + 4], f[j + 5]), h3 = __floats2half2_rn(f[j + 6], f[j + 7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h0), u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2), u.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(cp + j) = u;
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ---- mma.sync cross-check kernel: 64x64 tile, 4 warps (2x2), BK = 32 --------------------------------------------------------
+struct GemmMmaArgs {
+  const __half* a;
+  long long a_row_stride, a_batch_stride;
+  const __half* w;
+  GemmEpi ep;
+};
+__global__ void __launch_bounds__(128) gemm_mma_kernel(GemmMmaArgs g) {
+  __shared__ __align__(16) __half sA[64][40];
+  __shared__ __align__(16) __half sB[64][40];
+  const GemmEpi& ep = g.ep;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * 64, t0 = blockIdx.y * 64, b = blockIdx.z;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const int grp = lane >> 2, tq = lane & 3;
+  float acc[2][4][4] = {};
+  const __half* abase = g.a + (long long)b * g.a_batch_stride;
+  for (int k0 = 0; k0 < ep.K; k0 += 32) {
+    // 64 rows x 32 halves = 256 chunks of 8 halves for A and for W; 2 each per thread
+    for (int c = tid; c < 256; c += 128) {
+      const int r = c >> 2, kc = (c & 3) * 8;
+      uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
+      if (t0 + r < ep.rows && k0 + kc < ep.K) va = *reinterpret_cast<const uint4*>(abase + (long long)(t0 + r) * g.a_row_stride + k0 + kc);
+      if (n0 + r < ep.N && k0 + kc < ep.K) vb = *reinterpret_cast<const uint4*>(g.w + (long long)(n0 + r) * ep.K + k0 + kc);
+      *reinterpret_cast<uint4*>(&sA[r][kc]) = va;
+      *reinterpret_cast<uint4*>(&sB[r][kc]) = vb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 32; kk += 16) {
+      uint32_t af[2][4], bf[4][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int r = wm + i * 16 + grp;
+        af[i][0] = *reinterpret_cast<const uint32_t*>(&sA[r][kk + 2 * tq]);
+        af[i][1] = *reinterpret_cast<const uint32_t*>(&sA[r + 8][kk + 2 * tq]);
+        af[i][2] = *reinterpret_cast<const uint32_t*>(&sA[r][kk + 8 + 2 * tq]);
+        af[i][3] = *reinterpret_cast<const uint32_t*>(&sA[r + 8][kk + 8 + 2 * tq]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = wn + j * 8 + grp;
+        bf[j][0] = *reinterpret_cast<const uint32_t*>(&sB[r][kk + 2 * tq]);
+        bf[j][1] = *reinterpret_cast<const uint32_t*>(&sB[r][kk + 8 + 2 * tq]);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ptx::mma_16816(acc[i][j], af[i], bf[j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int t = t0 + wm + i * 16 + grp + (e >> 1) * 8;
+        const int n = n0 + wn + j * 8 + 2 * tq + (e & 1);
+        if (t >= ep.rows || n >= ep.N) continue;
+        const long long crow = (long long)b * ep.c_batch_rows + ep.c_row_off + t;
+        float v = acc[i][j][e];
+        if (ep.bias) v += ep.bias[n];
+        if (ep.gelu) v = gelu_erf(v);
+        if (ep.res_mode == 1) v += ep.res[crow * ep.ldc + n];
+        if (ep.res_mode == 2) v += ep.res[(long long)t * ep.N + n];
+        if (ep.c32) ep.c32[crow * ep.ldc + n] = v;
+        if (ep.c16) ep.c16[crow * ep.ldc + n] = __float2half_rn(v);
+      }
+}
+
+// ---- host: tensor maps ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct GemmContext {
+  PFN_encodeTiled encode = nullptr;
+  int use_mma = 0;
+  std::map<std::tuple<const void*, long long, long long, long long, long long, long long, int>, CUtensorMap> cache;
+};
+
+GemmContext* gemm_context_create() {
+  GemmContext* c = new GemmContext();
+  const char* impl = getenv("WB_GEMM_IMPL");
+  c->use_mma = impl && std::string(impl) == "mma";
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+      qres == cudaDriverEntryPointSuccess)
+    c->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  return c;
+}
+void gemm_context_destroy(GemmContext* c) { delete c; }
+
+// fp16 tensor (k, rows, batch) with element strides (1, row_stride, batch_stride); box (64, box_rows, 1); 128B swizzle
+static int get_tmap(GemmContext* ctx, const void* ptr, long long K, long long rows, long long nb, long long row_stride,
+                    long long batch_stride, int box_rows, CUtensorMap* out) {
+  auto key = std::make_tuple(ptr, K, rows, nb, row_stride, batch_stride, box_rows);
+  auto it = ctx->cache.find(key);
+  if (it != ctx->cache.end()) {
+    *out = it->second;
+    return 0;
+  }
+  if (!ctx->encode) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return -2;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)nb};
+  cuuint64_t strides[2] = {(cuuint64_t)row_stride * 2, (cuuint64_t)batch_stride * 2};
+  cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  const CUresult r = ctx->encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: %d (K=%lld rows=%lld nb=%lld rs=%lld bs=%lld)", (int)r, K, rows, nb,
+              row_stride, batch_stride);
+    return -2;
+  }
+  ctx->cache[key] = m;
+  *out = m;
+  return 0;
+}
+
+template <int BN>
+static int launch_tc(GemmContext* ctx, const GemmDesc& d, const GemmEpi& ep, cudaStream_t st) {
+  CUtensorMap tmA, tmB;
+  int rc = get_tmap(ctx, d.a, d.K, d.rows, d.n_batch, d.a_row_stride, d.a_batch_stride, kBM, &tmA);
+  if (rc) return rc;
+  // W as a 3-D map with a unit batch, so both operands share one encoder; the kernel loads it with 2-D coordinates
+  cuuint64_t dims[2] = {(cuuint64_t)d.K, (cuuint64_t)d.N};
+  cuuint64_t strides[1] = {(cuuint64_t)d.K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)BN};
+  cuuint32_t estr[2] = {1, 1};
+  auto key = std::make_tuple((const void*)d.w, (long long)d.K, (long long)d.N, -1LL, (long long)d.K, 0LL, BN);
+  auto it = ctx->cache.find(key);
+  if (it != ctx->cache.end()) {
+    tmB = it->second;
+  } else {
+    if (!ctx->encode) {
+      set_error("cuTensorMapEncodeTiled entry point not available");
+      return -2;
+    }
+    const CUresult r = ctx->encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(d.w), dims, strides, box,
+                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(W) failed: %d (N=%d K=%d)", (int)r, d.N, d.K);
+      return -2;
+    }
+    ctx->cache[key] = tmB;
+  }
+  auto kern = gemm_tc_kernel<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    WB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
+    attr_set = true;
+  }
+  dim3 grid(d.N / BN, (d.rows + kBM - 1) / kBM, d.n_batch);
+  kern<<<grid, kGemmThreads, GemmSmem<BN>::kTotal, st>>>(tmA, tmB, ep);
+  WB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_gemm(GemmContext* ctx, const GemmDesc& d, cudaStream_t st, int64_t* launches) {
+  if (d.N % 128 != 0 || d.K % 8 != 0 || d.a_row_stride % 8 != 0 || d.a_batch_stride % 8 != 0 || d.ldc % 8 != 0) {
+    set_error("launch_gemm: unsupported shape N=%d K=%d (N%%128, K%%8, strides%%8 required)", d.N, d.K);
+    return -1;
+  }
+  GemmEpi ep;
+  ep.bias = d.bias, ep.res = d.res, ep.c16 = d.c16, ep.c32 = d.c32;
+  ep.N = d.N, ep.K = d.K, ep.rows = d.rows, ep.gelu = d.gelu, ep.res_mode = d.res_mode, ep.ldc = d.ldc;
+  ep.c_row_off = d.c_row_off, ep.c_batch_rows = d.c_batch_rows;
+  if (launches) *launches += 1;
+  if (ctx->use_mma) {
+    GemmMmaArgs g{d.a, d.a_row_stride, d.a_batch_stride, d.w, ep};
+    dim3 grid(d.N / 64, (d.rows + 63) / 64, d.n_batch);
+    gemm_mma_kernel<<<grid, 128, 0, st>>>(g);
+    WB_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  return launch_tc<128>(ctx, d, ep, st);
+}
+
+}  // namespace wb

@@ -1,0 +1,208 @@
+// Log-mel front end on the GPU: kernels + launchers. See logmel.cuh for the per-phase math and the reference map.
+//
+// Data layout in HBM
+//   audio      f32 [B][480000] (throughput path)  or  f64 [B][480400] (legacy ABI, pads ignored on read)
+//   logspec    T   [B][80][3000]   log10(max(mel,1e-10))            (intermediate, lib.rs:76)
+//   gmax       ordered-uint per chunk                               (lib.rs:82-88)
+//   out        T   [B][80][3000]   (max(l, g-8)+4)/4                (lib.rs:96, layout lib.rs:116-121)
+//   melT       f16 [B][3002][80]   same values, time-major with one zero row either side: the A operand of the
+//                                  conv1 implicit GEMM (row t of the im2col matrix = 240 contiguous halves at t*80)
+//
+// Algorithmic bytes per chunk (f32 path): 480000*4 read + 80*3000*4 written = 2.88 MB.
+#include "logmel.cuh"
+
+#include <math.h>
+#include <string.h>
+
+#include "mel80_sparse.inc"
+
+namespace wb {
+
+template <typename T>
+struct OrderedMax;
+template <>
+struct OrderedMax<float> {
+  using U = unsigned int;
+  __device__ static U enc(float f) { return float_to_ordered(f); }
+  __device__ static float dec(U u) { return ordered_to_float(u); }
+};
+template <>
+struct OrderedMax<double> {
+  using U = unsigned long long;
+  __device__ static U enc(double f) {
+    U u = (U)__double_as_longlong(f);
+    return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+  }
+  __device__ static double dec(U u) {
+    u = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
+    return __longlong_as_double((long long)u);
+  }
+};
+
+// One CTA = F consecutive frames of one chunk.  grid = (3000 / F, B).
+template <typename T, int F, int NT>
+__global__ void __launch_bounds__(NT) logmel_kernel(const T* __restrict__ audio, size_t chunk_stride, int chunk_off,
+                                                    const LogmelTables<T>* __restrict__ gtab, T* __restrict__ logspec,
+                                                    typename OrderedMax<T>::U* __restrict__ gmax) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  LogmelSmem<T, F>& sm = *reinterpret_cast<LogmelSmem<T, F>*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x, b = blockIdx.y;
+  const T* clip = audio + (size_t)b * chunk_stride + chunk_off;
+
+  // tables -> smem (word copy)
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(gtab);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.tab);
+    for (int i = tid; i < (int)(sizeof(LogmelTables<T>) / 4); i += NT) dst[i] = src[i];
+  }
+  // samples of this tile, reflection folded into the index map (lib.rs:34-40); padded coordinate p0 + s
+  const int p0 = tile * F * WB_HOP;
+  for (int s = tid; s < tile_samples<F>(); s += NT) sm.region0[samp_index(s)] = clip[reflect_index(p0 + s)];
+  __syncthreads();
+
+  logmel_phase_a<T, F>(sm, tid);
+  __syncthreads();
+  for (int task = tid; task < F * 25; task += NT) logmel_phase_b<T, F>(sm, task);
+  __syncthreads();
+  for (int task = tid; task < F * 100; task += NT) logmel_phase_c1<T, F>(sm, task);
+  __syncthreads();
+
+  T vmax = (T)-1e30;
+  for (int task = tid; task < F * WB_N_MELS; task += NT) {
+    const int i = task / F, fl = task - i * F;
+    const T v = logmel_phase_c2<T, F>(sm, fl, i);
+    logspec[((size_t)b * WB_N_MELS + i) * WB_N_FRAMES + tile * F + fl] = v;
+    vmax = v > vmax ? v : vmax;
+  }
+  // block max -> one atomic per CTA
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const T other = __shfl_xor_sync(0xffffffffu, vmax, o);
+    vmax = other > vmax ? other : vmax;
+  }
+  if ((tid & 31) == 0) sm.red[tid >> 5] = vmax;
+  __syncthreads();
+  if (tid == 0) {
+    T m = sm.red[0];
+    for (int w = 1; w < NT / 32; ++w) m = sm.red[w] > m ? sm.red[w] : m;
+    atomicMax(&gmax[b], OrderedMax<T>::enc(m));
+  }
+}
+
+// (max(l, g-8)+4)/4 (lib.rs:96).  One CTA = 120 frames x 80 mels of one chunk.  grid = (25, B).
+// Writes the [80][3000] layout of the reference (optional) and the time-major fp16 layout for conv1 (optional).
+constexpr int kNormFrames = 120;
+template <typename T>
+__global__ void __launch_bounds__(256) logmel_normalize_kernel(const T* __restrict__ logspec,
+                                                               const typename OrderedMax<T>::U* __restrict__ gmax,
+                                                               T* __restrict__ out, __half* __restrict__ melT) {
+  __shared__ __half tile[kNormFrames][WB_N_MELS + 2];
+  const int b = blockIdx.y, f0 = blockIdx.x * kNormFrames;
+  const T floor_v = OrderedMax<T>::dec(gmax[b]) - (T)8.0;
+  for (int idx = threadIdx.x; idx < WB_N_MELS * kNormFrames; idx += 256) {
+    const int i = idx / kNormFrames, f = idx - i * kNormFrames;
+    const size_t g = ((size_t)b * WB_N_MELS + i) * WB_N_FRAMES + f0 + f;
+    T v = logspec[g];
+    v = v > floor_v ? v : floor_v;
+    v = (v + (T)4.0) / (T)4.0;
+    if (out) out[g] = v;
+    if (melT) tile[f][i] = __float2half_rn((float)v);
+  }
+  if (melT) {
+    __syncthreads();
+    __half* dst = melT + ((size_t)b * (WB_N_FRAMES + 2) + 1 + f0) * WB_N_MELS;
+    for (int idx = threadIdx.x; idx < WB_N_MELS * kNormFrames; idx += 256) {
+      const int f = idx / WB_N_MELS, i = idx - f * WB_N_MELS;
+      dst[idx] = tile[f][i];
+    }
+  }
+}
+
+// mel [B][80][3000] f32 (already normalised, encoder.prediction's input) -> melT fp16 [B][3002][80]
+__global__ void __launch_bounds__(256) mel_transpose_kernel(const float* __restrict__ mel, __half* __restrict__ melT) {
+  __shared__ __half tile[kNormFrames][WB_N_MELS + 2];
+  const int b = blockIdx.y, f0 = blockIdx.x * kNormFrames;
+  for (int idx = threadIdx.x; idx < WB_N_MELS * kNormFrames; idx += 256) {
+    const int i = idx / kNormFrames, f = idx - i * kNormFrames;
+    tile[f][i] = __float2half_rn(mel[((size_t)b * WB_N_MELS + i) * WB_N_FRAMES + f0 + f]);
+  }
+  __syncthreads();
+  __half* dst = melT + ((size_t)b * (WB_N_FRAMES + 2) + 1 + f0) * WB_N_MELS;
+  for (int idx = threadIdx.x; idx < WB_N_MELS * kNormFrames; idx += 256) {
+    const int f = idx / WB_N_MELS, i = idx - f * WB_N_MELS;
+    dst[idx] = tile[f][i];
+  }
+}
+
+template <typename U>
+__global__ void fill_kernel(U* p, U v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------
+template <typename T>
+void build_logmel_tables(LogmelTables<T>& t) {
+  const double PI = 3.14159265358979323846264338327950288;
+  for (int i = 0; i < 400; ++i) t.window[i] = (T)((1.0 - cos(((double)i * 2.0 * PI) / 400.0)) / 2.0);   // lib.rs:26
+  for (int k = 0; k < 200; ++k) t.tw200[k] = {(T)cos(2.0 * PI * k / 200.0), (T)(-sin(2.0 * PI * k / 200.0))};
+  for (int k = 0; k <= 100; ++k) t.tw400[k] = {(T)cos(2.0 * PI * k / 400.0), (T)(-sin(2.0 * PI * k / 400.0))};
+  for (int i = 0; i < MEL80_NNZ; ++i) {
+    float f;
+    const uint32_t bits = MEL80_W_BITS_H[i];
+    memcpy(&f, &bits, 4);
+    t.melw[i] = (T)f;                                                                                    // lib.rs:65
+  }
+  t.melw[MEL80_NNZ] = (T)0;
+  for (int i = 0; i < 80; ++i) {
+    t.mel_lo[i] = MEL80_LO_H[i];
+    t.mel_cnt[i] = MEL80_CNT_H[i];
+    t.mel_off[i] = MEL80_OFF_H[i];
+  }
+}
+template void build_logmel_tables<float>(LogmelTables<float>&);
+template void build_logmel_tables<double>(LogmelTables<double>&);
+
+template <typename T>
+struct LogmelCfg;
+template <>
+struct LogmelCfg<float> {
+  static constexpr int F = 30, NT = 256;
+};
+template <>
+struct LogmelCfg<double> {
+  static constexpr int F = 15, NT = 128;
+};
+
+// Enqueue: logspec/gmax are scratch ([B][80][3000] T and [B] ordered). Returns 0 or -2 (error text recorded).
+template <typename T>
+int launch_logmel(const T* audio, size_t chunk_stride, int chunk_off, int B, const LogmelTables<T>* dtab, T* logspec,
+                  void* gmax, T* out, __half* melT, cudaStream_t st, int64_t* launches) {
+  using Cfg = LogmelCfg<T>;
+  using U = typename OrderedMax<T>::U;
+  static_assert(WB_N_FRAMES % Cfg::F == 0, "tile must divide 3000 frames");
+  static_assert(Cfg::NT >= Cfg::F * 8, "phase A needs 8 threads per frame");
+  const size_t smem = sizeof(LogmelSmem<T, Cfg::F>);
+  auto kern = logmel_kernel<T, Cfg::F, Cfg::NT>;
+  WB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fill_kernel<U><<<(B + 127) / 128, 128, 0, st>>>((U*)gmax, (U)0, B);
+  kern<<<dim3(WB_N_FRAMES / Cfg::F, B), Cfg::NT, smem, st>>>(audio, chunk_stride, chunk_off, dtab, logspec, (U*)gmax);
+  logmel_normalize_kernel<T><<<dim3(WB_N_FRAMES / kNormFrames, B), 256, 0, st>>>(logspec, (const U*)gmax, out, melT);
+  if (launches) *launches += 3;
+  WB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+template int launch_logmel<float>(const float*, size_t, int, int, const LogmelTables<float>*, float*, void*, float*,
+                                  __half*, cudaStream_t, int64_t*);
+template int launch_logmel<double>(const double*, size_t, int, int, const LogmelTables<double>*, double*, void*,
+                                   double*, __half*, cudaStream_t, int64_t*);
+
+int launch_mel_transpose(const float* mel, int B, __half* melT, cudaStream_t st, int64_t* launches) {
+  mel_transpose_kernel<<<dim3(WB_N_FRAMES / kNormFrames, B), 256, 0, st>>>(mel, melT);
+  if (launches) *launches += 1;
+  WB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace wb

@@ -1,0 +1,1026 @@
+// Model instance: weight arena, workspaces, encoder forward, decoder step / greedy loop (CUDA-graph replayed), and the
+// extern "C" entry points declared in include/whisper_b200.h.
+//
+// HBM layout (one handle = one GPU):
+//   weight arena   one allocation, every tensor 256-byte aligned: fp16 matrices in [N][K] (K-major, the layout both the
+//                  TMA-fed tcgen05 GEMM and the weight-streaming decoder GEMM read), q/k/v fused to [3d][d], conv weights
+//                  permuted to [d_out][tap][c_in]; fp32 biases / LayerNorm / positional tables
+//   encoder ws     melT f16 [B][3002][80] | x1 f16 [B][3001][d] | x f32 [B*1500][d] | h f16 | qkv f16 [.][3d] | att f16 |
+//                  mlp f16 [.][4d] | xa f16 [B*1500][d]
+//   cross K/V      f16 [L][B][1500][d] each  (persistent across decode steps; 2*L*1500*d*2 bytes per chunk)
+//   self  K/V      f16 [L][Mb][n_text_ctx][d] each
+//   decode ws      tokens i32 [Mb][n_text_ctx+1] | x f32 [Mb][d] | q f32 | attention split partials | mlp f16 [Mb][4d] |
+//                  logits f32 [Mb][V] | DecodeState
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/whisper_b200.h"
+#include "logmel.cuh"
+#include "ops.cuh"
+
+namespace wb {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+size_t logmel_tables_bytes_f32() { return sizeof(LogmelTables<float>); }
+size_t logmel_tables_bytes_f64() { return sizeof(LogmelTables<double>); }
+
+struct LayerW {
+  float *ln1_g, *ln1_b;
+  __half* wqkv;
+  float* bqkv;
+  __half* wo;
+  float* bo;
+  float *ln2_g, *ln2_b;
+  __half* w1;
+  float* b1;
+  __half* w2;
+  float* b2;
+  // decoder only
+  float *lnc_g, *lnc_b;
+  __half* wq_c;
+  float* bq_c;
+  __half* wk_c;
+  __half* wv_c;
+  float* bv_c;
+  __half* wo_c;
+  float* bo_c;
+};
+
+enum WKind { WK_F32 = 0, WK_F16 = 1, WK_CONV = 2 };
+struct WEntry {
+  int kind;
+  void* dst;
+  size_t numel;
+  int conv_out, conv_in;   // WK_CONV: source [out][in][3] -> dest [out][3][in]
+  bool set;
+  float rnd_scale, rnd_offset;
+};
+
+struct Arena {
+  unsigned char* base = nullptr;
+  size_t size = 0, off = 0;
+  bool measure = true;
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = measure ? nullptr : reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+}  // namespace wb
+
+using namespace wb;
+
+struct wb_handle {
+  wb_dims dims;
+  int max_batch, max_beams, device;
+  cudaStream_t stream;
+  bool own_stream;
+  int64_t launches;
+  bool weights_ready;
+  int enc_batch;   // chunks whose features are resident (0 = none)
+
+  // weights
+  Arena arena;
+  std::unordered_map<std::string, WEntry> wmap;
+  __half *conv1_w, *conv2_w, *tok_emb;
+  float *conv1_b, *conv2_b, *enc_pos, *dec_pos, *lnpost_g, *lnpost_b, *lnf_g, *lnf_b;
+  std::vector<LayerW> enc, dec;
+
+  // log-mel
+  LogmelTables<float>* tab32;
+  float* audio_dev;
+  float* logspec;
+  void* gmax;
+  float* mel32;
+
+  // encoder workspace
+  Arena ws;
+  __half *melT, *x1, *h16, *qkv16, *att16, *mlp16, *xa16;
+  float *xenc, *xa32;
+  std::vector<__half*> crossK, crossV;
+  GemmContext* gemm;
+
+  // decoder workspace
+  int Mb_max;
+  std::vector<__half*> selfK, selfV;
+  int32_t* tokens;
+  int tokens_ld;
+  float *xdec, *q32, *part_ml, *part_acc, *logits, *sum_logprob;
+  __half* dmlp16;
+  int32_t *done, *suppress, *suppress_begin;
+  DecodeState* state;
+  int split_self, split_cross;
+
+  // graphs
+  cudaGraphExec_t g_step, g_sample;
+  int64_t nodes_step, nodes_sample;
+  std::string graph_key;
+
+  // host staging + timing
+  int32_t* h_done;
+  cudaEvent_t ev[4];
+  float timings[4];
+};
+
+namespace wb {
+
+static void add_entry(wb_handle* h, const std::string& name, int kind, void* dst, size_t numel, float rs, float ro,
+                      int co = 0, int ci = 0) {
+  h->wmap[name] = WEntry{kind, dst, numel, co, ci, false, rs, ro};
+}
+
+// Lays out every weight in the arena; called twice (measure, then assign).
+static void layout_weights(wb_handle* h) {
+  const wb_dims& D = h->dims;
+  Arena& A = h->arena;
+  const size_t d = D.n_audio_state, dt = D.n_text_state;
+  const bool reg = !A.measure;
+  h->conv1_w = A.take<__half>(d * 240);
+  h->conv1_b = A.take<float>(d);
+  h->conv2_w = A.take<__half>(d * 3 * d);
+  h->conv2_b = A.take<float>(d);
+  h->enc_pos = A.take<float>((size_t)D.n_audio_ctx * d);
+  if (reg) {
+    add_entry(h, "encoder.conv1.weight", WK_CONV, h->conv1_w, d * 240, 1.0f / sqrtf(240.f), 0, (int)d, 80);
+    add_entry(h, "encoder.conv1.bias", WK_F32, h->conv1_b, d, 0.02f, 0);
+    add_entry(h, "encoder.conv2.weight", WK_CONV, h->conv2_w, d * 3 * d, 1.0f / sqrtf(3.f * d), 0, (int)d, (int)d);
+    add_entry(h, "encoder.conv2.bias", WK_F32, h->conv2_b, d, 0.02f, 0);
+    add_entry(h, "encoder.positional_embedding", WK_F32, h->enc_pos, (size_t)D.n_audio_ctx * d, 0.3f, 0);
+  }
+  auto block = [&](const std::string& pre, LayerW& L, size_t n, bool cross) {
+    const float ws = 0.7f / sqrtf((float)n), qs = 2.0f / sqrtf((float)n);
+    L.ln1_g = A.take<float>(n), L.ln1_b = A.take<float>(n);
+    L.wqkv = A.take<__half>(3 * n * n), L.bqkv = A.take<float>(3 * n);
+    L.wo = A.take<__half>(n * n), L.bo = A.take<float>(n);
+    L.ln2_g = A.take<float>(n), L.ln2_b = A.take<float>(n);
+    L.w1 = A.take<__half>(4 * n * n), L.b1 = A.take<float>(4 * n);
+    L.w2 = A.take<__half>(4 * n * n), L.b2 = A.take<float>(n);
+    if (cross) {
+      L.lnc_g = A.take<float>(n), L.lnc_b = A.take<float>(n);
+      L.wq_c = A.take<__half>(n * n), L.bq_c = A.take<float>(n);
+      L.wk_c = A.take<__half>(n * n);
+      L.wv_c = A.take<__half>(n * n), L.bv_c = A.take<float>(n);
+      L.wo_c = A.take<__half>(n * n), L.bo_c = A.take<float>(n);
+    }
+    if (!reg) return;
+    add_entry(h, pre + ".attn_ln.weight", WK_F32, L.ln1_g, n, 0.1f, 1.0f);
+    add_entry(h, pre + ".attn_ln.bias", WK_F32, L.ln1_b, n, 0.05f, 0);
+    add_entry(h, pre + ".attn.query.weight", WK_F16, L.wqkv, n * n, qs, 0);
+    add_entry(h, pre + ".attn.key.weight", WK_F16, L.wqkv + n * n, n * n, qs, 0);
+    add_entry(h, pre + ".attn.value.weight", WK_F16, L.wqkv + 2 * n * n, n * n, ws, 0);
+    add_entry(h, pre + ".attn.query.bias", WK_F32, L.bqkv, n, 0.02f, 0);
+    add_entry(h, pre + ".attn.value.bias", WK_F32, L.bqkv + 2 * n, n, 0.02f, 0);
+    add_entry(h, pre + ".attn.out.weight", WK_F16, L.wo, n * n, ws, 0);
+    add_entry(h, pre + ".attn.out.bias", WK_F32, L.bo, n, 0.02f, 0);
+    add_entry(h, pre + ".mlp_ln.weight", WK_F32, L.ln2_g, n, 0.1f, 1.0f);
+    add_entry(h, pre + ".mlp_ln.bias", WK_F32, L.ln2_b, n, 0.05f, 0);
+    add_entry(h, pre + ".mlp.0.weight", WK_F16, L.w1, 4 * n * n, ws, 0);
+    add_entry(h, pre + ".mlp.0.bias", WK_F32, L.b1, 4 * n, 0.02f, 0);
+    add_entry(h, pre + ".mlp.2.weight", WK_F16, L.w2, 4 * n * n, 0.7f / sqrtf(4.f * n), 0);
+    add_entry(h, pre + ".mlp.2.bias", WK_F32, L.b2, n, 0.02f, 0);
+    if (cross) {
+      add_entry(h, pre + ".cross_attn_ln.weight", WK_F32, L.lnc_g, n, 0.1f, 1.0f);
+      add_entry(h, pre + ".cross_attn_ln.bias", WK_F32, L.lnc_b, n, 0.05f, 0);
+      add_entry(h, pre + ".cross_attn.query.weight", WK_F16, L.wq_c, n * n, qs, 0);
+      add_entry(h, pre + ".cross_attn.query.bias", WK_F32, L.bq_c, n, 0.02f, 0);
+      add_entry(h, pre + ".cross_attn.key.weight", WK_F16, L.wk_c, n * n, qs, 0);
+      add_entry(h, pre + ".cross_attn.value.weight", WK_F16, L.wv_c, n * n, ws, 0);
+      add_entry(h, pre + ".cross_attn.value.bias", WK_F32, L.bv_c, n, 0.02f, 0);
+      add_entry(h, pre + ".cross_attn.out.weight", WK_F16, L.wo_c, n * n, ws, 0);
+      add_entry(h, pre + ".cross_attn.out.bias", WK_F32, L.bo_c, n, 0.02f, 0);
+    }
+  };
+  h->enc.resize(D.n_audio_layer);
+  for (int i = 0; i < D.n_audio_layer; ++i) block("encoder.blocks." + std::to_string(i), h->enc[i], d, false);
+  h->lnpost_g = A.take<float>(d), h->lnpost_b = A.take<float>(d);
+  h->tok_emb = A.take<__half>((size_t)D.n_vocab * dt);
+  h->dec_pos = A.take<float>((size_t)D.n_text_ctx * dt);
+  h->dec.resize(D.n_text_layer);
+  for (int i = 0; i < D.n_text_layer; ++i) block("decoder.blocks." + std::to_string(i), h->dec[i], dt, true);
+  h->lnf_g = A.take<float>(dt), h->lnf_b = A.take<float>(dt);
+  if (reg) {
+    add_entry(h, "encoder.ln_post.weight", WK_F32, h->lnpost_g, d, 0.1f, 1.0f);
+    add_entry(h, "encoder.ln_post.bias", WK_F32, h->lnpost_b, d, 0.05f, 0);
+    add_entry(h, "decoder.token_embedding.weight", WK_F16, h->tok_emb, (size_t)D.n_vocab * dt, 0.05f, 0);
+    add_entry(h, "decoder.positional_embedding", WK_F32, h->dec_pos, (size_t)D.n_text_ctx * dt, 0.1f, 0);
+    add_entry(h, "decoder.ln.weight", WK_F32, h->lnf_g, dt, 0.1f, 1.0f);
+    add_entry(h, "decoder.ln.bias", WK_F32, h->lnf_b, dt, 0.05f, 0);
+  }
+}
+
+static void layout_workspace(wb_handle* h) {
+  const wb_dims& D = h->dims;
+  Arena& A = h->ws;
+  const size_t B = h->max_batch, d = D.n_audio_state, dt = D.n_text_state, T = D.n_audio_ctx, Mb = h->Mb_max;
+  h->tab32 = A.take<LogmelTables<float>>(1);
+  h->audio_dev = A.take<float>(B * WB_N_SAMPLES);
+  h->logspec = A.take<float>(B * WB_N_MELS * WB_N_FRAMES);
+  h->gmax = A.take<unsigned long long>(B);
+  h->mel32 = A.take<float>(B * WB_N_MELS * WB_N_FRAMES);
+  h->melT = A.take<__half>(B * (WB_N_FRAMES + 2) * WB_N_MELS);
+  h->x1 = A.take<__half>(B * (2 * T + 1) * d);
+  h->xenc = A.take<float>(B * T * d);
+  h->h16 = A.take<__half>(B * T * d);
+  h->qkv16 = A.take<__half>(B * T * 3 * d);
+  h->att16 = A.take<__half>(B * T * d);
+  h->mlp16 = A.take<__half>(B * T * 4 * d);
+  h->xa16 = A.take<__half>(B * T * d);
+  h->xa32 = A.take<float>(B * T * d);
+  h->crossK.resize(D.n_text_layer), h->crossV.resize(D.n_text_layer);
+  for (int l = 0; l < D.n_text_layer; ++l) {
+    h->crossK[l] = A.take<__half>(B * T * dt);
+    h->crossV[l] = A.take<__half>(B * T * dt);
+  }
+  h->selfK.resize(D.n_text_layer), h->selfV.resize(D.n_text_layer);
+  for (int l = 0; l < D.n_text_layer; ++l) {
+    h->selfK[l] = A.take<__half>(Mb * D.n_text_ctx * dt);
+    h->selfV[l] = A.take<__half>(Mb * D.n_text_ctx * dt);
+  }
+  h->tokens_ld = D.n_text_ctx + 8;
+  h->tokens = A.take<int32_t>(Mb * h->tokens_ld);
+  h->xdec = A.take<float>(Mb * dt);
+  h->q32 = A.take<float>(Mb * dt);
+  const size_t smax = 32;
+  h->part_ml = A.take<float>(Mb * smax * D.n_text_head * 2);
+  h->part_acc = A.take<float>(Mb * smax * dt);
+  h->dmlp16 = A.take<__half>(Mb * 4 * dt);
+  h->logits = A.take<float>(Mb * (size_t)D.n_vocab);
+  h->sum_logprob = A.take<float>(Mb);
+  h->done = A.take<int32_t>(Mb);
+  h->suppress = A.take<int32_t>(4096);
+  h->suppress_begin = A.take<int32_t>(256);
+  h->state = A.take<DecodeState>(1);
+}
+
+static int check_dims(const wb_dims& D) {
+  if (D.n_mels != 80 || D.n_audio_ctx != 1500) return -1;
+  if (D.n_audio_state <= 0 || D.n_audio_state % 128 || D.n_audio_state > 1280) return -1;
+  if (D.n_text_state != D.n_audio_state) return -1;
+  if (D.n_audio_head * 64 != D.n_audio_state || D.n_text_head * 64 != D.n_text_state) return -1;
+  if (D.n_audio_layer < 1 || D.n_text_layer < 1 || D.n_vocab < 1000 || D.n_text_ctx < 8 || D.n_text_ctx > 448) return -1;
+  return 0;
+}
+
+#define WB_TRY(expr)           \
+  do {                         \
+    const int _rc = (expr);    \
+    if (_rc != 0) return _rc;  \
+  } while (0)
+
+// ---- encoder -------------------------------------------------------------------------------------------------------------
+static int plain_gemm(wb_handle* h, const __half* a, int M, const __half* w, int N, int K, const float* bias, int gelu,
+                      const float* res, __half* c16, float* c32) {
+  GemmDesc g{};
+  g.a = a, g.a_row_stride = K, g.a_batch_stride = (long long)M * K, g.rows = M, g.n_batch = 1;
+  g.w = w, g.N = N, g.K = K, g.bias = bias, g.gelu = gelu, g.res_mode = res ? 1 : 0, g.res = res;
+  g.c16 = c16, g.c32 = c32, g.ldc = N, g.c_batch_rows = 0, g.c_row_off = 0;
+  return launch_gemm(h->gemm, g, h->stream, &h->launches);
+}
+
+// melT (already filled) -> xa16 / xa32 and the cross-attention K/V of every decoder layer
+static int encoder_forward(wb_handle* h, int B) {
+  const wb_dims& D = h->dims;
+  const int d = D.n_audio_state, T = D.n_audio_ctx, M = B * T;
+  cudaStream_t st = h->stream;
+  {   // conv1 + GELU: im2col row t = 240 contiguous halves at melT[b][t][0]
+    GemmDesc g{};
+    g.a = h->melT, g.a_row_stride = WB_N_MELS, g.a_batch_stride = (long long)(WB_N_FRAMES + 2) * WB_N_MELS;
+    g.rows = WB_N_FRAMES, g.n_batch = B, g.w = h->conv1_w, g.N = d, g.K = 3 * WB_N_MELS, g.bias = h->conv1_b, g.gelu = 1;
+    g.c16 = h->x1, g.ldc = d, g.c_batch_rows = 2 * T + 1, g.c_row_off = 1;
+    WB_TRY(launch_gemm(h->gemm, g, st, &h->launches));
+  }
+  {   // conv2 (stride 2) + GELU + sinusoidal positions: row t = 3d contiguous halves at x1[b][2t][0]
+    GemmDesc g{};
+    g.a = h->x1, g.a_row_stride = 2 * d, g.a_batch_stride = (long long)(2 * T + 1) * d;
+    g.rows = T, g.n_batch = B, g.w = h->conv2_w, g.N = d, g.K = 3 * d, g.bias = h->conv2_b, g.gelu = 1;
+    g.res_mode = 2, g.res = h->enc_pos, g.c32 = h->xenc, g.ldc = d, g.c_batch_rows = T, g.c_row_off = 0;
+    WB_TRY(launch_gemm(h->gemm, g, st, &h->launches));
+  }
+  for (int l = 0; l < D.n_audio_layer; ++l) {
+    const LayerW& L = h->enc[l];
+    WB_TRY(launch_layernorm(h->xenc, L.ln1_g, L.ln1_b, M, d, h->h16, nullptr, st, &h->launches));
+    WB_TRY(plain_gemm(h, h->h16, M, L.wqkv, 3 * d, d, L.bqkv, 0, nullptr, h->qkv16, nullptr));
+    WB_TRY(launch_encoder_attention(h->qkv16, B, T, D.n_audio_head, h->att16, st, &h->launches));
+    WB_TRY(plain_gemm(h, h->att16, M, L.wo, d, d, L.bo, 0, h->xenc, nullptr, h->xenc));
+    WB_TRY(launch_layernorm(h->xenc, L.ln2_g, L.ln2_b, M, d, h->h16, nullptr, st, &h->launches));
+    WB_TRY(plain_gemm(h, h->h16, M, L.w1, 4 * d, d, L.b1, 1, nullptr, h->mlp16, nullptr));
+    WB_TRY(plain_gemm(h, h->mlp16, M, L.w2, d, 4 * d, L.b2, 0, h->xenc, nullptr, h->xenc));
+  }
+  WB_TRY(launch_layernorm(h->xenc, h->lnpost_g, h->lnpost_b, M, d, h->xa16, h->xa32, st, &h->launches));
+  return 0;
+}
+
+static int cross_kv(wb_handle* h, int B) {
+  const wb_dims& D = h->dims;
+  const int d = D.n_text_state, M = B * D.n_audio_ctx;
+  for (int l = 0; l < D.n_text_layer; ++l) {
+    const LayerW& L = h->dec[l];
+    WB_TRY(plain_gemm(h, h->xa16, M, L.wk_c, d, d, nullptr, 0, nullptr, h->crossK[l], nullptr));
+    WB_TRY(plain_gemm(h, h->xa16, M, L.wv_c, d, d, L.bv_c, 0, nullptr, h->crossV[l], nullptr));
+  }
+  h->enc_batch = B;
+  return 0;
+}
+
+// ---- decoder ---------------------------------------------------------------------------------------------------------------
+struct StepOpts {
+  int Mb, beams;
+  int want_logits, sample;
+  SampleDesc sd;
+};
+
+static int decode_step(wb_handle* h, const StepOpts& o) {
+  const wb_dims& D = h->dims;
+  const int d = D.n_text_state, H = D.n_text_head, Mb = o.Mb;
+  cudaStream_t st = h->stream;
+  WB_TRY(launch_embed(h->tokens, h->tokens_ld, h->tok_emb, h->dec_pos, Mb, d, D.n_vocab, h->xdec, h->state, st, &h->launches));
+  for (int l = 0; l < D.n_text_layer; ++l) {
+    const LayerW& L = h->dec[l];
+    SkinnyDesc s{};
+    s.Mb = Mb, s.n_head = H, s.state = h->state;
+    // self attention
+    s.N = 3 * d, s.K = d, s.w = L.wqkv, s.bias = L.bqkv, s.in_mode = SKINNY_IN_LN, s.in = h->xdec, s.ln_g = L.ln1_g,
+    s.ln_b = L.ln1_b, s.out_mode = SKINNY_OUT_QKV, s.q32 = h->q32, s.kcache = h->selfK[l], s.vcache = h->selfV[l],
+    s.n_ctx = D.n_text_ctx;
+    WB_TRY(launch_skinny_gemm(s, st, &h->launches));
+    AttnDecodeDesc a{};
+    a.Mb = Mb, a.d = d, a.n_head = H, a.n_split = h->split_self, a.q = h->q32, a.k = h->selfK[l], a.v = h->selfV[l];
+    a.n_ctx = D.n_text_ctx, a.n_rows_fixed = 0, a.kv_share = 1, a.state = h->state, a.part_ml = h->part_ml, a.part_acc = h->part_acc;
+    WB_TRY(launch_attn_decode(a, st, &h->launches));
+    SkinnyDesc so{};
+    so.Mb = Mb, so.n_head = H, so.state = h->state, so.N = d, so.K = d, so.w = L.wo, so.bias = L.bo, so.in_mode = SKINNY_IN_ATTN;
+    so.part_ml = h->part_ml, so.part_acc = h->part_acc, so.n_split = h->split_self, so.out_mode = SKINNY_OUT_RESID, so.out = h->xdec;
+    WB_TRY(launch_skinny_gemm(so, st, &h->launches));
+    // cross attention
+    SkinnyDesc sq{};
+    sq.Mb = Mb, sq.n_head = H, sq.state = h->state, sq.N = d, sq.K = d, sq.w = L.wq_c, sq.bias = L.bq_c, sq.in_mode = SKINNY_IN_LN;
+    sq.in = h->xdec, sq.ln_g = L.lnc_g, sq.ln_b = L.lnc_b, sq.out_mode = SKINNY_OUT_F32, sq.out = h->q32;
+    WB_TRY(launch_skinny_gemm(sq, st, &h->launches));
+    AttnDecodeDesc c = a;
+    c.n_split = h->split_cross, c.k = h->crossK[l], c.v = h->crossV[l], c.n_ctx = D.n_audio_ctx, c.n_rows_fixed = D.n_audio_ctx;
+    c.kv_share = o.beams;
+    WB_TRY(launch_attn_decode(c, st, &h->launches));
+    SkinnyDesc sc = so;
+    sc.w = L.wo_c, sc.bias = L.bo_c, sc.n_split = h->split_cross;
+    WB_TRY(launch_skinny_gemm(sc, st, &h->launches));
+    // MLP
+    SkinnyDesc m1{};
+    m1.Mb = Mb, m1.n_head = H, m1.state = h->state, m1.N = 4 * d, m1.K = d, m1.w = L.w1, m1.bias = L.b1, m1.gelu = 1;
+    m1.in_mode = SKINNY_IN_LN, m1.in = h->xdec, m1.ln_g = L.ln2_g, m1.ln_b = L.ln2_b, m1.out_mode = SKINNY_OUT_F16, m1.out = h->dmlp16;
+    WB_TRY(launch_skinny_gemm(m1, st, &h->launches));
+    SkinnyDesc m2{};
+    m2.Mb = Mb, m2.n_head = H, m2.state = h->state, m2.N = d, m2.K = 4 * d, m2.w = L.w2, m2.bias = L.b2;
+    m2.in_mode = SKINNY_IN_F16, m2.in = h->dmlp16, m2.out_mode = SKINNY_OUT_RESID, m2.out = h->xdec;
+    WB_TRY(launch_skinny_gemm(m2, st, &h->launches));
+  }
+  if (o.want_logits || o.sample) {
+    SkinnyDesc lg{};
+    lg.Mb = Mb, lg.n_head = H, lg.state = h->state, lg.N = D.n_vocab, lg.K = d, lg.w = h->tok_emb, lg.in_mode = SKINNY_IN_LN;
+    lg.in = h->xdec, lg.ln_g = h->lnf_g, lg.ln_b = h->lnf_b, lg.out_mode = SKINNY_OUT_F32, lg.out = h->logits;
+    WB_TRY(launch_skinny_gemm(lg, st, &h->launches));
+  }
+  if (o.sample) WB_TRY(launch_sample_greedy(o.sd, st, &h->launches));
+  return 0;
+}
+
+static int reset_decode_state(wb_handle* h) {
+  WB_CUDA_OK(cudaMemsetAsync(h->state, 0, sizeof(DecodeState), h->stream));
+  return 0;
+}
+
+static void pick_splits(wb_handle* h, int Mb) {
+  // cross attention: enough CTAs for ~2 per SM; self attention: few rows, favour short chains
+  int sc = (296 + Mb - 1) / Mb;
+  sc = sc < 1 ? 1 : (sc > 32 ? 32 : sc);
+  h->split_cross = sc;
+  int ss = (148 + Mb - 1) / Mb;
+  ss = ss < 1 ? 1 : (ss > 8 ? 8 : ss);
+  h->split_self = ss;
+}
+
+static void destroy_graphs(wb_handle* h) {
+  if (h->g_step) cudaGraphExecDestroy(h->g_step);
+  if (h->g_sample) cudaGraphExecDestroy(h->g_sample);
+  h->g_step = h->g_sample = nullptr;
+  h->graph_key.clear();
+}
+
+static int capture(wb_handle* h, const StepOpts& o, cudaGraphExec_t* out, int64_t* nodes) {
+  cudaGraph_t g;
+  const int64_t before = h->launches;
+  WB_CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = decode_step(h, o);
+  const cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+  *nodes = h->launches - before;
+  h->launches = before;
+  if (rc) return rc;
+  WB_CUDA_OK(e);
+  WB_CUDA_OK(cudaGraphInstantiate(out, g, 0));
+  WB_CUDA_OK(cudaGraphDestroy(g));
+  return 0;
+}
+
+}  // namespace wb
+
+// ======================================================================================================================
+//                                                   extern "C"
+// ======================================================================================================================
+extern "C" {
+
+const char* wb_last_error(void) { return wb::get_error(); }
+int wb_version(void) { return 100; }
+
+static int select_device(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    set_error("no CUDA device available (this library has no CPU fallback)");
+    return WB_ERR_CUDA;
+  }
+  if (device < 0 || device >= n) {
+    set_error("device %d out of range (%d visible)", device, n);
+    return WB_ERR_ARG;
+  }
+  WB_CUDA_OK(cudaSetDevice(device));
+  return 0;
+}
+
+int wb_create(const wb_dims* dims, int32_t max_batch, int32_t max_beams, int32_t device, void* stream, wb_handle** out) {
+  if (!dims || !out || max_batch < 1 || max_beams < 1 || max_batch * max_beams > 40) {
+    set_error("wb_create: bad argument");
+    return WB_ERR_ARG;
+  }
+  if (check_dims(*dims)) {
+    set_error("wb_create: unsupported model dimensions");
+    return WB_ERR_ARG;
+  }
+  WB_TRY(select_device(device));
+  wb_handle* h = new wb_handle();
+  h->dims = *dims, h->max_batch = max_batch, h->max_beams = max_beams, h->device = device;
+  h->Mb_max = max_batch * max_beams;
+  h->launches = 0, h->weights_ready = false, h->enc_batch = 0;
+  h->g_step = h->g_sample = nullptr;
+  h->nodes_step = h->nodes_sample = 0;
+  h->own_stream = stream == nullptr;
+  if (h->own_stream)
+    WB_CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  else
+    h->stream = reinterpret_cast<cudaStream_t>(stream);
+  // weights
+  h->arena.measure = true, h->arena.off = 0;
+  layout_weights(h);
+  h->arena.size = (h->arena.off + 255) & ~(size_t)255;
+  if (cudaMalloc(&h->arena.base, h->arena.size) != cudaSuccess) {
+    set_error("wb_create: cudaMalloc(%zu) for weights failed", h->arena.size);
+    delete h;
+    return WB_ERR_NOMEM;
+  }
+  WB_CUDA_OK(cudaMemset(h->arena.base, 0, h->arena.size));
+  h->arena.measure = false, h->arena.off = 0;
+  layout_weights(h);
+  // workspace
+  h->ws.measure = true, h->ws.off = 0;
+  layout_workspace(h);
+  h->ws.size = (h->ws.off + 255) & ~(size_t)255;
+  if (cudaMalloc(&h->ws.base, h->ws.size) != cudaSuccess) {
+    set_error("wb_create: cudaMalloc(%zu) for workspace failed", h->ws.size);
+    cudaFree(h->arena.base);
+    delete h;
+    return WB_ERR_NOMEM;
+  }
+  WB_CUDA_OK(cudaMemset(h->ws.base, 0, h->ws.size));
+  h->ws.measure = false, h->ws.off = 0;
+  layout_workspace(h);
+  LogmelTables<float>* t = new LogmelTables<float>();
+  build_logmel_tables<float>(*t);
+  WB_CUDA_OK(cudaMemcpy(h->tab32, t, sizeof(*t), cudaMemcpyHostToDevice));
+  delete t;
+  h->gemm = gemm_context_create();
+  WB_CUDA_OK(cudaMallocHost(&h->h_done, sizeof(int32_t) * h->Mb_max));
+  for (int i = 0; i < 4; ++i) WB_CUDA_OK(cudaEventCreate(&h->ev[i]));
+  memset(h->timings, 0, sizeof(h->timings));
+  *out = h;
+  return WB_OK;
+}
+
+int wb_destroy(wb_handle* h) {
+  if (!h) return WB_ERR_ARG;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  destroy_graphs(h);
+  gemm_context_destroy(h->gemm);
+  for (int i = 0; i < 4; ++i) cudaEventDestroy(h->ev[i]);
+  cudaFreeHost(h->h_done);
+  cudaFree(h->arena.base);
+  cudaFree(h->ws.base);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return WB_OK;
+}
+
+int wb_get_dims(const wb_handle* h, wb_dims* out) {
+  if (!h || !out) return WB_ERR_ARG;
+  *out = h->dims;
+  return WB_OK;
+}
+
+int wb_set_weight(wb_handle* h, const char* name, const float* data, size_t numel) {
+  if (!h || !name || !data) return WB_ERR_ARG;
+  auto it = h->wmap.find(name);
+  if (it == h->wmap.end()) {
+    set_error("wb_set_weight: unknown tensor '%s'", name);
+    return WB_ERR_ARG;
+  }
+  WEntry& e = it->second;
+  if (numel != e.numel) {
+    set_error("wb_set_weight: '%s' expects %zu elements, got %zu", name, e.numel, numel);
+    return WB_ERR_ARG;
+  }
+  WB_CUDA_OK(cudaSetDevice(h->device));
+  if (e.kind == WK_F32) {
+    WB_CUDA_OK(cudaMemcpy(e.dst, data, numel * sizeof(float), cudaMemcpyHostToDevice));
+  } else {
+    std::vector<__half> tmp(numel);
+    if (e.kind == WK_F16) {
+      for (size_t i = 0; i < numel; ++i) tmp[i] = __float2half_rn(data[i]);
+    } else {   // [out][in][3] -> [out][3][in]
+      const size_t ci = e.conv_in;
+      for (size_t o = 0; o < (size_t)e.conv_out; ++o)
+        for (size_t c = 0; c < ci; ++c)
+          for (size_t t = 0; t < 3; ++t) tmp[(o * 3 + t) * ci + c] = __float2half_rn(data[(o * ci + c) * 3 + t]);
+    }
+    WB_CUDA_OK(cudaMemcpy(e.dst, tmp.data(), numel * sizeof(__half), cudaMemcpyHostToDevice));
+  }
+  e.set = true;
+  return WB_OK;
+}
+
+int wb_weights_commit(wb_handle* h) {
+  if (!h) return WB_ERR_ARG;
+  for (auto& kv : h->wmap)
+    if (!kv.second.set) {
+      set_error("wb_weights_commit: tensor '%s' was never set", kv.first.c_str());
+      return WB_ERR_STATE;
+    }
+  h->weights_ready = true;
+  return WB_OK;
+}
+
+int wb_init_random_weights(wb_handle* h, uint64_t seed) {
+  if (!h) return WB_ERR_ARG;
+  WB_CUDA_OK(cudaSetDevice(h->device));
+  uint64_t i = 0;
+  std::vector<std::string> names;
+  for (auto& kv : h->wmap) names.push_back(kv.first);
+  std::sort(names.begin(), names.end());
+  for (auto& nm : names) {
+    WEntry& e = h->wmap[nm];
+    WB_TRY(launch_fill_random(e.dst, e.numel, e.kind != WK_F32, e.rnd_scale, e.rnd_offset, seed * 1000003ull + (++i), h->stream,
+                              &h->launches));
+    e.set = true;
+  }
+  // encoder positions: upstream sinusoids (same table as the oracle's sinusoids())
+  const int T = h->dims.n_audio_ctx, d = h->dims.n_audio_state;
+  std::vector<float> pos((size_t)T * d);
+  const double inc = log(10000.0) / (d / 2 - 1);
+  for (int t = 0; t < T; ++t)
+    for (int c = 0; c < d / 2; ++c) {
+      const float inv = expf((float)(-inc * c));
+      pos[(size_t)t * d + c] = sinf((float)t * inv);
+      pos[(size_t)t * d + d / 2 + c] = cosf((float)t * inv);
+    }
+  WB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  WB_CUDA_OK(cudaMemcpy(h->enc_pos, pos.data(), pos.size() * sizeof(float), cudaMemcpyHostToDevice));
+  h->weights_ready = true;
+  return WB_OK;
+}
+
+int wb_weight_arena(wb_handle* h, void** device_ptr, size_t* bytes) {
+  if (!h || !device_ptr || !bytes) return WB_ERR_ARG;
+  *device_ptr = h->arena.base;
+  *bytes = h->arena.size;
+  return WB_OK;
+}
+
+int wb_weights_mark_loaded(wb_handle* h) {
+  if (!h) return WB_ERR_ARG;
+  for (auto& kv : h->wmap) kv.second.set = true;
+  h->weights_ready = true;
+  return WB_OK;
+}
+
+// ---- log-mel -------------------------------------------------------------------------------------------------------------
+static int check_batch(wb_handle* h, int32_t B) {
+  if (!h) return WB_ERR_ARG;
+  if (B < 1 || B > h->max_batch) {
+    set_error("batch %d out of range [1, %d]", B, h->max_batch);
+    return WB_ERR_ARG;
+  }
+  WB_CUDA_OK(cudaSetDevice(h->device));
+  return 0;
+}
+
+int wb_logmel_dev(wb_handle* h, const float* audio_dev, int32_t B, float* out_dev) {
+  WB_TRY(check_batch(h, B));
+  if (!audio_dev || !out_dev) return WB_ERR_ARG;
+  return launch_logmel<float>(audio_dev, WB_N_SAMPLES, 0, B, h->tab32, h->logspec, h->gmax, out_dev, nullptr, h->stream,
+                              &h->launches);
+}
+
+int wb_logmel(wb_handle* h, const float* audio, int32_t B, float* out) {
+  WB_TRY(check_batch(h, B));
+  if (!audio || !out) return WB_ERR_ARG;
+  WB_CUDA_OK(cudaMemcpyAsync(h->audio_dev, audio, (size_t)B * WB_N_SAMPLES * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  WB_TRY(wb_logmel_dev(h, h->audio_dev, B, h->mel32));
+  WB_CUDA_OK(cudaMemcpyAsync(out, h->mel32, (size_t)B * WB_N_MELS * WB_N_FRAMES * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  return WB_OK;
+}
+
+// ---- encoder -------------------------------------------------------------------------------------------------------------
+static int need_weights(wb_handle* h) {
+  if (!h->weights_ready) {
+    set_error("weights not loaded (wb_set_weight + wb_weights_commit, or wb_init_random_weights)");
+    return WB_ERR_STATE;
+  }
+  return 0;
+}
+
+int wb_encode_dev(wb_handle* h, const float* audio_dev, int32_t B) {
+  WB_TRY(check_batch(h, B));
+  WB_TRY(need_weights(h));
+  if (!audio_dev) return WB_ERR_ARG;
+  WB_CUDA_OK(cudaEventRecord(h->ev[0], h->stream));
+  WB_TRY(launch_logmel<float>(audio_dev, WB_N_SAMPLES, 0, B, h->tab32, h->logspec, h->gmax, nullptr, h->melT, h->stream, &h->launches));
+  WB_CUDA_OK(cudaEventRecord(h->ev[1], h->stream));
+  WB_TRY(encoder_forward(h, B));
+  WB_TRY(cross_kv(h, B));
+  WB_CUDA_OK(cudaEventRecord(h->ev[2], h->stream));
+  return WB_OK;
+}
+
+static int fetch_xa(wb_handle* h, int B, float* xa_out) {
+  if (xa_out)
+    WB_CUDA_OK(cudaMemcpyAsync(xa_out, h->xa32, (size_t)B * h->dims.n_audio_ctx * h->dims.n_audio_state * sizeof(float),
+                               cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int wb_encode(wb_handle* h, const float* audio, int32_t B, float* xa_out) {
+  WB_TRY(check_batch(h, B));
+  if (!audio) return WB_ERR_ARG;
+  WB_CUDA_OK(cudaMemcpyAsync(h->audio_dev, audio, (size_t)B * WB_N_SAMPLES * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  WB_TRY(wb_encode_dev(h, h->audio_dev, B));
+  return fetch_xa(h, B, xa_out);
+}
+
+int wb_encode_mel(wb_handle* h, const float* mel, int32_t B, float* xa_out) {
+  WB_TRY(check_batch(h, B));
+  WB_TRY(need_weights(h));
+  if (!mel) return WB_ERR_ARG;
+  WB_CUDA_OK(cudaMemcpyAsync(h->mel32, mel, (size_t)B * WB_N_MELS * WB_N_FRAMES * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  WB_TRY(launch_mel_transpose(h->mel32, B, h->melT, h->stream, &h->launches));
+  WB_TRY(encoder_forward(h, B));
+  WB_TRY(cross_kv(h, B));
+  return fetch_xa(h, B, xa_out);
+}
+
+int wb_set_audio_features(wb_handle* h, const float* xa, int32_t B) {
+  WB_TRY(check_batch(h, B));
+  WB_TRY(need_weights(h));
+  if (!xa) return WB_ERR_ARG;
+  const size_t n = (size_t)B * h->dims.n_audio_ctx * h->dims.n_audio_state;
+  WB_CUDA_OK(cudaMemcpyAsync(h->xa32, xa, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  WB_TRY(launch_f32_to_f16(h->xa32, h->xa16, n, h->stream, &h->launches));
+  WB_TRY(cross_kv(h, B));
+  WB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  return WB_OK;
+}
+
+// ---- decoder -------------------------------------------------------------------------------------------------------------
+static int need_features(wb_handle* h, int B) {
+  WB_TRY(need_weights(h));
+  if (h->enc_batch < B) {
+    set_error("audio features for %d chunk(s) are not resident (run wb_encode first; resident: %d)", B, h->enc_batch);
+    return WB_ERR_STATE;
+  }
+  return 0;
+}
+
+int wb_decoder_logits(wb_handle* h, const int32_t* tokens, int32_t B, int32_t t, float* logits) {
+  WB_TRY(check_batch(h, B));
+  WB_TRY(need_features(h, B));
+  if (!tokens || !logits || t < 1 || t > h->dims.n_text_ctx) {
+    set_error("wb_decoder_logits: bad argument");
+    return WB_ERR_ARG;
+  }
+  const int V = h->dims.n_vocab;
+  for (int b = 0; b < B; ++b)
+    for (int i = 0; i < t; ++i)
+      if (tokens[b * t + i] < 0 || tokens[b * t + i] >= V) {
+        set_error("wb_decoder_logits: token %d out of vocabulary", tokens[b * t + i]);
+        return WB_ERR_ARG;
+      }
+  WB_CUDA_OK(cudaMemcpy2DAsync(h->tokens, h->tokens_ld * sizeof(int32_t), tokens, t * sizeof(int32_t), t * sizeof(int32_t), B,
+                               cudaMemcpyHostToDevice, h->stream));
+  WB_TRY(reset_decode_state(h));
+  pick_splits(h, B);
+  StepOpts o{};
+  o.Mb = B, o.beams = 1, o.want_logits = 1, o.sample = 0;
+  for (int i = 0; i < t; ++i) {
+    WB_TRY(decode_step(h, o));
+    WB_CUDA_OK(cudaMemcpy2DAsync(logits + (size_t)i * V, (size_t)t * V * sizeof(float), h->logits, (size_t)V * sizeof(float),
+                                 (size_t)V * sizeof(float), B, cudaMemcpyDeviceToHost, h->stream));
+  }
+  WB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  return WB_OK;
+}
+
+int wb_decoder_logits_f32tok(wb_handle* h, const float* tokens, int32_t B, int32_t t, float* logits) {
+  if (!tokens || B < 1 || t < 1) return WB_ERR_ARG;
+  std::vector<int32_t> tk((size_t)B * t);
+  for (size_t i = 0; i < tk.size(); ++i) tk[i] = (int32_t)lrintf(tokens[i]);   // Whisper.swift:34-35 passes 50258.0
+  return wb_decoder_logits(h, tk.data(), B, t, logits);
+}
+
+int wb_detect_language(wb_handle* h, int32_t B, int32_t sot, int32_t lang0, int32_t* lang_idx) {
+  WB_TRY(check_batch(h, B));
+  WB_TRY(need_features(h, B));
+  if (!lang_idx) return WB_ERR_ARG;
+  if (sot <= 0) sot = 50258;      // Whisper.swift:35
+  if (lang0 <= 0) lang0 = 50259;  // Whisper.swift:37
+  const int V = h->dims.n_vocab;
+  if (lang0 + 99 > V || sot >= V) {
+    set_error("wb_detect_language: language tokens [%d,%d) outside the vocabulary (%d)", lang0, lang0 + 99, V);
+    return WB_ERR_ARG;
+  }
+  std::vector<int32_t> tk(B, sot);
+  WB_CUDA_OK(cudaMemcpy2DAsync(h->tokens, h->tokens_ld * sizeof(int32_t), tk.data(), sizeof(int32_t), sizeof(int32_t), B,
+                               cudaMemcpyHostToDevice, h->stream));
+  WB_TRY(reset_decode_state(h));
+  pick_splits(h, B);
+  StepOpts o{};
+  o.Mb = B, o.beams = 1, o.want_logits = 1, o.sample = 0;
+  WB_TRY(decode_step(h, o));
+  std::vector<float> conf((size_t)B * 99);
+  WB_CUDA_OK(cudaMemcpy2DAsync(conf.data(), 99 * sizeof(float), h->logits + lang0, (size_t)V * sizeof(float), 99 * sizeof(float), B,
+                               cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  for (int b = 0; b < B; ++b) {
+    // Swift `max { $0.element < $1.element }` keeps the LAST maximal element on ties (Whisper.swift:38)
+    int best = 0;
+    for (int i = 1; i < 99; ++i)
+      if (!(conf[b * 99 + i] < conf[b * 99 + best])) best = i;
+    lang_idx[b] = best;
+  }
+  return WB_OK;
+}
+
+static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, int32_t* tokens_out, int32_t* lens, float* sum_logprob) {
+  const wb_dims& D = h->dims;
+  const int n_init = opts->n_initial, total = n_init + opts->sample_len;
+  if (n_init < 1 || opts->sample_len < 1 || total > D.n_text_ctx || opts->n_suppress > 4096 || opts->n_suppress_begin > 256 ||
+      opts->n_suppress < 0 || opts->n_suppress_begin < 0 || !opts->initial_tokens) {
+    set_error("wb_decode: bad options (n_initial=%d sample_len=%d n_text_ctx=%d)", n_init, opts->sample_len, D.n_text_ctx);
+    return WB_ERR_ARG;
+  }
+  cudaStream_t st = h->stream;
+  // token rows: sot sequence, then eot padding
+  std::vector<int32_t> rows((size_t)B * h->tokens_ld, opts->eot);
+  for (int b = 0; b < B; ++b)
+    for (int i = 0; i < n_init; ++i) rows[(size_t)b * h->tokens_ld + i] = opts->initial_tokens[i];
+  WB_CUDA_OK(cudaMemcpyAsync(h->tokens, rows.data(), rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (opts->n_suppress)
+    WB_CUDA_OK(cudaMemcpyAsync(h->suppress, opts->suppress, opts->n_suppress * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (opts->n_suppress_begin)
+    WB_CUDA_OK(cudaMemcpyAsync(h->suppress_begin, opts->suppress_begin, opts->n_suppress_begin * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  WB_CUDA_OK(cudaMemsetAsync(h->sum_logprob, 0, sizeof(float) * B, st));
+  WB_CUDA_OK(cudaMemsetAsync(h->done, 0, sizeof(int32_t) * B, st));
+  WB_CUDA_OK(cudaStreamSynchronize(st));   // `rows` is pageable host memory
+
+  StepOpts plain{}, samp{};
+  plain.Mb = B, plain.beams = 1, plain.want_logits = 0, plain.sample = 0;
+  samp = plain;
+  samp.sample = 1;
+  SampleDesc& sd = samp.sd;
+  sd.Mb = B, sd.V = D.n_vocab, sd.logits = h->logits, sd.suppress = h->suppress, sd.n_suppress = opts->n_suppress;
+  sd.suppress_begin = h->suppress_begin, sd.n_suppress_begin = opts->n_suppress_begin, sd.n_initial = n_init, sd.eot = opts->eot;
+  sd.tokens = h->tokens, sd.tokens_ld = h->tokens_ld, sd.sum_logprob = h->sum_logprob, sd.done = h->done, sd.state = h->state;
+
+  char key[128];
+  snprintf(key, sizeof(key), "B%d i%d e%d s%d b%d", B, n_init, opts->eot, opts->n_suppress, opts->n_suppress_begin);
+  const bool use_graph = getenv("WB_NO_GRAPH") == nullptr;
+  if (use_graph && h->graph_key != key) {
+    destroy_graphs(h);
+    pick_splits(h, B);
+    // one eager pass of each variant first: sets function attributes and faults in code outside of capture
+    WB_TRY(reset_decode_state(h));
+    WB_TRY(decode_step(h, plain));
+    WB_TRY(decode_step(h, samp));
+    WB_CUDA_OK(cudaStreamSynchronize(st));
+    WB_TRY(capture(h, plain, &h->g_step, &h->nodes_step));
+    WB_TRY(capture(h, samp, &h->g_sample, &h->nodes_sample));
+    h->graph_key = key;
+    // the eager pass wrote a token and a log-prob: restore
+    WB_CUDA_OK(cudaMemcpyAsync(h->tokens, rows.data(), rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    WB_CUDA_OK(cudaMemsetAsync(h->sum_logprob, 0, sizeof(float) * B, st));
+    WB_CUDA_OK(cudaMemsetAsync(h->done, 0, sizeof(int32_t) * B, st));
+    WB_CUDA_OK(cudaStreamSynchronize(st));
+  } else if (!use_graph) {
+    pick_splits(h, B);
+  }
+  WB_TRY(reset_decode_state(h));
+  WB_CUDA_OK(cudaEventRecord(h->ev[2], st));
+  for (int i = 0; i + 1 < n_init; ++i) {
+    if (use_graph) {
+      WB_CUDA_OK(cudaGraphLaunch(h->g_step, st));
+      h->launches += h->nodes_step;
+    } else {
+      WB_TRY(decode_step(h, plain));
+    }
+  }
+  const int interval = opts->eot_check_interval > 0 ? opts->eot_check_interval : 8;
+  int steps = 0;
+  for (int s = 0; s < opts->sample_len; ++s) {
+    if (use_graph) {
+      WB_CUDA_OK(cudaGraphLaunch(h->g_sample, st));
+      h->launches += h->nodes_sample;
+    } else {
+      WB_TRY(decode_step(h, samp));
+    }
+    ++steps;
+    if ((s + 1) % interval == 0 && s + 1 < opts->sample_len) {
+      WB_CUDA_OK(cudaMemcpyAsync(h->h_done, h->done, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+      WB_CUDA_OK(cudaStreamSynchronize(st));
+      bool all = true;
+      for (int b = 0; b < B; ++b) all = all && h->h_done[b];
+      if (all) break;
+    }
+  }
+  WB_CUDA_OK(cudaEventRecord(h->ev[3], st));
+  h->timings[3] = (float)(steps + n_init - 1);
+  WB_CUDA_OK(cudaMemcpyAsync(rows.data(), h->tokens, rows.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  std::vector<float> slp(B);
+  WB_CUDA_OK(cudaMemcpyAsync(slp.data(), h->sum_logprob, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
+  WB_CUDA_OK(cudaStreamSynchronize(st));
+  for (int b = 0; b < B; ++b) {
+    const int32_t* r = &rows[(size_t)b * h->tokens_ld];
+    int len = total;
+    for (int i = n_init; i < total; ++i)
+      if (r[i] == opts->eot) {
+        len = i + 1;
+        break;
+      }
+    for (int i = 0; i < total; ++i) tokens_out[(size_t)b * total + i] = i < len ? r[i] : opts->eot;
+    if (lens) lens[b] = len;
+    if (sum_logprob) sum_logprob[b] = slp[b];
+  }
+  return WB_OK;
+}
+
+int wb_decode(wb_handle* h, int32_t B, const wb_decode_opts* opts, int32_t* tokens_out, int32_t* lens, float* sum_logprob) {
+  WB_TRY(check_batch(h, B));
+  WB_TRY(need_features(h, B));
+  if (!opts || !tokens_out) return WB_ERR_ARG;
+  if (opts->beam_size > 1) {
+    set_error("wb_decode: beam search is not implemented in this build (beam_size=%d)", opts->beam_size);
+    return WB_ERR_ARG;
+  }
+  return decode_greedy(h, B, opts, tokens_out, lens, sum_logprob);
+}
+
+int wb_transcribe_dev(wb_handle* h, const float* audio_dev, int32_t B, const wb_decode_opts* opts, int32_t* tokens_out,
+                      int32_t* lens, float* sum_logprob) {
+  WB_TRY(wb_encode_dev(h, audio_dev, B));
+  WB_TRY(wb_decode(h, B, opts, tokens_out, lens, sum_logprob));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->timings[0] = ms;
+  if (cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]) == cudaSuccess) h->timings[1] = ms;
+  if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) h->timings[2] = ms;
+  return WB_OK;
+}
+
+int wb_transcribe(wb_handle* h, const float* audio, int32_t B, const wb_decode_opts* opts, int32_t* tokens_out, int32_t* lens,
+                  float* sum_logprob) {
+  WB_TRY(check_batch(h, B));
+  if (!audio) return WB_ERR_ARG;
+  WB_CUDA_OK(cudaMemcpyAsync(h->audio_dev, audio, (size_t)B * WB_N_SAMPLES * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  return wb_transcribe_dev(h, h->audio_dev, B, opts, tokens_out, lens, sum_logprob);
+}
+
+int64_t wb_launch_count(const wb_handle* h) { return h ? h->launches : -1; }
+int wb_last_timings(const wb_handle* h, float out[4]) {
+  if (!h || !out) return WB_ERR_ARG;
+  for (int i = 0; i < 4; ++i) out[i] = h->timings[i];
+  return WB_OK;
+}
+int wb_sync(wb_handle* h) {
+  if (!h) return WB_ERR_ARG;
+  WB_CUDA_OK(cudaSetDevice(h->device));
+  WB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  return WB_OK;
+}
+
+// ---- operator-level entry points for the parity tests ---------------------------------------------------------------------------
+int wb_op_gemm(wb_handle* h, const void* A_f16, const void* W_f16, const float* bias, const float* residual, int32_t M, int32_t N,
+               int32_t K, int32_t gelu, void* C, int32_t c_is_f32) {
+  if (!h || !A_f16 || !W_f16 || !C) return WB_ERR_ARG;
+  WB_CUDA_OK(cudaSetDevice(h->device));
+  return plain_gemm(h, (const __half*)A_f16, M, (const __half*)W_f16, N, K, bias, gelu, residual, c_is_f32 ? nullptr : (__half*)C,
+                    c_is_f32 ? (float*)C : nullptr);
+}
+int wb_op_layernorm(wb_handle* h, const float* x, const float* gamma, const float* beta, int32_t M, int32_t d, void* out_f16) {
+  if (!h || !x || !out_f16) return WB_ERR_ARG;
+  WB_CUDA_OK(cudaSetDevice(h->device));
+  return launch_layernorm(x, gamma, beta, M, d, (__half*)out_f16, nullptr, h->stream, &h->launches);
+}
+int wb_op_attention(wb_handle* h, const void* qkv_f16, int32_t B, int32_t T, int32_t n_head, void* out_f16) {
+  if (!h || !qkv_f16 || !out_f16) return WB_ERR_ARG;
+  WB_CUDA_OK(cudaSetDevice(h->device));
+  return launch_encoder_attention((const __half*)qkv_f16, B, T, n_head, (__half*)out_f16, h->stream, &h->launches);
+}
+
+// ---- legacy f64 symbol (stft/src/lib.rs:110-122; bridge.h:11) --------------------------------------------------------------------
+int wb_generate_spectrogram_f64(double* audio, int32_t B, double* output) {
+  if (!audio || !output || B < 1) {
+    set_error("wb_generate_spectrogram_f64: bad argument");
+    return WB_ERR_ARG;
+  }
+  const char* dev_env = getenv("WB_DEVICE");
+  WB_TRY(select_device(dev_env ? atoi(dev_env) : 0));
+  // the in-place reflection of the two 200-sample pads (lib.rs:34-40) is part of the contract: do it on the host buffer
+  for (int b = 0; b < B; ++b) {
+    double* a = audio + (size_t)b * WB_N_SAMPLES_PADDED;
+    for (int i = 0; i < 200; ++i) {
+      a[i] = a[400 - i];
+      a[WB_N_SAMPLES + 200 + i] = a[200 + (WB_N_SAMPLES - 2) - i];
+    }
+  }
+  static LogmelTables<double>* dtab = nullptr;   // per-process, device-resident (like the crate's lazy_static GENERATOR)
+  static int dtab_device = -1;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (!dtab || dtab_device != cur) {
+    LogmelTables<double>* t = new LogmelTables<double>();
+    build_logmel_tables<double>(*t);
+    LogmelTables<double>* dptr = nullptr;
+    WB_CUDA_OK(cudaMalloc(&dptr, sizeof(*t)));
+    WB_CUDA_OK(cudaMemcpy(dptr, t, sizeof(*t), cudaMemcpyHostToDevice));
+    delete t;
+    dtab = dptr, dtab_device = cur;
+  }
+  double *d_audio = nullptr, *d_log = nullptr, *d_out = nullptr;
+  unsigned long long* d_max = nullptr;
+  const size_t na = (size_t)B * WB_N_SAMPLES_PADDED, no = (size_t)B * WB_N_MELS * WB_N_FRAMES;
+  int rc = WB_OK;
+  cudaStream_t st = nullptr;
+  do {
+    if (cudaMalloc(&d_audio, na * 8) != cudaSuccess || cudaMalloc(&d_log, no * 8) != cudaSuccess ||
+        cudaMalloc(&d_out, no * 8) != cudaSuccess || cudaMalloc(&d_max, 8 * (size_t)B) != cudaSuccess) {
+      set_error("wb_generate_spectrogram_f64: cudaMalloc failed");
+      rc = WB_ERR_NOMEM;
+      break;
+    }
+    if (cudaMemcpy(d_audio, audio, na * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("wb_generate_spectrogram_f64: H2D copy failed");
+      rc = WB_ERR_CUDA;
+      break;
+    }
+    rc = launch_logmel<double>(d_audio, WB_N_SAMPLES_PADDED, 200, B, dtab, d_log, d_max, d_out, nullptr, st, nullptr);
+    if (rc) break;
+    if (cudaMemcpy(output, d_out, no * 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
+      set_error("wb_generate_spectrogram_f64: D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = WB_ERR_CUDA;
+    }
+  } while (0);
+  cudaFree(d_audio), cudaFree(d_log), cudaFree(d_out), cudaFree(d_max);
+  return rc;
+}
+
+void generate_spectrogram(double* audio, double* output) {
+  const int rc = wb_generate_spectrogram_f64(audio, 1, output);
+  if (rc != WB_OK) {
+    fprintf(stderr, "generate_spectrogram: %s (status %d)\n", wb_last_error(), rc);
+    abort();   // the reference panics across the FFI boundary (lib.rs .unwrap()); there is no status to return
+  }
+}
+
+}  // extern "C"

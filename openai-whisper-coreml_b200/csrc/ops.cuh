@@ -1,0 +1,134 @@
+// Launcher declarations shared by model.cu / api.cu. Each launcher enqueues on `st`, returns 0 or a negative wb_status,
+// and adds the number of kernels it launched to *launches.
+#pragma once
+#include "common.cuh"
+
+namespace wb {
+
+// ---- log-mel (logmel.cu) ---------------------------------------------------------------------------------------------
+template <typename T>
+struct LogmelTables;
+template <typename T>
+void build_logmel_tables(LogmelTables<T>& t);
+template <typename T>
+int launch_logmel(const T* audio, size_t chunk_stride, int chunk_off, int B, const LogmelTables<T>* dtab, T* logspec,
+                  void* gmax, T* out, __half* melT, cudaStream_t st, int64_t* launches);
+int launch_mel_transpose(const float* mel, int B, __half* melT, cudaStream_t st, int64_t* launches);
+size_t logmel_tables_bytes_f32();
+size_t logmel_tables_bytes_f64();
+
+// ---- big GEMM (gemm.cu): tcgen05 + TMA ---------------------------------------------------------------------------------
+// C[b][t][n] = act( sum_k A[b][t][k] * W[n][k] + bias[n] ) (+ residual)
+//   A element (b,t,k) at a_ptr[b*a_batch_stride + t*a_row_stride + k]  (fp16; strides in elements, multiples of 8;
+//     rows may overlap: the conv layers are expressed this way, k >= K reads as zero)
+//   W fp16 [N][K] row-major (ldw = K)
+//   C row (b,t) at row index  b*c_batch_rows + c_row_off + t  of a row-major [.][ldc] matrix
+//   residual: mode 1 = fp32, same addressing as C;  mode 2 = fp32 [rows][N] indexed by t (positional table)
+struct GemmDesc {
+  const __half* a;
+  long long a_row_stride, a_batch_stride;
+  int rows, n_batch;   // rows per batch (t range), number of batches
+  const __half* w;
+  int N, K;
+  const float* bias;   // [N] or null
+  int gelu;
+  int res_mode;        // 0 none, 1 same-as-C fp32, 2 per-t table
+  const float* res;
+  __half* c16;         // optional fp16 output
+  float* c32;          // optional fp32 output
+  int ldc;
+  long long c_batch_rows;
+  int c_row_off;
+};
+struct GemmContext;   // tensor-map cache + driver entry point
+GemmContext* gemm_context_create();
+void gemm_context_destroy(GemmContext*);
+int launch_gemm(GemmContext* ctx, const GemmDesc& d, cudaStream_t st, int64_t* launches);
+
+// ---- row-wise ops (rowops.cu) ------------------------------------------------------------------------------------------
+int launch_layernorm(const float* x, const float* gamma, const float* beta, int M, int d, __half* out16, float* out32,
+                     cudaStream_t st, int64_t* launches);
+int launch_f32_to_f16(const float* in, __half* out, size_t n, cudaStream_t st, int64_t* launches);
+int launch_f16_to_f32(const __half* in, float* out, size_t n, cudaStream_t st, int64_t* launches);
+int launch_fill_random(void* ptr, size_t n, int is_f16, float scale, float offset, uint64_t seed, cudaStream_t st,
+                       int64_t* launches);
+
+// ---- encoder attention (attention_enc.cu) ---------------------------------------------------------------------------------
+// qkv fp16 [B*T][3d] (q | k | v, head h at columns h*64) -> out fp16 [B*T][d]; softmax(q k^T / 8) v, non-causal
+int launch_encoder_attention(const __half* qkv, int B, int T, int n_head, __half* out, cudaStream_t st, int64_t* launches);
+
+// ---- decoder step (decoder.cu) ---------------------------------------------------------------------------------------------
+struct DecodeState {      // lives in device memory; read by every kernel of a step (CUDA-graph friendly)
+  int cur_len;            // tokens consumed so far, including the one embedded by this step
+  int n_done;             // sequences whose last token is eot
+  int sample_step;        // number of sampling steps performed
+  int pad;
+};
+
+// Input transform of a skinny GEMM (how the [Mb][K] fp16 activation tile in shared memory is produced)
+enum SkinnyIn { SKINNY_IN_F16 = 0, SKINNY_IN_LN = 1, SKINNY_IN_ATTN = 2, SKINNY_IN_F32 = 3 };
+// Output transform
+enum SkinnyOut { SKINNY_OUT_F16 = 0, SKINNY_OUT_F32 = 1, SKINNY_OUT_RESID = 2, SKINNY_OUT_QKV = 3 };
+
+struct SkinnyDesc {
+  int Mb, N, K;
+  const __half* w;        // [N][K]
+  const float* bias;      // [N] or null
+  int gelu;
+  // input
+  int in_mode;
+  const void* in;         // F16: half [Mb][K]; LN / F32: float [Mb][K]
+  const float* ln_g;      // LN
+  const float* ln_b;
+  const float* part_ml;   // ATTN: [Mb][S][H][2] (m, l);  part_acc: [Mb][S][K]
+  const float* part_acc;
+  int n_split, n_head;
+  // output
+  int out_mode;
+  void* out;              // F16: half [Mb][N]; F32 / RESID: float [Mb][N] (RESID: +=)
+  // QKV scatter: n < d -> q32[b][n];  d <= n < 2d -> kcache[(b*n_ctx + pos)*d + n-d];  else vcache
+  float* q32;
+  __half* kcache;
+  __half* vcache;
+  int n_ctx;
+  const DecodeState* state;
+};
+int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches);
+
+// one query per (sequence, head) against rows [0, n_rows) of K/V [B][n_ctx][d] fp16; partial results per split
+struct AttnDecodeDesc {
+  int Mb, d, n_head, n_split;
+  const float* q;         // [Mb][d] fp32
+  const __half* k;        // [Mb / kv_share][n_ctx][d]
+  const __half* v;
+  int n_ctx;              // allocated rows per sequence
+  int n_rows_fixed;       // >0: fixed row count (cross attention, 1500); 0: rows = state->cur_len (self attention)
+  int kv_share;           // sequences per K/V slab (beam search: beams of one chunk share the cross K/V); >= 1
+  const DecodeState* state;
+  float* part_ml;         // [Mb][S][H][2]
+  float* part_acc;        // [Mb][S][d]
+};
+int launch_attn_decode(const AttnDecodeDesc& d, cudaStream_t st, int64_t* launches);
+
+// x[b][:] = tok_emb[tokens[b][cur_len]][:] + pos_emb[cur_len][:]; then cur_len += 1
+int launch_embed(const int32_t* tokens, int tokens_ld, const __half* tok_emb, const float* pos_emb, int Mb, int d, int V,
+                 float* x, DecodeState* state, cudaStream_t st, int64_t* launches);
+
+struct SampleDesc {
+  int Mb, V;
+  float* logits;              // [Mb][V], modified in place (suppressed entries become -inf)
+  const int32_t* suppress;    // device lists
+  int n_suppress;
+  const int32_t* suppress_begin;
+  int n_suppress_begin;
+  int n_initial;              // length of the sot sequence: sampling position 0 is cur_len == n_initial
+  int eot;
+  int32_t* tokens;            // [Mb][tokens_ld]
+  int tokens_ld;
+  float* sum_logprob;         // [Mb]
+  int32_t* done;              // [Mb]: 1 if the sequence's newest token is eot
+  DecodeState* state;
+};
+int launch_sample_greedy(const SampleDesc& d, cudaStream_t st, int64_t* launches);
+
+}  // namespace wb
