@@ -143,6 +143,10 @@ int64_t wb_launch_count(const wb_handle* h);
  * out[0]=logmel, out[1]=encoder (incl. cross K/V), out[2]=decode loop, out[3]=number of decode steps run. */
 int wb_last_timings(const wb_handle* h, float out[4]);
 int wb_sync(wb_handle* h);
+/* Times the decoder's KV-cache attention kernel alone on the resident cross-attention K/V of B chunks: `reps` launches
+ * cycling over the decoder layers (so successive launches stream different HBM), CUDA events on the handle's stream.
+ * avg_ms = mean device time per launch; bytes_per_launch = algorithmic K+V bytes one launch reads (B*2*1500*d*2). */
+int wb_profile_cross_attention(wb_handle* h, int32_t B, int32_t reps, float* avg_ms, double* bytes_per_launch);
 
 /* Low-level operator entry points used by the parity tests (device pointers, enqueue on the handle's stream).
  * C[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual); A,W fp16; fp32 accumulate; C fp16 or fp32. */

@@ -265,7 +265,7 @@ static void layout_workspace(wb_handle* h) {
   h->logits = A.take<float>(Mb * (size_t)D.n_vocab);
   h->sum_logprob = A.take<float>(Mb);
   h->done = A.take<int32_t>(Mb);
-  h->suppress = A.take<int32_t>(4096);
+  h->suppress = A.take<int32_t>((size_t)D.n_vocab);
   h->suppress_begin = A.take<int32_t>(256);
   h->state = A.take<DecodeState>(1);
 }
@@ -797,7 +797,7 @@ int wb_detect_language(wb_handle* h, int32_t B, int32_t sot, int32_t lang0, int3
 static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, int32_t* tokens_out, int32_t* lens, float* sum_logprob) {
   const wb_dims& D = h->dims;
   const int n_init = opts->n_initial, total = n_init + opts->sample_len;
-  if (n_init < 1 || opts->sample_len < 1 || total > D.n_text_ctx || opts->n_suppress > 4096 || opts->n_suppress_begin > 256 ||
+  if (n_init < 1 || opts->sample_len < 1 || total > D.n_text_ctx || opts->n_suppress > D.n_vocab || opts->n_suppress_begin > 256 ||
       opts->n_suppress < 0 || opts->n_suppress_begin < 0 || !opts->initial_tokens) {
     set_error("wb_decode: bad options (n_initial=%d sample_len=%d n_text_ctx=%d)", n_init, opts->sample_len, D.n_text_ctx);
     return WB_ERR_ARG;
@@ -936,6 +936,31 @@ int wb_sync(wb_handle* h) {
   if (!h) return WB_ERR_ARG;
   WB_CUDA_OK(cudaSetDevice(h->device));
   WB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  return WB_OK;
+}
+
+int wb_profile_cross_attention(wb_handle* h, int32_t B, int32_t reps, float* avg_ms, double* bytes_per_launch) {
+  WB_TRY(check_batch(h, B));
+  WB_TRY(need_features(h, B));
+  if (!avg_ms || reps < 1) return WB_ERR_ARG;
+  const wb_dims& D = h->dims;
+  pick_splits(h, B);
+  AttnDecodeDesc c{};
+  c.Mb = B, c.d = D.n_text_state, c.n_head = D.n_text_head, c.n_split = h->split_cross, c.q = h->q32;
+  c.n_ctx = D.n_audio_ctx, c.n_rows_fixed = D.n_audio_ctx, c.kv_share = 1, c.state = h->state;
+  c.part_ml = h->part_ml, c.part_acc = h->part_acc;
+  for (int i = -3; i < reps; ++i) {   // 3 warm-up launches
+    if (i == 0) WB_CUDA_OK(cudaEventRecord(h->ev[0], h->stream));
+    const int l = ((i % D.n_text_layer) + D.n_text_layer) % D.n_text_layer;
+    c.k = h->crossK[l], c.v = h->crossV[l];
+    WB_TRY(launch_attn_decode(c, h->stream, &h->launches));
+  }
+  WB_CUDA_OK(cudaEventRecord(h->ev[1], h->stream));
+  WB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  WB_CUDA_OK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+  *avg_ms = ms / reps;
+  if (bytes_per_launch) *bytes_per_launch = (double)B * 2.0 * D.n_audio_ctx * D.n_text_state * 2.0;
   return WB_OK;
 }
 

@@ -134,6 +134,7 @@ _SYMBOLS = {
     "wb_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "wb_last_timings": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "wb_sync": (ctypes.c_int, [ctypes.c_void_p]),
+    "wb_profile_cross_attention": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
     "wb_op_gemm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                   ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32]),
     "wb_op_layernorm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
@@ -365,6 +366,13 @@ class Whisper:
         t = np.zeros(4, dtype=np.float32)
         _check(self._lib.wb_last_timings(self._h, _ptr(t)), "wb_last_timings")
         return t
+
+    def profile_cross_attention(self, B: int, reps: int = 60):
+        """(mean ms per launch, algorithmic bytes per launch) of the KV-cache attention kernel on the resident cross K/V."""
+        ms, by = ctypes.c_float(), ctypes.c_double()
+        _check(self._lib.wb_profile_cross_attention(self._h, B, reps, ctypes.byref(ms), ctypes.byref(by)),
+               "wb_profile_cross_attention")
+        return float(ms.value), float(by.value)
 
     def sync(self) -> None:
         _check(self._lib.wb_sync(self._h), "wb_sync")

@@ -1,0 +1,289 @@
+"""GPU parity tests proper: every call goes through the C ABI (ctypes) into the hand-written CUDA kernels and is
+compared with the oracle on the same seeded inputs, with the committed golden vectors, and — at BASELINE.json's full
+size — through size-independent properties (determinism, batch-slot independence).
+
+Tolerances (stated once, SURVEY.md §8c / BASELINE.md §3):
+  log-mel fp32 kernel   max|d| <= 2e-4 on the normalised output        f64 legacy ABI  <= 1e-12
+  encoder features      max|d| <= 5e-2, rel-L2 <= 5e-3 (fp16 operands, fp32 accumulate / LayerNorm / softmax)
+  decoder logits        max|d| <= 5e-2, rel-L2 <= 5e-3 (teacher-forced)
+  greedy token IDs      identical to the oracle's
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+KINDS = ["noise", "sine", "chirp", "noise_then_zeros", "int16", "fullscale", "zeros"]
+TOL_MEL32, TOL_MEL64, TOL_ABS, TOL_REL = 2e-4, 1e-12, 5e-2, 5e-3
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+@pytest.fixture(scope="module")
+def tiny(wbm, ref):
+    dims = ref.DIMS["tiny.en"]
+    weights = ref.random_weights(dims, seed=0)
+    w = wbm.Whisper("tiny.en", weights=weights, max_batch=4)
+    yield w, ref.WhisperRef(dims, weights)
+    w.close()
+
+
+# ---- log-mel -----------------------------------------------------------------------------------------
+def test_logmel_f32_all_clip_kinds(tiny, ref, oracle_logmel):
+    w, _ = tiny
+    for i in range(0, len(KINDS), 4):
+        kinds = KINDS[i:i + 4]
+        a = np.stack([ref.synth_audio(11, k) for k in kinds]).astype(np.float32)
+        got = w.logmel(a)
+        for j, k in enumerate(kinds):
+            assert np.abs(got[j] - oracle_logmel(a[j].astype(np.float64))).max() <= TOL_MEL32, k
+
+
+def test_logmel_f32_vs_golden_torch_stft(tiny, ref, golden_dir):
+    w, _ = tiny
+    g = np.load(os.path.join(golden_dir, "logmel_torch_f64.npz"))
+    for k in ["noise", "chirp", "int16"]:
+        got = w.logmel(ref.synth_audio(11, k).astype(np.float32))[0].reshape(-1)[g["index"]]
+        assert np.abs(got - g[k]).max() <= TOL_MEL32 + 1e-5     # + fp32 rounding of the input clip itself
+
+
+@pytest.mark.parametrize("kind", ["noise", "chirp", "zeros"])
+def test_legacy_f64_symbol(wbm, ref, oracle_logmel, kind):
+    a = ref.synth_audio(3, kind)
+    got = wbm.generateSpectrogram(a).reshape(80, 3000)
+    assert np.abs(got - oracle_logmel(a)).max() <= TOL_MEL64
+
+
+def test_legacy_symbol_buffer_protocol_and_pad_mutation(wbm):
+    """stft.swift:10-15 + lib.rs:34-40: pads are overwritten in place with the reflection."""
+    lib = wbm.load_library()
+    buf = np.zeros(480400)
+    buf[200:480200] = np.arange(480000, dtype=np.float64) * 1e-6
+    out = np.zeros(240000)
+    lib.generate_spectrogram(buf.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p))
+    assert np.allclose(buf[:200], np.arange(200, 0, -1) * 1e-6, rtol=0, atol=0)
+    assert np.allclose(buf[480200:], (479998 - np.arange(200)) * 1e-6, rtol=0, atol=0)
+    assert np.isfinite(out).all() and out.max() <= 2.0
+
+
+def test_logmel_batch_slot_independence(tiny, ref):
+    w, _ = tiny
+    a = np.stack([ref.synth_audio(30 + i, "noise") for i in range(4)]).astype(np.float32)
+    full = w.logmel(a)
+    for i in range(4):
+        assert np.array_equal(w.logmel(a[i])[0], full[i])
+
+
+# ---- operators (rows a11/a13: GEMM, LayerNorm, attention) against fp32 torch --------------------------------------------------
+@pytest.mark.parametrize("M,N,K,gelu,bias,res,c32", [(128, 128, 64, 0, 0, 0, 1), (300, 256, 512, 0, 1, 0, 1), (1500, 384, 384, 1, 1, 0, 0),
+                                                      (3000, 512, 2048, 0, 1, 1, 1), (257, 1536, 512, 0, 1, 0, 0), (200, 128, 240, 1, 1, 0, 0),
+                                                      (48000, 512, 512, 0, 1, 1, 1)])
+def test_gemm_tcgen05(tiny, wbm, M, N, K, gelu, bias, res, c32):
+    w, _ = tiny
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).half().cuda()
+    W = (torch.randn(N, K, generator=g) * 0.05).half().cuda()
+    b = torch.randn(N, generator=g).cuda() if bias else None
+    r = torch.randn(M, N, generator=g).cuda() if res else None
+    C = torch.full((M, N), float("nan"), dtype=torch.float32 if c32 else torch.float16, device="cuda")
+    lib = wbm.load_library()
+    assert lib.wb_op_gemm(w.handle, ptr(A), ptr(W), ptr(b) if bias else None, ptr(r) if res else None, M, N, K, gelu, ptr(C), c32) == 0
+    w.sync()
+    want = A.float() @ W.float().t()
+    want = want + b if bias else want
+    want = torch.nn.functional.gelu(want) if gelu else want
+    want = want + r if res else want
+    tol = (2e-3 if c32 else 4e-3) * max(1.0, want.abs().max().item())
+    assert (C.float() - want).abs().max().item() <= tol
+
+
+def test_gemm_linearity_at_full_size(tiny, wbm):
+    """Size-independent property at BASELINE size (M = 32*1500): C(A1 + A2) == C(A1) + C(A2) up to fp32 accumulation."""
+    w, _ = tiny
+    M, N, K = 48000, 512, 512
+    g = torch.Generator().manual_seed(1)
+    A1 = (torch.randint(-8, 9, (M, K), generator=g).float() / 8).half().cuda()      # exactly representable sums
+    A2 = (torch.randint(-8, 9, (M, K), generator=g).float() / 8).half().cuda()
+    W = (torch.randint(-8, 9, (N, K), generator=g).float() / 16).half().cuda()
+    lib = wbm.load_library()
+    outs = []
+    for A in (A1, A2, (A1 + A2)):
+        C = torch.empty((M, N), dtype=torch.float32, device="cuda")
+        assert lib.wb_op_gemm(w.handle, ptr(A), ptr(W), None, None, M, N, K, 0, ptr(C), 1) == 0
+        w.sync()
+        outs.append(C)
+    assert torch.equal(outs[0] + outs[1], outs[2])       # all partial sums are exact in fp32 for these inputs
+
+
+@pytest.mark.parametrize("d", [384, 512, 768, 1024, 1280])
+def test_layernorm(tiny, wbm, d):
+    w, _ = tiny
+    x = torch.randn(777, d, device="cuda") * 2 + 0.3
+    g, b = torch.randn(d, device="cuda"), torch.randn(d, device="cuda")
+    o = torch.empty(777, d, dtype=torch.float16, device="cuda")
+    assert wbm.load_library().wb_op_layernorm(w.handle, ptr(x), ptr(g), ptr(b), 777, d, ptr(o)) == 0
+    w.sync()
+    want = torch.nn.functional.layer_norm(x, (d,), g, b, 1e-5)
+    assert (o.float() - want).abs().max().item() <= 1e-2
+
+
+@pytest.mark.parametrize("B,T,H", [(1, 64, 2), (2, 200, 6), (2, 1500, 6), (1, 1500, 20), (1, 129, 1)])
+def test_encoder_attention(tiny, wbm, B, T, H):
+    w, _ = tiny
+    d = H * 64
+    qkv = (torch.randn(B * T, 3 * d, device="cuda") * 1.5).half()
+    o = torch.full((B * T, d), float("nan"), dtype=torch.float16, device="cuda")
+    assert wbm.load_library().wb_op_attention(w.handle, ptr(qkv), B, T, H, ptr(o)) == 0
+    w.sync()
+    q, k, v = [t.float().view(B, T, H, 64).transpose(1, 2) for t in qkv.view(B, T, 3, d).unbind(2)]
+    want = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1) @ v).transpose(1, 2).reshape(B * T, d)
+    assert (o.float() - want).abs().max().item() <= 1e-2
+
+
+# ---- encoder / decoder vs the oracle (rows a10-a14) -----------------------------------------------------------------------------
+def _rel(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+def test_encode_matches_oracle(tiny, ref, oracle_logmel):
+    w, oracle = tiny
+    audio = np.stack([ref.synth_audio(100 + i, k) for i, k in enumerate(["noise", "int16"])])
+    mel = torch.from_numpy(np.stack([oracle_logmel(a) for a in audio])).float()
+    want = oracle.encode(mel)
+    got = torch.from_numpy(w.encode(audio.astype(np.float32)))
+    assert (got - want).abs().max().item() <= TOL_ABS and _rel(got, want) <= TOL_REL
+    got2 = torch.from_numpy(w.encode_mel(mel.numpy()))            # encoder.prediction(x_1:) alone
+    assert (got2 - want).abs().max().item() <= TOL_ABS and _rel(got2, want) <= TOL_REL
+
+
+@pytest.mark.parametrize("t", [1, 5, 37])
+def test_decoder_logits_match_oracle(tiny, ref, oracle_logmel, t):
+    w, oracle = tiny
+    audio = np.stack([ref.synth_audio(100 + i, "noise") for i in range(2)])
+    xa_ref = oracle.encode(torch.from_numpy(np.stack([oracle_logmel(a) for a in audio])).float())
+    w.encode(audio.astype(np.float32), return_features=False)
+    toks = torch.randint(0, 50000, (2, t), generator=torch.Generator().manual_seed(t))
+    want = oracle.decoder_logits(toks, xa_ref)
+    got = torch.from_numpy(w.decoder_logits(toks.numpy()))
+    assert (got - want).abs().max().item() <= TOL_ABS and _rel(got, want) <= TOL_REL
+
+
+def test_decoder_on_external_features_f32_token(tiny, ref, wbm):
+    """decoder.prediction(x_1: [[50258.0]], xa:) with features supplied by the caller (Whisper.swift:34-36)."""
+    w, oracle = tiny
+    xa = torch.randn(1, 1500, 384, generator=torch.Generator().manual_seed(9))
+    w.set_audio_features(xa.numpy())
+    lib = wbm.load_library()
+    tok = np.array([[50257.0]], dtype=np.float32)
+    out = np.empty((1, 1, 51864), dtype=np.float32)
+    assert lib.wb_decoder_logits_f32tok(w.handle, tok.ctypes.data_as(ctypes.c_void_p), 1, 1, out.ctypes.data_as(ctypes.c_void_p)) == 0
+    want = oracle.decoder_logits(torch.tensor([[50257]]), xa.half().float())
+    assert (torch.from_numpy(out) - want).abs().max().item() <= TOL_ABS
+
+
+def test_greedy_tokens_identical_to_oracle(tiny, ref, wbm, oracle_logmel):
+    w, oracle = tiny
+    audio = np.stack([ref.synth_audio(200 + i, "noise") for i in range(3)])
+    xa_ref = oracle.encode(torch.from_numpy(np.stack([oracle_logmel(a) for a in audio])).float())
+    opts_ref = ref.DecodeOptions.default_for(oracle.dims, sample_len=24)
+    tok_ref, slp_ref, _ = oracle.greedy(xa_ref, opts_ref)
+    tok, lens, slp = w.transcribe(audio.astype(np.float32), wbm.DecodeOptions.default_for(wbm.DIMS["tiny.en"], sample_len=24))
+    n = tok_ref.shape[1]
+    mism = (torch.from_numpy(tok[:, :n].astype(np.int64)) != tok_ref).any(0).nonzero()
+    assert mism.numel() == 0, f"first divergence at position {int(mism[0])}"
+    assert np.abs(slp - slp_ref.numpy()).max() <= 0.05
+
+
+def test_eot_forcing_and_lengths(tiny, ref, wbm):
+    """With everything but {eot, 1234} suppressed the decoder must pick one of the two each step; after the first EOT the
+    row is EOT-padded, the length includes it, and the result equals the oracle's."""
+    w, oracle = tiny
+    xa = torch.randn(2, 1500, 384, generator=torch.Generator().manual_seed(4)).half().float()
+    w.set_audio_features(xa.numpy())
+    eot = oracle.vocab.eot
+    sup = [i for i in range(51864) if i not in (eot, 1234)]
+    tok_ref, slp_ref, _ = oracle.greedy(xa, ref.DecodeOptions([50257, 50362], sample_len=10, suppress=sup))
+    o = wbm.DecodeOptions([50257, 50362], eot, sample_len=10, suppress=sup, eot_check_interval=2)
+    tok, lens, slp = w.greedy(2, o)
+    for b in range(2):
+        r = tok_ref[b].tolist()
+        r = r + [eot] * (12 - len(r))
+        assert tok[b].tolist() == r
+        body = r[2:]
+        assert lens[b] == (2 + body.index(eot) + 1 if eot in body else 12)
+    assert np.abs(slp - slp_ref.numpy()).max() <= 0.05
+
+
+@pytest.mark.parametrize("tag", ["small_en", "small_ml"])
+def test_against_golden_hf_vectors(wbm, ref, golden_dir, small_dims, small_dims_ml, tag):
+    dims = small_dims if tag == "small_en" else small_dims_ml
+    g = np.load(os.path.join(golden_dir, f"whisper_{tag}_hf.npz"))
+    pd = wbm.ModelDims(*[getattr(dims, f) for f in dims.__dataclass_fields__])
+    w = wbm.Whisper(pd, weights=ref.random_weights(dims, seed=3), max_batch=1)
+    xa = w.encode(ref.synth_audio(21, "noise").astype(np.float32))
+    assert np.abs(xa[0, ::75] - g["xa_rows"]).max() <= TOL_ABS
+    lg = w.decoder_logits(g["tokens"])[0][:, g["logit_cols"]]
+    assert np.abs(lg - g["logits"]).max() <= TOL_ABS
+    init = [int(t) for t in g["greedy"][0, :2]]
+    tok, _, _ = w.greedy(1, wbm.DecodeOptions(init, eot=dims.n_vocab - 1, sample_len=12))
+    assert np.array_equal(tok, g["greedy"])
+    if dims.is_multilingual:
+        assert int(w.detect_language(1)[0]) == int(g["lang"][0])
+    w.close()
+
+
+def test_whisper_decode_language_id(wbm, ref, oracle_logmel, capsys):
+    """Whisper.decode(audioFeatures:) (Whisper.swift:33-40) on the multilingual vocabulary."""
+    dims = ref.DIMS["tiny"]
+    weights = ref.random_weights(dims, seed=0)
+    oracle = ref.WhisperRef(dims, weights)
+    w = wbm.Whisper("tiny", weights=weights, max_batch=2)
+    audio = np.stack([ref.synth_audio(300 + i, "noise") for i in range(2)])
+    xa = w.encode(audio.astype(np.float32))
+    want = oracle.detect_language(torch.from_numpy(xa)).tolist()
+    codes = w.decode(xa)
+    assert codes == [wbm.LANGUAGES[i] for i in want]
+    assert capsys.readouterr().out.split() == codes
+    w.close()
+
+
+# ---- BASELINE.json full size: base.en, 32 chunks, 224 tokens — size-independent properties -------------------------------------
+def test_full_size_determinism_and_slot_independence(wbm):
+    w = wbm.Whisper("base.en", seed=0, max_batch=32)
+    o = wbm.DecodeOptions.default_for(wbm.DIMS["base.en"], sample_len=224)
+    o.suppress = list(o.suppress) + [o.eot]
+    audio = np.stack([(np.random.default_rng(1000 + i).standard_normal(480000) * 0.1).astype(np.float32) for i in range(32)])
+    t1, l1, s1 = w.transcribe(audio, o)
+    t2, l2, s2 = w.transcribe(audio, o)
+    assert np.array_equal(t1, t2) and np.array_equal(s1, s2)                 # run-to-run bit identity
+    assert (l1 == 226).all() and (t1[:, 2:] != o.eot).all()
+    perm = np.roll(np.arange(32), 5)
+    t3, _, s3 = w.transcribe(audio[perm], o)                                   # a chunk's result does not depend on its slot
+    assert np.array_equal(t3, t1[perm])
+    t4, _, _ = w.transcribe(audio[:3], o)                                      # ... nor on the batch size
+    assert np.array_equal(t4[:, :40], t1[:3, :40])
+    assert w.launch_count() > 0
+    w.close()
+
+
+def test_error_paths(tiny, wbm):
+    w, _ = tiny
+    lib = wbm.load_library()
+    with pytest.raises(wbm.WhisperB200Error, match="out of range"):
+        w.logmel(np.zeros((5, 480000), dtype=np.float32))                       # max_batch = 4
+    with pytest.raises(wbm.WhisperB200Error, match="unknown tensor"):
+        w.load_state_dict({"encoder.nope": np.zeros(3, dtype=np.float32)})
+    fresh = wbm.Whisper("tiny.en", seed=None)
+    with pytest.raises(wbm.WhisperB200Error, match="weights not loaded"):
+        fresh.encode(np.zeros(480000, dtype=np.float32))
+    fresh.close()
+    w2 = wbm.Whisper("tiny.en", seed=1)
+    with pytest.raises(wbm.WhisperB200Error, match="not resident"):
+        w2.decoder_logits(np.array([[1]]))
+    w2.close()

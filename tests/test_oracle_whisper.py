@@ -1,0 +1,86 @@
+"""CPU: pins oracle/whisper_ref.py (restatement of upstream whisper's AudioEncoder/TextDecoder/greedy) against the
+independent transformers implementation — live on small dims and through the committed golden vectors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+
+@pytest.fixture(scope="module")
+def small(ref, small_dims):
+    w = ref.random_weights(small_dims, seed=3)
+    return ref.WhisperRef(small_dims, w), w
+
+
+def _mel(ref, oracle_logmel, seed=21):
+    return torch.from_numpy(oracle_logmel(ref.synth_audio(seed, "noise"))).float()[None]
+
+
+def test_restatement_matches_hf_live(ref, small_dims, small, oracle_logmel):
+    model, w = small
+    hf = ref.to_hf(small_dims, w)
+    mel = _mel(ref, oracle_logmel)
+    xa = model.encode(mel)
+    with torch.no_grad():
+        xa_hf = hf.model.encoder(mel).last_hidden_state
+        toks = torch.tensor([[50257, 50362, 7, 8, 9]])
+        lg_hf = hf(input_features=mel, decoder_input_ids=toks).logits
+    assert (xa - xa_hf).abs().max() <= 1e-4
+    assert (model.decoder_logits(toks, xa) - lg_hf).abs().max() <= 1e-4
+
+
+@pytest.mark.parametrize("tag", ["small_en", "small_ml"])
+def test_restatement_matches_golden(ref, small_dims, small_dims_ml, golden_dir, oracle_logmel, tag):
+    dims = small_dims if tag == "small_en" else small_dims_ml
+    g = np.load(os.path.join(golden_dir, f"whisper_{tag}_hf.npz"))
+    model = ref.WhisperRef(dims, ref.random_weights(dims, seed=3))
+    mel = _mel(ref, oracle_logmel)
+    xa = model.encode(mel)
+    assert np.abs(xa[0, ::75].numpy() - g["xa_rows"]).max() <= 1e-4
+    toks = torch.from_numpy(g["tokens"])
+    lg = model.decoder_logits(toks, xa)[0][:, g["logit_cols"]].numpy()
+    assert np.abs(lg - g["logits"]).max() <= 1e-4
+    opts = ref.DecodeOptions(list(g["greedy"][0, :2]), sample_len=12)          # no filters, like the fixture
+    out, _, _ = model.greedy(xa, opts)
+    assert np.array_equal(out.numpy(), g["greedy"])
+    if dims.is_multilingual:
+        assert int(model.detect_language(xa)[0]) == int(g["lang"][0])
+
+
+def test_kv_cache_equals_uncached(small, ref, oracle_logmel):
+    model, _ = small
+    xa = model.encode(_mel(ref, oracle_logmel))
+    toks = torch.tensor([[50257, 50362, 11, 12, 13, 14]])
+    full = model.decoder_logits(toks, xa)
+    cache = [None] * model.dims.n_text_layer
+    cross = model.cross_kv(xa)
+    step = torch.cat([model.decoder_logits(toks[:, i:i + 1], xa, cross, cache) for i in range(toks.shape[1])], dim=1)
+    assert (full - step).abs().max() <= 1e-4
+
+
+def test_language_argmax_is_last_max(ref):
+    """Whisper.swift:38 `max { $0.element < $1.element }` returns the LAST maximal element."""
+    lg = torch.zeros(1, 51865)
+    lg[0, 50259 + 4] = 3.0
+    lg[0, 50259 + 17] = 3.0
+    assert int(ref.language_argmax(lg)[0]) == 17
+    lg[0, 50259 + 98] = 5.0
+    assert int(ref.language_argmax(lg)[0]) == 98
+
+
+def test_eot_forcing_and_logprob_mask(ref, small_dims):
+    """After a sequence samples EOT every later token is EOT and its log-probs stop accumulating."""
+    dims = small_dims
+    model = ref.WhisperRef(dims, ref.random_weights(dims, seed=3))
+    xa = torch.zeros(2, 1500, dims.n_audio_state)
+    eot = model.vocab.eot
+    keep = {eot, 1234}
+    opts = ref.DecodeOptions([50257, 50362], sample_len=6, suppress=[i for i in range(dims.n_vocab) if i not in keep])
+    toks, slp, _ = model.greedy(xa, opts)
+    for row in toks.tolist():
+        body = row[2:]
+        if eot in body:
+            k = body.index(eot)
+            assert all(t == eot for t in body[k:])
+    assert torch.isfinite(slp).all()
