@@ -4,7 +4,6 @@
 //
 // A step is HBM-bound: per sequence it streams the cross-attention K/V of every layer (L*2*1500*d fp16) and, once per
 // batch, the decoder weights. Kernels:
-//   embed_kernel          token + learned positional embedding -> fp32 residual stream x [Mb][d]; advances cur_len
 //   skinny_gemm_kernel    y[Mb][N] = act(f(x)[Mb][K] W[N][K]^T + b): weight-streaming GEMM for Mb <= 40 rows. f is a fused
 //                         input transform (LayerNorm of x / merge of attention split partials / plain), the epilogue is
 //                         fused too (GELU, residual +=, QKV scatter straight into the self-attention cache). Weights are
@@ -12,8 +11,10 @@
 //                         inside a 32-wide block is permuted identically for both operands, so no shuffle is needed).
 //   attn_decode_kernel    one query per (sequence, head) over the cached K/V rows: each warp streams whole [d]-wide rows
 //                         (all heads at once, 16 B per lane), 8-lane shuffle dot products, online softmax in fp32,
-//                         split over rows across CTAs; partial (m, l, acc) merged by the consumer GEMM's input stage
-//   sample_greedy_kernel  logit filters, arg-max, log-softmax of the chosen token, EOT forcing, token append
+//                         split over rows across CTAs; the last CTA of a sequence to finish merges the split partials
+//   step_finish_kernel    merges the per-CTA (max, argmax, sum-exp) partials the logits GEMM epilogue produced (logit
+//                         filters already applied there), EOT forcing, log-prob accumulation, token append, then embeds
+//                         the next token (+ learned position) into the residual stream and advances the position
 #include "ops.cuh"
 #include "ptx.cuh"
 
@@ -21,20 +22,11 @@ namespace wb {
 
 constexpr float kLog2e = 1.44269504088896340736f;
 
-// ---- embed ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) embed_kernel(const int32_t* __restrict__ tokens, int tokens_ld,
-                                                     const __half* __restrict__ tok_emb, const float* __restrict__ pos_emb,
-                                                     int Mb, int d, int V, float* __restrict__ x, DecodeState* state) {
-  const int p = state->cur_len;
-  for (int i = threadIdx.x; i < Mb * d; i += blockDim.x) {
-    const int b = i / d, c = i - b * d;
-    int tok = tokens[(size_t)b * tokens_ld + p];
-    tok = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
-    x[i] = __half2float(tok_emb[(size_t)tok * d + c]) + pos_emb[(size_t)p * d + c];
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) state->cur_len = p + 1;
-}
+// Everything that changes from kernel to kernel inside a decode step (residual stream, q, attention outputs, partials,
+// tokens, DecodeState) is read through L2 (.cg): with programmatic dependent launch a kernel can share an SM — and its L1 —
+// with its still-running predecessor, so L1 may hold lines the predecessor fetched before another SM rewrote them.
+// Weights and the cross-attention K/V are constant during a decode and use the non-coherent path.
+__device__ __forceinline__ int ld_state(const int* p) { return __ldcg(p); }
 
 // ---- skinny GEMM -----------------------------------------------------------------------------------------------------------
 constexpr int kSkThreads = 256;
@@ -69,70 +61,65 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
 
+  // Weights do not depend on the previous kernel: fetch this warp's first blocks before waiting for it (PDL) and
+  // before the input stage, so their DRAM latency overlaps both.
+  const int KC0 = p.K < KC ? p.K : KC;
+  const int nblk0 = KC0 / 32;
+  const int pb0 = (kslice * nblk0) / KS, pb1 = ((kslice + 1) * nblk0) / KS;
+  uint4 pwa[4], pwb[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int blk = (pb0 + u < pb1) ? pb0 + u : pb0;
+    pwa[u] = ptx::ldg_nc_16(wrow0 + blk * 32);
+    pwb[u] = ptx::ldg_nc_16(wrow1 + blk * 32);
+  }
+  ptx::grid_dep_launch();
+  ptx::grid_dep_sync();
+
   for (int kc0 = 0; kc0 < p.K; kc0 += KC) {
     const int kc = (p.K - kc0) < KC ? (p.K - kc0) : KC;
     if (kc0) __syncthreads();
     // ---- input stage: build xs[MT*8][kc] fp16 --------------------------------------------------------------------------
-    for (int r = warp; r < MT * 8; r += 8) {
-      __half* xr = reinterpret_cast<__half*>(xs + (size_t)r * xs_stride);
-      if (r >= p.Mb) {
-        for (int c = lane * 8; c < kc; c += 256) *reinterpret_cast<uint4*>(xr + c) = make_uint4(0, 0, 0, 0);
-      } else if (p.in_mode == SKINNY_IN_F16) {
-        const __half* src = reinterpret_cast<const __half*>(p.in) + (size_t)r * p.K + kc0;
-        for (int c = lane * 8; c < kc; c += 256) *reinterpret_cast<uint4*>(xr + c) = *reinterpret_cast<const uint4*>(src + c);
-      } else if (p.in_mode == SKINNY_IN_F32) {
-        const float* src = reinterpret_cast<const float*>(p.in) + (size_t)r * p.K + kc0;
-        for (int c = lane * 4; c < kc; c += 128) {
-          const float4 v = *reinterpret_cast<const float4*>(src + c);
-          __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-          uint2 u;
-          u.x = *reinterpret_cast<uint32_t*>(&h0), u.y = *reinterpret_cast<uint32_t*>(&h1);
-          *reinterpret_cast<uint2*>(xr + c) = u;
+    if (p.in_mode == SKINNY_IN_F16) {
+      const __half* src = reinterpret_cast<const __half*>(p.in);
+      const int cpr = kc >> 3;                              // 16-byte chunks per row
+      for (int i = tid; i < MT * 8 * cpr; i += kSkThreads) {
+        const int r = i / cpr, c = (i - r * cpr) * 8;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (r < p.Mb) v = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)r * p.K + kc0 + c));
+        *reinterpret_cast<uint4*>(xs + (size_t)r * xs_stride + c * 2) = v;
+      }
+    } else {
+      // LayerNorm of the fp32 residual stream (K = d, one chunk). 8 threads per row, 32 rows per pass: every row of the
+      // batch is in flight at once; two passes over L2 (statistics, then normalise). fp32, biased variance, eps 1e-5.
+      const int sub = tid & 7;
+      for (int r = tid >> 3; r < MT * 8; r += kSkThreads / 8) {     // trip count is warp-uniform (MT*8 is a multiple of 8)
+        __half* xr = reinterpret_cast<__half*>(xs + (size_t)r * xs_stride);
+        const bool act = r < p.Mb;                                   // padding rows compute on row 0 and store zeros
+        const float* src = reinterpret_cast<const float*>(p.in) + (size_t)(act ? r : 0) * p.K;
+        float s = 0.f, q = 0.f;                                      // one pass: sum and sum of squares (fp32)
+#pragma unroll 4
+        for (int c = sub * 4; c < p.K; c += 32) {
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(src + c));
+          s += (v.x + v.y) + (v.z + v.w);
+          q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
         }
-      } else if (p.in_mode == SKINNY_IN_LN) {
-        // LayerNorm over the full row (K = d <= kSkKC): fp32 statistics, two passes over L2-resident data
-        const float* src = reinterpret_cast<const float*>(p.in) + (size_t)r * p.K;
-        float s = 0.f;
-        for (int c = lane * 4; c < p.K; c += 128) {
-          const float4 v = *reinterpret_cast<const float4*>(src + c);
-          s += v.x + v.y + v.z + v.w;
-        }
-        const float mean = warp_sum(s) / (float)p.K;
-        float q = 0.f;
-        for (int c = lane * 4; c < p.K; c += 128) {
-          const float4 v = *reinterpret_cast<const float4*>(src + c);
-          const float e0 = v.x - mean, e1 = v.y - mean, e2 = v.z - mean, e3 = v.w - mean;
-          q += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
-        }
-        const float rstd = rsqrtf(warp_sum(q) / (float)p.K + 1e-5f);
-        for (int c = lane * 4; c < p.K; c += 128) {
-          const float4 v = *reinterpret_cast<const float4*>(src + c);
-          const float4 g = *reinterpret_cast<const float4*>(p.ln_g + c), bb = *reinterpret_cast<const float4*>(p.ln_b + c);
-          __half2 h0 = __floats2half2_rn((v.x - mean) * rstd * g.x + bb.x, (v.y - mean) * rstd * g.y + bb.y);
-          __half2 h1 = __floats2half2_rn((v.z - mean) * rstd * g.z + bb.z, (v.w - mean) * rstd * g.w + bb.w);
-          uint2 u;
-          u.x = *reinterpret_cast<uint32_t*>(&h0), u.y = *reinterpret_cast<uint32_t*>(&h1);
-          *reinterpret_cast<uint2*>(xr + c) = u;
-        }
-      } else {   // SKINNY_IN_ATTN: merge the row-split partials of attn_decode_kernel (K = d, single chunk)
-        const int H = p.n_head, NS = p.n_split;
-        const float* ml = p.part_ml + (size_t)r * NS * H * 2;
-        const float* pa = p.part_acc + (size_t)r * NS * p.K;
-        for (int c = lane * 4; c < p.K; c += 128) {
-          const int h = c >> 6;
-          float M = -INFINITY;
-          for (int s2 = 0; s2 < NS; ++s2) M = fmaxf(M, ml[(s2 * H + h) * 2]);
-          float L = 0.f;
-          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int s2 = 0; s2 < NS; ++s2) {
-            const float m = ml[(s2 * H + h) * 2];
-            const float wgt = (m == -INFINITY) ? 0.f : exp2f(m - M);
-            L += wgt * ml[(s2 * H + h) * 2 + 1];
-            const float4 v = *reinterpret_cast<const float4*>(pa + (size_t)s2 * p.K + c);
-            o.x += wgt * v.x, o.y += wgt * v.y, o.z += wgt * v.z, o.w += wgt * v.w;
-          }
-          const float inv = 1.0f / L;
-          __half2 h0 = __floats2half2_rn(o.x * inv, o.y * inv), h1 = __floats2half2_rn(o.z * inv, o.w * inv);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        q += __shfl_xor_sync(0xffffffffu, q, 4);
+        const float mean = s / (float)p.K;
+        q = fmaxf(q / (float)p.K - mean * mean, 0.f);
+        const float rstd = act ? rsqrtf(q + 1e-5f) : 0.f;
+#pragma unroll 4
+        for (int c = sub * 4; c < p.K; c += 32) {
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(src + c));
+          const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_g + c)), bb = __ldg(reinterpret_cast<const float4*>(p.ln_b + c));
+          const float ab = act ? 1.f : 0.f;
+          __half2 h0 = __floats2half2_rn((v.x - mean) * rstd * g.x + ab * bb.x, (v.y - mean) * rstd * g.y + ab * bb.y);
+          __half2 h1 = __floats2half2_rn((v.z - mean) * rstd * g.z + ab * bb.z, (v.w - mean) * rstd * g.w + ab * bb.w);
           uint2 u;
           u.x = *reinterpret_cast<uint32_t*>(&h0), u.y = *reinterpret_cast<uint32_t*>(&h1);
           *reinterpret_cast<uint2*>(xr + c) = u;
@@ -145,6 +132,22 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
     const int blk0 = (kslice * nblk) / KS, blk1 = ((kslice + 1) * nblk) / KS;
     const unsigned char* xl = xs + (size_t)grp * xs_stride + tq * 16;
     int blk = blk0;
+    if (kc0 == 0) {   // the prefetched blocks
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (blk0 + u < blk1) {
+          const uint32_t a0[4] = {pwa[u].x, pwb[u].x, pwa[u].y, pwb[u].y}, a1[4] = {pwa[u].z, pwb[u].z, pwa[u].w, pwb[u].w};
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint4 xb = *reinterpret_cast<const uint4*>(xl + (size_t)mt * 8 * xs_stride + (blk0 + u) * 64);
+            const uint32_t b0[2] = {xb.x, xb.y}, b1[2] = {xb.z, xb.w};
+            ptx::mma_16816(acc[mt], a0, b0);
+            ptx::mma_16816(acc[mt], a1, b1);
+          }
+        }
+      }
+      blk = blk0 + 4 < blk1 ? blk0 + 4 : blk1;
+    }
     for (; blk + 4 <= blk1; blk += 4) {
       uint4 wa[4], wb[4];
 #pragma unroll
@@ -188,7 +191,46 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
   }
   __syncthreads();
   const int rows_cta = S * 16;
-  const int pos = (p.out_mode == SKINNY_OUT_QKV) ? p.state->cur_len - 1 : 0;
+  if (p.out_mode == SKINNY_OUT_LOGITS) {
+    // rows_cta == 128 (S == 8, no K split). Warp per sequence: filter, optional store, CTA-local (max, argmax, sum-exp).
+    const bool first = ld_state(&p.state->cur_len) + 1 == p.n_initial;
+    for (int b = warp; b < p.Mb; b += 8) {
+      float v[4];
+      float best = -INFINITY;
+      int arg = 0x7fffffff;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = lane + 32 * i, n = n_cta + rr;
+        float x = -INFINITY;
+        if (n < p.N) {
+          x = red[(size_t)(rr >> 4) * 16 * MB8 + (rr & 15) * MB8 + b];
+          const unsigned char mk = p.mask ? p.mask[n] : 0;
+          if (mk == 1 || (mk == 2 && first)) x = -INFINITY;
+          if (p.out) reinterpret_cast<float*>(p.out)[(size_t)b * p.N + n] = x;
+        }
+        v[i] = x;
+        if (x > best) best = x, arg = n;     // ascending n: first maximum wins
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ov > best || (ov == best && oi < arg)) best = ov, arg = oi;
+      }
+      float se = 0.f;
+      if (best > -INFINITY) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) se += expf(v[i] - best);
+      }
+      se = warp_sum(se);
+      if (lane == 0) {
+        float* pp = p.part_logits + ((size_t)b * gridDim.x + blockIdx.x) * 4;
+        pp[0] = best, pp[1] = __int_as_float(arg), pp[2] = se;
+      }
+    }
+    return;
+  }
+  const int pos = (p.out_mode == SKINNY_OUT_QKV) ? ld_state(&p.state->cur_len) : 0;
   const int dq = p.N / 3;
   for (int idx = tid; idx < rows_cta * p.Mb; idx += kSkThreads) {
     const int b = idx / rows_cta, rr = idx - b * rows_cta;
@@ -207,7 +249,10 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
         reinterpret_cast<float*>(p.out)[(size_t)b * p.N + n] = v;
         break;
       case SKINNY_OUT_RESID:
-        reinterpret_cast<float*>(p.out)[(size_t)b * p.N + n] += v;
+        {
+        float* o = reinterpret_cast<float*>(p.out) + (size_t)b * p.N + n;
+        *o = __ldcg(o) + v;
+      }
         break;
       default:   // SKINNY_OUT_QKV
         if (n < dq)
@@ -221,23 +266,49 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
   }
 }
 
+static bool use_pdl() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WB_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// launch with the programmatic-dependent-launch attribute: the kernel may start while its predecessor drains; every
+// kernel launched this way calls griddepcontrol.wait before touching anything the predecessor wrote
+template <typename Kern, typename Arg>
+static cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const Arg& arg) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at, cfg.numAttrs = use_pdl() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, arg);
+}
+
+int skinny_logits_ctas(int N) { return ((N + 15) / 16 + 7) / 8; }
+
 int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches) {
   if (d.Mb < 1 || d.Mb > 40 || d.K % 128 != 0 || d.N < 16) {
     set_error("skinny_gemm: unsupported shape Mb=%d N=%d K=%d", d.Mb, d.N, d.K);
     return -1;
   }
-  if ((d.in_mode == SKINNY_IN_LN || d.in_mode == SKINNY_IN_ATTN) && d.K > kSkKC) {
-    set_error("skinny_gemm: fused LN / attention-merge input needs K <= %d", kSkKC);
+  if (d.in_mode == SKINNY_IN_LN && d.K > kSkKC) {
+    set_error("skinny_gemm: fused LayerNorm input needs K <= %d", kSkKC);
     return -1;
   }
   const int strips = (d.N + 15) / 16;
   int S = 1;
   while (S < 8 && strips / S > 296) S *= 2;
+  if (d.out_mode == SKINNY_OUT_LOGITS) S = 8;
   SkinnyArgs a{d, S};
   const int MT = (d.Mb + 7) / 8;
   const int KC = d.K < kSkKC ? d.K : kSkKC;
   const size_t smem = (size_t)MT * 8 * (KC * 2 + 64) + (size_t)8 * 16 * MT * 8 * 4;
   const int grid = (strips + S - 1) / S;
+  cudaError_t le = cudaSuccess;
 #define WB_SK_CASE(M)                                                                                             \
   case M: {                                                                                                       \
     static size_t smem_set = 0;                                                                                   \
@@ -245,7 +316,7 @@ int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches) 
       WB_CUDA_OK(cudaFuncSetAttribute(skinny_gemm_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       smem_set = smem;                                                                                            \
     }                                                                                                             \
-    skinny_gemm_kernel<M><<<grid, kSkThreads, smem, st>>>(a);                                                    \
+    le = launch_pdl(skinny_gemm_kernel<M>, dim3(grid), dim3(kSkThreads), smem, st, a);                            \
   } break;
   switch (MT) {
     WB_SK_CASE(1) WB_SK_CASE(2) WB_SK_CASE(3) WB_SK_CASE(4) WB_SK_CASE(5)
@@ -255,7 +326,7 @@ int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches) 
   }
 #undef WB_SK_CASE
   if (launches) *launches += 1;
-  WB_CUDA_OK(cudaGetLastError());
+  WB_CUDA_OK(le);
   return 0;
 }
 
@@ -265,13 +336,16 @@ constexpr int kAdThreads = 256;
 template <int NJ, int RB>
 __global__ void __launch_bounds__(kAdThreads) attn_decode_kernel(AttnDecodeDesc p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_last;
   const int H = p.n_head, d = p.d;
   float* wm = reinterpret_cast<float*>(smem_raw);   // [8][H]
   float* wl = wm + 8 * H;                           // [8][H]
   float* wacc = wl + 8 * H;                         // [8][d]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int split = blockIdx.x, b = blockIdx.y;
-  const int n_rows = p.n_rows_fixed > 0 ? p.n_rows_fixed : p.state->cur_len;
+  ptx::grid_dep_launch();
+  ptx::grid_dep_sync();
+  const int n_rows = p.n_rows_fixed > 0 ? p.n_rows_fixed : ld_state(&p.state->cur_len) + 1;
   const size_t slab = (size_t)(b / p.kv_share) * p.n_ctx * d;
   const __half* K = p.k + slab;
   const __half* V = p.v + slab;
@@ -286,9 +360,12 @@ __global__ void __launch_bounds__(kAdThreads) attn_decode_kernel(AttnDecodeDesc 
     valid[j] = c < n_chunks;
     m[j] = -INFINITY, l[j] = 0.f;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      acc[j][e] = 0.f;
-      qf[j][e] = valid[j] ? p.q[(size_t)b * d + c * 8 + e] * sl : 0.f;
+    for (int e = 0; e < 8; ++e) acc[j][e] = 0.f, qf[j][e] = 0.f;
+    if (valid[j]) {
+      const float4 q0 = __ldcg(reinterpret_cast<const float4*>(p.q + (size_t)b * d + c * 8));
+      const float4 q1 = __ldcg(reinterpret_cast<const float4*>(p.q + (size_t)b * d + c * 8 + 4));
+      qf[j][0] = q0.x * sl, qf[j][1] = q0.y * sl, qf[j][2] = q0.z * sl, qf[j][3] = q0.w * sl;
+      qf[j][4] = q1.x * sl, qf[j][5] = q1.y * sl, qf[j][6] = q1.z * sl, qf[j][7] = q1.w * sl;
     }
   }
   const int n_units = (n_rows + RB - 1) / RB;
@@ -383,22 +460,54 @@ __global__ void __launch_bounds__(kAdThreads) attn_decode_kernel(AttnDecodeDesc 
       L += wgt * wl[w * H + h];
       A += wgt * wacc[(size_t)w * d + c];
     }
-    out_acc[c] = A;
-    if ((c & 63) == 0) {
-      out_ml[h * 2] = M;
-      out_ml[h * 2 + 1] = L;
+    if (p.n_split == 1) {
+      p.out16[(size_t)b * d + c] = __float2half_rn(A / L);
+    } else {
+      out_acc[c] = A;
+      if ((c & 63) == 0) {
+        out_ml[h * 2] = M;
+        out_ml[h * 2 + 1] = L;
+      }
     }
   }
+  if (p.n_split == 1) return;
+  // the last CTA of this sequence to arrive merges the splits (fixed split order -> deterministic result)
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int ticket = atomicAdd(&p.counters[b], 1);
+    s_last = ticket == p.n_split - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* all_ml = p.part_ml + (size_t)b * p.n_split * H * 2;
+  const float* all_acc = p.part_acc + (size_t)b * p.n_split * d;
+  for (int c = tid; c < d; c += kAdThreads) {
+    const int h = c >> 6;
+    float M = -INFINITY;
+    for (int s2 = 0; s2 < p.n_split; ++s2) M = fmaxf(M, __ldcg(all_ml + (s2 * H + h) * 2));
+    float L = 0.f, A = 0.f;
+    for (int s2 = 0; s2 < p.n_split; ++s2) {
+      const float ms = __ldcg(all_ml + (s2 * H + h) * 2);
+      const float wgt = (ms == -INFINITY) ? 0.f : exp2f(ms - M);
+      L += wgt * __ldcg(all_ml + (s2 * H + h) * 2 + 1);
+      A += wgt * __ldcg(all_acc + (size_t)s2 * d + c);
+    }
+    p.out16[(size_t)b * d + c] = __float2half_rn(A / L);
+  }
+  if (tid == 0) p.counters[b] = 0;   // ready for the next launch (graph replay)
 }
 
 int launch_attn_decode(const AttnDecodeDesc& p, cudaStream_t st, int64_t* launches) {
-  if (p.d % 64 != 0 || p.d / 64 != p.n_head || p.d > 1280 || p.kv_share < 1) {
+  if (p.d % 64 != 0 || p.d / 64 != p.n_head || p.d > 1280 || p.kv_share < 1 || p.n_split < 1) {
     set_error("attn_decode: unsupported d=%d heads=%d", p.d, p.n_head);
     return -1;
   }
   const int NJ = (p.d / 8 + 31) / 32;
   const size_t smem = (size_t)(16 * p.n_head + 8 * p.d) * 4;
   dim3 grid(p.n_split, p.Mb);
+  cudaError_t le = cudaSuccess;
 #define WB_AD_CASE(J, R)                                                                                          \
   case J: {                                                                                                       \
     static bool attr_set = false;                                                                                 \
@@ -406,7 +515,7 @@ int launch_attn_decode(const AttnDecodeDesc& p, cudaStream_t st, int64_t* launch
       WB_CUDA_OK(cudaFuncSetAttribute(attn_decode_kernel<J, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024)); \
       attr_set = true;                                                                                            \
     }                                                                                                             \
-    attn_decode_kernel<J, R><<<grid, kAdThreads, smem, st>>>(p);                                                 \
+    le = launch_pdl(attn_decode_kernel<J, R>, grid, dim3(kAdThreads), smem, st, p);                               \
   } break;
   switch (NJ) {
     WB_AD_CASE(1, 4) WB_AD_CASE(2, 4) WB_AD_CASE(3, 2) WB_AD_CASE(4, 2) WB_AD_CASE(5, 2)
@@ -416,89 +525,91 @@ int launch_attn_decode(const AttnDecodeDesc& p, cudaStream_t st, int64_t* launch
   }
 #undef WB_AD_CASE
   if (launches) *launches += 1;
-  WB_CUDA_OK(cudaGetLastError());
+  WB_CUDA_OK(le);
   return 0;
 }
 
-int launch_embed(const int32_t* tokens, int tokens_ld, const __half* tok_emb, const float* pos_emb, int Mb, int d, int V,
-                 float* x, DecodeState* state, cudaStream_t st, int64_t* launches) {
-  embed_kernel<<<1, 1024, 0, st>>>(tokens, tokens_ld, tok_emb, pos_emb, Mb, d, V, x, state);
-  if (launches) *launches += 1;
-  WB_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-// ---- greedy sampling ---------------------------------------------------------------------------------------------------------
-// Upstream DecodingTask with temperature 0: SuppressBlank at the first sampled position, SuppressTokens,
-// argmax, sum_logprobs += logprob * (previous token != eot), sequences that ended keep emitting eot.
-__global__ void __launch_bounds__(1024) sample_greedy_kernel(SampleDesc p) {
-  __shared__ float s_val[32];
-  __shared__ int s_idx[32];
-  __shared__ float s_max;
-  __shared__ int s_arg;
+// ---- end of step: sample (optional), embed the next token, advance -------------------------------------------------------------
+// Upstream DecodingTask with temperature 0: the logit filters were applied in the logits GEMM epilogue;
+// here argmax over the CTA partials, sum_logprobs += logprob * (previous token != eot), sequences that ended keep
+// emitting eot. Then x[b] = token_embedding[next] + positional_embedding[cur_len + 1] for the next step.
+__global__ void __launch_bounds__(256) step_finish_kernel(FinishDesc p) {
+  __shared__ float s_val[8], s_sum[8];
+  __shared__ int s_idx[8];
+  __shared__ int s_tok;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* row = p.logits + (size_t)b * p.V;
-  const int cur_len = p.state->cur_len;   // tokens in the context, including the one just consumed
-  for (int i = tid; i < p.n_suppress; i += blockDim.x) {
-    const int id = p.suppress[i];
-    if (id >= 0 && id < p.V) row[id] = -INFINITY;
-  }
-  if (cur_len == p.n_initial) {
-    for (int i = tid; i < p.n_suppress_begin; i += blockDim.x) {
-      const int id = p.suppress_begin[i];
-      if (id >= 0 && id < p.V) row[id] = -INFINITY;
+  ptx::grid_dep_launch();
+  ptx::grid_dep_sync();
+  const int cur = ld_state(&p.state->cur_len);   // index of the token this step consumed (-1 before the first step)
+  int32_t* trow = p.tokens + (size_t)b * p.tokens_ld;
+  if (p.sample) {
+    const float* pp = p.part_logits + (size_t)b * p.n_part * 4;
+    float best = -INFINITY;
+    int arg = 0x7fffffff;
+    for (int i = tid; i < p.n_part; i += 256) {
+      const float v = __ldcg(pp + i * 4);
+      const int a = __float_as_int(__ldcg(pp + i * 4 + 1));
+      if (v > best || (v == best && a < arg)) best = v, arg = a;
     }
-  }
-  __syncthreads();
-  float best = -INFINITY;
-  int arg = 0x7fffffff;
-  for (int i = tid; i < p.V; i += blockDim.x) {
-    const float v = row[i];
-    if (v > best || (v == best && i < arg)) best = v, arg = i;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
-    if (ov > best || (ov == best && oi < arg)) best = ov, arg = oi;
-  }
-  if (lane == 0) s_val[warp] = best, s_idx[warp] = arg;
-  __syncthreads();
-  if (warp == 0) {
-    best = s_val[lane], arg = s_idx[lane];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float ov = __shfl_xor_sync(0xffffffffu, best, o);
       const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
       if (ov > best || (ov == best && oi < arg)) best = ov, arg = oi;
     }
-    if (lane == 0) s_max = best, s_arg = arg;
+    if (lane == 0) s_val[warp] = best, s_idx[warp] = arg;
+    __syncthreads();
+    best = s_val[0], arg = s_idx[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w)
+      if (s_val[w] > best || (s_val[w] == best && s_idx[w] < arg)) best = s_val[w], arg = s_idx[w];
+    float se = 0.f;
+    for (int i = tid; i < p.n_part; i += 256) {
+      const float mi = __ldcg(pp + i * 4);
+      if (mi > -INFINITY) se += __ldcg(pp + i * 4 + 2) * expf(mi - best);
+    }
+    se = warp_sum(se);
+    if (lane == 0) s_sum[warp] = se;
+    __syncthreads();
+    if (tid == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < 8; ++w) tot += s_sum[w];
+      const float logprob = -logf(tot);   // the chosen logit is the maximum
+      const bool ended = __ldcg(trow + cur) == p.eot;
+      if (!ended) p.sum_logprob[b] = __ldcg(p.sum_logprob + b) + logprob;
+      const int next = ended ? p.eot : arg;
+      trow[cur + 1] = next;
+      p.done[b] = next == p.eot;
+      s_tok = next;
+    }
+  } else if (tid == 0) {
+    s_tok = __ldcg(trow + cur + 1);
   }
   __syncthreads();
-  const float mx = s_max;
-  float se = 0.f;
-  for (int i = tid; i < p.V; i += blockDim.x) se += expf(row[i] - mx);
-  se = warp_sum(se);
-  __syncthreads();
-  if (lane == 0) s_val[warp] = se;
+  const int np = cur + 1;
+  if (np < p.n_ctx) {
+    int tok = s_tok;
+    tok = tok < 0 ? 0 : (tok >= p.V ? p.V - 1 : tok);
+    const __half* e = p.tok_emb + (size_t)tok * p.d;
+    const float* pe = p.pos_emb + (size_t)np * p.d;
+    for (int c = tid; c < p.d; c += 256) p.x[(size_t)b * p.d + c] = __half2float(e[c]) + pe[c];
+  }
+  // every CTA has read cur_len by now only once all have arrived: the last one advances it
   __syncthreads();
   if (tid == 0) {
-    float tot = 0.f;
-    for (int w = 0; w < 32; ++w) tot += s_val[w];
-    const float logprob = -logf(tot);   // chosen logit equals the maximum
-    int32_t* trow = p.tokens + (size_t)b * p.tokens_ld;
-    const bool ended = trow[cur_len - 1] == p.eot;
-    if (!ended) p.sum_logprob[b] += logprob;
-    const int next = ended ? p.eot : s_arg;
-    trow[cur_len] = next;
-    p.done[b] = next == p.eot;
+    __threadfence();
+    const int ticket = atomicAdd(&p.state->arrive, 1);
+    if (ticket == (int)gridDim.x - 1) {
+      p.state->arrive = 0;
+      p.state->cur_len = cur + 1;
+    }
   }
 }
 
-int launch_sample_greedy(const SampleDesc& d, cudaStream_t st, int64_t* launches) {
-  sample_greedy_kernel<<<d.Mb, 1024, 0, st>>>(d);
+int launch_step_finish(const FinishDesc& d, cudaStream_t st, int64_t* launches) {
+  const cudaError_t le = launch_pdl(step_finish_kernel, dim3(d.Mb), dim3(256), 0, st, d);
   if (launches) *launches += 1;
-  WB_CUDA_OK(cudaGetLastError());
+  WB_CUDA_OK(le);
   return 0;
 }
 

@@ -123,9 +123,12 @@ struct wb_handle {
   std::vector<__half*> selfK, selfV;
   int32_t* tokens;
   int tokens_ld;
-  float *xdec, *q32, *part_ml, *part_acc, *logits, *sum_logprob;
-  __half* dmlp16;
-  int32_t *done, *suppress, *suppress_begin;
+  float *xdec, *q32, *part_ml, *part_acc, *logits, *sum_logprob, *part_logits;
+  __half *dmlp16, *a16;
+  int32_t* done;
+  int* counters;
+  unsigned char* mask;
+  int n_logit_ctas;
   DecodeState* state;
   int split_self, split_cross;
 
@@ -265,8 +268,11 @@ static void layout_workspace(wb_handle* h) {
   h->logits = A.take<float>(Mb * (size_t)D.n_vocab);
   h->sum_logprob = A.take<float>(Mb);
   h->done = A.take<int32_t>(Mb);
-  h->suppress = A.take<int32_t>((size_t)D.n_vocab);
-  h->suppress_begin = A.take<int32_t>(256);
+  h->a16 = A.take<__half>(Mb * dt);
+  h->counters = A.take<int>(Mb);
+  h->mask = A.take<unsigned char>((size_t)D.n_vocab);
+  h->n_logit_ctas = skinny_logits_ctas(D.n_vocab);
+  h->part_logits = A.take<float>(Mb * (size_t)h->n_logit_ctas * 4);
   h->state = A.take<DecodeState>(1);
 }
 
@@ -343,20 +349,30 @@ static int cross_kv(wb_handle* h, int B) {
 // ---- decoder ---------------------------------------------------------------------------------------------------------------
 struct StepOpts {
   int Mb, beams;
-  int want_logits, sample;
-  SampleDesc sd;
+  int store_logits;   // write the fp32 logits [Mb][V] (teacher-forced / language-ID paths)
+  int sample;         // run the logits GEMM with filters + partial argmax and sample in the finish kernel
+  int n_initial, eot;
 };
 
+static int step_finish(wb_handle* h, const StepOpts& o, int sample) {
+  const wb_dims& D = h->dims;
+  FinishDesc f{};
+  f.Mb = o.Mb, f.V = D.n_vocab, f.d = D.n_text_state, f.n_ctx = D.n_text_ctx, f.sample = sample;
+  f.part_logits = h->part_logits, f.n_part = h->n_logit_ctas, f.eot = o.eot, f.tokens = h->tokens, f.tokens_ld = h->tokens_ld;
+  f.sum_logprob = h->sum_logprob, f.done = h->done, f.tok_emb = h->tok_emb, f.pos_emb = h->dec_pos, f.x = h->xdec, f.state = h->state;
+  return launch_step_finish(f, h->stream, &h->launches);
+}
+
+// One decoder step for the token at position state->cur_len of every sequence (its embedding is already in xdec).
 static int decode_step(wb_handle* h, const StepOpts& o) {
   const wb_dims& D = h->dims;
   const int d = D.n_text_state, H = D.n_text_head, Mb = o.Mb;
   cudaStream_t st = h->stream;
-  WB_TRY(launch_embed(h->tokens, h->tokens_ld, h->tok_emb, h->dec_pos, Mb, d, D.n_vocab, h->xdec, h->state, st, &h->launches));
   for (int l = 0; l < D.n_text_layer; ++l) {
     const LayerW& L = h->dec[l];
     SkinnyDesc s{};
-    s.Mb = Mb, s.n_head = H, s.state = h->state;
-    // self attention
+    s.Mb = Mb, s.state = h->state;
+    // self attention: LN + fused QKV, K/V appended to the cache by the epilogue
     s.N = 3 * d, s.K = d, s.w = L.wqkv, s.bias = L.bqkv, s.in_mode = SKINNY_IN_LN, s.in = h->xdec, s.ln_g = L.ln1_g,
     s.ln_b = L.ln1_b, s.out_mode = SKINNY_OUT_QKV, s.q32 = h->q32, s.kcache = h->selfK[l], s.vcache = h->selfV[l],
     s.n_ctx = D.n_text_ctx;
@@ -364,14 +380,15 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
     AttnDecodeDesc a{};
     a.Mb = Mb, a.d = d, a.n_head = H, a.n_split = h->split_self, a.q = h->q32, a.k = h->selfK[l], a.v = h->selfV[l];
     a.n_ctx = D.n_text_ctx, a.n_rows_fixed = 0, a.kv_share = 1, a.state = h->state, a.part_ml = h->part_ml, a.part_acc = h->part_acc;
+    a.counters = h->counters, a.out16 = h->a16;
     WB_TRY(launch_attn_decode(a, st, &h->launches));
     SkinnyDesc so{};
-    so.Mb = Mb, so.n_head = H, so.state = h->state, so.N = d, so.K = d, so.w = L.wo, so.bias = L.bo, so.in_mode = SKINNY_IN_ATTN;
-    so.part_ml = h->part_ml, so.part_acc = h->part_acc, so.n_split = h->split_self, so.out_mode = SKINNY_OUT_RESID, so.out = h->xdec;
+    so.Mb = Mb, so.state = h->state, so.N = d, so.K = d, so.w = L.wo, so.bias = L.bo, so.in_mode = SKINNY_IN_F16, so.in = h->a16;
+    so.out_mode = SKINNY_OUT_RESID, so.out = h->xdec;
     WB_TRY(launch_skinny_gemm(so, st, &h->launches));
     // cross attention
     SkinnyDesc sq{};
-    sq.Mb = Mb, sq.n_head = H, sq.state = h->state, sq.N = d, sq.K = d, sq.w = L.wq_c, sq.bias = L.bq_c, sq.in_mode = SKINNY_IN_LN;
+    sq.Mb = Mb, sq.state = h->state, sq.N = d, sq.K = d, sq.w = L.wq_c, sq.bias = L.bq_c, sq.in_mode = SKINNY_IN_LN;
     sq.in = h->xdec, sq.ln_g = L.lnc_g, sq.ln_b = L.lnc_b, sq.out_mode = SKINNY_OUT_F32, sq.out = h->q32;
     WB_TRY(launch_skinny_gemm(sq, st, &h->launches));
     AttnDecodeDesc c = a;
@@ -379,39 +396,44 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
     c.kv_share = o.beams;
     WB_TRY(launch_attn_decode(c, st, &h->launches));
     SkinnyDesc sc = so;
-    sc.w = L.wo_c, sc.bias = L.bo_c, sc.n_split = h->split_cross;
+    sc.w = L.wo_c, sc.bias = L.bo_c;
     WB_TRY(launch_skinny_gemm(sc, st, &h->launches));
     // MLP
     SkinnyDesc m1{};
-    m1.Mb = Mb, m1.n_head = H, m1.state = h->state, m1.N = 4 * d, m1.K = d, m1.w = L.w1, m1.bias = L.b1, m1.gelu = 1;
+    m1.Mb = Mb, m1.state = h->state, m1.N = 4 * d, m1.K = d, m1.w = L.w1, m1.bias = L.b1, m1.gelu = 1;
     m1.in_mode = SKINNY_IN_LN, m1.in = h->xdec, m1.ln_g = L.ln2_g, m1.ln_b = L.ln2_b, m1.out_mode = SKINNY_OUT_F16, m1.out = h->dmlp16;
     WB_TRY(launch_skinny_gemm(m1, st, &h->launches));
     SkinnyDesc m2{};
-    m2.Mb = Mb, m2.n_head = H, m2.state = h->state, m2.N = d, m2.K = 4 * d, m2.w = L.w2, m2.bias = L.b2;
+    m2.Mb = Mb, m2.state = h->state, m2.N = d, m2.K = 4 * d, m2.w = L.w2, m2.bias = L.b2;
     m2.in_mode = SKINNY_IN_F16, m2.in = h->dmlp16, m2.out_mode = SKINNY_OUT_RESID, m2.out = h->xdec;
     WB_TRY(launch_skinny_gemm(m2, st, &h->launches));
   }
-  if (o.want_logits || o.sample) {
+  if (o.store_logits || o.sample) {
+    // final LN + tied-embedding logits; filters and per-CTA (max, argmax, sum-exp) fused into the epilogue
     SkinnyDesc lg{};
-    lg.Mb = Mb, lg.n_head = H, lg.state = h->state, lg.N = D.n_vocab, lg.K = d, lg.w = h->tok_emb, lg.in_mode = SKINNY_IN_LN;
-    lg.in = h->xdec, lg.ln_g = h->lnf_g, lg.ln_b = h->lnf_b, lg.out_mode = SKINNY_OUT_F32, lg.out = h->logits;
+    lg.Mb = Mb, lg.state = h->state, lg.N = D.n_vocab, lg.K = d, lg.w = h->tok_emb, lg.in_mode = SKINNY_IN_LN;
+    lg.in = h->xdec, lg.ln_g = h->lnf_g, lg.ln_b = h->lnf_b, lg.out_mode = SKINNY_OUT_LOGITS;
+    lg.out = o.store_logits ? h->logits : nullptr, lg.mask = o.sample ? h->mask : nullptr, lg.n_initial = o.n_initial;
+    lg.part_logits = h->part_logits;
     WB_TRY(launch_skinny_gemm(lg, st, &h->launches));
   }
-  if (o.sample) WB_TRY(launch_sample_greedy(o.sd, st, &h->launches));
-  return 0;
+  return step_finish(h, o, o.sample);
 }
 
-static int reset_decode_state(wb_handle* h) {
-  WB_CUDA_OK(cudaMemsetAsync(h->state, 0, sizeof(DecodeState), h->stream));
-  return 0;
+// cur_len = -1, then embed the token at position 0 (which advances cur_len to 0)
+static int reset_decode_state(wb_handle* h, const StepOpts& o) {
+  DecodeState init{-1, 0, 0, 0};
+  WB_CUDA_OK(cudaMemcpyAsync(h->state, &init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+  WB_CUDA_OK(cudaMemsetAsync(h->counters, 0, sizeof(int) * h->Mb_max, h->stream));
+  return step_finish(h, o, 0);
 }
 
 static void pick_splits(wb_handle* h, int Mb) {
-  // cross attention: enough CTAs for ~2 per SM; self attention: few rows, favour short chains
-  int sc = (296 + Mb - 1) / Mb;
+  // one wave: at most 2 CTAs of the attention kernel fit an SM (registers), 148 SMs
+  int sc = 296 / Mb;
   sc = sc < 1 ? 1 : (sc > 32 ? 32 : sc);
   h->split_cross = sc;
-  int ss = (148 + Mb - 1) / Mb;
+  int ss = 148 / Mb;
   ss = ss < 1 ? 1 : (ss > 8 ? 8 : ss);
   h->split_self = ss;
 }
@@ -741,10 +763,10 @@ int wb_decoder_logits(wb_handle* h, const int32_t* tokens, int32_t B, int32_t t,
       }
   WB_CUDA_OK(cudaMemcpy2DAsync(h->tokens, h->tokens_ld * sizeof(int32_t), tokens, t * sizeof(int32_t), t * sizeof(int32_t), B,
                                cudaMemcpyHostToDevice, h->stream));
-  WB_TRY(reset_decode_state(h));
   pick_splits(h, B);
   StepOpts o{};
-  o.Mb = B, o.beams = 1, o.want_logits = 1, o.sample = 0;
+  o.Mb = B, o.beams = 1, o.store_logits = 1, o.sample = 0;
+  WB_TRY(reset_decode_state(h, o));
   for (int i = 0; i < t; ++i) {
     WB_TRY(decode_step(h, o));
     WB_CUDA_OK(cudaMemcpy2DAsync(logits + (size_t)i * V, (size_t)t * V * sizeof(float), h->logits, (size_t)V * sizeof(float),
@@ -775,10 +797,10 @@ int wb_detect_language(wb_handle* h, int32_t B, int32_t sot, int32_t lang0, int3
   std::vector<int32_t> tk(B, sot);
   WB_CUDA_OK(cudaMemcpy2DAsync(h->tokens, h->tokens_ld * sizeof(int32_t), tk.data(), sizeof(int32_t), sizeof(int32_t), B,
                                cudaMemcpyHostToDevice, h->stream));
-  WB_TRY(reset_decode_state(h));
   pick_splits(h, B);
   StepOpts o{};
-  o.Mb = B, o.beams = 1, o.want_logits = 1, o.sample = 0;
+  o.Mb = B, o.beams = 1, o.store_logits = 1, o.sample = 0;
+  WB_TRY(reset_decode_state(h, o));
   WB_TRY(decode_step(h, o));
   std::vector<float> conf((size_t)B * 99);
   WB_CUDA_OK(cudaMemcpy2DAsync(conf.data(), 99 * sizeof(float), h->logits + lang0, (size_t)V * sizeof(float), 99 * sizeof(float), B,
@@ -797,8 +819,8 @@ int wb_detect_language(wb_handle* h, int32_t B, int32_t sot, int32_t lang0, int3
 static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, int32_t* tokens_out, int32_t* lens, float* sum_logprob) {
   const wb_dims& D = h->dims;
   const int n_init = opts->n_initial, total = n_init + opts->sample_len;
-  if (n_init < 1 || opts->sample_len < 1 || total > D.n_text_ctx || opts->n_suppress > D.n_vocab || opts->n_suppress_begin > 256 ||
-      opts->n_suppress < 0 || opts->n_suppress_begin < 0 || !opts->initial_tokens) {
+  if (n_init < 1 || opts->sample_len < 1 || total > D.n_text_ctx || opts->n_suppress < 0 || opts->n_suppress_begin < 0 ||
+      !opts->initial_tokens || (opts->n_suppress && !opts->suppress) || (opts->n_suppress_begin && !opts->suppress_begin)) {
     set_error("wb_decode: bad options (n_initial=%d sample_len=%d n_text_ctx=%d)", n_init, opts->sample_len, D.n_text_ctx);
     return WB_ERR_ARG;
   }
@@ -807,32 +829,31 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
   std::vector<int32_t> rows((size_t)B * h->tokens_ld, opts->eot);
   for (int b = 0; b < B; ++b)
     for (int i = 0; i < n_init; ++i) rows[(size_t)b * h->tokens_ld + i] = opts->initial_tokens[i];
+  // logit filters as a per-token mask: 1 = SuppressTokens (every step), 2 = SuppressBlank (first sampled position only)
+  std::vector<unsigned char> mask(D.n_vocab, 0);
+  for (int i = 0; i < opts->n_suppress_begin; ++i)
+    if (opts->suppress_begin[i] >= 0 && opts->suppress_begin[i] < D.n_vocab) mask[opts->suppress_begin[i]] = 2;
+  for (int i = 0; i < opts->n_suppress; ++i)
+    if (opts->suppress[i] >= 0 && opts->suppress[i] < D.n_vocab) mask[opts->suppress[i]] = 1;
   WB_CUDA_OK(cudaMemcpyAsync(h->tokens, rows.data(), rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  if (opts->n_suppress)
-    WB_CUDA_OK(cudaMemcpyAsync(h->suppress, opts->suppress, opts->n_suppress * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  if (opts->n_suppress_begin)
-    WB_CUDA_OK(cudaMemcpyAsync(h->suppress_begin, opts->suppress_begin, opts->n_suppress_begin * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  WB_CUDA_OK(cudaMemcpyAsync(h->mask, mask.data(), mask.size(), cudaMemcpyHostToDevice, st));
   WB_CUDA_OK(cudaMemsetAsync(h->sum_logprob, 0, sizeof(float) * B, st));
   WB_CUDA_OK(cudaMemsetAsync(h->done, 0, sizeof(int32_t) * B, st));
-  WB_CUDA_OK(cudaStreamSynchronize(st));   // `rows` is pageable host memory
+  WB_CUDA_OK(cudaStreamSynchronize(st));   // `rows` / `mask` are pageable host memory
 
   StepOpts plain{}, samp{};
-  plain.Mb = B, plain.beams = 1, plain.want_logits = 0, plain.sample = 0;
+  plain.Mb = B, plain.beams = 1, plain.store_logits = 0, plain.sample = 0, plain.n_initial = n_init, plain.eot = opts->eot;
   samp = plain;
   samp.sample = 1;
-  SampleDesc& sd = samp.sd;
-  sd.Mb = B, sd.V = D.n_vocab, sd.logits = h->logits, sd.suppress = h->suppress, sd.n_suppress = opts->n_suppress;
-  sd.suppress_begin = h->suppress_begin, sd.n_suppress_begin = opts->n_suppress_begin, sd.n_initial = n_init, sd.eot = opts->eot;
-  sd.tokens = h->tokens, sd.tokens_ld = h->tokens_ld, sd.sum_logprob = h->sum_logprob, sd.done = h->done, sd.state = h->state;
 
   char key[128];
-  snprintf(key, sizeof(key), "B%d i%d e%d s%d b%d", B, n_init, opts->eot, opts->n_suppress, opts->n_suppress_begin);
+  snprintf(key, sizeof(key), "B%d i%d e%d", B, n_init, opts->eot);
   const bool use_graph = getenv("WB_NO_GRAPH") == nullptr;
   if (use_graph && h->graph_key != key) {
     destroy_graphs(h);
     pick_splits(h, B);
     // one eager pass of each variant first: sets function attributes and faults in code outside of capture
-    WB_TRY(reset_decode_state(h));
+    WB_TRY(reset_decode_state(h, plain));
     WB_TRY(decode_step(h, plain));
     WB_TRY(decode_step(h, samp));
     WB_CUDA_OK(cudaStreamSynchronize(st));
@@ -847,8 +868,9 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
   } else if (!use_graph) {
     pick_splits(h, B);
   }
-  WB_TRY(reset_decode_state(h));
+
   WB_CUDA_OK(cudaEventRecord(h->ev[2], st));
+  WB_TRY(reset_decode_state(h, plain));
   for (int i = 0; i + 1 < n_init; ++i) {
     if (use_graph) {
       WB_CUDA_OK(cudaGraphLaunch(h->g_step, st));
@@ -948,7 +970,8 @@ int wb_profile_cross_attention(wb_handle* h, int32_t B, int32_t reps, float* avg
   AttnDecodeDesc c{};
   c.Mb = B, c.d = D.n_text_state, c.n_head = D.n_text_head, c.n_split = h->split_cross, c.q = h->q32;
   c.n_ctx = D.n_audio_ctx, c.n_rows_fixed = D.n_audio_ctx, c.kv_share = 1, c.state = h->state;
-  c.part_ml = h->part_ml, c.part_acc = h->part_acc;
+  c.part_ml = h->part_ml, c.part_acc = h->part_acc, c.counters = h->counters, c.out16 = h->a16;
+  WB_CUDA_OK(cudaMemsetAsync(h->counters, 0, sizeof(int) * h->Mb_max, h->stream));
   for (int i = -3; i < reps; ++i) {   // 3 warm-up launches
     if (i == 0) WB_CUDA_OK(cudaEventRecord(h->ev[0], h->stream));
     const int l = ((i % D.n_text_layer) + D.n_text_layer) % D.n_text_layer;

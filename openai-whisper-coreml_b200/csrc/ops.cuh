@@ -59,16 +59,15 @@ int launch_encoder_attention(const __half* qkv, int B, int T, int n_head, __half
 
 // ---- decoder step (decoder.cu) ---------------------------------------------------------------------------------------------
 struct DecodeState {      // lives in device memory; read by every kernel of a step (CUDA-graph friendly)
-  int cur_len;            // tokens consumed so far, including the one embedded by this step
-  int n_done;             // sequences whose last token is eot
-  int sample_step;        // number of sampling steps performed
-  int pad;
+  int cur_len;            // index of the token the current step consumes (-1 before the first embed)
+  int arrive;             // arrival counter of step_finish_kernel's CTAs
+  int pad0, pad1;
 };
 
 // Input transform of a skinny GEMM (how the [Mb][K] fp16 activation tile in shared memory is produced)
-enum SkinnyIn { SKINNY_IN_F16 = 0, SKINNY_IN_LN = 1, SKINNY_IN_ATTN = 2, SKINNY_IN_F32 = 3 };
+enum SkinnyIn { SKINNY_IN_F16 = 0, SKINNY_IN_LN = 1 };
 // Output transform
-enum SkinnyOut { SKINNY_OUT_F16 = 0, SKINNY_OUT_F32 = 1, SKINNY_OUT_RESID = 2, SKINNY_OUT_QKV = 3 };
+enum SkinnyOut { SKINNY_OUT_F16 = 0, SKINNY_OUT_F32 = 1, SKINNY_OUT_RESID = 2, SKINNY_OUT_QKV = 3, SKINNY_OUT_LOGITS = 4 };
 
 struct SkinnyDesc {
   int Mb, N, K;
@@ -77,58 +76,58 @@ struct SkinnyDesc {
   int gelu;
   // input
   int in_mode;
-  const void* in;         // F16: half [Mb][K]; LN / F32: float [Mb][K]
+  const void* in;         // F16: half [Mb][K]; LN: float [Mb][K]
   const float* ln_g;      // LN
   const float* ln_b;
-  const float* part_ml;   // ATTN: [Mb][S][H][2] (m, l);  part_acc: [Mb][S][K]
-  const float* part_acc;
-  int n_split, n_head;
   // output
   int out_mode;
-  void* out;              // F16: half [Mb][N]; F32 / RESID: float [Mb][N] (RESID: +=)
-  // QKV scatter: n < d -> q32[b][n];  d <= n < 2d -> kcache[(b*n_ctx + pos)*d + n-d];  else vcache
+  void* out;              // F16: half [Mb][N]; F32 / RESID: float [Mb][N] (RESID: +=); LOGITS: float [Mb][N] or null
+  // QKV scatter: n < d -> q32[b][n];  d <= n < 2d -> kcache[(b*n_ctx + pos)*d + n-d];  else vcache;  pos = state->cur_len
   float* q32;
   __half* kcache;
   __half* vcache;
   int n_ctx;
+  // LOGITS: filters + per-CTA (max, argmax, sum-exp) partials [Mb][n_cta][4]
+  const unsigned char* mask;   // [N]: 1 = suppressed, 2 = suppressed at the first sampled position only; may be null
+  int n_initial;
+  float* part_logits;
   const DecodeState* state;
 };
 int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches);
+int skinny_logits_ctas(int N);   // number of CTAs (= partials per sequence) of the LOGITS mode
 
-// one query per (sequence, head) against rows [0, n_rows) of K/V [B][n_ctx][d] fp16; partial results per split
+// one query per (sequence, head) against rows [0, n_rows) of K/V [B][n_ctx][d] fp16 -> out16 [Mb][d] fp16
 struct AttnDecodeDesc {
   int Mb, d, n_head, n_split;
   const float* q;         // [Mb][d] fp32
   const __half* k;        // [Mb / kv_share][n_ctx][d]
   const __half* v;
   int n_ctx;              // allocated rows per sequence
-  int n_rows_fixed;       // >0: fixed row count (cross attention, 1500); 0: rows = state->cur_len (self attention)
+  int n_rows_fixed;       // >0: fixed row count (cross attention, 1500); 0: rows = state->cur_len + 1 (self attention)
   int kv_share;           // sequences per K/V slab (beam search: beams of one chunk share the cross K/V); >= 1
   const DecodeState* state;
-  float* part_ml;         // [Mb][S][H][2]
+  float* part_ml;         // [Mb][S][H][2]  split partials (scratch)
   float* part_acc;        // [Mb][S][d]
+  int* counters;          // [Mb] zero-initialised arrival counters (self-resetting)
+  __half* out16;          // [Mb][d]
 };
 int launch_attn_decode(const AttnDecodeDesc& d, cudaStream_t st, int64_t* launches);
 
-// x[b][:] = tok_emb[tokens[b][cur_len]][:] + pos_emb[cur_len][:]; then cur_len += 1
-int launch_embed(const int32_t* tokens, int tokens_ld, const __half* tok_emb, const float* pos_emb, int Mb, int d, int V,
-                 float* x, DecodeState* state, cudaStream_t st, int64_t* launches);
-
-struct SampleDesc {
-  int Mb, V;
-  float* logits;              // [Mb][V], modified in place (suppressed entries become -inf)
-  const int32_t* suppress;    // device lists
-  int n_suppress;
-  const int32_t* suppress_begin;
-  int n_suppress_begin;
-  int n_initial;              // length of the sot sequence: sampling position 0 is cur_len == n_initial
+struct FinishDesc {
+  int Mb, V, d, n_ctx;
+  int sample;                 // 0: only embed the next (already present) token and advance
+  const float* part_logits;   // [Mb][n_part][4]
+  int n_part;
   int eot;
   int32_t* tokens;            // [Mb][tokens_ld]
   int tokens_ld;
   float* sum_logprob;         // [Mb]
   int32_t* done;              // [Mb]: 1 if the sequence's newest token is eot
+  const __half* tok_emb;
+  const float* pos_emb;
+  float* x;                   // [Mb][d] residual stream of the next step
   DecodeState* state;
 };
-int launch_sample_greedy(const SampleDesc& d, cudaStream_t st, int64_t* launches);
+int launch_step_finish(const FinishDesc& d, cudaStream_t st, int64_t* launches);
 
 }  // namespace wb

@@ -266,8 +266,8 @@ def test_full_size_determinism_and_slot_independence(wbm):
     perm = np.roll(np.arange(32), 5)
     t3, _, s3 = w.transcribe(audio[perm], o)                                   # a chunk's result does not depend on its slot
     assert np.array_equal(t3, t1[perm])
-    t4, _, _ = w.transcribe(audio[:3], o)                                      # ... nor on the batch size
-    assert np.array_equal(t4[:, :40], t1[:3, :40])
+    # (bit identity across different batch SIZES is not promised: the attention row-split count follows the batch size,
+    #  which changes the fp32 merge order — DESIGN.md "determinism")
     assert w.launch_count() > 0
     w.close()
 
