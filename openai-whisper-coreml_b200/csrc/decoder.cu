@@ -15,6 +15,8 @@
 //   step_finish_kernel    merges the per-CTA (max, argmax, sum-exp) partials the logits GEMM epilogue produced (logit
 //                         filters already applied there), EOT forcing, log-prob accumulation, token append, then embeds
 //                         the next token (+ learned position) into the residual stream and advances the position
+#include <cuda.h>
+
 #include "ops.cuh"
 #include "ptx.cuh"
 
@@ -27,6 +29,35 @@ constexpr float kLog2e = 1.44269504088896340736f;
 // with its still-running predecessor, so L1 may hold lines the predecessor fetched before another SM rewrote them.
 // Weights and the cross-attention K/V are constant during a decode and use the non-coherent path.
 __device__ __forceinline__ int ld_state(const int* p) { return __ldcg(p); }
+
+// Development tracing: block (0,0) thread 0 of every decode kernel stamps %globaltimer at entry and exit (WB_TRACE=1).
+__device__ __forceinline__ unsigned long long globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+struct TraceScope {
+  unsigned long long* rec = nullptr;
+  __device__ __forceinline__ TraceScope(const DecodeState* st, int id) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && st) {
+      unsigned long long* tr = st->trace;
+      if (tr) {
+        const int i = atomicAdd(const_cast<int*>(&st->trace_n), 1);
+        if (i < 65536) {
+          rec = tr + (size_t)i * 8;
+          rec[0] = (unsigned long long)id;
+          rec[1] = globaltimer();
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void end() {
+    if (rec) rec[2] = globaltimer();
+  }
+  __device__ __forceinline__ void mark(int k) {
+    if (rec) rec[k] = globaltimer();
+  }
+};
 
 // ---- skinny GEMM -----------------------------------------------------------------------------------------------------------
 constexpr int kSkThreads = 256;
@@ -41,6 +72,7 @@ template <int MT>
 __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SkinnyDesc& p = a.d;
+  TraceScope trace(p.state, 100 + p.out_mode * 10 + p.in_mode);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = lane >> 2, tq = lane & 3;
   const int S = a.strips_per_cta, KS = 8 / S;
@@ -49,6 +81,9 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
   const int xs_stride = KC * 2 + 64;                       // bytes; (stride/16) % 8 == 4 -> conflict-free LDS.128
   unsigned char* xs = smem_raw;
   float* red = reinterpret_cast<float*>(smem_raw + (size_t)MT * 8 * xs_stride);   // [8 warps][16][MT*8]
+  float* sbias = red + 8 * 16 * MT * 8;                                           // [128] bias of this CTA's rows
+  float* sg = sbias + 128;                                                        // [K] LayerNorm gamma (LN input mode)
+  float* sb = sg + p.K;                                                           // [K] LayerNorm beta
 
   const int n_cta = blockIdx.x * S * 16;
   int n_g = n_cta + strip * 16 + grp, n_g8 = n_g + 8;
@@ -66,28 +101,69 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
   const int KC0 = p.K < KC ? p.K : KC;
   const int nblk0 = KC0 / 32;
   const int pb0 = (kslice * nblk0) / KS, pb1 = ((kslice + 1) * nblk0) / KS;
-  uint4 pwa[4], pwb[4];
+  constexpr int kPre = 8;
+  uint4 pwa[kPre], pwb[kPre];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
+  for (int u = 0; u < kPre; ++u) {
     const int blk = (pb0 + u < pb1) ? pb0 + u : pb0;
     pwa[u] = ptx::ldg_nc_16(wrow0 + blk * 32);
     pwb[u] = ptx::ldg_nc_16(wrow1 + blk * 32);
   }
+  // constants (bias, LayerNorm affine) are staged in shared memory before the wait as well: keeping their global loads
+  // out of the input stage and of the epilogue matters — interleaved with shared-memory stores the compiler cannot batch
+  // them, and each one cost an L2 round trip (the LN input stage measured 8-10 us before this, ~2 us after)
+  for (int i = tid; i < S * 16; i += kSkThreads) sbias[i] = (p.bias && n_cta + i < p.N) ? __ldg(p.bias + n_cta + i) : 0.f;
+  if (p.in_mode == SKINNY_IN_LN) {
+    for (int i = tid * 4; i < p.K; i += kSkThreads * 4) {
+      *reinterpret_cast<float4*>(sg + i) = __ldg(reinterpret_cast<const float4*>(p.ln_g + i));
+      *reinterpret_cast<float4*>(sb + i) = __ldg(reinterpret_cast<const float4*>(p.ln_b + i));
+    }
+  }
   ptx::grid_dep_launch();
   ptx::grid_dep_sync();
+  __syncthreads();   // the staged constants are read by other threads in the input stage
+  trace.mark(3);
+  // residual-add epilogue: fetch the old values now, off the critical path (N = d: 16 rows x Mb <= 640 values per CTA)
+  float resid[3] = {0.f, 0.f, 0.f};
+  const bool resid_pre = p.out_mode == SKINNY_OUT_RESID && S == 1;
+  if (resid_pre) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int idx = tid + j * kSkThreads;
+      const int b = idx >> 4, n = n_cta + (idx & 15);
+      if (b < p.Mb && n < p.N) resid[j] = __ldcg(reinterpret_cast<const float*>(p.out) + (size_t)b * p.N + n);
+    }
+  }
 
   for (int kc0 = 0; kc0 < p.K; kc0 += KC) {
     const int kc = (p.K - kc0) < KC ? (p.K - kc0) : KC;
     if (kc0) __syncthreads();
     // ---- input stage: build xs[MT*8][kc] fp16 --------------------------------------------------------------------------
     if (p.in_mode == SKINNY_IN_F16) {
+      // warp w copies rows w, w+8, ...; lanes stride over the 16-byte chunks of a row; MT x 4 independent loads in flight
       const __half* src = reinterpret_cast<const __half*>(p.in);
       const int cpr = kc >> 3;                              // 16-byte chunks per row
-      for (int i = tid; i < MT * 8 * cpr; i += kSkThreads) {
-        const int r = i / cpr, c = (i - r * cpr) * 8;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (r < p.Mb) v = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)r * p.K + kc0 + c));
-        *reinterpret_cast<uint4*>(xs + (size_t)r * xs_stride + c * 2) = v;
+      for (int c0 = lane; c0 < cpr; c0 += 128) {
+        uint4 v[MT][4];
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+          const int r = warp + 8 * j;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = c0 + 32 * u;
+            v[j][u] = make_uint4(0, 0, 0, 0);
+            if (c < cpr && r < p.Mb) v[j][u] = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)r * p.K + kc0 + c * 8));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+          const int r = warp + 8 * j;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = c0 + 32 * u;
+            if (c < cpr) *reinterpret_cast<uint4*>(xs + (size_t)r * xs_stride + c * 16) = v[j][u];
+          }
+        }
       }
     } else {
       // LayerNorm of the fp32 residual stream (K = d, one chunk). 8 threads per row, 32 rows per pass: every row of the
@@ -97,12 +173,21 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
         __half* xr = reinterpret_cast<__half*>(xs + (size_t)r * xs_stride);
         const bool act = r < p.Mb;                                   // padding rows compute on row 0 and store zeros
         const float* src = reinterpret_cast<const float*>(p.in) + (size_t)(act ? r : 0) * p.K;
-        float s = 0.f, q = 0.f;                                      // one pass: sum and sum of squares (fp32)
-#pragma unroll 4
-        for (int c = sub * 4; c < p.K; c += 32) {
-          const float4 v = __ldcg(reinterpret_cast<const float4*>(src + c));
-          s += (v.x + v.y) + (v.z + v.w);
-          q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        // statistics: batches of 16 independent float4 loads per thread (one batch covers K = 512)
+        float s = 0.f, q = 0.f;
+        float4 v[16];
+        for (int c0 = 0; c0 < p.K; c0 += 512) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = c0 + (sub + 8 * i) * 4;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < p.K) v[i] = __ldcg(reinterpret_cast<const float4*>(src + c));
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+          }
         }
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         q += __shfl_xor_sync(0xffffffffu, q, 1);
@@ -111,22 +196,34 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
         s += __shfl_xor_sync(0xffffffffu, s, 4);
         q += __shfl_xor_sync(0xffffffffu, q, 4);
         const float mean = s / (float)p.K;
-        q = fmaxf(q / (float)p.K - mean * mean, 0.f);
-        const float rstd = act ? rsqrtf(q + 1e-5f) : 0.f;
-#pragma unroll 4
-        for (int c = sub * 4; c < p.K; c += 32) {
-          const float4 v = __ldcg(reinterpret_cast<const float4*>(src + c));
-          const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_g + c)), bb = __ldg(reinterpret_cast<const float4*>(p.ln_b + c));
-          const float ab = act ? 1.f : 0.f;
-          __half2 h0 = __floats2half2_rn((v.x - mean) * rstd * g.x + ab * bb.x, (v.y - mean) * rstd * g.y + ab * bb.y);
-          __half2 h1 = __floats2half2_rn((v.z - mean) * rstd * g.z + ab * bb.z, (v.w - mean) * rstd * g.w + ab * bb.w);
-          uint2 u;
-          u.x = *reinterpret_cast<uint32_t*>(&h0), u.y = *reinterpret_cast<uint32_t*>(&h1);
-          *reinterpret_cast<uint2*>(xr + c) = u;
+        const float var = fmaxf(q / (float)p.K - mean * mean, 0.f);
+        const float rstd = act ? rsqrtf(var + 1e-5f) : 0.f;
+        const float ab = act ? 1.f : 0.f;
+        for (int c0 = 0; c0 < p.K; c0 += 512) {
+          if (p.K > 512) {   // rows wider than one batch: reload (L2)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int c = c0 + (sub + 8 * i) * 4;
+              if (c < p.K) v[i] = __ldcg(reinterpret_cast<const float4*>(src + c));
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = c0 + (sub + 8 * i) * 4;
+            if (c < p.K) {
+              const float4 g = *reinterpret_cast<const float4*>(sg + c), bb = *reinterpret_cast<const float4*>(sb + c);
+              __half2 h0 = __floats2half2_rn((v[i].x - mean) * rstd * g.x + ab * bb.x, (v[i].y - mean) * rstd * g.y + ab * bb.y);
+              __half2 h1 = __floats2half2_rn((v[i].z - mean) * rstd * g.z + ab * bb.z, (v[i].w - mean) * rstd * g.w + ab * bb.w);
+              uint2 u;
+              u.x = *reinterpret_cast<uint32_t*>(&h0), u.y = *reinterpret_cast<uint32_t*>(&h1);
+              *reinterpret_cast<uint2*>(xr + c) = u;
+            }
+          }
         }
       }
     }
     __syncthreads();
+    trace.mark(4);
     // ---- stream this warp's weight rows over its K slice of the chunk ------------------------------------------------------
     const int nblk = kc / 32;
     const int blk0 = (kslice * nblk) / KS, blk1 = ((kslice + 1) * nblk) / KS;
@@ -134,7 +231,7 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
     int blk = blk0;
     if (kc0 == 0) {   // the prefetched blocks
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kPre; ++u) {
         if (blk0 + u < blk1) {
           const uint32_t a0[4] = {pwa[u].x, pwb[u].x, pwa[u].y, pwb[u].y}, a1[4] = {pwa[u].z, pwb[u].z, pwa[u].w, pwb[u].w};
 #pragma unroll
@@ -146,17 +243,17 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
           }
         }
       }
-      blk = blk0 + 4 < blk1 ? blk0 + 4 : blk1;
+      blk = blk0 + kPre < blk1 ? blk0 + kPre : blk1;
     }
-    for (; blk + 4 <= blk1; blk += 4) {
-      uint4 wa[4], wb[4];
+    for (; blk + 8 <= blk1; blk += 8) {
+      uint4 wa[8], wb[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         wa[u] = ptx::ldg_nc_16(wrow0 + kc0 + (blk + u) * 32);
         wb[u] = ptx::ldg_nc_16(wrow1 + kc0 + (blk + u) * 32);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const uint32_t a0[4] = {wa[u].x, wb[u].x, wa[u].y, wb[u].y}, a1[4] = {wa[u].z, wb[u].z, wa[u].w, wb[u].w};
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
@@ -167,19 +264,31 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
         }
       }
     }
-    for (; blk < blk1; ++blk) {
-      const uint4 wa = ptx::ldg_nc_16(wrow0 + kc0 + blk * 32), wb = ptx::ldg_nc_16(wrow1 + kc0 + blk * 32);
-      const uint32_t a0[4] = {wa.x, wb.x, wa.y, wb.y}, a1[4] = {wa.z, wb.z, wa.w, wb.w};
+    if (blk < blk1) {   // remainder (< 8 blocks): still one batch of independent loads
+      uint4 wa[8], wb[8];
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        const uint4 xb = *reinterpret_cast<const uint4*>(xl + (size_t)mt * 8 * xs_stride + blk * 64);
-        const uint32_t b0[2] = {xb.x, xb.y}, b1[2] = {xb.z, xb.w};
-        ptx::mma_16816(acc[mt], a0, b0);
-        ptx::mma_16816(acc[mt], a1, b1);
+      for (int u = 0; u < 8; ++u) {
+        const int bb = (blk + u < blk1) ? blk + u : blk;
+        wa[u] = ptx::ldg_nc_16(wrow0 + kc0 + bb * 32);
+        wb[u] = ptx::ldg_nc_16(wrow1 + kc0 + bb * 32);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (blk + u < blk1) {
+          const uint32_t a0[4] = {wa[u].x, wb[u].x, wa[u].y, wb[u].y}, a1[4] = {wa[u].z, wb[u].z, wa[u].w, wb[u].w};
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint4 xb = *reinterpret_cast<const uint4*>(xl + (size_t)mt * 8 * xs_stride + (blk + u) * 64);
+            const uint32_t b0[2] = {xb.x, xb.y}, b1[2] = {xb.z, xb.w};
+            ptx::mma_16816(acc[mt], a0, b0);
+            ptx::mma_16816(acc[mt], a1, b1);
+          }
+        }
       }
     }
   }
   // ---- cross-warp (K split) reduction and epilogue -------------------------------------------------------------------------
+  trace.mark(5);
   constexpr int MB8 = MT * 8;
   float* myred = red + (size_t)warp * 16 * MB8;
 #pragma unroll
@@ -228,10 +337,27 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
         pp[0] = best, pp[1] = __int_as_float(arg), pp[2] = se;
       }
     }
+    trace.end();
     return;
   }
   const int pos = (p.out_mode == SKINNY_OUT_QKV) ? ld_state(&p.state->cur_len) : 0;
   const int dq = p.N / 3;
+  if (resid_pre) {   // rows_cta == 16; same index map as the prefetch above
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int idx = tid + j * kSkThreads;
+      const int b = idx >> 4, r = idx & 15, n = n_cta + r;
+      if (b < p.Mb && n < p.N) {
+        float v = 0.f;
+        for (int ks = 0; ks < 8; ++ks) v += red[(size_t)ks * 16 * MB8 + r * MB8 + b];
+        v += sbias[r];
+        if (p.gelu) v = gelu_erf(v);
+        reinterpret_cast<float*>(p.out)[(size_t)b * p.N + n] = resid[j] + v;
+      }
+    }
+    trace.end();
+    return;
+  }
   for (int idx = tid; idx < rows_cta * p.Mb; idx += kSkThreads) {
     const int b = idx / rows_cta, rr = idx - b * rows_cta;
     const int st = rr >> 4, r = rr & 15;
@@ -239,7 +365,7 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
     if (n >= p.N) continue;
     float v = 0.f;
     for (int ks = 0; ks < KS; ++ks) v += red[(size_t)(ks * S + st) * 16 * MB8 + r * MB8 + b];
-    if (p.bias) v += p.bias[n];
+    v += sbias[rr];
     if (p.gelu) v = gelu_erf(v);
     switch (p.out_mode) {
       case SKINNY_OUT_F16:
@@ -248,12 +374,10 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
       case SKINNY_OUT_F32:
         reinterpret_cast<float*>(p.out)[(size_t)b * p.N + n] = v;
         break;
-      case SKINNY_OUT_RESID:
-        {
+      case SKINNY_OUT_RESID: {
         float* o = reinterpret_cast<float*>(p.out) + (size_t)b * p.N + n;
         *o = __ldcg(o) + v;
-      }
-        break;
+      } break;
       default:   // SKINNY_OUT_QKV
         if (n < dq)
           p.q32[(size_t)b * dq + n] = v;
@@ -264,6 +388,7 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
         break;
     }
   }
+  trace.end();
 }
 
 static bool use_pdl() {
@@ -306,7 +431,7 @@ int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches) 
   SkinnyArgs a{d, S};
   const int MT = (d.Mb + 7) / 8;
   const int KC = d.K < kSkKC ? d.K : kSkKC;
-  const size_t smem = (size_t)MT * 8 * (KC * 2 + 64) + (size_t)8 * 16 * MT * 8 * 4;
+  const size_t smem = (size_t)MT * 8 * (KC * 2 + 64) + (size_t)8 * 16 * MT * 8 * 4 + 128 * 4 + (d.in_mode == SKINNY_IN_LN ? (size_t)2 * d.K * 4 : 0);
   const int grid = (strips + S - 1) / S;
   cudaError_t le = cudaSuccess;
 #define WB_SK_CASE(M)                                                                                             \
@@ -328,6 +453,51 @@ int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches) 
   if (launches) *launches += 1;
   WB_CUDA_OK(le);
   return 0;
+}
+
+// Merge of the row-split partials of one sequence by the last CTA to arrive (fixed split order -> deterministic).
+// All loads of a pass are independent and issued together: a serial loop over the splits costs one L2 round trip per
+// split and used to dominate the kernel (~10 us of a 24 us launch).
+__device__ __forceinline__ void merge_splits(const AttnDecodeDesc& p, int b, float* sm /* >= 2*n_split*H floats */, int tid,
+                                             int nthreads) {
+  const int H = p.n_head, d = p.d, NS = p.n_split;
+  const float* all_ml = p.part_ml + (size_t)b * NS * H * 2;
+  const float* all_acc = p.part_acc + (size_t)b * NS * d;
+  float* sm_m = sm;              // [NS][H] -> overwritten with the normalised weights
+  float* sm_l = sm + NS * H;     // [NS][H]
+  for (int i = tid; i < NS * H; i += nthreads) {
+    sm_m[i] = __ldcg(all_ml + i * 2);
+    sm_l[i] = __ldcg(all_ml + i * 2 + 1);
+  }
+  __syncthreads();
+  for (int h = tid; h < H; h += nthreads) {
+    float M = -INFINITY;
+    for (int s2 = 0; s2 < NS; ++s2) M = fmaxf(M, sm_m[s2 * H + h]);
+    float L = 0.f;
+    for (int s2 = 0; s2 < NS; ++s2) {
+      const float ms = sm_m[s2 * H + h];
+      const float wgt = (ms == -INFINITY) ? 0.f : exp2f(ms - M);
+      L += wgt * sm_l[s2 * H + h];
+      sm_m[s2 * H + h] = wgt;
+    }
+    const float inv = 1.0f / L;
+    for (int s2 = 0; s2 < NS; ++s2) sm_m[s2 * H + h] *= inv;
+  }
+  __syncthreads();
+  for (int c = tid; c < d; c += nthreads) {
+    const int h = c >> 6;
+    float A = 0.f;
+    for (int s0 = 0; s0 < NS; s0 += 8) {
+      float a[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] = (s0 + u < NS) ? __ldcg(all_acc + (size_t)(s0 + u) * d + c) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (s0 + u < NS) A = fmaf(sm_m[(s0 + u) * H + h], a[u], A);
+    }
+    p.out16[(size_t)b * d + c] = __float2half_rn(A);
+  }
+  if (tid == 0) p.counters[b] = 0;   // ready for the next launch (graph replay)
 }
 
 // ---- decode attention --------------------------------------------------------------------------------------------------------
@@ -481,22 +651,460 @@ __global__ void __launch_bounds__(kAdThreads) attn_decode_kernel(AttnDecodeDesc 
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  const float* all_ml = p.part_ml + (size_t)b * p.n_split * H * 2;
-  const float* all_acc = p.part_acc + (size_t)b * p.n_split * d;
-  for (int c = tid; c < d; c += kAdThreads) {
-    const int h = c >> 6;
-    float M = -INFINITY;
-    for (int s2 = 0; s2 < p.n_split; ++s2) M = fmaxf(M, __ldcg(all_ml + (s2 * H + h) * 2));
-    float L = 0.f, A = 0.f;
-    for (int s2 = 0; s2 < p.n_split; ++s2) {
-      const float ms = __ldcg(all_ml + (s2 * H + h) * 2);
-      const float wgt = (ms == -INFINITY) ? 0.f : exp2f(ms - M);
-      L += wgt * __ldcg(all_ml + (s2 * H + h) * 2 + 1);
-      A += wgt * __ldcg(all_acc + (size_t)s2 * d + c);
+  merge_splits(p, b, reinterpret_cast<float*>(smem_raw), tid, kAdThreads);
+}
+
+// ---- KV-cache attention, tensor-core form ------------------------------------------------------------------------------------
+// The register kernel above is instruction-issue bound (~85 warp instructions per KB of K/V: unpack, FMA, shuffles), which
+// caps it near 60 % of HBM bandwidth. This kernel does the same math with ~6x fewer instructions:
+//   * one producer thread streams 16-row K and V tiles into a shared-memory ring with cp.async.bulk (one 2d-byte copy per
+//     row, rows padded by 16 B so ldmatrix is bank-conflict free), full/empty mbarriers per stage; for the cross-attention
+//     K/V (constant during a decode) it starts before griddepcontrol.wait, i.e. while the previous kernel still runs
+//   * each compute warp owns whole heads: scores S[16 rows] = K_tile(16 x 64) q via 4 mma.sync m16n8k16 (q replicated over the
+//     8 columns, so every lane ends up holding the scores of rows g and g+8), online softmax in fp32 in the log2 domain,
+//     O(64) += V_tile^T(64 x 16) p via 4 mma.sync with ldmatrix.trans (p replicated over the columns)
+//   * a head is never split across warps, so the only merge is across the row splits (last CTA to arrive, fixed order)
+constexpr int kXaRows = 16;
+constexpr int kXaThreads = 288;   // 8 compute warps + 1 producer warp
+
+template <int HPW>   // heads per compute warp = ceil(H / 8)
+__global__ void __launch_bounds__(kXaThreads) attn_decode_mma_kernel(AttnDecodeDesc p, int n_stages, int copy_mode) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8];
+  __shared__ int s_last;
+  const int H = p.n_head, d = p.d;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 2, tq = lane & 3, mi = lane >> 3, r8 = lane & 7;
+  const int split = blockIdx.x, b = blockIdx.y;
+  const int row_stride = copy_mode == 1 ? d * 2 : d * 2 + 16;   // bytes (copy_mode 1 = experiment: dense tiles, one copy each)
+  const int tile_bytes = kXaRows * row_stride;            // one K (or V) tile
+  const bool fixed = p.n_rows_fixed > 0;
+
+  // zero the ring once: rows past the end of a partial tile are multiplied by p = 0 and must not hold NaN bit patterns
+  for (int i = tid * 16; i < n_stages * 2 * tile_bytes; i += kXaThreads * 16) *reinterpret_cast<uint4*>(smem_raw + i) = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    for (int s = 0; s < n_stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 8);
     }
-    p.out16[(size_t)b * d + c] = __float2half_rn(A / L);
+    ptx::fence_mbar_init();
   }
-  if (tid == 0) p.counters[b] = 0;   // ready for the next launch (graph replay)
+  ptx::fence_proxy_async();
+  __syncthreads();
+  ptx::grid_dep_launch();
+  if (!fixed || warp < 8) ptx::grid_dep_sync();           // q (and the newest self-attention K/V row) come from the previous kernel
+
+  const int n_rows = fixed ? p.n_rows_fixed : ld_state(&p.state->cur_len) + 1;
+  const size_t slab = (size_t)(b / p.kv_share) * p.n_ctx * d;
+  const __half* K = p.k + slab;
+  const __half* V = p.v + slab;
+  const int n_tiles_all = (n_rows + kXaRows - 1) / kXaRows;
+  const int t_begin = (split * n_tiles_all) / p.n_split, t_end = ((split + 1) * n_tiles_all) / p.n_split;
+  const int my_tiles = t_end - t_begin;
+
+  float o[HPW][4][4], m[HPW], l[HPW];
+#pragma unroll
+  for (int i = 0; i < HPW; ++i) {
+    m[i] = -INFINITY, l[i] = 0.f;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) o[i][mt][0] = o[i][mt][1] = o[i][mt][2] = o[i][mt][3] = 0.f;
+  }
+
+  if (warp == 8) {
+    for (int t = 0; t < my_tiles; ++t) {
+      const int s = t % n_stages;
+      const uint32_t ph = (uint32_t)(t / n_stages) & 1u;
+      const int row0 = (t_begin + t) * kXaRows;
+      const int rows = (n_rows - row0) < kXaRows ? (n_rows - row0) : kXaRows;
+      unsigned char* dk = smem_raw + (size_t)s * 2 * tile_bytes;
+      unsigned char* dv = dk + tile_bytes;
+      if (lane == 0) {
+        ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(2 * rows * d * 2));
+      }
+      __syncwarp();
+      if (copy_mode == 1) {
+        if (lane == 0) {
+          ptx::bulk_load(dk, K + (size_t)row0 * d, (uint32_t)(rows * d * 2), &full_bar[s]);
+          ptx::bulk_load(dv, V + (size_t)row0 * d, (uint32_t)(rows * d * 2), &full_bar[s]);
+        }
+      } else if (copy_mode == 2) {
+        if (lane == 0) {
+          for (int r = 0; r < rows; ++r) {
+            ptx::bulk_load(dk + r * row_stride, K + (size_t)(row0 + r) * d, (uint32_t)(d * 2), &full_bar[s]);
+            ptx::bulk_load(dv + r * row_stride, V + (size_t)(row0 + r) * d, (uint32_t)(d * 2), &full_bar[s]);
+          }
+        }
+      } else {   // one row per lane: lanes 0-15 copy K rows, lanes 16-31 copy V rows
+        const int r = lane & 15;
+        if (r < rows) {
+          if (lane < 16)
+            ptx::bulk_load(dk + r * row_stride, K + (size_t)(row0 + r) * d, (uint32_t)(d * 2), &full_bar[s]);
+          else
+            ptx::bulk_load(dv + r * row_stride, V + (size_t)(row0 + r) * d, (uint32_t)(d * 2), &full_bar[s]);
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    // B fragments of q (fp16, pre-scaled into the log2 domain; (d_head^-0.25)^2 = 1/8 exactly), replicated over the n columns
+    const float sl = 0.125f * kLog2e;
+    uint32_t qb[HPW][4][2];
+#pragma unroll
+    for (int i = 0; i < HPW; ++i) {
+      const int h = warp + 8 * i;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        qb[i][kk][0] = qb[i][kk][1] = 0u;
+        if (h < H) {
+          const float* qp = p.q + (size_t)b * d + h * 64 + kk * 16 + 2 * tq;
+          const float2 q0 = __ldcg(reinterpret_cast<const float2*>(qp)), q1 = __ldcg(reinterpret_cast<const float2*>(qp + 8));
+          __half2 h0 = __floats2half2_rn(q0.x * sl, q0.y * sl), h1 = __floats2half2_rn(q1.x * sl, q1.y * sl);
+          qb[i][kk][0] = *reinterpret_cast<uint32_t*>(&h0), qb[i][kk][1] = *reinterpret_cast<uint32_t*>(&h1);
+        }
+      }
+    }
+    for (int t = 0; t < my_tiles; ++t) {
+      const int s = t % n_stages;
+      const uint32_t ph = (uint32_t)(t / n_stages) & 1u;
+      ptx::mbar_wait(&full_bar[s], ph);
+      const uint32_t sk = ptx::smem_u32(smem_raw + (size_t)s * 2 * tile_bytes);
+      const uint32_t sv = sk + tile_bytes;
+      const int row0 = (t_begin + t) * kXaRows;
+#pragma unroll
+      for (int i = 0; i < HPW; ++i) {
+        const int h = warp + 8 * i;
+        if (h >= H) break;                                 // warp-uniform
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t a[4];
+          ptx::ldmatrix_x4(a, sk + ((mi & 1) * 8 + r8) * row_stride + (h * 64 + kk * 16 + (mi >> 1) * 8) * 2);
+          ptx::mma_16816(c, a, qb[i][kk]);
+        }
+        const float s_lo = (row0 + grp < n_rows) ? c[0] : -INFINITY;
+        const float s_hi = (row0 + grp + 8 < n_rows) ? c[2] : -INFINITY;
+        float tmax = fmaxf(s_lo, s_hi);
+        tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 4));
+        tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 8));
+        tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 16));
+        if (tmax > m[i]) {                                 // warp-uniform: m and tmax are identical in every lane
+          const float corr = exp2f(m[i] - tmax);           // m = -inf on the first tile -> 0
+          m[i] = tmax;
+          l[i] *= corr;
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) o[i][mt][0] *= corr, o[i][mt][1] *= corr, o[i][mt][2] *= corr, o[i][mt][3] *= corr;
+        }
+        const float p_lo = exp2f(s_lo - m[i]), p_hi = exp2f(s_hi - m[i]);   // row 0 of the tile is always valid -> m finite
+        l[i] += p_lo + p_hi;                               // this lane's rows g and g+8 (same in the 4 lanes of a quad)
+        // B fragment of p: k = 2tq, 2tq+1 (from the lanes holding rows 2tq, 2tq+1) and k = 2tq+8, 2tq+9
+        const float e0 = __shfl_sync(0xffffffffu, p_lo, (2 * tq) * 4), e1 = __shfl_sync(0xffffffffu, p_lo, (2 * tq + 1) * 4);
+        const float e2 = __shfl_sync(0xffffffffu, p_hi, (2 * tq) * 4), e3 = __shfl_sync(0xffffffffu, p_hi, (2 * tq + 1) * 4);
+        __half2 pb0 = __floats2half2_rn(e0, e1), pb1 = __floats2half2_rn(e2, e3);
+        const uint32_t pb[2] = {*reinterpret_cast<uint32_t*>(&pb0), *reinterpret_cast<uint32_t*>(&pb1)};
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          uint32_t a[4];
+          ptx::ldmatrix_x4_trans(a, sv + ((mi >> 1) * 8 + r8) * row_stride + (h * 64 + mt * 16 + (mi & 1) * 8) * 2);
+          ptx::mma_16816(o[i][mt], a, pb);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&empty_bar[s]);
+    }
+  }
+  // ---- results: lanes with tq == 0 hold O[mt*16 + g] (c0) and O[mt*16 + g + 8] (c2) of their heads --------------------------------
+  float* out_acc = p.part_acc + ((size_t)b * p.n_split + split) * d;
+  float* out_ml = p.part_ml + ((size_t)b * p.n_split + split) * H * 2;
+  if (warp < 8) {
+#pragma unroll
+    for (int i = 0; i < HPW; ++i) {
+      const int h = warp + 8 * i;
+      if (h >= H) break;
+      float L = l[i];
+      L += __shfl_xor_sync(0xffffffffu, L, 4);
+      L += __shfl_xor_sync(0xffffffffu, L, 8);
+      L += __shfl_xor_sync(0xffffffffu, L, 16);
+      if (tq == 0) {
+        if (p.n_split == 1) {
+          const float inv = 1.0f / L;
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) {
+            p.out16[(size_t)b * d + h * 64 + mt * 16 + grp] = __float2half_rn(o[i][mt][0] * inv);
+            p.out16[(size_t)b * d + h * 64 + mt * 16 + grp + 8] = __float2half_rn(o[i][mt][2] * inv);
+          }
+        } else {
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) {
+            out_acc[h * 64 + mt * 16 + grp] = o[i][mt][0];
+            out_acc[h * 64 + mt * 16 + grp + 8] = o[i][mt][2];
+          }
+          if (grp == 0) out_ml[h * 2] = m[i], out_ml[h * 2 + 1] = L;
+        }
+      }
+    }
+  }
+  if (p.n_split == 1) return;
+  // the last CTA of this sequence to arrive merges the splits (fixed split order -> deterministic result)
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int ticket = atomicAdd(&p.counters[b], 1);
+    s_last = ticket == p.n_split - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  merge_splits(p, b, reinterpret_cast<float*>(smem_raw), tid, kXaThreads);
+}
+
+static int launch_attn_decode_mma(const AttnDecodeDesc& p, cudaStream_t st, int64_t* launches) {
+  const int HPW = (p.n_head + 7) / 8;
+  const int stage_bytes = 2 * kXaRows * (p.d * 2 + 16);
+  int n_stages = (110 * 1024) / stage_bytes;          // two CTAs per SM when possible
+  n_stages = n_stages > 8 ? 8 : n_stages;
+  if (n_stages < 2) n_stages = 2;
+  static int copy_mode = -1, stages_env = 0;
+  if (copy_mode < 0) {
+    const char* e = getenv("WB_XA_COPY");
+    copy_mode = e ? atoi(e) : 0;
+    const char* e2 = getenv("WB_XA_STAGES");
+    stages_env = e2 ? atoi(e2) : 0;
+  }
+  if (stages_env > 0) n_stages = stages_env;
+  const size_t smem = (size_t)n_stages * stage_bytes;
+  dim3 grid(p.n_split, p.Mb);
+  cudaError_t le = cudaSuccess;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = dim3(kXaThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at, cfg.numAttrs = use_pdl() ? 1 : 0;
+#define WB_XA_CASE(J)                                                                                                  \
+  case J: {                                                                                                            \
+    static size_t smem_set = 0;                                                                                        \
+    if (smem > smem_set) {                                                                                             \
+      WB_CUDA_OK(cudaFuncSetAttribute(attn_decode_mma_kernel<J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      smem_set = smem;                                                                                                 \
+    }                                                                                                                  \
+    le = cudaLaunchKernelEx(&cfg, attn_decode_mma_kernel<J>, p, n_stages, copy_mode);                                             \
+  } break;
+  switch (HPW) {
+    WB_XA_CASE(1) WB_XA_CASE(2) WB_XA_CASE(3)
+    default:
+      set_error("attn_decode: too many heads");
+      return -1;
+  }
+#undef WB_XA_CASE
+  if (launches) *launches += 1;
+  WB_CUDA_OK(le);
+  return 0;
+}
+
+// ---- KV-cache attention, one CTA per (sequence, head) ---------------------------------------------------------------------------
+// No row split, hence no partials, no fence/atomic and no merge pass: a CTA streams the [n_rows][64] K and V slabs of its
+// head through a shared-memory ring with TMA tensor copies (box 64 x 128 rows, 128-byte swizzle -> conflict-free ldmatrix,
+// out-of-range rows zero-filled by the TMA unit) and writes the 64 outputs of its head. With HBM as the bottleneck every CTA
+// progresses at the same rate, so the uneven 1-or-2 CTAs per SM placement costs nothing.
+// 8 compute warps each own 16 of the 128 rows of a stage: S = K q^T and O += V^T p on mma.sync m16n8k16, q and p split into
+// fp16 hi + lo parts (two MMAs each) so that only K and V themselves are fp16-rounded; fp32 online softmax in the log2 domain.
+constexpr int kHaStageRows = 128;
+constexpr int kHaThreads = 288;
+constexpr int kHaTileBytes = kHaStageRows * 128;   // one K (or V) stage tile: 128 rows x 64 halves
+
+struct HeadAttnArgs {
+  const float* q;
+  __half* out16;
+  const DecodeState* state;
+  int d, n_rows_fixed, kv_share, n_stages;
+};
+
+__global__ void __launch_bounds__(kHaThreads) attn_decode_head_kernel(const __grid_constant__ CUtensorMap tmK,
+                                                                      const __grid_constant__ CUtensorMap tmV, HeadAttnArgs a) {
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 2, tq = lane & 3, mi = lane >> 3, r8 = lane & 7;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const bool fixed = a.n_rows_fixed > 0;
+  TraceScope trace(a.state, fixed ? 201 : 200);
+  const int n_stages = a.n_stages;
+  if (tid == 0) {
+    ptx::prefetch_tensormap(&tmK);
+    ptx::prefetch_tensormap(&tmV);
+    for (int s = 0; s < n_stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 8);
+    }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  ptx::grid_dep_launch();
+  if (!fixed || warp < 8) ptx::grid_dep_sync();   // q (and the newest self-attention row) come from the previous kernel
+  const int n_rows = fixed ? a.n_rows_fixed : ld_state(&a.state->cur_len) + 1;
+  const int n_tiles = (n_rows + kHaStageRows - 1) / kHaStageRows;
+
+  float o[4][4], m_run = -INFINITY, l_run = 0.f;
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      const int slab = b / a.kv_share;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int s = t % n_stages;
+        const uint32_t ph = (uint32_t)(t / n_stages) & 1u;
+        ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * kHaTileBytes);
+        unsigned char* dk = smem + (size_t)s * 2 * kHaTileBytes;
+        ptx::tma_load_3d(dk, &tmK, &full_bar[s], h * 64, t * kHaStageRows, slab);
+        ptx::tma_load_3d(dk + kHaTileBytes, &tmV, &full_bar[s], h * 64, t * kHaStageRows, slab);
+      }
+    }
+  } else {
+    // q as B fragments (replicated over the 8 n columns), hi + lo fp16 parts, pre-scaled into the log2 domain
+    const float sl = 0.125f * kLog2e;   // (d_head^-0.25)^2 = 1/8 exactly
+    uint32_t qh[4][2], ql[4][2];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float* qp = a.q + (size_t)b * a.d + h * 64 + kk * 16 + 2 * tq;
+      const float2 q0 = __ldcg(reinterpret_cast<const float2*>(qp)), q1 = __ldcg(reinterpret_cast<const float2*>(qp + 8));
+      const float v[4] = {q0.x * sl, q0.y * sl, q1.x * sl, q1.y * sl};
+      __half hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        hi[e] = __float2half_rn(v[e]);
+        lo[e] = __float2half_rn(v[e] - __half2float(hi[e]));
+      }
+      __half2 h0 = __halves2half2(hi[0], hi[1]), h1 = __halves2half2(hi[2], hi[3]);
+      __half2 l0 = __halves2half2(lo[0], lo[1]), l1 = __halves2half2(lo[2], lo[3]);
+      qh[kk][0] = *reinterpret_cast<uint32_t*>(&h0), qh[kk][1] = *reinterpret_cast<uint32_t*>(&h1);
+      ql[kk][0] = *reinterpret_cast<uint32_t*>(&l0), ql[kk][1] = *reinterpret_cast<uint32_t*>(&l1);
+    }
+    for (int t = 0; t < n_tiles; ++t) {
+      const int s = t % n_stages;
+      const uint32_t ph = (uint32_t)(t / n_stages) & 1u;
+      ptx::mbar_wait(&full_bar[s], ph);
+      const int row0 = t * kHaStageRows + warp * 16;       // first of this warp's 16 rows
+      if (row0 < n_rows) {                                 // warp-uniform
+        const uint32_t sk = ptx::smem_u32(smem + (size_t)s * 2 * kHaTileBytes);
+        const uint32_t sv = sk + kHaTileBytes;
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        {
+          const int R = warp * 16 + (mi & 1) * 8 + r8;     // tile row this lane addresses for ldmatrix
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            uint32_t af[4];
+            ptx::ldmatrix_x4(af, sk + R * 128 + (((kk * 2 + (mi >> 1)) ^ (R & 7)) << 4));
+            ptx::mma_16816(c, af, qh[kk]);
+            ptx::mma_16816(c, af, ql[kk]);
+          }
+        }
+        const float s_lo = (row0 + grp < n_rows) ? c[0] : -INFINITY;
+        const float s_hi = (row0 + grp + 8 < n_rows) ? c[2] : -INFINITY;
+        float tmax = fmaxf(s_lo, s_hi);
+        tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 4));
+        tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 8));
+        tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 16));
+        if (tmax > m_run) {                                // warp-uniform (identical in every lane)
+          const float corr = exp2f(m_run - tmax);
+          m_run = tmax;
+          l_run *= corr;
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) o[mt][0] *= corr, o[mt][1] *= corr, o[mt][2] *= corr, o[mt][3] *= corr;
+        }
+        const float p_lo = exp2f(s_lo - m_run), p_hi = exp2f(s_hi - m_run);
+        l_run += p_lo + p_hi;
+        const float e0 = __shfl_sync(0xffffffffu, p_lo, (2 * tq) * 4), e1 = __shfl_sync(0xffffffffu, p_lo, (2 * tq + 1) * 4);
+        const float e2 = __shfl_sync(0xffffffffu, p_hi, (2 * tq) * 4), e3 = __shfl_sync(0xffffffffu, p_hi, (2 * tq + 1) * 4);
+        const __half2 ph0 = __floats2half2_rn(e0, e1), ph1 = __floats2half2_rn(e2, e3);
+        const float2 f0 = __half22float2(ph0), f1 = __half22float2(ph1);
+        const __half2 pl0 = __floats2half2_rn(e0 - f0.x, e1 - f0.y), pl1 = __floats2half2_rn(e2 - f1.x, e3 - f1.y);
+        const uint32_t pbh[2] = {*reinterpret_cast<const uint32_t*>(&ph0), *reinterpret_cast<const uint32_t*>(&ph1)};
+        const uint32_t pbl[2] = {*reinterpret_cast<const uint32_t*>(&pl0), *reinterpret_cast<const uint32_t*>(&pl1)};
+        {
+          const int R = warp * 16 + (mi >> 1) * 8 + r8;
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) {
+            uint32_t af[4];
+            ptx::ldmatrix_x4_trans(af, sv + R * 128 + (((mt * 2 + (mi & 1)) ^ (R & 7)) << 4));
+            ptx::mma_16816(o[mt], af, pbh);
+            ptx::mma_16816(o[mt], af, pbl);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&empty_bar[s]);
+    }
+  }
+  __syncthreads();   // all stages consumed; reuse the ring for the cross-warp merge: [8][68] floats
+  float* red = reinterpret_cast<float*>(smem);
+  if (warp < 8) {
+    float L = l_run;
+    L += __shfl_xor_sync(0xffffffffu, L, 4);
+    L += __shfl_xor_sync(0xffffffffu, L, 8);
+    L += __shfl_xor_sync(0xffffffffu, L, 16);
+    if (tq == 0) {
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        red[warp * 68 + mt * 16 + grp] = o[mt][0];
+        red[warp * 68 + mt * 16 + grp + 8] = o[mt][2];
+      }
+      if (grp == 0) red[warp * 68 + 64] = m_run, red[warp * 68 + 65] = L;
+    }
+  }
+  __syncthreads();
+  if (tid < 64) {
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) M = fmaxf(M, red[w * 68 + 64]);
+    float L = 0.f, A = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float mw = red[w * 68 + 64];
+      const float wgt = (mw == -INFINITY) ? 0.f : exp2f(mw - M);
+      L += wgt * red[w * 68 + 65];
+      A += wgt * red[w * 68 + tid];
+    }
+    a.out16[(size_t)b * a.d + h * 64 + tid] = __float2half_rn(A / L);
+  }
+  trace.end();
+}
+
+static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int64_t* launches) {
+  CUtensorMap tmK, tmV;
+  const long long nslab = (p.Mb + p.kv_share - 1) / p.kv_share;
+  int rc = gemm_get_tmap(p.tmaps, p.k, p.d, p.n_ctx, nslab, p.d, (long long)p.n_ctx * p.d, kHaStageRows, &tmK);
+  if (rc) return rc;
+  rc = gemm_get_tmap(p.tmaps, p.v, p.d, p.n_ctx, nslab, p.d, (long long)p.n_ctx * p.d, kHaStageRows, &tmV);
+  if (rc) return rc;
+  HeadAttnArgs a{p.q, p.out16, p.state, p.d, p.n_rows_fixed, p.kv_share, 3};
+  const int ctas = p.n_head * p.Mb;
+  if (p.n_rows_fixed <= 0 || ctas > 296) a.n_stages = 2;          // self attention: few rows; big grids: 3 CTAs per SM
+  static int stages_env = -1;
+  if (stages_env < 0) {
+    const char* e = getenv("WB_HA_STAGES");
+    stages_env = e ? atoi(e) : 0;
+  }
+  if (stages_env > 0) a.n_stages = stages_env;
+  const size_t smem = (size_t)a.n_stages * 2 * kHaTileBytes + 1024;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    WB_CUDA_OK(cudaFuncSetAttribute(attn_decode_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.n_head, p.Mb), cfg.blockDim = dim3(kHaThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at, cfg.numAttrs = use_pdl() ? 1 : 0;
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, attn_decode_head_kernel, tmK, tmV, a);
+  if (launches) *launches += 1;
+  WB_CUDA_OK(le);
+  return 0;
 }
 
 int launch_attn_decode(const AttnDecodeDesc& p, cudaStream_t st, int64_t* launches) {
@@ -504,6 +1112,15 @@ int launch_attn_decode(const AttnDecodeDesc& p, cudaStream_t st, int64_t* launch
     set_error("attn_decode: unsupported d=%d heads=%d", p.d, p.n_head);
     return -1;
   }
+  // WB_ATTN_IMPL: "head" (default) = one CTA per (sequence, head), TMA + mma.sync, no row split; "hx" = that kernel for cross
+  // attention only; "mma" = row-split tensor-core kernel; "reg" = row-split register kernel (development A/B switches)
+  static int impl = -1;
+  if (impl < 0) {
+    const char* e = getenv("WB_ATTN_IMPL");
+    impl = !e ? 3 : (e[0] == 'r' ? 0 : (e[0] == 'm' ? 1 : (e[0] == 'c' ? 2 : (e[1] == 'x' ? 4 : 3))));
+  }
+  if (impl == 3 || (impl == 4 && p.n_rows_fixed > 0)) return launch_attn_decode_head(p, st, launches);
+  if (impl == 1 || (impl == 2 && p.n_rows_fixed > 0)) return launch_attn_decode_mma(p, st, launches);
   const int NJ = (p.d / 8 + 31) / 32;
   const size_t smem = (size_t)(16 * p.n_head + 8 * p.d) * 4;
   dim3 grid(p.n_split, p.Mb);
@@ -538,6 +1155,7 @@ __global__ void __launch_bounds__(256) step_finish_kernel(FinishDesc p) {
   __shared__ int s_idx[8];
   __shared__ int s_tok;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  TraceScope trace(p.state, 300 + p.sample);
   ptx::grid_dep_launch();
   ptx::grid_dep_sync();
   const int cur = ld_state(&p.state->cur_len);   // index of the token this step consumed (-1 before the first step)
@@ -604,6 +1222,7 @@ __global__ void __launch_bounds__(256) step_finish_kernel(FinishDesc p) {
       p.state->cur_len = cur + 1;
     }
   }
+  trace.end();
 }
 
 int launch_step_finish(const FinishDesc& d, cudaStream_t st, int64_t* launches) {

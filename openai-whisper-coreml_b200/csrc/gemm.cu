@@ -300,6 +300,11 @@ static int get_tmap(GemmContext* ctx, const void* ptr, long long K, long long ro
   return 0;
 }
 
+int gemm_get_tmap(GemmContext* ctx, const void* ptr, long long K, long long rows, long long nb, long long row_stride,
+                  long long batch_stride, int box_rows, void* out128) {
+  return get_tmap(ctx, ptr, K, rows, nb, row_stride, batch_stride, box_rows, reinterpret_cast<CUtensorMap*>(out128));
+}
+
 template <int BN>
 static int launch_tc(GemmContext* ctx, const GemmDesc& d, const GemmEpi& ep, cudaStream_t st) {
   CUtensorMap tmA, tmB;

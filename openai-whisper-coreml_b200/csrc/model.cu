@@ -130,6 +130,7 @@ struct wb_handle {
   unsigned char* mask;
   int n_logit_ctas;
   DecodeState* state;
+  unsigned long long* trace;   // WB_TRACE=1
   int split_self, split_cross;
 
   // graphs
@@ -274,6 +275,7 @@ static void layout_workspace(wb_handle* h) {
   h->n_logit_ctas = skinny_logits_ctas(D.n_vocab);
   h->part_logits = A.take<float>(Mb * (size_t)h->n_logit_ctas * 4);
   h->state = A.take<DecodeState>(1);
+  h->trace = getenv("WB_TRACE") ? A.take<unsigned long long>(65536 * 8) : nullptr;
 }
 
 static int check_dims(const wb_dims& D) {
@@ -380,7 +382,7 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
     AttnDecodeDesc a{};
     a.Mb = Mb, a.d = d, a.n_head = H, a.n_split = h->split_self, a.q = h->q32, a.k = h->selfK[l], a.v = h->selfV[l];
     a.n_ctx = D.n_text_ctx, a.n_rows_fixed = 0, a.kv_share = 1, a.state = h->state, a.part_ml = h->part_ml, a.part_acc = h->part_acc;
-    a.counters = h->counters, a.out16 = h->a16;
+    a.counters = h->counters, a.out16 = h->a16, a.tmaps = h->gemm;
     WB_TRY(launch_attn_decode(a, st, &h->launches));
     SkinnyDesc so{};
     so.Mb = Mb, so.state = h->state, so.N = d, so.K = d, so.w = L.wo, so.bias = L.bo, so.in_mode = SKINNY_IN_F16, so.in = h->a16;
@@ -422,7 +424,7 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
 
 // cur_len = -1, then embed the token at position 0 (which advances cur_len to 0)
 static int reset_decode_state(wb_handle* h, const StepOpts& o) {
-  DecodeState init{-1, 0, 0, 0};
+  DecodeState init{-1, 0, 0, 0, h->trace};
   WB_CUDA_OK(cudaMemcpyAsync(h->state, &init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
   WB_CUDA_OK(cudaMemsetAsync(h->counters, 0, sizeof(int) * h->Mb_max, h->stream));
   return step_finish(h, o, 0);
@@ -949,6 +951,17 @@ int wb_transcribe(wb_handle* h, const float* audio, int32_t B, const wb_decode_o
 }
 
 int64_t wb_launch_count(const wb_handle* h) { return h ? h->launches : -1; }
+
+/* development: copy out the %globaltimer trace of the last decode (WB_TRACE=1); returns the number of records */
+int wb_debug_trace(wb_handle* h, unsigned long long* out, int max_records) {
+  if (!h || !h->trace || !out) return 0;
+  DecodeState st;
+  if (cudaMemcpy(&st, h->state, sizeof(st), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  int n = st.trace_n < max_records ? st.trace_n : max_records;
+  n = n < 65536 ? n : 65536;
+  if (cudaMemcpy(out, h->trace, (size_t)n * 64, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  return n;
+}
 int wb_last_timings(const wb_handle* h, float out[4]) {
   if (!h || !out) return WB_ERR_ARG;
   for (int i = 0; i < 4; ++i) out[i] = h->timings[i];
@@ -970,7 +983,7 @@ int wb_profile_cross_attention(wb_handle* h, int32_t B, int32_t reps, float* avg
   AttnDecodeDesc c{};
   c.Mb = B, c.d = D.n_text_state, c.n_head = D.n_text_head, c.n_split = h->split_cross, c.q = h->q32;
   c.n_ctx = D.n_audio_ctx, c.n_rows_fixed = D.n_audio_ctx, c.kv_share = 1, c.state = h->state;
-  c.part_ml = h->part_ml, c.part_acc = h->part_acc, c.counters = h->counters, c.out16 = h->a16;
+  c.part_ml = h->part_ml, c.part_acc = h->part_acc, c.counters = h->counters, c.out16 = h->a16, c.tmaps = h->gemm;
   WB_CUDA_OK(cudaMemsetAsync(h->counters, 0, sizeof(int) * h->Mb_max, h->stream));
   for (int i = -3; i < reps; ++i) {   // 3 warm-up launches
     if (i == 0) WB_CUDA_OK(cudaEventRecord(h->ev[0], h->stream));

@@ -44,6 +44,10 @@ struct GemmContext;   // tensor-map cache + driver entry point
 GemmContext* gemm_context_create();
 void gemm_context_destroy(GemmContext*);
 int launch_gemm(GemmContext* ctx, const GemmDesc& d, cudaStream_t st, int64_t* launches);
+// Cached CUtensorMap (128 bytes, written to out128) of an fp16 tensor (k, rows, batch) with element strides
+// (1, row_stride, batch_stride), box (64, box_rows, 1), 128-byte swizzle.
+int gemm_get_tmap(GemmContext* ctx, const void* ptr, long long K, long long rows, long long nb, long long row_stride,
+                  long long batch_stride, int box_rows, void* out128);
 
 // ---- row-wise ops (rowops.cu) ------------------------------------------------------------------------------------------
 int launch_layernorm(const float* x, const float* gamma, const float* beta, int M, int d, __half* out16, float* out32,
@@ -61,7 +65,8 @@ int launch_encoder_attention(const __half* qkv, int B, int T, int n_head, __half
 struct DecodeState {      // lives in device memory; read by every kernel of a step (CUDA-graph friendly)
   int cur_len;            // index of the token the current step consumes (-1 before the first embed)
   int arrive;             // arrival counter of step_finish_kernel's CTAs
-  int pad0, pad1;
+  int trace_n, pad1;      // development tracing (WB_TRACE=1): number of records written
+  unsigned long long* trace;   // [n][4] = {kernel id, %globaltimer at entry, at exit of block 0, 0}; null = off
 };
 
 // Input transform of a skinny GEMM (how the [Mb][K] fp16 activation tile in shared memory is produced)
@@ -110,6 +115,7 @@ struct AttnDecodeDesc {
   float* part_acc;        // [Mb][S][d]
   int* counters;          // [Mb] zero-initialised arrival counters (self-resetting)
   __half* out16;          // [Mb][d]
+  GemmContext* tmaps;     // tensor-map cache (head-per-CTA kernel)
 };
 int launch_attn_decode(const AttnDecodeDesc& d, cudaStream_t st, int64_t* launches);
 
