@@ -225,7 +225,7 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("attn_decode_cross_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("attn_decode_head_cross_dram_bytes_per_launch")
     except (OSError, ValueError):
         pass
     achieved = k_bytes / (k_ms * 1e-3) / 1e9
@@ -239,7 +239,7 @@ def main():
                     "d2h_bytes_per_step": int(tokens.nbytes + lens.nbytes + slp.nbytes), "ms_per_step": ms_step_e2e},
             "gpu_launches": int(launches),
             "phase_ms": {"logmel": phase[0], "encoder_and_cross_kv": phase[1], "decode": phase[2], "decode_steps": phase[3]},
-            "roofline": {"kernel": "attn_decode_kernel (decoder cross-attention over the persistent KV cache)", "bound": "hbm",
+            "roofline": {"kernel": "attn_decode_head_kernel (decoder cross-attention over the persistent KV cache, one CTA per sequence x head)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst; kernel timed alone)" if peaks else "fallback 6650",
                          "algorithmic_bytes_per_launch": k_bytes, "us_per_launch": k_ms * 1e3, "traffic": traffic},

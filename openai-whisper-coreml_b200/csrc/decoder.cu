@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
           for (int u = 0; u < 4; ++u) {
             const int c = c0 + 32 * u;
             v[j][u] = make_uint4(0, 0, 0, 0);
-            if (c < cpr && r < p.Mb) v[j][u] = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)r * p.K + kc0 + c * 8));
+            if (c < cpr && r < p.Mb) v[j][u] = ptx::ldg_nc_16(src + (size_t)r * p.K + kc0 + c * 8);
           }
         }
 #pragma unroll
@@ -300,46 +300,6 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
   }
   __syncthreads();
   const int rows_cta = S * 16;
-  if (p.out_mode == SKINNY_OUT_LOGITS) {
-    // rows_cta == 128 (S == 8, no K split). Warp per sequence: filter, optional store, CTA-local (max, argmax, sum-exp).
-    const bool first = ld_state(&p.state->cur_len) + 1 == p.n_initial;
-    for (int b = warp; b < p.Mb; b += 8) {
-      float v[4];
-      float best = -INFINITY;
-      int arg = 0x7fffffff;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int rr = lane + 32 * i, n = n_cta + rr;
-        float x = -INFINITY;
-        if (n < p.N) {
-          x = red[(size_t)(rr >> 4) * 16 * MB8 + (rr & 15) * MB8 + b];
-          const unsigned char mk = p.mask ? p.mask[n] : 0;
-          if (mk == 1 || (mk == 2 && first)) x = -INFINITY;
-          if (p.out) reinterpret_cast<float*>(p.out)[(size_t)b * p.N + n] = x;
-        }
-        v[i] = x;
-        if (x > best) best = x, arg = n;     // ascending n: first maximum wins
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
-        if (ov > best || (ov == best && oi < arg)) best = ov, arg = oi;
-      }
-      float se = 0.f;
-      if (best > -INFINITY) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) se += expf(v[i] - best);
-      }
-      se = warp_sum(se);
-      if (lane == 0) {
-        float* pp = p.part_logits + ((size_t)b * gridDim.x + blockIdx.x) * 4;
-        pp[0] = best, pp[1] = __int_as_float(arg), pp[2] = se;
-      }
-    }
-    trace.end();
-    return;
-  }
   const int pos = (p.out_mode == SKINNY_OUT_QKV) ? ld_state(&p.state->cur_len) : 0;
   const int dq = p.N / 3;
   if (resid_pre) {   // rows_cta == 16; same index map as the prefetch above
@@ -391,6 +351,195 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
   trace.end();
 }
 
+// ---- logits GEMM: final LayerNorm + tied-embedding projection + logit filters + per-group (max, argmax, sum-exp) -----------------
+// Persistent: one CTA per SM normalises the Mb rows once, then loops over 128-row groups of the [V][d] embedding matrix
+// (the only weight-streaming GEMM of the step that is bandwidth- rather than latency-bound: V*d*2 = 53 MB for base.en).
+// Warp w owns rows 16w..16w+15 of a group over the whole K; the next group's first blocks are requested before the
+// epilogue of the current one.
+template <int MT>
+__global__ void __launch_bounds__(kSkThreads) logits_gemm_kernel(SkinnyDesc p, int n_groups) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TraceScope trace(p.state, 141);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 2, tq = lane & 3;
+  const int xs_stride = p.K * 2 + 64;
+  unsigned char* xs = smem_raw;
+  constexpr int MB8 = MT * 8;
+  float* red = reinterpret_cast<float*>(smem_raw + (size_t)MB8 * xs_stride);   // [128][MB8]
+  float* sg = red + 128 * MB8;
+  float* sb = sg + p.K;
+  const int nblk = p.K / 32;
+  constexpr int kPre = 8;
+
+  auto row_ptr = [&](int g, int half) {
+    int n = g * 128 + warp * 16 + grp + half * 8;
+    n = n < p.N ? n : p.N - 1;
+    return p.w + (size_t)n * p.K + tq * 8;
+  };
+  int g = blockIdx.x;
+  const __half* wrow0 = row_ptr(g, 0);
+  const __half* wrow1 = row_ptr(g, 1);
+  uint4 pwa[kPre], pwb[kPre];
+#pragma unroll
+  for (int u = 0; u < kPre; ++u) {
+    const int blk = u < nblk ? u : 0;
+    pwa[u] = ptx::ldg_nc_16(wrow0 + blk * 32);
+    pwb[u] = ptx::ldg_nc_16(wrow1 + blk * 32);
+  }
+  for (int i = tid * 4; i < p.K; i += kSkThreads * 4) {
+    *reinterpret_cast<float4*>(sg + i) = __ldg(reinterpret_cast<const float4*>(p.ln_g + i));
+    *reinterpret_cast<float4*>(sb + i) = __ldg(reinterpret_cast<const float4*>(p.ln_b + i));
+  }
+  ptx::grid_dep_launch();
+  ptx::grid_dep_sync();
+  __syncthreads();
+  trace.mark(3);
+  {   // LayerNorm of the residual stream into xs (same scheme as skinny_gemm_kernel)
+    const int sub = tid & 7;
+    for (int r = tid >> 3; r < MB8; r += kSkThreads / 8) {
+      __half* xr = reinterpret_cast<__half*>(xs + (size_t)r * xs_stride);
+      const bool act = r < p.Mb;
+      const float* src = reinterpret_cast<const float*>(p.in) + (size_t)(act ? r : 0) * p.K;
+      float s = 0.f, q = 0.f;
+      float4 v[16];
+      for (int c0 = 0; c0 < p.K; c0 += 512) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int c = c0 + (sub + 8 * i) * 4;
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c < p.K) v[i] = __ldcg(reinterpret_cast<const float4*>(src + c));
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+          q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+        }
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      q += __shfl_xor_sync(0xffffffffu, q, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      q += __shfl_xor_sync(0xffffffffu, q, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      q += __shfl_xor_sync(0xffffffffu, q, 4);
+      const float mean = s / (float)p.K;
+      const float var = fmaxf(q / (float)p.K - mean * mean, 0.f);
+      const float rstd = act ? rsqrtf(var + 1e-5f) : 0.f;
+      const float ab = act ? 1.f : 0.f;
+      for (int c0 = 0; c0 < p.K; c0 += 512) {
+        if (p.K > 512) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = c0 + (sub + 8 * i) * 4;
+            if (c < p.K) v[i] = __ldcg(reinterpret_cast<const float4*>(src + c));
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int c = c0 + (sub + 8 * i) * 4;
+          if (c < p.K) {
+            const float4 gm = *reinterpret_cast<const float4*>(sg + c), bb = *reinterpret_cast<const float4*>(sb + c);
+            __half2 h0 = __floats2half2_rn((v[i].x - mean) * rstd * gm.x + ab * bb.x, (v[i].y - mean) * rstd * gm.y + ab * bb.y);
+            __half2 h1 = __floats2half2_rn((v[i].z - mean) * rstd * gm.z + ab * bb.z, (v[i].w - mean) * rstd * gm.w + ab * bb.w);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h0), u.y = *reinterpret_cast<uint32_t*>(&h1);
+            *reinterpret_cast<uint2*>(xr + c) = u;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  trace.mark(4);
+  const bool first = ld_state(&p.state->cur_len) + 1 == p.n_initial;
+  const unsigned char* xl = xs + (size_t)grp * xs_stride + tq * 16;
+  while (true) {
+    float acc[MT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
+    auto mma_block = [&](const uint4& wa, const uint4& wb, int blk) {
+      const uint32_t a0[4] = {wa.x, wb.x, wa.y, wb.y}, a1[4] = {wa.z, wb.z, wa.w, wb.w};
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const uint4 xb = *reinterpret_cast<const uint4*>(xl + (size_t)mt * 8 * xs_stride + blk * 64);
+        const uint32_t b0[2] = {xb.x, xb.y}, b1[2] = {xb.z, xb.w};
+        ptx::mma_16816(acc[mt], a0, b0);
+        ptx::mma_16816(acc[mt], a1, b1);
+      }
+    };
+#pragma unroll
+    for (int u = 0; u < kPre; ++u)
+      if (u < nblk) mma_block(pwa[u], pwb[u], u);
+    for (int blk = kPre; blk < nblk; blk += 8) {
+      uint4 wa[8], wb[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int bb = blk + u < nblk ? blk + u : blk;
+        wa[u] = ptx::ldg_nc_16(wrow0 + bb * 32);
+        wb[u] = ptx::ldg_nc_16(wrow1 + bb * 32);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (blk + u < nblk) mma_block(wa[u], wb[u], blk + u);
+    }
+    const int g_next = g + gridDim.x;
+    if (g_next < n_groups) {   // request the next group's first blocks before the epilogue
+      wrow0 = row_ptr(g_next, 0);
+      wrow1 = row_ptr(g_next, 1);
+#pragma unroll
+      for (int u = 0; u < kPre; ++u) {
+        const int blk = u < nblk ? u : 0;
+        pwa[u] = ptx::ldg_nc_16(wrow0 + blk * 32);
+        pwb[u] = ptx::ldg_nc_16(wrow1 + blk * 32);
+      }
+    }
+    // accumulators -> red[row in group][sequence]
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      red[(warp * 16 + grp) * MB8 + mt * 8 + 2 * tq] = acc[mt][0];
+      red[(warp * 16 + grp) * MB8 + mt * 8 + 2 * tq + 1] = acc[mt][1];
+      red[(warp * 16 + grp + 8) * MB8 + mt * 8 + 2 * tq] = acc[mt][2];
+      red[(warp * 16 + grp + 8) * MB8 + mt * 8 + 2 * tq + 1] = acc[mt][3];
+    }
+    __syncthreads();
+    // warp per sequence: filter, optional store, group-local (max, argmax, sum-exp)
+    for (int b = warp; b < p.Mb; b += 8) {
+      float v[4];
+      float best = -INFINITY;
+      int arg = 0x7fffffff;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = lane + 32 * i, n = g * 128 + rr;
+        float x = -INFINITY;
+        if (n < p.N) {
+          x = red[rr * MB8 + b];
+          const unsigned char mk = p.mask ? p.mask[n] : 0;
+          if (mk == 1 || (mk == 2 && first)) x = -INFINITY;
+          if (p.out) reinterpret_cast<float*>(p.out)[(size_t)b * p.N + n] = x;
+        }
+        v[i] = x;
+        if (x > best) best = x, arg = n;     // ascending n: first maximum wins
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ov > best || (ov == best && oi < arg)) best = ov, arg = oi;
+      }
+      float se = 0.f;
+      if (best > -INFINITY) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) se += expf(v[i] - best);
+      }
+      se = warp_sum(se);
+      if (lane == 0) *reinterpret_cast<float4*>(p.part_logits + ((size_t)b * n_groups + g) * 4) = make_float4(best, __int_as_float(arg), se, 0.f);
+    }
+    if (g_next >= n_groups) break;
+    g = g_next;
+    __syncthreads();   // red is rewritten by the next group
+  }
+  trace.end();
+}
+
 static bool use_pdl() {
   static int v = -1;
   if (v < 0) {
@@ -424,10 +573,52 @@ int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches) 
     set_error("skinny_gemm: fused LayerNorm input needs K <= %d", kSkKC);
     return -1;
   }
+  if (d.out_mode == SKINNY_OUT_LOGITS) {
+    if (d.in_mode != SKINNY_IN_LN || d.K > kSkKC) {
+      set_error("logits GEMM: LayerNorm input with K <= %d required", kSkKC);
+      return -1;
+    }
+    const int n_groups = skinny_logits_ctas(d.N);
+    const int MTl = (d.Mb + 7) / 8;
+    const size_t sm = (size_t)MTl * 8 * (d.K * 2 + 64) + (size_t)128 * MTl * 8 * 4 + (size_t)2 * d.K * 4;
+    static int n_sm = 0;
+    if (!n_sm) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+      if (n_sm <= 0) n_sm = 148;
+    }
+    const int grid = n_groups < n_sm ? n_groups : n_sm;
+    cudaError_t le2 = cudaSuccess;
+#define WB_LG_CASE(M)                                                                                                 \
+  case M: {                                                                                                           \
+    static size_t smem_set = 0;                                                                                       \
+    if (sm > smem_set) {                                                                                              \
+      WB_CUDA_OK(cudaFuncSetAttribute(logits_gemm_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+      smem_set = sm;                                                                                                  \
+    }                                                                                                                 \
+    cudaLaunchConfig_t cfg{};                                                                                         \
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kSkThreads), cfg.dynamicSmemBytes = sm, cfg.stream = st;           \
+    cudaLaunchAttribute at[1];                                                                                        \
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                    \
+    at[0].val.programmaticStreamSerializationAllowed = 1;                                                             \
+    cfg.attrs = at, cfg.numAttrs = use_pdl() ? 1 : 0;                                                                 \
+    le2 = cudaLaunchKernelEx(&cfg, logits_gemm_kernel<M>, d, n_groups);                                               \
+  } break;
+    switch (MTl) {
+      WB_LG_CASE(1) WB_LG_CASE(2) WB_LG_CASE(3) WB_LG_CASE(4) WB_LG_CASE(5)
+      default:
+        set_error("logits GEMM: Mb too large");
+        return -1;
+    }
+#undef WB_LG_CASE
+    if (launches) *launches += 1;
+    WB_CUDA_OK(le2);
+    return 0;
+  }
   const int strips = (d.N + 15) / 16;
   int S = 1;
   while (S < 8 && strips / S > 296) S *= 2;
-  if (d.out_mode == SKINNY_OUT_LOGITS) S = 8;
   SkinnyArgs a{d, S};
   const int MT = (d.Mb + 7) / 8;
   const int KC = d.K < kSkKC ? d.K : kSkKC;
@@ -918,6 +1109,7 @@ struct HeadAttnArgs {
   __half* out16;
   const DecodeState* state;
   int d, n_rows_fixed, kv_share, n_stages;
+  int l2_prefetch_tiles;   // cross attention: stage tiles beyond the ring requested into L2 while q is still being computed
 };
 
 __global__ void __launch_bounds__(kHaThreads) attn_decode_head_kernel(const __grid_constant__ CUtensorMap tmK,
@@ -953,6 +1145,13 @@ __global__ void __launch_bounds__(kHaThreads) attn_decode_head_kernel(const __gr
   if (warp == 8) {
     if (lane == 0) {
       const int slab = b / a.kv_share;
+      if (fixed) {   // the producer of a cross-attention CTA runs ahead of q: pull the tiles after the ring into L2 meanwhile
+        const int pf_end = n_stages + a.l2_prefetch_tiles < n_tiles ? n_stages + a.l2_prefetch_tiles : n_tiles;
+        for (int t = n_stages; t < pf_end; ++t) {
+          ptx::tma_prefetch_l2_3d(&tmK, h * 64, t * kHaStageRows, slab);
+          ptx::tma_prefetch_l2_3d(&tmV, h * 64, t * kHaStageRows, slab);
+        }
+      }
       for (int t = 0; t < n_tiles; ++t) {
         const int s = t % n_stages;
         const uint32_t ph = (uint32_t)(t / n_stages) & 1u;
@@ -1080,7 +1279,7 @@ static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int
   if (rc) return rc;
   rc = gemm_get_tmap(p.tmaps, p.v, p.d, p.n_ctx, nslab, p.d, (long long)p.n_ctx * p.d, kHaStageRows, &tmV);
   if (rc) return rc;
-  HeadAttnArgs a{p.q, p.out16, p.state, p.d, p.n_rows_fixed, p.kv_share, 3};
+  HeadAttnArgs a{p.q, p.out16, p.state, p.d, p.n_rows_fixed, p.kv_share, 3, 0};   // L2 prefetch measured slightly negative in-step: off
   const int ctas = p.n_head * p.Mb;
   if (p.n_rows_fixed <= 0 || ctas > 296) a.n_stages = 2;          // self attention: few rows; big grids: 3 CTAs per SM
   static int stages_env = -1;
@@ -1089,6 +1288,12 @@ static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int
     stages_env = e ? atoi(e) : 0;
   }
   if (stages_env > 0) a.n_stages = stages_env;
+  static int pf_env = -1;
+  if (pf_env < 0) {
+    const char* e = getenv("WB_HA_L2PF");
+    pf_env = e ? atoi(e) + 1000 : 0;
+  }
+  if (pf_env >= 1000) a.l2_prefetch_tiles = pf_env - 1000;
   const size_t smem = (size_t)a.n_stages * 2 * kHaTileBytes + 1024;
   static size_t smem_set = 0;
   if (smem > smem_set) {
@@ -1153,21 +1358,55 @@ int launch_attn_decode(const AttnDecodeDesc& p, cudaStream_t st, int64_t* launch
 __global__ void __launch_bounds__(256) step_finish_kernel(FinishDesc p) {
   __shared__ float s_val[8], s_sum[8];
   __shared__ int s_idx[8];
-  __shared__ int s_tok;
+  __shared__ int s_tok, s_cur;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   TraceScope trace(p.state, 300 + p.sample);
   ptx::grid_dep_launch();
   ptx::grid_dep_sync();
-  const int cur = ld_state(&p.state->cur_len);   // index of the token this step consumed (-1 before the first step)
   int32_t* trow = p.tokens + (size_t)b * p.tokens_ld;
+  int prev_tok = 0;
+  float slp_old = 0.f;
+  if (tid == 0) {
+    // one reader per CTA, then the arrival ticket: the last CTA to have read cur_len advances it (nothing later in this
+    // kernel reads it again; the kernels of the next step see the new value)
+    const int c = ld_state(&p.state->cur_len);   // index of the token this step consumed (-1 before the first step)
+    s_cur = c;
+    const int ticket = atomicAdd(&p.state->arrive, 1);
+    if (ticket == (int)gridDim.x - 1) {
+      p.state->arrive = 0;
+      p.state->cur_len = c + 1;
+    }
+    if (p.sample) {
+      prev_tok = __ldcg(trow + c);
+      slp_old = __ldcg(p.sum_logprob + b);
+    } else {
+      s_tok = __ldcg(trow + c + 1);
+    }
+  }
+  // everything that does not depend on the sampled token is fetched in one batch: the logits partials of this sequence
+  float4 rec[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = tid + j * 256;
+    rec[j] = make_float4(-INFINITY, __int_as_float(0x7fffffff), 0.f, 0.f);
+    if (p.sample && i < p.n_part) rec[j] = __ldcg(reinterpret_cast<const float4*>(p.part_logits + ((size_t)b * p.n_part + i) * 4));
+  }
+  __syncthreads();
+  const int cur = s_cur;
+  const int np = cur + 1;
+  float pe_v[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const int c = tid + j * 256;
+    pe_v[j] = (np < p.n_ctx && c < p.d) ? __ldg(p.pos_emb + (size_t)np * p.d + c) : 0.f;
+  }
   if (p.sample) {
-    const float* pp = p.part_logits + (size_t)b * p.n_part * 4;
     float best = -INFINITY;
     int arg = 0x7fffffff;
-    for (int i = tid; i < p.n_part; i += 256) {
-      const float v = __ldcg(pp + i * 4);
-      const int a = __float_as_int(__ldcg(pp + i * 4 + 1));
-      if (v > best || (v == best && a < arg)) best = v, arg = a;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int a = __float_as_int(rec[j].y);
+      if (rec[j].x > best || (rec[j].x == best && a < arg)) best = rec[j].x, arg = a;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -1182,10 +1421,9 @@ __global__ void __launch_bounds__(256) step_finish_kernel(FinishDesc p) {
     for (int w = 1; w < 8; ++w)
       if (s_val[w] > best || (s_val[w] == best && s_idx[w] < arg)) best = s_val[w], arg = s_idx[w];
     float se = 0.f;
-    for (int i = tid; i < p.n_part; i += 256) {
-      const float mi = __ldcg(pp + i * 4);
-      if (mi > -INFINITY) se += __ldcg(pp + i * 4 + 2) * expf(mi - best);
-    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (rec[j].x > -INFINITY) se += rec[j].z * expf(rec[j].x - best);
     se = warp_sum(se);
     if (lane == 0) s_sum[warp] = se;
     __syncthreads();
@@ -1193,33 +1431,23 @@ __global__ void __launch_bounds__(256) step_finish_kernel(FinishDesc p) {
       float tot = 0.f;
       for (int w = 0; w < 8; ++w) tot += s_sum[w];
       const float logprob = -logf(tot);   // the chosen logit is the maximum
-      const bool ended = __ldcg(trow + cur) == p.eot;
-      if (!ended) p.sum_logprob[b] = __ldcg(p.sum_logprob + b) + logprob;
+      const bool ended = prev_tok == p.eot;
+      if (!ended) p.sum_logprob[b] = slp_old + logprob;
       const int next = ended ? p.eot : arg;
       trow[cur + 1] = next;
       p.done[b] = next == p.eot;
       s_tok = next;
     }
-  } else if (tid == 0) {
-    s_tok = __ldcg(trow + cur + 1);
+    __syncthreads();
   }
-  __syncthreads();
-  const int np = cur + 1;
   if (np < p.n_ctx) {
     int tok = s_tok;
     tok = tok < 0 ? 0 : (tok >= p.V ? p.V - 1 : tok);
     const __half* e = p.tok_emb + (size_t)tok * p.d;
-    const float* pe = p.pos_emb + (size_t)np * p.d;
-    for (int c = tid; c < p.d; c += 256) p.x[(size_t)b * p.d + c] = __half2float(e[c]) + pe[c];
-  }
-  // every CTA has read cur_len by now only once all have arrived: the last one advances it
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    const int ticket = atomicAdd(&p.state->arrive, 1);
-    if (ticket == (int)gridDim.x - 1) {
-      p.state->arrive = 0;
-      p.state->cur_len = cur + 1;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int c = tid + j * 256;
+      if (c < p.d) p.x[(size_t)b * p.d + c] = __half2float(__ldg(e + c)) + pe_v[j];
     }
   }
   trace.end();

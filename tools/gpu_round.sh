@@ -12,10 +12,10 @@ echo "== ncu launch list =="
 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/profile_step.py base.en 32 4 > gpurun_out/profile_step.log 2>&1
 tail -2 gpurun_out/profile_step.log
 echo "== ncu full: attn_decode ==" 
-timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:attn_decode -s 2 -c 2 -f -o gpurun_out/prof_attn_decode python tools/profile_step.py base.en 32 2 > gpurun_out/prof1.log 2>&1; tail -2 gpurun_out/prof1.log
+timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:attn_decode_head -s 2 -c 2 -f -o gpurun_out/prof_attn_decode python tools/profile_step.py base.en 32 2 > gpurun_out/prof1.log 2>&1; tail -2 gpurun_out/prof1.log
 echo "== ncu full: gemm_tc ==" 
 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:gemm_tc -s 2 -c 3 -f -o gpurun_out/prof_gemm_tc python tools/profile_step.py base.en 32 1 > gpurun_out/prof2.log 2>&1; tail -2 gpurun_out/prof2.log
 echo "== ncu full: skinny + enc attention ==" 
-timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"skinny|encoder_attention" -s 1 -c 10 -f -o gpurun_out/prof_misc python tools/profile_step.py base.en 32 1 > gpurun_out/prof3.log 2>&1; tail -2 gpurun_out/prof3.log
+timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"skinny|encoder_attention|logits_gemm|step_finish" -s 1 -c 12 -f -o gpurun_out/prof_misc python tools/profile_step.py base.en 32 1 > gpurun_out/prof3.log 2>&1; tail -2 gpurun_out/prof3.log
 fi
 ls -la gpurun_out
