@@ -60,6 +60,15 @@ struct TraceScope {
 };
 
 // ---- skinny GEMM -----------------------------------------------------------------------------------------------------------
+#ifdef WB_EXPERIMENT_XLD_NC
+__device__ __forceinline__ float4 ld_x4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+#else
+__device__ __forceinline__ float4 ld_x4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+#endif
 constexpr int kSkThreads = 256;
 constexpr int kSkKC = 2048;   // activation columns staged in shared memory at a time
 
@@ -80,8 +89,9 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
   const int KC = p.K < kSkKC ? p.K : kSkKC;
   const int xs_stride = KC * 2 + 64;                       // bytes; (stride/16) % 8 == 4 -> conflict-free LDS.128
   unsigned char* xs = smem_raw;
-  float* red = reinterpret_cast<float*>(smem_raw + (size_t)MT * 8 * xs_stride);   // [8 warps][16][MT*8]
-  float* sbias = red + 8 * 16 * MT * 8;                                           // [128] bias of this CTA's rows
+  constexpr int RS = MT * 8 + 1;                                                  // padded row stride of red: conflict-free epilogue
+  float* red = reinterpret_cast<float*>(smem_raw + (size_t)MT * 8 * xs_stride);   // [8 warps][16][RS]
+  float* sbias = red + 8 * 16 * RS;                                           // [128] bias of this CTA's rows
   float* sg = sbias + 128;                                                        // [K] LayerNorm gamma (LN input mode)
   float* sb = sg + p.K;                                                           // [K] LayerNorm beta
 
@@ -123,6 +133,7 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
   ptx::grid_dep_sync();
   __syncthreads();   // the staged constants are read by other threads in the input stage
   trace.mark(3);
+  const int pos = (p.out_mode == SKINNY_OUT_QKV) ? ld_state(&p.state->cur_len) : 0;   // cache row of this step (prefetched)
   // residual-add epilogue: fetch the old values now, off the critical path (N = d: 16 rows x Mb <= 640 values per CTA)
   float resid[3] = {0.f, 0.f, 0.f};
   const bool resid_pre = p.out_mode == SKINNY_OUT_RESID && S == 1;
@@ -181,7 +192,7 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
           for (int i = 0; i < 16; ++i) {
             const int c = c0 + (sub + 8 * i) * 4;
             v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c < p.K) v[i] = __ldcg(reinterpret_cast<const float4*>(src + c));
+            if (c < p.K) v[i] = ld_x4(src + c);
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -204,7 +215,7 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const int c = c0 + (sub + 8 * i) * 4;
-              if (c < p.K) v[i] = __ldcg(reinterpret_cast<const float4*>(src + c));
+              if (c < p.K) v[i] = ld_x4(src + c);
             }
           }
 #pragma unroll
@@ -289,18 +300,16 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
   }
   // ---- cross-warp (K split) reduction and epilogue -------------------------------------------------------------------------
   trace.mark(5);
-  constexpr int MB8 = MT * 8;
-  float* myred = red + (size_t)warp * 16 * MB8;
+  float* myred = red + (size_t)warp * 16 * RS;
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
-    myred[grp * MB8 + mt * 8 + 2 * tq] = acc[mt][0];
-    myred[grp * MB8 + mt * 8 + 2 * tq + 1] = acc[mt][1];
-    myred[(grp + 8) * MB8 + mt * 8 + 2 * tq] = acc[mt][2];
-    myred[(grp + 8) * MB8 + mt * 8 + 2 * tq + 1] = acc[mt][3];
+    myred[grp * RS + mt * 8 + 2 * tq] = acc[mt][0];
+    myred[grp * RS + mt * 8 + 2 * tq + 1] = acc[mt][1];
+    myred[(grp + 8) * RS + mt * 8 + 2 * tq] = acc[mt][2];
+    myred[(grp + 8) * RS + mt * 8 + 2 * tq + 1] = acc[mt][3];
   }
   __syncthreads();
   const int rows_cta = S * 16;
-  const int pos = (p.out_mode == SKINNY_OUT_QKV) ? ld_state(&p.state->cur_len) : 0;
   const int dq = p.N / 3;
   if (resid_pre) {   // rows_cta == 16; same index map as the prefetch above
 #pragma unroll
@@ -309,7 +318,7 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
       const int b = idx >> 4, r = idx & 15, n = n_cta + r;
       if (b < p.Mb && n < p.N) {
         float v = 0.f;
-        for (int ks = 0; ks < 8; ++ks) v += red[(size_t)ks * 16 * MB8 + r * MB8 + b];
+        for (int ks = 0; ks < 8; ++ks) v += red[(size_t)ks * 16 * RS + r * RS + b];
         v += sbias[r];
         if (p.gelu) v = gelu_erf(v);
         reinterpret_cast<float*>(p.out)[(size_t)b * p.N + n] = resid[j] + v;
@@ -324,7 +333,7 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
     const int n = n_cta + rr;
     if (n >= p.N) continue;
     float v = 0.f;
-    for (int ks = 0; ks < KS; ++ks) v += red[(size_t)(ks * S + st) * 16 * MB8 + r * MB8 + b];
+    for (int ks = 0; ks < KS; ++ks) v += red[(size_t)(ks * S + st) * 16 * RS + r * RS + b];
     v += sbias[rr];
     if (p.gelu) v = gelu_erf(v);
     switch (p.out_mode) {
@@ -365,8 +374,9 @@ __global__ void __launch_bounds__(kSkThreads) logits_gemm_kernel(SkinnyDesc p, i
   const int xs_stride = p.K * 2 + 64;
   unsigned char* xs = smem_raw;
   constexpr int MB8 = MT * 8;
-  float* red = reinterpret_cast<float*>(smem_raw + (size_t)MB8 * xs_stride);   // [128][MB8]
-  float* sg = red + 128 * MB8;
+  constexpr int RS = MB8 + 1;                                                  // padded: conflict-free transposed reads
+  float* red = reinterpret_cast<float*>(smem_raw + (size_t)MB8 * xs_stride);   // [128][RS]
+  float* sg = red + 128 * RS;
   float* sb = sg + p.K;
   const int nblk = p.K / 32;
   constexpr int kPre = 8;
@@ -407,7 +417,7 @@ __global__ void __launch_bounds__(kSkThreads) logits_gemm_kernel(SkinnyDesc p, i
         for (int i = 0; i < 16; ++i) {
           const int c = c0 + (sub + 8 * i) * 4;
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (c < p.K) v[i] = __ldcg(reinterpret_cast<const float4*>(src + c));
+          if (c < p.K) v[i] = ld_x4(src + c);
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -430,7 +440,7 @@ __global__ void __launch_bounds__(kSkThreads) logits_gemm_kernel(SkinnyDesc p, i
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int c = c0 + (sub + 8 * i) * 4;
-            if (c < p.K) v[i] = __ldcg(reinterpret_cast<const float4*>(src + c));
+            if (c < p.K) v[i] = ld_x4(src + c);
           }
         }
 #pragma unroll
@@ -495,10 +505,10 @@ __global__ void __launch_bounds__(kSkThreads) logits_gemm_kernel(SkinnyDesc p, i
     // accumulators -> red[row in group][sequence]
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-      red[(warp * 16 + grp) * MB8 + mt * 8 + 2 * tq] = acc[mt][0];
-      red[(warp * 16 + grp) * MB8 + mt * 8 + 2 * tq + 1] = acc[mt][1];
-      red[(warp * 16 + grp + 8) * MB8 + mt * 8 + 2 * tq] = acc[mt][2];
-      red[(warp * 16 + grp + 8) * MB8 + mt * 8 + 2 * tq + 1] = acc[mt][3];
+      red[(warp * 16 + grp) * RS + mt * 8 + 2 * tq] = acc[mt][0];
+      red[(warp * 16 + grp) * RS + mt * 8 + 2 * tq + 1] = acc[mt][1];
+      red[(warp * 16 + grp + 8) * RS + mt * 8 + 2 * tq] = acc[mt][2];
+      red[(warp * 16 + grp + 8) * RS + mt * 8 + 2 * tq + 1] = acc[mt][3];
     }
     __syncthreads();
     // warp per sequence: filter, optional store, group-local (max, argmax, sum-exp)
@@ -511,7 +521,7 @@ __global__ void __launch_bounds__(kSkThreads) logits_gemm_kernel(SkinnyDesc p, i
         const int rr = lane + 32 * i, n = g * 128 + rr;
         float x = -INFINITY;
         if (n < p.N) {
-          x = red[rr * MB8 + b];
+          x = red[rr * RS + b];
           const unsigned char mk = p.mask ? p.mask[n] : 0;
           if (mk == 1 || (mk == 2 && first)) x = -INFINITY;
           if (p.out) reinterpret_cast<float*>(p.out)[(size_t)b * p.N + n] = x;
@@ -580,7 +590,7 @@ int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches) 
     }
     const int n_groups = skinny_logits_ctas(d.N);
     const int MTl = (d.Mb + 7) / 8;
-    const size_t sm = (size_t)MTl * 8 * (d.K * 2 + 64) + (size_t)128 * MTl * 8 * 4 + (size_t)2 * d.K * 4;
+    const size_t sm = (size_t)MTl * 8 * (d.K * 2 + 64) + (size_t)128 * (MTl * 8 + 1) * 4 + 16 + (size_t)2 * d.K * 4;
     static int n_sm = 0;
     if (!n_sm) {
       int dev = 0;
@@ -622,7 +632,7 @@ int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches) 
   SkinnyArgs a{d, S};
   const int MT = (d.Mb + 7) / 8;
   const int KC = d.K < kSkKC ? d.K : kSkKC;
-  const size_t smem = (size_t)MT * 8 * (KC * 2 + 64) + (size_t)8 * 16 * MT * 8 * 4 + 128 * 4 + (d.in_mode == SKINNY_IN_LN ? (size_t)2 * d.K * 4 : 0);
+  const size_t smem = (size_t)MT * 8 * (KC * 2 + 64) + (size_t)8 * 16 * (MT * 8 + 1) * 4 + 128 * 4 + (d.in_mode == SKINNY_IN_LN ? (size_t)2 * d.K * 4 : 0);
   const int grid = (strips + S - 1) / S;
   cudaError_t le = cudaSuccess;
 #define WB_SK_CASE(M)                                                                                             \

@@ -1,2 +1,6 @@
 cd /root/repo
-for pf in 0 2 4 6 9; do echo "== L2PF=$pf"; WB_HA_L2PF=$pf timeout 300 python tools/gpu_bringup.py bench 2>&1 | tail -1 | grep -o "| [0-9.]*ms timings.*" | tail -c 100; done
+(cd oracle && make -s)
+python tools/det.py
+echo "== pytest =="; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python tools/trace_step.py base.en 32 24 2>&1 | tail -13
+timeout 300 python tools/gpu_bringup.py bench 2>&1 | tail -1 | grep -o "| [0-9.]*ms timings.*" | tail -c 110

@@ -30,8 +30,8 @@ prev_end = t0
 print(f"{n} records; last step has {e - s} kernels")
 for i in range(s, e):
     kid, st, en = int(rec[i, 0]), int(rec[i, 1]), int(rec[i, 2])
-    marks = " ".join(f"{(int(rec[i, k]) - t0) / 1e3:7.2f}" if rec[i, k] else "      -" for k in (3, 4, 5))
-    print(f"{names.get(kid, kid):22s} start {((st - t0) / 1e3):8.2f} end {((en - t0) / 1e3):8.2f}  after_prev_end {((en - prev_end) / 1e3):6.2f} | wait/prologue/mainloop done at {marks}")
+    marks = " ".join(f"{(int(rec[i, k]) - t0) / 1e3:7.2f}" if rec[i, k] else "      -" for k in (3, 6, 7, 4, 5))
+    print(f"{names.get(kid, kid):22s} start {((st - t0) / 1e3):8.2f} end {((en - t0) / 1e3):8.2f}  after_prev_end {((en - prev_end) / 1e3):6.2f} | wait/ld+sum/shfl/prologue/mainloop done at {marks}")
     prev_end = en
 print("step total us", (int(rec[e - 1, 2]) - t0) / 1e3)
 w.close()
