@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwhisper_b200.so")
 SOURCES = ["logmel.cu", "gemm.cu", "rowops.cu", "attention_enc.cu", "decoder.cu", "model.cu"]
-NVCC_FLAGS = (["-DWB_EXPERIMENT_XLD_NC"] if os.environ.get("WB_EXPERIMENT_XLD_NC") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-cudart", "static"]
 
 

@@ -9,9 +9,8 @@
 //                         fused too (GELU, residual +=, QKV scatter straight into the self-attention cache). Weights are
 //                         read exactly once with 16-byte coalesced loads directly into mma.sync A fragments (the k index
 //                         inside a 32-wide block is permuted identically for both operands, so no shuffle is needed).
-//   attn_decode_kernel    one query per (sequence, head) over the cached K/V rows: each warp streams whole [d]-wide rows
-//                         (all heads at once, 16 B per lane), 8-lane shuffle dot products, online softmax in fp32,
-//                         split over rows across CTAs; the last CTA of a sequence to finish merges the split partials
+//   attn_decode_head_kernel  one CTA per (sequence, head): K/V streamed by TMA through a shared-memory ring, scores and
+//                         P*V on mma.sync, fp32 online softmax; no row split, so no partials and no merge
 //   step_finish_kernel    merges the per-CTA (max, argmax, sum-exp) partials the logits GEMM epilogue produced (logit
 //                         filters already applied there), EOT forcing, log-prob accumulation, token append, then embeds
 //                         the next token (+ learned position) into the residual stream and advances the position
@@ -60,15 +59,7 @@ struct TraceScope {
 };
 
 // ---- skinny GEMM -----------------------------------------------------------------------------------------------------------
-#ifdef WB_EXPERIMENT_XLD_NC
-__device__ __forceinline__ float4 ld_x4(const float* p) {
-  float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-  return r;
-}
-#else
 __device__ __forceinline__ float4 ld_x4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
-#endif
 constexpr int kSkThreads = 256;
 constexpr int kSkKC = 2048;   // activation columns staged in shared memory at a time
 
@@ -656,453 +647,6 @@ int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches) 
   return 0;
 }
 
-// Merge of the row-split partials of one sequence by the last CTA to arrive (fixed split order -> deterministic).
-// All loads of a pass are independent and issued together: a serial loop over the splits costs one L2 round trip per
-// split and used to dominate the kernel (~10 us of a 24 us launch).
-__device__ __forceinline__ void merge_splits(const AttnDecodeDesc& p, int b, float* sm /* >= 2*n_split*H floats */, int tid,
-                                             int nthreads) {
-  const int H = p.n_head, d = p.d, NS = p.n_split;
-  const float* all_ml = p.part_ml + (size_t)b * NS * H * 2;
-  const float* all_acc = p.part_acc + (size_t)b * NS * d;
-  float* sm_m = sm;              // [NS][H] -> overwritten with the normalised weights
-  float* sm_l = sm + NS * H;     // [NS][H]
-  for (int i = tid; i < NS * H; i += nthreads) {
-    sm_m[i] = __ldcg(all_ml + i * 2);
-    sm_l[i] = __ldcg(all_ml + i * 2 + 1);
-  }
-  __syncthreads();
-  for (int h = tid; h < H; h += nthreads) {
-    float M = -INFINITY;
-    for (int s2 = 0; s2 < NS; ++s2) M = fmaxf(M, sm_m[s2 * H + h]);
-    float L = 0.f;
-    for (int s2 = 0; s2 < NS; ++s2) {
-      const float ms = sm_m[s2 * H + h];
-      const float wgt = (ms == -INFINITY) ? 0.f : exp2f(ms - M);
-      L += wgt * sm_l[s2 * H + h];
-      sm_m[s2 * H + h] = wgt;
-    }
-    const float inv = 1.0f / L;
-    for (int s2 = 0; s2 < NS; ++s2) sm_m[s2 * H + h] *= inv;
-  }
-  __syncthreads();
-  for (int c = tid; c < d; c += nthreads) {
-    const int h = c >> 6;
-    float A = 0.f;
-    for (int s0 = 0; s0 < NS; s0 += 8) {
-      float a[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) a[u] = (s0 + u < NS) ? __ldcg(all_acc + (size_t)(s0 + u) * d + c) : 0.f;
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (s0 + u < NS) A = fmaf(sm_m[(s0 + u) * H + h], a[u], A);
-    }
-    p.out16[(size_t)b * d + c] = __float2half_rn(A);
-  }
-  if (tid == 0) p.counters[b] = 0;   // ready for the next launch (graph replay)
-}
-
-// ---- decode attention --------------------------------------------------------------------------------------------------------
-constexpr int kAdThreads = 256;
-
-template <int NJ, int RB>
-__global__ void __launch_bounds__(kAdThreads) attn_decode_kernel(AttnDecodeDesc p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_last;
-  const int H = p.n_head, d = p.d;
-  float* wm = reinterpret_cast<float*>(smem_raw);   // [8][H]
-  float* wl = wm + 8 * H;                           // [8][H]
-  float* wacc = wl + 8 * H;                         // [8][d]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int split = blockIdx.x, b = blockIdx.y;
-  ptx::grid_dep_launch();
-  ptx::grid_dep_sync();
-  const int n_rows = p.n_rows_fixed > 0 ? p.n_rows_fixed : ld_state(&p.state->cur_len) + 1;
-  const size_t slab = (size_t)(b / p.kv_share) * p.n_ctx * d;
-  const __half* K = p.k + slab;
-  const __half* V = p.v + slab;
-  const int n_chunks = d >> 3;
-  const float sl = 0.125f * kLog2e;   // (d_head^-0.25)^2 = 1/8 exactly; scores kept in the log2 domain
-
-  float qf[NJ][8], acc[NJ][8], m[NJ], l[NJ];
-  bool valid[NJ];
-#pragma unroll
-  for (int j = 0; j < NJ; ++j) {
-    const int c = lane + 32 * j;
-    valid[j] = c < n_chunks;
-    m[j] = -INFINITY, l[j] = 0.f;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[j][e] = 0.f, qf[j][e] = 0.f;
-    if (valid[j]) {
-      const float4 q0 = __ldcg(reinterpret_cast<const float4*>(p.q + (size_t)b * d + c * 8));
-      const float4 q1 = __ldcg(reinterpret_cast<const float4*>(p.q + (size_t)b * d + c * 8 + 4));
-      qf[j][0] = q0.x * sl, qf[j][1] = q0.y * sl, qf[j][2] = q0.z * sl, qf[j][3] = q0.w * sl;
-      qf[j][4] = q1.x * sl, qf[j][5] = q1.y * sl, qf[j][6] = q1.z * sl, qf[j][7] = q1.w * sl;
-    }
-  }
-  const int n_units = (n_rows + RB - 1) / RB;
-  for (int u = split * 8 + warp; u < n_units; u += p.n_split * 8) {
-    const int r0 = u * RB;
-    uint4 kr[RB][NJ], vr[RB][NJ];
-#pragma unroll
-    for (int i = 0; i < RB; ++i) {
-      const int row = (r0 + i < n_rows) ? r0 + i : n_rows - 1;
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        if (valid[j]) {
-          kr[i][j] = ptx::ldg_nc_16(K + (size_t)row * d + (lane + 32 * j) * 8);
-          vr[i][j] = ptx::ldg_nc_16(V + (size_t)row * d + (lane + 32 * j) * 8);
-        } else {
-          kr[i][j] = make_uint4(0, 0, 0, 0);
-          vr[i][j] = make_uint4(0, 0, 0, 0);
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      float sc[RB];
-#pragma unroll
-      for (int i = 0; i < RB; ++i) {
-        const __half2* kh = reinterpret_cast<const __half2*>(&kr[i][j]);
-        float s = 0.f;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 kf = __half22float2(kh[e]);
-          s = fmaf(qf[j][2 * e], kf.x, s);
-          s = fmaf(qf[j][2 * e + 1], kf.y, s);
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        sc[i] = (r0 + i < n_rows) ? s : -INFINITY;
-      }
-      float mx = sc[0];
-#pragma unroll
-      for (int i = 1; i < RB; ++i) mx = fmaxf(mx, sc[i]);
-      const float m_new = fmaxf(m[j], mx);
-      const float corr = exp2f(m[j] - m_new);
-      float pr[RB], ps = 0.f;
-#pragma unroll
-      for (int i = 0; i < RB; ++i) {
-        pr[i] = exp2f(sc[i] - m_new);
-        ps += pr[i];
-      }
-      l[j] = l[j] * corr + ps;
-      m[j] = m_new;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[j][e] *= corr;
-#pragma unroll
-      for (int i = 0; i < RB; ++i) {
-        const __half2* vh = reinterpret_cast<const __half2*>(&vr[i][j]);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 vf = __half22float2(vh[e]);
-          acc[j][2 * e] = fmaf(pr[i], vf.x, acc[j][2 * e]);
-          acc[j][2 * e + 1] = fmaf(pr[i], vf.y, acc[j][2 * e + 1]);
-        }
-      }
-    }
-  }
-  // per-warp partials -> shared
-#pragma unroll
-  for (int j = 0; j < NJ; ++j) {
-    if (valid[j]) {
-      const int c = lane + 32 * j;
-      if ((c & 7) == 0) {
-        wm[warp * H + (c >> 3)] = m[j];
-        wl[warp * H + (c >> 3)] = l[j];
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) wacc[(size_t)warp * d + c * 8 + e] = acc[j][e];
-    }
-  }
-  __syncthreads();
-  float* out_acc = p.part_acc + ((size_t)b * p.n_split + split) * d;
-  float* out_ml = p.part_ml + ((size_t)b * p.n_split + split) * H * 2;
-  for (int c = tid; c < d; c += kAdThreads) {
-    const int h = c >> 6;
-    float M = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) M = fmaxf(M, wm[w * H + h]);
-    float L = 0.f, A = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      const float mw = wm[w * H + h];
-      const float wgt = (mw == -INFINITY) ? 0.f : exp2f(mw - M);
-      L += wgt * wl[w * H + h];
-      A += wgt * wacc[(size_t)w * d + c];
-    }
-    if (p.n_split == 1) {
-      p.out16[(size_t)b * d + c] = __float2half_rn(A / L);
-    } else {
-      out_acc[c] = A;
-      if ((c & 63) == 0) {
-        out_ml[h * 2] = M;
-        out_ml[h * 2 + 1] = L;
-      }
-    }
-  }
-  if (p.n_split == 1) return;
-  // the last CTA of this sequence to arrive merges the splits (fixed split order -> deterministic result)
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const int ticket = atomicAdd(&p.counters[b], 1);
-    s_last = ticket == p.n_split - 1;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  merge_splits(p, b, reinterpret_cast<float*>(smem_raw), tid, kAdThreads);
-}
-
-// ---- KV-cache attention, tensor-core form ------------------------------------------------------------------------------------
-// The register kernel above is instruction-issue bound (~85 warp instructions per KB of K/V: unpack, FMA, shuffles), which
-// caps it near 60 % of HBM bandwidth. This kernel does the same math with ~6x fewer instructions:
-//   * one producer thread streams 16-row K and V tiles into a shared-memory ring with cp.async.bulk (one 2d-byte copy per
-//     row, rows padded by 16 B so ldmatrix is bank-conflict free), full/empty mbarriers per stage; for the cross-attention
-//     K/V (constant during a decode) it starts before griddepcontrol.wait, i.e. while the previous kernel still runs
-//   * each compute warp owns whole heads: scores S[16 rows] = K_tile(16 x 64) q via 4 mma.sync m16n8k16 (q replicated over the
-//     8 columns, so every lane ends up holding the scores of rows g and g+8), online softmax in fp32 in the log2 domain,
-//     O(64) += V_tile^T(64 x 16) p via 4 mma.sync with ldmatrix.trans (p replicated over the columns)
-//   * a head is never split across warps, so the only merge is across the row splits (last CTA to arrive, fixed order)
-constexpr int kXaRows = 16;
-constexpr int kXaThreads = 288;   // 8 compute warps + 1 producer warp
-
-template <int HPW>   // heads per compute warp = ceil(H / 8)
-__global__ void __launch_bounds__(kXaThreads) attn_decode_mma_kernel(AttnDecodeDesc p, int n_stages, int copy_mode) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8];
-  __shared__ int s_last;
-  const int H = p.n_head, d = p.d;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int grp = lane >> 2, tq = lane & 3, mi = lane >> 3, r8 = lane & 7;
-  const int split = blockIdx.x, b = blockIdx.y;
-  const int row_stride = copy_mode == 1 ? d * 2 : d * 2 + 16;   // bytes (copy_mode 1 = experiment: dense tiles, one copy each)
-  const int tile_bytes = kXaRows * row_stride;            // one K (or V) tile
-  const bool fixed = p.n_rows_fixed > 0;
-
-  // zero the ring once: rows past the end of a partial tile are multiplied by p = 0 and must not hold NaN bit patterns
-  for (int i = tid * 16; i < n_stages * 2 * tile_bytes; i += kXaThreads * 16) *reinterpret_cast<uint4*>(smem_raw + i) = make_uint4(0, 0, 0, 0);
-  if (tid == 0) {
-    for (int s = 0; s < n_stages; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 8);
-    }
-    ptx::fence_mbar_init();
-  }
-  ptx::fence_proxy_async();
-  __syncthreads();
-  ptx::grid_dep_launch();
-  if (!fixed || warp < 8) ptx::grid_dep_sync();           // q (and the newest self-attention K/V row) come from the previous kernel
-
-  const int n_rows = fixed ? p.n_rows_fixed : ld_state(&p.state->cur_len) + 1;
-  const size_t slab = (size_t)(b / p.kv_share) * p.n_ctx * d;
-  const __half* K = p.k + slab;
-  const __half* V = p.v + slab;
-  const int n_tiles_all = (n_rows + kXaRows - 1) / kXaRows;
-  const int t_begin = (split * n_tiles_all) / p.n_split, t_end = ((split + 1) * n_tiles_all) / p.n_split;
-  const int my_tiles = t_end - t_begin;
-
-  float o[HPW][4][4], m[HPW], l[HPW];
-#pragma unroll
-  for (int i = 0; i < HPW; ++i) {
-    m[i] = -INFINITY, l[i] = 0.f;
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt) o[i][mt][0] = o[i][mt][1] = o[i][mt][2] = o[i][mt][3] = 0.f;
-  }
-
-  if (warp == 8) {
-    for (int t = 0; t < my_tiles; ++t) {
-      const int s = t % n_stages;
-      const uint32_t ph = (uint32_t)(t / n_stages) & 1u;
-      const int row0 = (t_begin + t) * kXaRows;
-      const int rows = (n_rows - row0) < kXaRows ? (n_rows - row0) : kXaRows;
-      unsigned char* dk = smem_raw + (size_t)s * 2 * tile_bytes;
-      unsigned char* dv = dk + tile_bytes;
-      if (lane == 0) {
-        ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
-        ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(2 * rows * d * 2));
-      }
-      __syncwarp();
-      if (copy_mode == 1) {
-        if (lane == 0) {
-          ptx::bulk_load(dk, K + (size_t)row0 * d, (uint32_t)(rows * d * 2), &full_bar[s]);
-          ptx::bulk_load(dv, V + (size_t)row0 * d, (uint32_t)(rows * d * 2), &full_bar[s]);
-        }
-      } else if (copy_mode == 2) {
-        if (lane == 0) {
-          for (int r = 0; r < rows; ++r) {
-            ptx::bulk_load(dk + r * row_stride, K + (size_t)(row0 + r) * d, (uint32_t)(d * 2), &full_bar[s]);
-            ptx::bulk_load(dv + r * row_stride, V + (size_t)(row0 + r) * d, (uint32_t)(d * 2), &full_bar[s]);
-          }
-        }
-      } else {   // one row per lane: lanes 0-15 copy K rows, lanes 16-31 copy V rows
-        const int r = lane & 15;
-        if (r < rows) {
-          if (lane < 16)
-            ptx::bulk_load(dk + r * row_stride, K + (size_t)(row0 + r) * d, (uint32_t)(d * 2), &full_bar[s]);
-          else
-            ptx::bulk_load(dv + r * row_stride, V + (size_t)(row0 + r) * d, (uint32_t)(d * 2), &full_bar[s]);
-        }
-      }
-      __syncwarp();
-    }
-  } else {
-    // B fragments of q (fp16, pre-scaled into the log2 domain; (d_head^-0.25)^2 = 1/8 exactly), replicated over the n columns
-    const float sl = 0.125f * kLog2e;
-    uint32_t qb[HPW][4][2];
-#pragma unroll
-    for (int i = 0; i < HPW; ++i) {
-      const int h = warp + 8 * i;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        qb[i][kk][0] = qb[i][kk][1] = 0u;
-        if (h < H) {
-          const float* qp = p.q + (size_t)b * d + h * 64 + kk * 16 + 2 * tq;
-          const float2 q0 = __ldcg(reinterpret_cast<const float2*>(qp)), q1 = __ldcg(reinterpret_cast<const float2*>(qp + 8));
-          __half2 h0 = __floats2half2_rn(q0.x * sl, q0.y * sl), h1 = __floats2half2_rn(q1.x * sl, q1.y * sl);
-          qb[i][kk][0] = *reinterpret_cast<uint32_t*>(&h0), qb[i][kk][1] = *reinterpret_cast<uint32_t*>(&h1);
-        }
-      }
-    }
-    for (int t = 0; t < my_tiles; ++t) {
-      const int s = t % n_stages;
-      const uint32_t ph = (uint32_t)(t / n_stages) & 1u;
-      ptx::mbar_wait(&full_bar[s], ph);
-      const uint32_t sk = ptx::smem_u32(smem_raw + (size_t)s * 2 * tile_bytes);
-      const uint32_t sv = sk + tile_bytes;
-      const int row0 = (t_begin + t) * kXaRows;
-#pragma unroll
-      for (int i = 0; i < HPW; ++i) {
-        const int h = warp + 8 * i;
-        if (h >= H) break;                                 // warp-uniform
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          uint32_t a[4];
-          ptx::ldmatrix_x4(a, sk + ((mi & 1) * 8 + r8) * row_stride + (h * 64 + kk * 16 + (mi >> 1) * 8) * 2);
-          ptx::mma_16816(c, a, qb[i][kk]);
-        }
-        const float s_lo = (row0 + grp < n_rows) ? c[0] : -INFINITY;
-        const float s_hi = (row0 + grp + 8 < n_rows) ? c[2] : -INFINITY;
-        float tmax = fmaxf(s_lo, s_hi);
-        tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 4));
-        tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 8));
-        tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 16));
-        if (tmax > m[i]) {                                 // warp-uniform: m and tmax are identical in every lane
-          const float corr = exp2f(m[i] - tmax);           // m = -inf on the first tile -> 0
-          m[i] = tmax;
-          l[i] *= corr;
-#pragma unroll
-          for (int mt = 0; mt < 4; ++mt) o[i][mt][0] *= corr, o[i][mt][1] *= corr, o[i][mt][2] *= corr, o[i][mt][3] *= corr;
-        }
-        const float p_lo = exp2f(s_lo - m[i]), p_hi = exp2f(s_hi - m[i]);   // row 0 of the tile is always valid -> m finite
-        l[i] += p_lo + p_hi;                               // this lane's rows g and g+8 (same in the 4 lanes of a quad)
-        // B fragment of p: k = 2tq, 2tq+1 (from the lanes holding rows 2tq, 2tq+1) and k = 2tq+8, 2tq+9
-        const float e0 = __shfl_sync(0xffffffffu, p_lo, (2 * tq) * 4), e1 = __shfl_sync(0xffffffffu, p_lo, (2 * tq + 1) * 4);
-        const float e2 = __shfl_sync(0xffffffffu, p_hi, (2 * tq) * 4), e3 = __shfl_sync(0xffffffffu, p_hi, (2 * tq + 1) * 4);
-        __half2 pb0 = __floats2half2_rn(e0, e1), pb1 = __floats2half2_rn(e2, e3);
-        const uint32_t pb[2] = {*reinterpret_cast<uint32_t*>(&pb0), *reinterpret_cast<uint32_t*>(&pb1)};
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
-          uint32_t a[4];
-          ptx::ldmatrix_x4_trans(a, sv + ((mi >> 1) * 8 + r8) * row_stride + (h * 64 + mt * 16 + (mi & 1) * 8) * 2);
-          ptx::mma_16816(o[i][mt], a, pb);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&empty_bar[s]);
-    }
-  }
-  // ---- results: lanes with tq == 0 hold O[mt*16 + g] (c0) and O[mt*16 + g + 8] (c2) of their heads --------------------------------
-  float* out_acc = p.part_acc + ((size_t)b * p.n_split + split) * d;
-  float* out_ml = p.part_ml + ((size_t)b * p.n_split + split) * H * 2;
-  if (warp < 8) {
-#pragma unroll
-    for (int i = 0; i < HPW; ++i) {
-      const int h = warp + 8 * i;
-      if (h >= H) break;
-      float L = l[i];
-      L += __shfl_xor_sync(0xffffffffu, L, 4);
-      L += __shfl_xor_sync(0xffffffffu, L, 8);
-      L += __shfl_xor_sync(0xffffffffu, L, 16);
-      if (tq == 0) {
-        if (p.n_split == 1) {
-          const float inv = 1.0f / L;
-#pragma unroll
-          for (int mt = 0; mt < 4; ++mt) {
-            p.out16[(size_t)b * d + h * 64 + mt * 16 + grp] = __float2half_rn(o[i][mt][0] * inv);
-            p.out16[(size_t)b * d + h * 64 + mt * 16 + grp + 8] = __float2half_rn(o[i][mt][2] * inv);
-          }
-        } else {
-#pragma unroll
-          for (int mt = 0; mt < 4; ++mt) {
-            out_acc[h * 64 + mt * 16 + grp] = o[i][mt][0];
-            out_acc[h * 64 + mt * 16 + grp + 8] = o[i][mt][2];
-          }
-          if (grp == 0) out_ml[h * 2] = m[i], out_ml[h * 2 + 1] = L;
-        }
-      }
-    }
-  }
-  if (p.n_split == 1) return;
-  // the last CTA of this sequence to arrive merges the splits (fixed split order -> deterministic result)
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const int ticket = atomicAdd(&p.counters[b], 1);
-    s_last = ticket == p.n_split - 1;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  merge_splits(p, b, reinterpret_cast<float*>(smem_raw), tid, kXaThreads);
-}
-
-static int launch_attn_decode_mma(const AttnDecodeDesc& p, cudaStream_t st, int64_t* launches) {
-  const int HPW = (p.n_head + 7) / 8;
-  const int stage_bytes = 2 * kXaRows * (p.d * 2 + 16);
-  int n_stages = (110 * 1024) / stage_bytes;          // two CTAs per SM when possible
-  n_stages = n_stages > 8 ? 8 : n_stages;
-  if (n_stages < 2) n_stages = 2;
-  static int copy_mode = -1, stages_env = 0;
-  if (copy_mode < 0) {
-    const char* e = getenv("WB_XA_COPY");
-    copy_mode = e ? atoi(e) : 0;
-    const char* e2 = getenv("WB_XA_STAGES");
-    stages_env = e2 ? atoi(e2) : 0;
-  }
-  if (stages_env > 0) n_stages = stages_env;
-  const size_t smem = (size_t)n_stages * stage_bytes;
-  dim3 grid(p.n_split, p.Mb);
-  cudaError_t le = cudaSuccess;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid, cfg.blockDim = dim3(kXaThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at, cfg.numAttrs = use_pdl() ? 1 : 0;
-#define WB_XA_CASE(J)                                                                                                  \
-  case J: {                                                                                                            \
-    static size_t smem_set = 0;                                                                                        \
-    if (smem > smem_set) {                                                                                             \
-      WB_CUDA_OK(cudaFuncSetAttribute(attn_decode_mma_kernel<J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      smem_set = smem;                                                                                                 \
-    }                                                                                                                  \
-    le = cudaLaunchKernelEx(&cfg, attn_decode_mma_kernel<J>, p, n_stages, copy_mode);                                             \
-  } break;
-  switch (HPW) {
-    WB_XA_CASE(1) WB_XA_CASE(2) WB_XA_CASE(3)
-    default:
-      set_error("attn_decode: too many heads");
-      return -1;
-  }
-#undef WB_XA_CASE
-  if (launches) *launches += 1;
-  WB_CUDA_OK(le);
-  return 0;
-}
-
 // ---- KV-cache attention, one CTA per (sequence, head) ---------------------------------------------------------------------------
 // No row split, hence no partials, no fence/atomic and no merge pass: a CTA streams the [n_rows][64] K and V slabs of its
 // head through a shared-memory ring with TMA tensor copies (box 64 x 128 rows, 128-byte swizzle -> conflict-free ldmatrix,
@@ -1323,42 +867,11 @@ static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int
 }
 
 int launch_attn_decode(const AttnDecodeDesc& p, cudaStream_t st, int64_t* launches) {
-  if (p.d % 64 != 0 || p.d / 64 != p.n_head || p.d > 1280 || p.kv_share < 1 || p.n_split < 1) {
+  if (p.d % 64 != 0 || p.d / 64 != p.n_head || p.d > 1280 || p.kv_share < 1) {
     set_error("attn_decode: unsupported d=%d heads=%d", p.d, p.n_head);
     return -1;
   }
-  // WB_ATTN_IMPL: "head" (default) = one CTA per (sequence, head), TMA + mma.sync, no row split; "hx" = that kernel for cross
-  // attention only; "mma" = row-split tensor-core kernel; "reg" = row-split register kernel (development A/B switches)
-  static int impl = -1;
-  if (impl < 0) {
-    const char* e = getenv("WB_ATTN_IMPL");
-    impl = !e ? 3 : (e[0] == 'r' ? 0 : (e[0] == 'm' ? 1 : (e[0] == 'c' ? 2 : (e[1] == 'x' ? 4 : 3))));
-  }
-  if (impl == 3 || (impl == 4 && p.n_rows_fixed > 0)) return launch_attn_decode_head(p, st, launches);
-  if (impl == 1 || (impl == 2 && p.n_rows_fixed > 0)) return launch_attn_decode_mma(p, st, launches);
-  const int NJ = (p.d / 8 + 31) / 32;
-  const size_t smem = (size_t)(16 * p.n_head + 8 * p.d) * 4;
-  dim3 grid(p.n_split, p.Mb);
-  cudaError_t le = cudaSuccess;
-#define WB_AD_CASE(J, R)                                                                                          \
-  case J: {                                                                                                       \
-    static bool attr_set = false;                                                                                 \
-    if (!attr_set) {                                                                                              \
-      WB_CUDA_OK(cudaFuncSetAttribute(attn_decode_kernel<J, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024)); \
-      attr_set = true;                                                                                            \
-    }                                                                                                             \
-    le = launch_pdl(attn_decode_kernel<J, R>, grid, dim3(kAdThreads), smem, st, p);                               \
-  } break;
-  switch (NJ) {
-    WB_AD_CASE(1, 4) WB_AD_CASE(2, 4) WB_AD_CASE(3, 2) WB_AD_CASE(4, 2) WB_AD_CASE(5, 2)
-    default:
-      set_error("attn_decode: width too large");
-      return -1;
-  }
-#undef WB_AD_CASE
-  if (launches) *launches += 1;
-  WB_CUDA_OK(le);
-  return 0;
+  return launch_attn_decode_head(p, st, launches);
 }
 
 // ---- end of step: sample (optional), embed the next token, advance -------------------------------------------------------------

@@ -9,8 +9,6 @@
 //   warp 1   TMEM allocator + MMA issuer: 4 x tcgen05.mma (M=128, N=BN, K=16) per stage, tcgen05.commit frees the stage
 //   warps 2-5 epilogue: tcgen05.ld the fp32 accumulator (one TMEM lane = one output row per thread), bias / exact-erf
 //            GELU / residual in registers, fp16 and/or fp32 stores
-// A second kernel (gemm_mma_kernel, mma.sync) computes the same contract without TMA/tcgen05. It exists for bring-up
-// and as the in-GPU cross-check of the tcgen05 path (env WB_GEMM_IMPL=mma selects it); the product path is tcgen05.
 #include <cuda.h>
 
 #include <map>
@@ -173,78 +171,6 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
   }
 }
 
-// ---- mma.sync cross-check kernel: 64x64 tile, 4 warps (2x2), BK = 32 --------------------------------------------------------
-struct GemmMmaArgs {
-  const __half* a;
-  long long a_row_stride, a_batch_stride;
-  const __half* w;
-  GemmEpi ep;
-};
-__global__ void __launch_bounds__(128) gemm_mma_kernel(GemmMmaArgs g) {
-  __shared__ __align__(16) __half sA[64][40];
-  __shared__ __align__(16) __half sB[64][40];
-  const GemmEpi& ep = g.ep;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n0 = blockIdx.x * 64, t0 = blockIdx.y * 64, b = blockIdx.z;
-  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
-  const int grp = lane >> 2, tq = lane & 3;
-  float acc[2][4][4] = {};
-  const __half* abase = g.a + (long long)b * g.a_batch_stride;
-  for (int k0 = 0; k0 < ep.K; k0 += 32) {
-    // 64 rows x 32 halves = 256 chunks of 8 halves for A and for W; 2 each per thread
-    for (int c = tid; c < 256; c += 128) {
-      const int r = c >> 2, kc = (c & 3) * 8;
-      uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
-      if (t0 + r < ep.rows && k0 + kc < ep.K) va = *reinterpret_cast<const uint4*>(abase + (long long)(t0 + r) * g.a_row_stride + k0 + kc);
-      if (n0 + r < ep.N && k0 + kc < ep.K) vb = *reinterpret_cast<const uint4*>(g.w + (long long)(n0 + r) * ep.K + k0 + kc);
-      *reinterpret_cast<uint4*>(&sA[r][kc]) = va;
-      *reinterpret_cast<uint4*>(&sB[r][kc]) = vb;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < 32; kk += 16) {
-      uint32_t af[2][4], bf[4][2];
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int r = wm + i * 16 + grp;
-        af[i][0] = *reinterpret_cast<const uint32_t*>(&sA[r][kk + 2 * tq]);
-        af[i][1] = *reinterpret_cast<const uint32_t*>(&sA[r + 8][kk + 2 * tq]);
-        af[i][2] = *reinterpret_cast<const uint32_t*>(&sA[r][kk + 8 + 2 * tq]);
-        af[i][3] = *reinterpret_cast<const uint32_t*>(&sA[r + 8][kk + 8 + 2 * tq]);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = wn + j * 8 + grp;
-        bf[j][0] = *reinterpret_cast<const uint32_t*>(&sB[r][kk + 2 * tq]);
-        bf[j][1] = *reinterpret_cast<const uint32_t*>(&sB[r][kk + 8 + 2 * tq]);
-      }
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) ptx::mma_16816(acc[i][j], af[i], bf[j]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int t = t0 + wm + i * 16 + grp + (e >> 1) * 8;
-        const int n = n0 + wn + j * 8 + 2 * tq + (e & 1);
-        if (t >= ep.rows || n >= ep.N) continue;
-        const long long crow = (long long)b * ep.c_batch_rows + ep.c_row_off + t;
-        float v = acc[i][j][e];
-        if (ep.bias) v += ep.bias[n];
-        if (ep.gelu) v = gelu_erf(v);
-        if (ep.res_mode == 1) v += ep.res[crow * ep.ldc + n];
-        if (ep.res_mode == 2) v += ep.res[(long long)t * ep.N + n];
-        if (ep.c32) ep.c32[crow * ep.ldc + n] = v;
-        if (ep.c16) ep.c16[crow * ep.ldc + n] = __float2half_rn(v);
-      }
-}
-
 // ---- host: tensor maps ------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -252,14 +178,11 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 struct GemmContext {
   PFN_encodeTiled encode = nullptr;
-  int use_mma = 0;
   std::map<std::tuple<const void*, long long, long long, long long, long long, long long, int>, CUtensorMap> cache;
 };
 
 GemmContext* gemm_context_create() {
   GemmContext* c = new GemmContext();
-  const char* impl = getenv("WB_GEMM_IMPL");
-  c->use_mma = impl && std::string(impl) == "mma";
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
@@ -355,13 +278,6 @@ int launch_gemm(GemmContext* ctx, const GemmDesc& d, cudaStream_t st, int64_t* l
   ep.N = d.N, ep.K = d.K, ep.rows = d.rows, ep.gelu = d.gelu, ep.res_mode = d.res_mode, ep.ldc = d.ldc;
   ep.c_row_off = d.c_row_off, ep.c_batch_rows = d.c_batch_rows;
   if (launches) *launches += 1;
-  if (ctx->use_mma) {
-    GemmMmaArgs g{d.a, d.a_row_stride, d.a_batch_stride, d.w, ep};
-    dim3 grid(d.N / 64, (d.rows + 63) / 64, d.n_batch);
-    gemm_mma_kernel<<<grid, 128, 0, st>>>(g);
-    WB_CUDA_OK(cudaGetLastError());
-    return 0;
-  }
   return launch_tc<128>(ctx, d, ep, st);
 }
 

@@ -123,15 +123,13 @@ struct wb_handle {
   std::vector<__half*> selfK, selfV;
   int32_t* tokens;
   int tokens_ld;
-  float *xdec, *q32, *part_ml, *part_acc, *logits, *sum_logprob, *part_logits;
+  float *xdec, *q32, *logits, *sum_logprob, *part_logits;
   __half *dmlp16, *a16;
   int32_t* done;
-  int* counters;
   unsigned char* mask;
   int n_logit_ctas;
   DecodeState* state;
   unsigned long long* trace;   // WB_TRACE=1
-  int split_self, split_cross;
 
   // graphs
   cudaGraphExec_t g_step, g_sample;
@@ -262,15 +260,11 @@ static void layout_workspace(wb_handle* h) {
   h->tokens = A.take<int32_t>(Mb * h->tokens_ld);
   h->xdec = A.take<float>(Mb * dt);
   h->q32 = A.take<float>(Mb * dt);
-  const size_t smax = 32;
-  h->part_ml = A.take<float>(Mb * smax * D.n_text_head * 2);
-  h->part_acc = A.take<float>(Mb * smax * dt);
   h->dmlp16 = A.take<__half>(Mb * 4 * dt);
   h->logits = A.take<float>(Mb * (size_t)D.n_vocab);
   h->sum_logprob = A.take<float>(Mb);
   h->done = A.take<int32_t>(Mb);
   h->a16 = A.take<__half>(Mb * dt);
-  h->counters = A.take<int>(Mb);
   h->mask = A.take<unsigned char>((size_t)D.n_vocab);
   h->n_logit_ctas = skinny_logits_ctas(D.n_vocab);
   h->part_logits = A.take<float>(Mb * (size_t)h->n_logit_ctas * 4);
@@ -380,9 +374,8 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
     s.n_ctx = D.n_text_ctx;
     WB_TRY(launch_skinny_gemm(s, st, &h->launches));
     AttnDecodeDesc a{};
-    a.Mb = Mb, a.d = d, a.n_head = H, a.n_split = h->split_self, a.q = h->q32, a.k = h->selfK[l], a.v = h->selfV[l];
-    a.n_ctx = D.n_text_ctx, a.n_rows_fixed = 0, a.kv_share = 1, a.state = h->state, a.part_ml = h->part_ml, a.part_acc = h->part_acc;
-    a.counters = h->counters, a.out16 = h->a16, a.tmaps = h->gemm;
+    a.Mb = Mb, a.d = d, a.n_head = H, a.q = h->q32, a.k = h->selfK[l], a.v = h->selfV[l];
+    a.n_ctx = D.n_text_ctx, a.n_rows_fixed = 0, a.kv_share = 1, a.state = h->state, a.out16 = h->a16, a.tmaps = h->gemm;
     WB_TRY(launch_attn_decode(a, st, &h->launches));
     SkinnyDesc so{};
     so.Mb = Mb, so.state = h->state, so.N = d, so.K = d, so.w = L.wo, so.bias = L.bo, so.in_mode = SKINNY_IN_F16, so.in = h->a16;
@@ -394,7 +387,7 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
     sq.in = h->xdec, sq.ln_g = L.lnc_g, sq.ln_b = L.lnc_b, sq.out_mode = SKINNY_OUT_F32, sq.out = h->q32;
     WB_TRY(launch_skinny_gemm(sq, st, &h->launches));
     AttnDecodeDesc c = a;
-    c.n_split = h->split_cross, c.k = h->crossK[l], c.v = h->crossV[l], c.n_ctx = D.n_audio_ctx, c.n_rows_fixed = D.n_audio_ctx;
+    c.k = h->crossK[l], c.v = h->crossV[l], c.n_ctx = D.n_audio_ctx, c.n_rows_fixed = D.n_audio_ctx;
     c.kv_share = o.beams;
     WB_TRY(launch_attn_decode(c, st, &h->launches));
     SkinnyDesc sc = so;
@@ -426,18 +419,7 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
 static int reset_decode_state(wb_handle* h, const StepOpts& o) {
   DecodeState init{-1, 0, 0, 0, h->trace};
   WB_CUDA_OK(cudaMemcpyAsync(h->state, &init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
-  WB_CUDA_OK(cudaMemsetAsync(h->counters, 0, sizeof(int) * h->Mb_max, h->stream));
   return step_finish(h, o, 0);
-}
-
-static void pick_splits(wb_handle* h, int Mb) {
-  // one wave: at most 2 CTAs of the attention kernel fit an SM (registers), 148 SMs
-  int sc = 296 / Mb;
-  sc = sc < 1 ? 1 : (sc > 32 ? 32 : sc);
-  h->split_cross = sc;
-  int ss = 148 / Mb;
-  ss = ss < 1 ? 1 : (ss > 8 ? 8 : ss);
-  h->split_self = ss;
 }
 
 static void destroy_graphs(wb_handle* h) {
@@ -765,7 +747,6 @@ int wb_decoder_logits(wb_handle* h, const int32_t* tokens, int32_t B, int32_t t,
       }
   WB_CUDA_OK(cudaMemcpy2DAsync(h->tokens, h->tokens_ld * sizeof(int32_t), tokens, t * sizeof(int32_t), t * sizeof(int32_t), B,
                                cudaMemcpyHostToDevice, h->stream));
-  pick_splits(h, B);
   StepOpts o{};
   o.Mb = B, o.beams = 1, o.store_logits = 1, o.sample = 0;
   WB_TRY(reset_decode_state(h, o));
@@ -799,7 +780,6 @@ int wb_detect_language(wb_handle* h, int32_t B, int32_t sot, int32_t lang0, int3
   std::vector<int32_t> tk(B, sot);
   WB_CUDA_OK(cudaMemcpy2DAsync(h->tokens, h->tokens_ld * sizeof(int32_t), tk.data(), sizeof(int32_t), sizeof(int32_t), B,
                                cudaMemcpyHostToDevice, h->stream));
-  pick_splits(h, B);
   StepOpts o{};
   o.Mb = B, o.beams = 1, o.store_logits = 1, o.sample = 0;
   WB_TRY(reset_decode_state(h, o));
@@ -853,7 +833,6 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
   const bool use_graph = getenv("WB_NO_GRAPH") == nullptr;
   if (use_graph && h->graph_key != key) {
     destroy_graphs(h);
-    pick_splits(h, B);
     // one eager pass of each variant first: sets function attributes and faults in code outside of capture
     WB_TRY(reset_decode_state(h, plain));
     WB_TRY(decode_step(h, plain));
@@ -867,8 +846,6 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
     WB_CUDA_OK(cudaMemsetAsync(h->sum_logprob, 0, sizeof(float) * B, st));
     WB_CUDA_OK(cudaMemsetAsync(h->done, 0, sizeof(int32_t) * B, st));
     WB_CUDA_OK(cudaStreamSynchronize(st));
-  } else if (!use_graph) {
-    pick_splits(h, B);
   }
 
   WB_CUDA_OK(cudaEventRecord(h->ev[2], st));
@@ -979,12 +956,9 @@ int wb_profile_cross_attention(wb_handle* h, int32_t B, int32_t reps, float* avg
   WB_TRY(need_features(h, B));
   if (!avg_ms || reps < 1) return WB_ERR_ARG;
   const wb_dims& D = h->dims;
-  pick_splits(h, B);
   AttnDecodeDesc c{};
-  c.Mb = B, c.d = D.n_text_state, c.n_head = D.n_text_head, c.n_split = h->split_cross, c.q = h->q32;
-  c.n_ctx = D.n_audio_ctx, c.n_rows_fixed = D.n_audio_ctx, c.kv_share = 1, c.state = h->state;
-  c.part_ml = h->part_ml, c.part_acc = h->part_acc, c.counters = h->counters, c.out16 = h->a16, c.tmaps = h->gemm;
-  WB_CUDA_OK(cudaMemsetAsync(h->counters, 0, sizeof(int) * h->Mb_max, h->stream));
+  c.Mb = B, c.d = D.n_text_state, c.n_head = D.n_text_head, c.q = h->q32;
+  c.n_ctx = D.n_audio_ctx, c.n_rows_fixed = D.n_audio_ctx, c.kv_share = 1, c.state = h->state, c.out16 = h->a16, c.tmaps = h->gemm;
   for (int i = -3; i < reps; ++i) {   // 3 warm-up launches
     if (i == 0) WB_CUDA_OK(cudaEventRecord(h->ev[0], h->stream));
     const int l = ((i % D.n_text_layer) + D.n_text_layer) % D.n_text_layer;

@@ -103,7 +103,7 @@ int skinny_logits_ctas(int N);   // number of CTAs (= partials per sequence) of 
 
 // one query per (sequence, head) against rows [0, n_rows) of K/V [B][n_ctx][d] fp16 -> out16 [Mb][d] fp16
 struct AttnDecodeDesc {
-  int Mb, d, n_head, n_split;
+  int Mb, d, n_head;
   const float* q;         // [Mb][d] fp32
   const __half* k;        // [Mb / kv_share][n_ctx][d]
   const __half* v;
@@ -111,11 +111,8 @@ struct AttnDecodeDesc {
   int n_rows_fixed;       // >0: fixed row count (cross attention, 1500); 0: rows = state->cur_len + 1 (self attention)
   int kv_share;           // sequences per K/V slab (beam search: beams of one chunk share the cross K/V); >= 1
   const DecodeState* state;
-  float* part_ml;         // [Mb][S][H][2]  split partials (scratch)
-  float* part_acc;        // [Mb][S][d]
-  int* counters;          // [Mb] zero-initialised arrival counters (self-resetting)
   __half* out16;          // [Mb][d]
-  GemmContext* tmaps;     // tensor-map cache (head-per-CTA kernel)
+  GemmContext* tmaps;     // tensor-map cache
 };
 int launch_attn_decode(const AttnDecodeDesc& d, cudaStream_t st, int64_t* launches);
 

@@ -111,22 +111,9 @@ def run_gemm_cases(w):
 
 @section("gemm_tcgen05")
 def t_gemm_tc():
-    os.environ.pop("WB_GEMM_IMPL", None)
     w = wbm.Whisper("tiny.en", seed=1)
     r = run_gemm_cases(w)
     w.close()
-    return r
-
-
-@section("gemm_mma_crosscheck")
-def t_gemm_mma():
-    os.environ["WB_GEMM_IMPL"] = "mma"
-    try:
-        w = wbm.Whisper("tiny.en", seed=1)
-        r = run_gemm_cases(w)
-        w.close()
-    finally:
-        os.environ.pop("WB_GEMM_IMPL", None)
     return r
 
 
@@ -170,16 +157,11 @@ def t_att():
     return ("FAIL " if bad else "") + " ".join(msgs)
 
 
-def model_case(name, B, n_tok, sample_len, mma=False):
+def model_case(name, B, n_tok, sample_len):
     dims_ref = ref.DIMS[name]
     weights = ref.random_weights(dims_ref, seed=0)
     oracle = ref.WhisperRef(dims_ref, weights)
-    if mma:
-        os.environ["WB_GEMM_IMPL"] = "mma"
-    try:
-        w = wbm.Whisper(name, weights=weights, max_batch=B)
-    finally:
-        os.environ.pop("WB_GEMM_IMPL", None)
+    w = wbm.Whisper(name, weights=weights, max_batch=B)
     audio = np.stack([ref.synth_audio(100 + i, "noise") for i in range(B)])
     mel = torch.from_numpy(oracle_logmel(audio)).float()
     xa_ref = oracle.encode(mel)
@@ -213,11 +195,6 @@ def model_case(name, B, n_tok, sample_len, mma=False):
             f"greedy identical={same} first_div={first_div} slp d={np.abs(slp - slp_ref.numpy()).max():.3e} lang={lang}")
 
 
-@section("model_tiny.en_mma")
-def t_model_tiny_mma():
-    return model_case("tiny.en", 2, 5, 12, mma=True)
-
-
 @section("model_tiny.en_tc")
 def t_model_tiny():
     return model_case("tiny.en", 2, 5, 12)
@@ -247,8 +224,8 @@ def t_bench():
 if __name__ == "__main__":
     only = sys.argv[1:]
     print(torch.cuda.get_device_name(0), flush=True)
-    table = {"logmel": t_logmel, "legacy": t_legacy, "gemm_mma": t_gemm_mma, "gemm_tc": t_gemm_tc, "ln": t_ln, "att": t_att,
-             "tiny_mma": t_model_tiny_mma, "tiny_tc": t_model_tiny, "tiny_ml": t_model_tiny_ml, "bench": t_bench}
+    table = {"logmel": t_logmel, "legacy": t_legacy, "gemm_tc": t_gemm_tc, "ln": t_ln, "att": t_att,
+             "tiny_tc": t_model_tiny, "tiny_ml": t_model_tiny_ml, "bench": t_bench}
     for k, fn in table.items():
         if not only or k in only:
             fn()
