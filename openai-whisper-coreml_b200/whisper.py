@@ -101,6 +101,38 @@ class DecodeOptions:
         return DecodeOptions(init, eot, sample_len, suppress, [220, eot])
 
 
+_HF_RULES = (("layers.", "blocks."), (".encoder_attn_layer_norm.", ".cross_attn_ln."), (".self_attn_layer_norm.", ".attn_ln."),
+             (".final_layer_norm.", ".mlp_ln."), (".encoder_attn.", ".cross_attn."), (".self_attn.", ".attn."),
+             (".q_proj.", ".query."), (".k_proj.", ".key."), (".v_proj.", ".value."), (".out_proj.", ".out."),
+             (".fc1.", ".mlp.0."), (".fc2.", ".mlp.2."))
+
+
+def hf_to_upstream_name(key: str) -> Optional[str]:
+    """Maps a transformers WhisperForConditionalGeneration state-dict key to the upstream openai-whisper name the C ABI
+    uses (SURVEY.md §8c weight-name map). Returns None for tensors that have no upstream counterpart (the tied
+    `proj_out.weight`, the always-zero `k_proj.bias`)."""
+    if key == "proj_out.weight" or key.endswith("k_proj.bias"):
+        return None
+    k = key[len("model."):] if key.startswith("model.") else key
+    for a, b in _HF_RULES:
+        k = k.replace(a, b)
+    k = k.replace("encoder.layer_norm.", "encoder.ln_post.").replace("decoder.layer_norm.", "decoder.ln.")
+    k = k.replace("encoder.embed_positions.weight", "encoder.positional_embedding")
+    k = k.replace("decoder.embed_positions.weight", "decoder.positional_embedding")
+    k = k.replace("decoder.embed_tokens.", "decoder.token_embedding.")
+    return k
+
+
+def split_windows(pcm: Sequence[float], window: int = N_SAMPLES) -> np.ndarray:
+    """Cuts a long 16 kHz stream into consecutive fixed 30 s windows, zero-padding the last one (BASELINE config 5: a
+    30 min stream = 60 independent windows; each window follows the pad/truncate contract of ContentView.swift:57-60)."""
+    a = np.asarray(pcm, dtype=np.float32).reshape(-1)
+    n = max(1, -(-a.shape[0] // window))
+    out = np.zeros((n, window), dtype=np.float32)
+    out.reshape(-1)[: a.shape[0]] = a
+    return out
+
+
 _LIB: Optional[ctypes.CDLL] = None
 _SYMBOLS = {
     "generate_spectrogram": (None, [ctypes.c_void_p, ctypes.c_void_p]),
@@ -242,6 +274,15 @@ class Whisper:
             _check(self._lib.wb_set_weight(self._h, name.encode(), _ptr(a), a.size), f"wb_set_weight({name})")
         _check(self._lib.wb_weights_commit(self._h), "wb_weights_commit")
 
+    def load_hf_state_dict(self, weights: Dict[str, object]) -> None:
+        """Same, from a transformers Whisper checkpoint (safetensors / state_dict key names)."""
+        mapped = {}
+        for k, t in weights.items():
+            u = hf_to_upstream_name(k)
+            if u is not None:
+                mapped[u] = t
+        self.load_state_dict(mapped)
+
     def weight_arena(self):
         p, n = ctypes.c_void_p(), ctypes.c_size_t()
         _check(self._lib.wb_weight_arena(self._h, ctypes.byref(p), ctypes.byref(n)), "wb_weight_arena")
@@ -347,6 +388,16 @@ class Whisper:
         _check(self._lib.wb_transcribe(self._h, _ptr(a), B, ctypes.byref(c), _ptr(tokens), _ptr(lens), _ptr(slp)),
                "wb_transcribe")
         return tokens, lens, slp
+
+    def transcribe_long(self, pcm, opts: Optional[DecodeOptions] = None):
+        """A stream longer than 30 s as independent fixed windows, max_batch at a time: (tokens [n_windows, L], lens)."""
+        win = split_windows(pcm)
+        toks, lens = [], []
+        for i in range(0, win.shape[0], self.max_batch):
+            t, l, _ = self.transcribe(win[i:i + self.max_batch], opts)
+            toks.append(t)
+            lens.append(l)
+        return np.concatenate(toks, axis=0), np.concatenate(lens, axis=0)
 
     def transcribe_dev(self, audio_dev_ptr: int, B: int, opts: DecodeOptions):
         c, keep = self._opts(opts)

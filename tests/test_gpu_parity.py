@@ -296,6 +296,24 @@ def test_full_size_determinism_and_slot_independence(wbm):
     w.close()
 
 
+def test_long_stream_as_windows_and_hf_checkpoint_names(wbm, ref):
+    """BASELINE config 5 shape: a stream longer than 30 s = independent windows; weights loaded under HF key names."""
+    dims = ref.DIMS["tiny.en"]
+    weights = ref.random_weights(dims, seed=0)
+    hf_sd = {k: v for k, v in ref.to_hf(dims, weights).state_dict().items()}
+    w = wbm.Whisper("tiny.en", seed=None, max_batch=2)
+    w.load_hf_state_dict(hf_sd)
+    pcm = np.concatenate([ref.synth_audio(500 + i, "noise") for i in range(3)])[: 480000 * 2 + 123456].astype(np.float32)
+    o = wbm.DecodeOptions.default_for(wbm.DIMS["tiny.en"], sample_len=8)
+    toks, lens = w.transcribe_long(pcm, o)
+    assert toks.shape == (3, 10)
+    win = wbm.split_windows(pcm)
+    w2 = wbm.Whisper("tiny.en", weights=weights, max_batch=3)
+    t2, l2, _ = w2.transcribe(win, o)
+    assert np.array_equal(toks, t2) and np.array_equal(lens, l2)
+    w.close(), w2.close()
+
+
 def test_error_paths(tiny, wbm):
     w, _ = tiny
     lib = wbm.load_library()

@@ -45,6 +45,21 @@ def test_generate_spectrogram_validates_length(wbm):
         wbm.generateSpectrogram(np.zeros(1000))
 
 
+def test_hf_name_map_covers_every_upstream_tensor(wbm, ref, small_dims):
+    """transformers checkpoint keys -> upstream names (SURVEY §8c map), checked on a live HF model."""
+    hf = ref.to_hf(small_dims, ref.random_weights(small_dims, seed=3))
+    mapped = {wbm.hf_to_upstream_name(k) for k in hf.state_dict().keys()} - {None}
+    assert mapped == set(ref.weight_shapes(small_dims).keys())
+
+
+def test_split_windows(wbm):
+    pcm = np.arange(480000 * 2 + 1000, dtype=np.float32)
+    w = wbm.split_windows(pcm)
+    assert w.shape == (3, 480000)
+    assert w[1, 0] == 480000 and w[2, 999] == 480000 * 2 + 999 and not w[2, 1000:].any()
+    assert wbm.split_windows([]).shape == (1, 480000)
+
+
 def test_partition(wbm):
     from importlib import import_module
     sh = import_module("openai-whisper-coreml_b200.sharding")
