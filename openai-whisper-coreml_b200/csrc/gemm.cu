@@ -4,11 +4,12 @@
 // AudioEncoder): conv1/conv2 (as implicit GEMMs over overlapping-row tensor maps), the fused QKV / out / MLP linears,
 // and the decoder's cross-attention K/V projection of the audio features.
 //
-// Kernel (gemm_tc_kernel), one CTA per 128 x BN output tile, 192 threads:
-//   warp 0   TMA producer: cp.async.bulk.tensor (128B swizzle) of a 128x64 A tile and a BNx64 W tile per stage
-//   warp 1   TMEM allocator + MMA issuer: 4 x tcgen05.mma (M=128, N=BN, K=16) per stage, tcgen05.commit frees the stage
-//   warps 2-5 epilogue: tcgen05.ld the fp32 accumulator (one TMEM lane = one output row per thread), bias / exact-erf
-//            GELU / residual in registers, fp16 and/or fp32 stores
+// Kernel (gemm_tc_kernel): persistent, one CTA per SM looping over 128 x BN output tiles (BN = 256 when N allows), 320 threads:
+//   warp 0    TMA producer: cp.async.bulk.tensor (128B swizzle) of a 128x64 A tile and a BNx64 W tile per stage
+//   warp 1    TMEM allocator + MMA issuer: 4 x tcgen05.mma (M=128, N=BN, K=16) per stage, tcgen05.commit frees the stage;
+//             two accumulator buffers in TMEM, so tile i+1 is multiplied while tile i is drained
+//   warps 2-9 epilogue: tcgen05.ld the fp32 accumulator (one TMEM lane = one output row per thread), bias / GELU /
+//             residual in registers, fp16 and/or fp32 stores
 #include <cuda.h>
 
 #include <map>
@@ -21,8 +22,8 @@
 
 namespace wb {
 
-constexpr int kBM = 128, kBK = 64, kStages = 3;
-constexpr int kGemmThreads = 192;
+constexpr int kBM = 128, kBK = 64;
+constexpr int kGemmThreads = 320;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
 
 struct GemmEpi {
   const float* bias;
@@ -31,10 +32,12 @@ struct GemmEpi {
   float* c32;
   int N, K, rows, gelu, res_mode, ldc, c_row_off;
   long long c_batch_rows;
+  int tiles_m, tiles_n, n_tiles;   // per batch: tiles_m x tiles_n; n_tiles = n_batch * tiles_m * tiles_n
 };
 
 template <int BN>
 struct GemmSmem {
+  static constexpr int kStages = BN == 256 ? 4 : 6;
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -42,19 +45,37 @@ struct GemmSmem {
   static constexpr int kTotal = kBarOff + 256 + 1024;   // barriers + slack for the 1024-byte alignment
 };
 
+// exact-erf GELU evaluated with the Abramowitz-Stegun 7.1.26 rational form (|erf error| <= 1.5e-7, far below the fp16
+// rounding of the stored result): ~18 instructions instead of erff's two divergent branches, which matters because the
+// GELU epilogue of the MLP GEMM is what paces that kernel
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float erf_abs = fmaf(-p * t, __expf(-z * z), 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+
+// Persistent: one CTA per SM loops over output tiles (n fastest, so the CTAs running at the same time share A tiles in
+// L2). The TMA->MMA shared-memory ring runs continuously across tiles; the fp32 accumulator is double-buffered in TMEM
+// (2 x BN columns), so the epilogue of tile i (8 warps: TMEM lane quadrant x column half) overlaps the MMAs of tile i+1.
 template <int BN>
-__global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                               const __grid_constant__ CUtensorMap tmB, GemmEpi ep) {
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                  const __grid_constant__ CUtensorMap tmB, GemmEpi ep) {
   using S = GemmSmem<BN>;
+  constexpr int kStages = S::kStages;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
   uint64_t* empty = full + kStages;
-  uint64_t* tmem_full = empty + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tfull = empty + kStages;     // [2] accumulator buffer ready for the epilogue
+  uint64_t* tempty = tfull + 2;          // [2] accumulator buffer drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, t0 = blockIdx.y * kBM, b = blockIdx.z;
   const int nkb = (ep.K + kBK - 1) / kBK;
 
   if (warp == 0 && lane == 0) {
@@ -64,10 +85,13 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], 1);
     }
-    ptx::mbar_init(tmem_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull[i], 1);
+      ptx::mbar_init(&tempty[i], 8);
+    }
     ptx::fence_mbar_init();
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_slot, BN);
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, 2 * BN);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -75,89 +99,111 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
-        ptx::mbar_wait(&empty[s], ph ^ 1u);
-        ptx::mbar_arrive_expect_tx(&full[s], S::kStageBytes);
-        unsigned char* sa = smem + s * S::kStageBytes;
-        ptx::tma_load_3d(sa, &tmA, &full[s], kb * kBK, t0, b);
-        ptx::tma_load_2d(sa + S::kABytes, &tmB, &full[s], kb * kBK, n0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ep.n_tiles; tile += gridDim.x) {
+        const int nt = tile % ep.tiles_n, mt = (tile / ep.tiles_n) % ep.tiles_m, b = tile / (ep.tiles_n * ep.tiles_m);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1u;
+          ptx::mbar_wait(&empty[s], ph ^ 1u);
+          ptx::mbar_arrive_expect_tx(&full[s], S::kStageBytes);
+          unsigned char* sa = smem + s * S::kStageBytes;
+          ptx::tma_load_3d(sa, &tmA, &full[s], kb * kBK, mt * kBM, b);
+          ptx::tma_load_2d(sa + S::kABytes, &tmB, &full[s], kb * kBK, nt * BN);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_f16(kBM, BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
-        ptx::mbar_wait(&full[s], ph);
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < ep.n_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t buf = lt & 1u, tph = (lt >> 1) & 1u;
+        ptx::mbar_wait(&tempty[buf], tph ^ 1u);   // epilogue has drained this accumulator buffer
         ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(smem + s * S::kStageBytes);
-        const uint64_t adesc = ptx::umma_desc_sw128_kmajor(sa);
-        const uint64_t bdesc = ptx::umma_desc_sw128_kmajor(sa + S::kABytes);
+        const uint32_t tacc = tmem_base + buf * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1u;
+          ptx::mbar_wait(&full[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + s * S::kStageBytes);
+          const uint64_t adesc = ptx::umma_desc_sw128_kmajor(sa);
+          const uint64_t bdesc = ptx::umma_desc_sw128_kmajor(sa + S::kABytes);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom: +2 in 16-byte units
-          ptx::umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom: +2 in 16-byte units
+            ptx::umma_f16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          ptx::umma_commit(&empty[s]);
         }
-        ptx::umma_commit(&empty[s]);
+        ptx::umma_commit(&tfull[buf]);
       }
-      ptx::umma_commit(tmem_full);
     }
   } else {
-    // epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int t = t0 + row;
-    const bool row_ok = t < ep.rows;
-    const long long crow = (long long)b * ep.c_batch_rows + ep.c_row_off + t;
-    ptx::mbar_wait(tmem_full, 0);
-    ptx::tc_fence_after();
+    // epilogue: warp w may touch TMEM lanes [32*(w%4), +32); warps 2-5 take the first column half, 6-9 the second
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    constexpr int kChunks = BN / 64;   // 32-column chunks per warp
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < ep.n_tiles; tile += gridDim.x, ++lt) {
+      const int nt = tile % ep.tiles_n, mt = (tile / ep.tiles_n) % ep.tiles_m, b = tile / (ep.tiles_n * ep.tiles_m);
+      const uint32_t buf = lt & 1u, tph = (lt >> 1) & 1u;
+      const int t = mt * kBM + q * 32 + lane;
+      const bool row_ok = t < ep.rows;
+      const long long crow = (long long)b * ep.c_batch_rows + ep.c_row_off + t;
+      ptx::mbar_wait(&tfull[buf], tph);
+      ptx::tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      ptx::tmem_ld_wait();
-      const int nb = n0 + c * 32;
-      if (row_ok) {
-        float f[32];
+      for (int c = 0; c < kChunks; ++c) {
+        const int col = half * (BN / 2) + c * 32;
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tmem_base + buf * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v);
+        ptx::tmem_ld_wait();
+        if (c == kChunks - 1) {   // everything this warp needs from the buffer is in registers: hand it back to the MMA warp
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tempty[buf]);
+        }
+        const int nb = nt * BN + col;
+        if (row_ok) {
+          float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (ep.bias) {
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (ep.bias) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 bb = *reinterpret_cast<const float4*>(ep.bias + nb + j);
-            f[j] += bb.x, f[j + 1] += bb.y, f[j + 2] += bb.z, f[j + 3] += bb.w;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.bias + nb + j));
+              f[j] += bb.x, f[j + 1] += bb.y, f[j + 2] += bb.z, f[j + 3] += bb.w;
+            }
           }
-        }
-        if (ep.gelu) {
+          if (ep.gelu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-        }
-        if (ep.res_mode) {
-          const float* rp = ep.res + (ep.res_mode == 1 ? crow * ep.ldc : (long long)t * ep.N) + nb;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 rr = *reinterpret_cast<const float4*>(rp + j);
-            f[j] += rr.x, f[j + 1] += rr.y, f[j + 2] += rr.z, f[j + 3] += rr.w;
+            for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
           }
-        }
-        if (ep.c32) {
-          float* cp = ep.c32 + crow * ep.ldc + nb;
+          if (ep.res_mode) {
+            const float* rp = ep.res + (ep.res_mode == 1 ? crow * ep.ldc : (long long)t * ep.N) + nb;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-        }
-        if (ep.c16) {
-          __half* cp = ep.c16 + crow * ep.ldc + nb;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 rr = *reinterpret_cast<const float4*>(rp + j);
+              f[j] += rr.x, f[j + 1] += rr.y, f[j + 2] += rr.z, f[j + 3] += rr.w;
+            }
+          }
+          if (ep.c32) {
+            float* cp = ep.c32 + crow * ep.ldc + nb;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            __half2 h0 = __floats2half2_rn(f[j], f[j + 1]), h1 = __floats2half2_rn(f[j + 2], f[j + 3]);
-            __half2 h2 = __floats2half2_rn(f[j + 4], f[j + 5]), h3 = __floats2half2_rn(f[j + 6], f[j + 7]);
-            uint4 u;
-            u.x = *reinterpret_cast<uint32_t*>(&h0), u.y = *reinterpret_cast<uint32_t*>(&h1);
-            u.z = *reinterpret_cast<uint32_t*>(&h2), u.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(cp + j) = u;
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          }
+          if (ep.c16) {
+            __half* cp = ep.c16 + crow * ep.ldc + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              __half2 h0 = __floats2half2_rn(f[j], f[j + 1]), h1 = __floats2half2_rn(f[j + 2], f[j + 3]);
+              __half2 h2 = __floats2half2_rn(f[j + 4], f[j + 5]), h3 = __floats2half2_rn(f[j + 6], f[j + 7]);
+              uint4 u;
+              u.x = *reinterpret_cast<uint32_t*>(&h0), u.y = *reinterpret_cast<uint32_t*>(&h1);
+              u.z = *reinterpret_cast<uint32_t*>(&h2), u.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(cp + j) = u;
+            }
           }
         }
       }
@@ -167,7 +213,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, BN);
+    ptx::tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -262,8 +308,17 @@ static int launch_tc(GemmContext* ctx, const GemmDesc& d, const GemmEpi& ep, cud
     WB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
     attr_set = true;
   }
-  dim3 grid(d.N / BN, (d.rows + kBM - 1) / kBM, d.n_batch);
-  kern<<<grid, kGemmThreads, GemmSmem<BN>::kTotal, st>>>(tmA, tmB, ep);
+  GemmEpi e2 = ep;
+  e2.tiles_n = d.N / BN, e2.tiles_m = (d.rows + kBM - 1) / kBM, e2.n_tiles = e2.tiles_n * e2.tiles_m * d.n_batch;
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  const int grid = e2.n_tiles < n_sm ? e2.n_tiles : n_sm;   // persistent: one CTA per SM
+  kern<<<grid, kGemmThreads, GemmSmem<BN>::kTotal, st>>>(tmA, tmB, e2);
   WB_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -278,6 +333,14 @@ int launch_gemm(GemmContext* ctx, const GemmDesc& d, cudaStream_t st, int64_t* l
   ep.N = d.N, ep.K = d.K, ep.rows = d.rows, ep.gelu = d.gelu, ep.res_mode = d.res_mode, ep.ldc = d.ldc;
   ep.c_row_off = d.c_row_off, ep.c_batch_rows = d.c_batch_rows;
   if (launches) *launches += 1;
+  static int force_bn = -1;   // WB_GEMM_BN=128|256: development override of the tile width
+  if (force_bn < 0) {
+    const char* e = getenv("WB_GEMM_BN");
+    force_bn = e ? atoi(e) : 0;
+  }
+  if ((d.N % 256 == 0 && force_bn != 128) || force_bn == 256) {
+    if (d.N % 256 == 0) return launch_tc<256>(ctx, d, ep, st);
+  }
   return launch_tc<128>(ctx, d, ep, st);
 }
 
