@@ -50,7 +50,7 @@ typedef struct wb_decode_opts {
   int32_t n_suppress;
   const int32_t* suppress_begin; /* SuppressBlank: -inf at the first sampled position only                          */
   int32_t n_suppress_begin;
-  int32_t beam_size;             /* 0 or 1 = greedy; >1 = beam search with patience 1                               */
+  int32_t beam_size;             /* 0 or 1 = greedy; 2..7 = beam search, patience 1 (needs max_beams >= beam_size)  */
   int32_t eot_check_interval;    /* how often (in steps) the host polls "all sequences ended"; 0 = default (8)      */
 } wb_decode_opts;
 
@@ -127,7 +127,8 @@ int wb_decoder_logits_f32tok(wb_handle* h, const float* tokens, int32_t B, int32
 int wb_detect_language(wb_handle* h, int32_t B, int32_t sot, int32_t lang0, int32_t* lang_idx);
 
 /* Greedy / beam decode of the resident features. tokens_out [B][n_initial + sample_len] (padded with eot), lens [B]
- * (initial tokens included, first eot included), sum_logprob [B]. */
+ * (initial tokens included, first eot included), sum_logprob [B]. Beam search returns, per chunk, the candidate with the
+ * best sum_logprob / length (upstream MaximumLikelihoodRanker without length penalty). */
 int wb_decode(wb_handle* h, int32_t B, const wb_decode_opts* opts, int32_t* tokens_out, int32_t* lens, float* sum_logprob);
 /* audio -> tokens in one call (= wb_encode + wb_decode). Host pointers. */
 int wb_transcribe(wb_handle* h, const float* audio, int32_t B, const wb_decode_opts* opts, int32_t* tokens_out,

@@ -983,4 +983,125 @@ int launch_step_finish(const FinishDesc& d, cudaStream_t st, int64_t* launches) 
   return 0;
 }
 
+// ---- beam search support -----------------------------------------------------------------------------------------------------------
+// Top-k of one logits row (k <= 8) and its log-sum-exp: every thread keeps a sorted top-k of its strided elements and an
+// online (max, sum-exp); the candidates are merged through shared memory by one warp. Output log-probabilities = logit - LSE
+// (upstream: F.log_softmax(logits).topk(beam_size + 1)).
+__global__ void __launch_bounds__(256) topk_logprobs_kernel(const float* __restrict__ logits, int V, int k, float* __restrict__ top_lp,
+                                                            int32_t* __restrict__ top_idx) {
+  __shared__ float c_val[256 * 8];
+  __shared__ int c_idx[256 * 8];
+  __shared__ float s_m[8], s_s[8];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* row = logits + (size_t)b * V;
+  float tv[8];
+  int ti[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) tv[j] = -INFINITY, ti[j] = 0x7fffffff;
+  float m = -INFINITY, ssum = 0.f;
+  for (int i = tid; i < V; i += 256) {
+    const float x = row[i];
+    if (x > m) {
+      ssum = ssum * expf(m - x) + 1.0f;
+      m = x;
+    } else if (x > -INFINITY) {
+      ssum += expf(x - m);
+    }
+    if (x > tv[7]) {   // insert into the sorted list (descending; earlier index wins ties)
+      tv[7] = x, ti[7] = i;
+#pragma unroll
+      for (int j = 7; j > 0; --j) {
+        if (tv[j] > tv[j - 1]) {
+          const float fv = tv[j]; tv[j] = tv[j - 1]; tv[j - 1] = fv;
+          const int iv = ti[j]; ti[j] = ti[j - 1]; ti[j - 1] = iv;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) c_val[tid * 8 + j] = tv[j], c_idx[tid * 8 + j] = ti[j];
+  // block LSE
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, ssum, o);
+    const float nm = fmaxf(m, om);
+    ssum = (m > -INFINITY ? ssum * expf(m - nm) : 0.f) + (om > -INFINITY ? os * expf(om - nm) : 0.f);
+    m = nm;
+  }
+  if (lane == 0) s_m[warp] = m, s_s[warp] = ssum;
+  __syncthreads();
+  if (warp == 0) {
+    float M = -INFINITY;
+    for (int w = 0; w < 8; ++w) M = fmaxf(M, s_m[w]);
+    float S = 0.f;
+    for (int w = 0; w < 8; ++w) S += s_m[w] > -INFINITY ? s_s[w] * expf(s_m[w] - M) : 0.f;
+    const float lse = M + logf(S);
+    for (int r = 0; r < k; ++r) {
+      float best = -INFINITY;
+      int bi = 0x7fffffff, bslot = -1;
+      for (int c = lane; c < 256 * 8; c += 32) {
+        const float v = c_val[c];
+        const int ix = c_idx[c];
+        if (v > best || (v == best && ix < bi)) best = v, bi = ix, bslot = c;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o), os = __shfl_xor_sync(0xffffffffu, bslot, o);
+        if (ov > best || (ov == best && oi < bi)) best = ov, bi = oi, bslot = os;
+      }
+      if (lane == 0) {
+        top_lp[(size_t)b * 8 + r] = best - lse;
+        top_idx[(size_t)b * 8 + r] = bi;
+        if (bslot >= 0) c_val[bslot] = -INFINITY;
+      }
+      __syncwarp();
+    }
+  }
+}
+
+int launch_topk_logprobs(const float* logits, int Mb, int V, int k, float* top_logprob, int32_t* top_index, cudaStream_t st,
+                         int64_t* launches) {
+  if (k < 1 || k > 8) {
+    set_error("topk: k=%d out of range [1,8]", k);
+    return -1;
+  }
+  topk_logprobs_kernel<<<Mb, 256, 0, st>>>(logits, V, k, top_logprob, top_index);
+  if (launches) *launches += 1;
+  WB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// dst[l][b][0..cur_len] = src[l][source[b]][0..cur_len] for K and V of every layer (upstream rearrange_kv_cache)
+struct ReorderArgs {
+  const __half* src_k[32];
+  const __half* src_v[32];
+  __half* dst_k[32];
+  __half* dst_v[32];
+};
+__global__ void __launch_bounds__(256) reorder_kv_kernel(ReorderArgs a, int n_ctx, int d, const int32_t* __restrict__ source,
+                                                         const DecodeState* state) {
+  const int b = blockIdx.x, l = blockIdx.y >> 1, is_v = blockIdx.y & 1;
+  const int n_rows = ld_state(&state->cur_len) + 1;
+  const int sb = source[b];
+  const uint4* src = reinterpret_cast<const uint4*>((is_v ? a.src_v[l] : a.src_k[l]) + (size_t)sb * n_ctx * d);
+  uint4* dst = reinterpret_cast<uint4*>((is_v ? a.dst_v[l] : a.dst_k[l]) + (size_t)b * n_ctx * d);
+  const int n = n_rows * d / 8;
+  for (int i = threadIdx.x; i < n; i += 256) dst[i] = src[i];
+}
+
+int launch_reorder_kv(const __half* const* src_k, const __half* const* src_v, __half* const* dst_k, __half* const* dst_v, int n_layer,
+                      int Mb, int n_ctx, int d, const int32_t* source, const DecodeState* state, cudaStream_t st, int64_t* launches) {
+  if (n_layer > 32) {
+    set_error("reorder_kv: too many layers");
+    return -1;
+  }
+  ReorderArgs a{};
+  for (int l = 0; l < n_layer; ++l) a.src_k[l] = src_k[l], a.src_v[l] = src_v[l], a.dst_k[l] = dst_k[l], a.dst_v[l] = dst_v[l];
+  reorder_kv_kernel<<<dim3(Mb, n_layer * 2), 256, 0, st>>>(a, n_ctx, d, source, state);
+  if (launches) *launches += 1;
+  WB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace wb

@@ -120,7 +120,9 @@ struct wb_handle {
 
   // decoder workspace
   int Mb_max;
-  std::vector<__half*> selfK, selfV;
+  std::vector<__half*> selfK, selfV, selfK_alt, selfV_alt;   // *_alt: ping-pong target of the beam re-indexing
+  float* top_lp;
+  int32_t *top_idx, *beam_src;
   int32_t* tokens;
   int tokens_ld;
   float *xdec, *q32, *logits, *sum_logprob, *part_logits;
@@ -256,6 +258,16 @@ static void layout_workspace(wb_handle* h) {
     h->selfK[l] = A.take<__half>(Mb * D.n_text_ctx * dt);
     h->selfV[l] = A.take<__half>(Mb * D.n_text_ctx * dt);
   }
+  if (h->max_beams > 1) {
+    h->selfK_alt.resize(D.n_text_layer), h->selfV_alt.resize(D.n_text_layer);
+    for (int l = 0; l < D.n_text_layer; ++l) {
+      h->selfK_alt[l] = A.take<__half>(Mb * D.n_text_ctx * dt);
+      h->selfV_alt[l] = A.take<__half>(Mb * D.n_text_ctx * dt);
+    }
+  }
+  h->top_lp = A.take<float>(Mb * 8);
+  h->top_idx = A.take<int32_t>(Mb * 8);
+  h->beam_src = A.take<int32_t>(Mb);
   h->tokens_ld = D.n_text_ctx + 8;
   h->tokens = A.take<int32_t>(Mb * h->tokens_ld);
   h->xdec = A.take<float>(Mb * dt);
@@ -348,6 +360,7 @@ struct StepOpts {
   int store_logits;   // write the fp32 logits [Mb][V] (teacher-forced / language-ID paths)
   int sample;         // run the logits GEMM with filters + partial argmax and sample in the finish kernel
   int n_initial, eot;
+  int no_finish;      // beam search: the host picks the next tokens between the logits and the finish kernel
 };
 
 static int step_finish(wb_handle* h, const StepOpts& o, int sample) {
@@ -412,6 +425,7 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
     lg.part_logits = h->part_logits;
     WB_TRY(launch_skinny_gemm(lg, st, &h->launches));
   }
+  if (o.no_finish) return 0;
   return step_finish(h, o, o.sample);
 }
 
@@ -897,14 +911,184 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
   return WB_OK;
 }
 
+// Beam search (upstream whisper/decoding.py BeamSearchDecoder + MaximumLikelihoodRanker): the device runs the
+// decoder step for n_audio*beam sequences (cross K/V shared by the beams of a chunk) and extracts the top beam+1
+// log-probabilities per row; the candidate bookkeeping of a step is a few hundred scalar operations and runs on the host;
+// the self-attention cache is re-indexed by source beam on the device.
+static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int32_t* tokens_out, int32_t* lens, float* sum_logprob) {
+  const wb_dims& D = h->dims;
+  const int beam = opts->beam_size, Mb = B * beam, K = beam + 1;
+  const int n_init = opts->n_initial, total = n_init + opts->sample_len, eot = opts->eot;
+  if (beam > h->max_beams || beam > 7 || Mb > h->Mb_max || h->selfK_alt.empty()) {
+    set_error("wb_decode: beam_size %d exceeds the handle's max_beams %d (or 7), or batch*beam %d exceeds %d", beam, h->max_beams, Mb, h->Mb_max);
+    return WB_ERR_ARG;
+  }
+  if (n_init < 1 || opts->sample_len < 1 || total > D.n_text_ctx || !opts->initial_tokens) {
+    set_error("wb_decode: bad options");
+    return WB_ERR_ARG;
+  }
+  cudaStream_t st = h->stream;
+  std::vector<int32_t> rows((size_t)Mb * h->tokens_ld, eot);
+  for (int b = 0; b < Mb; ++b)
+    for (int i = 0; i < n_init; ++i) rows[(size_t)b * h->tokens_ld + i] = opts->initial_tokens[i];
+  std::vector<unsigned char> mask(D.n_vocab, 0);
+  for (int i = 0; i < opts->n_suppress_begin; ++i)
+    if (opts->suppress_begin[i] >= 0 && opts->suppress_begin[i] < D.n_vocab) mask[opts->suppress_begin[i]] = 2;
+  for (int i = 0; i < opts->n_suppress; ++i)
+    if (opts->suppress[i] >= 0 && opts->suppress[i] < D.n_vocab) mask[opts->suppress[i]] = 1;
+  WB_CUDA_OK(cudaMemcpyAsync(h->tokens, rows.data(), rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  WB_CUDA_OK(cudaMemcpyAsync(h->mask, mask.data(), mask.size(), cudaMemcpyHostToDevice, st));
+  WB_CUDA_OK(cudaStreamSynchronize(st));
+
+  StepOpts plain{}, scored{};
+  plain.Mb = Mb, plain.beams = beam, plain.n_initial = n_init, plain.eot = eot;
+  scored = plain;
+  scored.sample = 1, scored.store_logits = 1, scored.no_finish = 1;   // filtered logits stored, host decides the next tokens
+  WB_CUDA_OK(cudaEventRecord(h->ev[2], st));
+  WB_TRY(reset_decode_state(h, plain));
+  for (int i = 0; i + 1 < n_init; ++i) WB_TRY(decode_step(h, plain));
+
+  typedef std::vector<int32_t> Seq;
+  std::vector<Seq> seqs(Mb, Seq(opts->initial_tokens, opts->initial_tokens + n_init));
+  std::vector<float> slp(Mb, 0.f);
+  std::vector<std::vector<std::pair<Seq, float>>> finished(B);   // insertion-ordered, unique keys (Python dict semantics)
+  const size_t max_candidates = (size_t)beam;                    // round(beam_size * patience), patience = 1
+  std::vector<float> top_lp((size_t)Mb * 8);
+  std::vector<int32_t> top_idx((size_t)Mb * 8), src(Mb), next_col(Mb);
+  int steps = 0;
+  for (int s = 0; s < opts->sample_len; ++s) {
+    WB_TRY(decode_step(h, scored));
+    WB_TRY(launch_topk_logprobs(h->logits, Mb, D.n_vocab, K, h->top_lp, h->top_idx, st, &h->launches));
+    WB_CUDA_OK(cudaMemcpyAsync(top_lp.data(), h->top_lp, top_lp.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+    WB_CUDA_OK(cudaMemcpyAsync(top_idx.data(), h->top_idx, top_idx.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    WB_CUDA_OK(cudaStreamSynchronize(st));
+    ++steps;
+    std::vector<Seq> next_seqs;
+    std::vector<float> next_slp;
+    std::vector<int32_t> next_src;
+    for (int a = 0; a < B; ++a) {
+      // STEP 1: cumulative log-probabilities of the candidates, keyed by sequence (identical prefixes collapse)
+      struct Cand { Seq seq; float score; int source; };
+      std::vector<Cand> cands;
+      for (int j = 0; j < beam; ++j) {
+        const int idx = a * beam + j;
+        for (int c = 0; c < K; ++c) {
+          Seq sq = seqs[idx];
+          sq.push_back(top_idx[(size_t)idx * 8 + c]);
+          const float sc = slp[idx] + top_lp[(size_t)idx * 8 + c];
+          bool found = false;
+          for (auto& e : cands)
+            if (e.seq == sq) {
+              e.score = sc, e.source = idx, found = true;
+              break;
+            }
+          if (!found) cands.push_back(Cand{sq, sc, idx});
+        }
+      }
+      // STEP 2: rank, keep the best `beam` unfinished sequences; sequences ending in eot are set aside
+      std::stable_sort(cands.begin(), cands.end(), [](const Cand& x, const Cand& y) { return x.score > y.score; });
+      std::vector<std::pair<Seq, float>> newly;
+      int saved = 0;
+      for (auto& e : cands) {
+        if (e.seq.back() == eot) {
+          newly.emplace_back(e.seq, e.score);
+        } else {
+          next_seqs.push_back(e.seq), next_slp.push_back(e.score), next_src.push_back(e.source);
+          if (++saved == beam) break;
+        }
+      }
+      while (saved < beam) {   // cannot happen with beam+1 candidates per beam and one eot token, kept for safety
+        next_seqs.push_back(next_seqs.back()), next_slp.push_back(-INFINITY), next_src.push_back(next_src.back());
+        ++saved;
+      }
+      for (auto& nf : newly) {   // already in descending score order
+        if (finished[a].size() >= max_candidates) break;
+        bool found = false;
+        for (auto& pf : finished[a])
+          if (pf.first == nf.first) {
+            pf.second = nf.second, found = true;
+            break;
+          }
+        if (!found) finished[a].push_back(nf);
+      }
+    }
+    seqs.swap(next_seqs), slp.swap(next_slp);
+    bool completed = true;
+    for (int a = 0; a < B; ++a) completed = completed && finished[a].size() >= max_candidates;
+    if (completed || s + 1 == opts->sample_len) break;
+    // device side of the update: newest token column, cache re-indexing, then embed + advance
+    bool identity = true;
+    for (int b = 0; b < Mb; ++b) {
+      src[b] = next_src[b], next_col[b] = seqs[b].back();
+      identity = identity && src[b] == b;
+    }
+    const int col = n_init + s;
+    WB_CUDA_OK(cudaMemcpy2DAsync(h->tokens + col, h->tokens_ld * sizeof(int32_t), next_col.data(), sizeof(int32_t), sizeof(int32_t), Mb,
+                                 cudaMemcpyHostToDevice, st));
+    if (!identity) {
+      WB_CUDA_OK(cudaMemcpyAsync(h->beam_src, src.data(), Mb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      WB_TRY(launch_reorder_kv(h->selfK.data(), h->selfV.data(), h->selfK_alt.data(), h->selfV_alt.data(), D.n_text_layer, Mb,
+                               D.n_text_ctx, D.n_text_state, h->beam_src, h->state, st, &h->launches));
+      h->selfK.swap(h->selfK_alt), h->selfV.swap(h->selfV_alt);
+    }
+    WB_TRY(step_finish(h, plain, 0));
+    WB_CUDA_OK(cudaStreamSynchronize(st));   // next_col / src are reused next iteration
+  }
+  WB_CUDA_OK(cudaEventRecord(h->ev[3], st));
+  h->timings[3] = (float)(steps + n_init - 1);
+  // finalize: unfinished beams (eot appended) fill up to `beam` candidates; rank by sum_logprob / length
+  for (int a = 0; a < B; ++a) {
+    auto& fin = finished[a];
+    if ((int)fin.size() < beam) {
+      std::vector<int> order(beam);
+      for (int j = 0; j < beam; ++j) order[j] = j;
+      std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return slp[a * beam + x] > slp[a * beam + y]; });
+      for (int j : order) {
+        Seq sq = seqs[a * beam + j];
+        sq.push_back(eot);
+        bool found = false;
+        for (auto& pf : fin)
+          if (pf.first == sq) {
+            pf.second = slp[a * beam + j], found = true;
+            break;
+          }
+        if (!found) fin.emplace_back(sq, slp[a * beam + j]);
+        if ((int)fin.size() >= beam) break;
+      }
+    }
+    int best = 0;
+    float best_rank = -INFINITY;
+    std::vector<Seq> trimmed(fin.size());
+    for (size_t c = 0; c < fin.size(); ++c) {
+      const Seq& sq = fin[c].first;
+      size_t end = sq.size();
+      for (size_t i = n_init; i < sq.size(); ++i)
+        if (sq[i] == eot) {
+          end = i;
+          break;
+        }
+      trimmed[c].assign(sq.begin() + n_init, sq.begin() + end);
+      const float rank = trimmed[c].empty() ? -INFINITY : fin[c].second / (float)trimmed[c].size();
+      if (rank > best_rank) best_rank = rank, best = (int)c;
+    }
+    int len = n_init + (int)trimmed[best].size();
+    for (int i = 0; i < total; ++i) {
+      int32_t tk = eot;
+      if (i < n_init) tk = opts->initial_tokens[i];
+      else if (i < len) tk = trimmed[best][i - n_init];
+      tokens_out[(size_t)a * total + i] = tk;
+    }
+    if (lens) lens[a] = len + 1 <= total ? len + 1 : total;
+    if (sum_logprob) sum_logprob[a] = fin[best].second;
+  }
+  return WB_OK;
+}
+
 int wb_decode(wb_handle* h, int32_t B, const wb_decode_opts* opts, int32_t* tokens_out, int32_t* lens, float* sum_logprob) {
   WB_TRY(check_batch(h, B));
   WB_TRY(need_features(h, B));
   if (!opts || !tokens_out) return WB_ERR_ARG;
-  if (opts->beam_size > 1) {
-    set_error("wb_decode: beam search is not implemented in this build (beam_size=%d)", opts->beam_size);
-    return WB_ERR_ARG;
-  }
+  if (opts->beam_size > 1) return decode_beam(h, B, opts, tokens_out, lens, sum_logprob);
   return decode_greedy(h, B, opts, tokens_out, lens, sum_logprob);
 }
 

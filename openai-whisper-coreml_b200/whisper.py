@@ -376,6 +376,11 @@ class Whisper:
         _check(self._lib.wb_decode(self._h, B, ctypes.byref(c), _ptr(tokens), _ptr(lens), _ptr(slp)), "wb_decode")
         return tokens, lens, slp
 
+    def decode_tokens(self, B: int, opts: DecodeOptions):
+        """Greedy (beam_size <= 1) or beam-search (beam_size > 1, needs max_beams >= beam_size at construction) decode of
+        the resident features. Beam search returns, per chunk, the best candidate by sum_logprob / length."""
+        return self.greedy(B, opts)
+
     def transcribe(self, audio, opts: Optional[DecodeOptions] = None):
         a = self._as_batch(audio)
         opts = opts or DecodeOptions.default_for(self.dims)

@@ -306,6 +306,86 @@ class WhisperRef:
         return tokens, sum_logprobs, torch.stack(all_logits, dim=1)
 
 
+    # ---- beam search (upstream DecodingTask with beam_size, BeamSearchDecoder, MaximumLikelihoodRanker) -----------------
+    @torch.no_grad()
+    def beam_search(self, xa: torch.Tensor, opts: "DecodeOptions", beam_size: int = 5, patience: float = 1.0):
+        """Restatement of upstream whisper/decoding.py: BeamSearchDecoder.update / finalize and the length-normalised
+        ranking (length_penalty=None -> sum_logprob / len). UNPINNED beyond the published algorithm: no independent
+        implementation of this exact procedure exists in the image (transformers' beam search is a different algorithm).
+        Returns (best token list per audio incl. the sot sequence, without the final eot; best sum_logprob per audio)."""
+        v = self.vocab
+        n_audio = xa.shape[0]
+        init = list(opts.initial_tokens)
+        sample_begin = len(init)
+        max_candidates = round(beam_size * patience)
+        xa_rep = xa.repeat_interleave(beam_size, dim=0)
+        cross = self.cross_kv(xa_rep)
+        tokens = torch.tensor([init] * (n_audio * beam_size), dtype=torch.long)
+        sum_logprobs = torch.zeros(n_audio * beam_size)
+        cache: List[Optional[tuple]] = [None] * self.dims.n_text_layer
+        finished_sequences = [dict() for _ in range(n_audio)]
+        for i in range(opts.sample_len):
+            feed = tokens if i == 0 else tokens[:, -1:]
+            logits = self.decoder_logits(feed, xa_rep, cross, cache)[:, -1].clone()
+            if tokens.shape[1] == sample_begin and len(opts.suppress_begin):
+                logits[:, list(opts.suppress_begin)] = float("-inf")
+            if len(opts.suppress):
+                logits[:, list(opts.suppress)] = float("-inf")
+            logprobs = F.log_softmax(logits.float(), dim=-1)
+            next_tokens, source_indices, newly = [], [], []
+            for a in range(n_audio):
+                scores, sources, finished = {}, {}, {}
+                for j in range(beam_size):
+                    idx = a * beam_size + j
+                    prefix = tokens[idx].tolist()
+                    for logprob, token in zip(*logprobs[idx].topk(beam_size + 1)):
+                        sequence = tuple(prefix + [token.item()])
+                        scores[sequence] = (sum_logprobs[idx] + logprob).item()
+                        sources[sequence] = idx
+                saved = 0
+                for sequence in sorted(scores, key=scores.get, reverse=True):
+                    if sequence[-1] == v.eot:
+                        finished[sequence] = scores[sequence]
+                    else:
+                        sum_logprobs[len(next_tokens)] = scores[sequence]
+                        next_tokens.append(sequence)
+                        source_indices.append(sources[sequence])
+                        saved += 1
+                        if saved == beam_size:
+                            break
+                newly.append(finished)
+            tokens = torch.tensor(next_tokens, dtype=torch.long)
+            src = torch.tensor(source_indices, dtype=torch.long)
+            cache = [(k.index_select(0, src), vv.index_select(0, src)) for (k, vv) in cache]     # rearrange_kv_cache
+            for prev, new in zip(finished_sequences, newly):
+                for seq in sorted(new, key=new.get, reverse=True):
+                    if len(prev) >= max_candidates:
+                        break
+                    prev[seq] = new[seq]
+            completed = all(len(s) >= max_candidates for s in finished_sequences)
+            if completed or tokens.shape[-1] > self.dims.n_text_ctx:
+                break
+        # finalize: add unfinished beams (with eot appended) when not enough sequences finished
+        tokens = tokens.reshape(n_audio, beam_size, -1)
+        slp = sum_logprobs.reshape(n_audio, beam_size)
+        best_tokens, best_scores = [], []
+        for a, sequences in enumerate(finished_sequences):
+            if len(sequences) < beam_size:
+                for j in list(np.argsort(slp[a].numpy()))[::-1]:
+                    sequence = tokens[a, j].tolist() + [v.eot]
+                    sequences[tuple(sequence)] = slp[a][j].item()
+                    if len(sequences) >= beam_size:
+                        break
+            cands = [list(seq) for seq in sequences.keys()]
+            vals = list(sequences.values())
+            trimmed = [c[sample_begin:c.index(v.eot, sample_begin)] if v.eot in c[sample_begin:] else c[sample_begin:] for c in cands]
+            ranks = [val / len(t) if len(t) else float("-inf") for val, t in zip(vals, trimmed)]   # MaximumLikelihoodRanker, no penalty
+            k = int(np.argmax(ranks))
+            best_tokens.append(init + trimmed[k])
+            best_scores.append(vals[k])
+        return best_tokens, best_scores
+
+
 def language_argmax(logits: torch.Tensor, lang0: int = 50259) -> torch.Tensor:
     """Whisper.swift:37-38: `(50259...50357).map{...}.enumerated().max{ $0.element < $1.element }`.
     Swift's `max(by:)` returns the LAST maximal element on ties."""

@@ -314,6 +314,35 @@ def test_long_stream_as_windows_and_hf_checkpoint_names(wbm, ref):
     w.close(), w2.close()
 
 
+@pytest.mark.parametrize("multilingual,beam,B", [(False, 5, 2), (True, 3, 1)])
+def test_beam_search_matches_oracle(wbm, ref, small_dims, small_dims_ml, oracle_logmel, multilingual, beam, B):
+    """BASELINE config 4 (beam decode) at test size: upstream BeamSearchDecoder semantics, best candidate per chunk."""
+    dims = small_dims_ml if multilingual else small_dims
+    weights = ref.random_weights(dims, seed=3)
+    oracle = ref.WhisperRef(dims, weights)
+    pd = wbm.ModelDims(*[getattr(dims, f) for f in dims.__dataclass_fields__])
+    w = wbm.Whisper(pd, weights=weights, max_batch=B, max_beams=beam)
+    audio = np.stack([ref.synth_audio(600 + i, "noise") for i in range(B)])
+    xa_ref = oracle.encode(torch.from_numpy(np.stack([oracle_logmel(a) for a in audio])).float())
+    w.encode(audio.astype(np.float32), return_features=False)
+    opts_ref = ref.DecodeOptions.default_for(dims, sample_len=9)
+    want_tokens, want_scores = oracle.beam_search(xa_ref, opts_ref, beam_size=beam)
+    o = wbm.DecodeOptions.default_for(pd, sample_len=9)
+    o.beam_size = beam
+    tok, lens, slp = w.decode_tokens(B, o)
+    for b in range(B):
+        n = len(want_tokens[b])
+        assert tok[b, :n].tolist() == want_tokens[b], (b, tok[b].tolist(), want_tokens[b])
+        assert (tok[b, n:] == o.eot).all()
+        assert abs(float(slp[b]) - want_scores[b]) <= 0.05
+    # greedy still works on the same handle afterwards (cache pointers were ping-ponged)
+    o.beam_size = 0
+    g_ref, _, _ = oracle.greedy(xa_ref, opts_ref)
+    g, _, _ = w.decode_tokens(B, o)
+    assert np.array_equal(g[:, :g_ref.shape[1]].astype(np.int64), g_ref.numpy())
+    w.close()
+
+
 def test_error_paths(tiny, wbm):
     w, _ = tiny
     lib = wbm.load_library()

@@ -84,3 +84,27 @@ def test_eot_forcing_and_logprob_mask(ref, small_dims):
             k = body.index(eot)
             assert all(t == eot for t in body[k:])
     assert torch.isfinite(slp).all()
+
+
+def test_beam_size_one_reduces_to_greedy(ref, small_dims):
+    """Sanity pin of the beam restatement: with one beam and no EOT in reach it must follow the greedy path and
+    accumulate the same log-probabilities."""
+    model = ref.WhisperRef(small_dims, ref.random_weights(small_dims, seed=3))
+    xa = torch.randn(2, 1500, small_dims.n_audio_state, generator=torch.Generator().manual_seed(2))
+    opts = ref.DecodeOptions.default_for(small_dims, sample_len=6)
+    opts.suppress = list(opts.suppress) + [model.vocab.eot]
+    g, slp, _ = model.greedy(xa, opts)
+    bt, bs = model.beam_search(xa, opts, beam_size=1)
+    for b in range(2):
+        assert bt[b] == g[b].tolist()
+        assert abs(bs[b] - float(slp[b])) <= 1e-3
+
+
+def test_beam_finds_at_least_greedy_likelihood(ref, small_dims):
+    model = ref.WhisperRef(small_dims, ref.random_weights(small_dims, seed=3))
+    xa = torch.randn(1, 1500, small_dims.n_audio_state, generator=torch.Generator().manual_seed(5))
+    opts = ref.DecodeOptions.default_for(small_dims, sample_len=6)
+    opts.suppress = list(opts.suppress) + [model.vocab.eot]
+    _, slp, _ = model.greedy(xa, opts)
+    _, bs = model.beam_search(xa, opts, beam_size=4)
+    assert bs[0] >= float(slp[0]) - 1e-4
