@@ -659,17 +659,25 @@ constexpr int kHaThreads = 288;
 constexpr int kHaTileBytes = kHaStageRows * 128;   // one K (or V) stage tile: 128 rows x 64 halves
 
 struct HeadAttnArgs {
-  const float* q;
+  const float* q;          // [Mb][d] query (self attention), or null when the query projection is fused:
+  const float* x;          //   residual stream [Mb][d]; q = LayerNorm(x; ln_g, ln_b) Wq^T + bq computed by the CTA for its head
+  const float* ln_g;
+  const float* ln_b;
+  const __half* wq;        //   [d][d]
+  const float* bq;         //   [d]
   __half* out16;
   const DecodeState* state;
   int d, n_rows_fixed, kv_share, n_stages;
   int l2_prefetch_tiles;   // cross attention: stage tiles beyond the ring requested into L2 while q is still being computed
 };
 
-__global__ void __launch_bounds__(kHaThreads) attn_decode_head_kernel(const __grid_constant__ CUtensorMap tmK,
+template <int NJW>   // ceil(d / 256): 16-byte weight chunks per lane and row in the fused query projection
+__global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head_kernel(const __grid_constant__ CUtensorMap tmK,
                                                                       const __grid_constant__ CUtensorMap tmV, HeadAttnArgs a) {
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8];
+  __shared__ __align__(16) float s_x[NJW * 256];   // normalised residual row (fused query projection)
+  __shared__ float s_q[64], s_red[16];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = lane >> 2, tq = lane & 3, mi = lane >> 3, r8 = lane & 7;
@@ -688,13 +696,11 @@ __global__ void __launch_bounds__(kHaThreads) attn_decode_head_kernel(const __gr
   }
   __syncthreads();
   ptx::grid_dep_launch();
-  if (!fixed || warp < 8) ptx::grid_dep_sync();   // q (and the newest self-attention row) come from the previous kernel
+  if (!fixed) ptx::grid_dep_sync();   // self attention: the row count and the newest K/V row come from the previous kernel
   const int n_rows = fixed ? a.n_rows_fixed : ld_state(&a.state->cur_len) + 1;
   const int n_tiles = (n_rows + kHaStageRows - 1) / kHaStageRows;
 
   float o[4][4], m_run = -INFINITY, l_run = 0.f;
-#pragma unroll
-  for (int mt = 0; mt < 4; ++mt) o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f;
 
   if (warp == 8) {
     if (lane == 0) {
@@ -717,13 +723,105 @@ __global__ void __launch_bounds__(kHaThreads) attn_decode_head_kernel(const __gr
       }
     }
   } else {
-    // q as B fragments (replicated over the 8 n columns), hi + lo fp16 parts, pre-scaled into the log2 domain
     const float sl = 0.125f * kLog2e;   // (d_head^-0.25)^2 = 1/8 exactly
+    const float* qsrc;                  // 64 query values of this head
+    if (a.wq) {
+      // ---- fused LayerNorm + query projection for this (sequence, head): q_h = LN(x[b]) Wq[h*64..+64]^T + bq -----------------
+      // Saves a whole kernel of the latency chain per layer. The weight rows of this warp (8 of the 64) and the LayerNorm
+      // affine do not depend on the previous kernel and are requested before griddepcontrol.wait; meanwhile the producer
+      // warp is already streaming K/V.
+      const int d = a.d, n_chunks = d >> 3;
+      const int ct = tid;                                   // 256 compute threads: columns ct, ct+256, ...
+      const __half* wbase = a.wq + (size_t)(h * 64 + warp * 8) * d;
+      uint4 w0[4][NJW];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int j = 0; j < NJW; ++j) {
+          const int c = lane + 32 * j;
+          w0[r][j] = c < n_chunks ? ptx::ldg_nc_16(wbase + (size_t)r * d + c * 8) : make_uint4(0, 0, 0, 0);
+        }
+      float gv[NJW], bv[NJW];
+#pragma unroll
+      for (int j = 0; j < NJW; ++j) {
+        const int c = ct + 256 * j;
+        gv[j] = c < d ? __ldg(a.ln_g + c) : 0.f;
+        bv[j] = c < d ? __ldg(a.ln_b + c) : 0.f;
+      }
+      const float bias = lane < 8 ? __ldg(a.bq + h * 64 + warp * 8 + lane) : 0.f;
+      ptx::grid_dep_sync();                                 // x comes from the previous kernel
+      uint4 w1[4][NJW];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int j = 0; j < NJW; ++j) {
+          const int c = lane + 32 * j;
+          w1[r][j] = c < n_chunks ? ptx::ldg_nc_16(wbase + (size_t)(4 + r) * d + c * 8) : make_uint4(0, 0, 0, 0);
+        }
+      float xv[NJW], sum = 0.f, sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJW; ++j) {
+        const int c = ct + 256 * j;
+        xv[j] = c < d ? __ldcg(a.x + (size_t)b * d + c) : 0.f;
+        sum += xv[j], sq += xv[j] * xv[j];
+      }
+      sum = warp_sum(sum), sq = warp_sum(sq);
+      if (lane == 0) s_red[warp] = sum, s_red[8 + warp] = sq;
+      asm volatile("bar.sync 1, 256;" ::: "memory");        // the 8 compute warps only
+      float tsum = 0.f, tsq = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) tsum += s_red[w8], tsq += s_red[8 + w8];
+      const float mean = tsum / (float)d;
+      const float rstd = rsqrtf(fmaxf(tsq / (float)d - mean * mean, 0.f) + 1e-5f);
+#pragma unroll
+      for (int j = 0; j < NJW; ++j) {
+        const int c = ct + 256 * j;
+        if (c < NJW * 256) s_x[c] = c < d ? (xv[j] - mean) * rstd * gv[j] + bv[j] : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float accq[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) accq[r] = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJW; ++j) {
+        const int c = lane + 32 * j;
+        const float4 x0 = *reinterpret_cast<const float4*>(s_x + c * 8), x1 = *reinterpret_cast<const float4*>(s_x + c * 8 + 4);
+        const float xs8[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const uint4 wv = r < 4 ? w0[r][j] : w1[r - 4][j];
+          const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 wf = __half22float2(wh[e]);
+            accq[r] = fmaf(wf.x, xs8[2 * e], accq[r]);
+            accq[r] = fmaf(wf.y, xs8[2 * e + 1], accq[r]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) accq[r] = warp_sum(accq[r]);
+      float mine = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) mine = lane == r ? accq[r] : mine;
+      if (lane < 8) s_q[warp * 8 + lane] = mine + bias;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      qsrc = s_q;
+    } else {
+      qsrc = nullptr;
+    }
+    // q as B fragments (replicated over the 8 n columns), hi + lo fp16 parts, pre-scaled into the log2 domain
     uint32_t qh[4][2], ql[4][2];
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      const float* qp = a.q + (size_t)b * a.d + h * 64 + kk * 16 + 2 * tq;
-      const float2 q0 = __ldcg(reinterpret_cast<const float2*>(qp)), q1 = __ldcg(reinterpret_cast<const float2*>(qp + 8));
+      float2 q0, q1;
+      if (qsrc) {
+        q0 = *reinterpret_cast<const float2*>(qsrc + kk * 16 + 2 * tq);
+        q1 = *reinterpret_cast<const float2*>(qsrc + kk * 16 + 2 * tq + 8);
+      } else {
+        const float* qp = a.q + (size_t)b * a.d + h * 64 + kk * 16 + 2 * tq;
+        q0 = __ldcg(reinterpret_cast<const float2*>(qp)), q1 = __ldcg(reinterpret_cast<const float2*>(qp + 8));
+      }
       const float v[4] = {q0.x * sl, q0.y * sl, q1.x * sl, q1.y * sl};
       __half hi[4], lo[4];
 #pragma unroll
@@ -736,6 +834,8 @@ __global__ void __launch_bounds__(kHaThreads) attn_decode_head_kernel(const __gr
       qh[kk][0] = *reinterpret_cast<uint32_t*>(&h0), qh[kk][1] = *reinterpret_cast<uint32_t*>(&h1);
       ql[kk][0] = *reinterpret_cast<uint32_t*>(&l0), ql[kk][1] = *reinterpret_cast<uint32_t*>(&l1);
     }
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f;
     for (int t = 0; t < n_tiles; ++t) {
       const int s = t % n_stages;
       const uint32_t ph = (uint32_t)(t / n_stages) & 1u;
@@ -833,7 +933,7 @@ static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int
   if (rc) return rc;
   rc = gemm_get_tmap(p.tmaps, p.v, p.d, p.n_ctx, nslab, p.d, (long long)p.n_ctx * p.d, kHaStageRows, &tmV);
   if (rc) return rc;
-  HeadAttnArgs a{p.q, p.out16, p.state, p.d, p.n_rows_fixed, p.kv_share, 3, 0};   // L2 prefetch measured slightly negative in-step: off
+  HeadAttnArgs a{p.q, p.x, p.ln_g, p.ln_b, p.wq, p.bq, p.out16, p.state, p.d, p.n_rows_fixed, p.kv_share, 3, 0};   // L2 prefetch measured slightly negative in-step: off
   const int ctas = p.n_head * p.Mb;
   if (p.n_rows_fixed <= 0 || ctas > 296) a.n_stages = 2;          // self attention: few rows; big grids: 3 CTAs per SM
   static int stages_env = -1;
@@ -849,18 +949,29 @@ static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int
   }
   if (pf_env >= 1000) a.l2_prefetch_tiles = pf_env - 1000;
   const size_t smem = (size_t)a.n_stages * 2 * kHaTileBytes + 1024;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    WB_CUDA_OK(cudaFuncSetAttribute(attn_decode_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p.n_head, p.Mb), cfg.blockDim = dim3(kHaThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at, cfg.numAttrs = use_pdl() ? 1 : 0;
-  const cudaError_t le = cudaLaunchKernelEx(&cfg, attn_decode_head_kernel, tmK, tmV, a);
+  cudaError_t le = cudaSuccess;
+#define WB_HA_CASE(J)                                                                                                     \
+  case J: {                                                                                                               \
+    static size_t smem_set = 0;                                                                                           \
+    if (smem > smem_set) {                                                                                                \
+      WB_CUDA_OK(cudaFuncSetAttribute(attn_decode_head_kernel<J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      smem_set = smem;                                                                                                    \
+    }                                                                                                                     \
+    le = cudaLaunchKernelEx(&cfg, attn_decode_head_kernel<J>, tmK, tmV, a);                                               \
+  } break;
+  switch ((p.d + 255) / 256) {
+    WB_HA_CASE(1) WB_HA_CASE(2) WB_HA_CASE(3) WB_HA_CASE(4) WB_HA_CASE(5)
+    default:
+      set_error("attn_decode: unsupported width %d", p.d);
+      return -1;
+  }
+#undef WB_HA_CASE
   if (launches) *launches += 1;
   WB_CUDA_OK(le);
   return 0;

@@ -104,7 +104,12 @@ int skinny_logits_ctas(int N);   // number of CTAs (= partials per sequence) of 
 // one query per (sequence, head) against rows [0, n_rows) of K/V [B][n_ctx][d] fp16 -> out16 [Mb][d] fp16
 struct AttnDecodeDesc {
   int Mb, d, n_head;
-  const float* q;         // [Mb][d] fp32
+  const float* q;         // [Mb][d] fp32, or null with the fused query projection below (cross attention)
+  const float* x;         // residual stream [Mb][d]: q = LayerNorm(x; ln_g, ln_b) wq^T + bq, computed per (sequence, head)
+  const float* ln_g;
+  const float* ln_b;
+  const __half* wq;       // [d][d]
+  const float* bq;
   const __half* k;        // [Mb / kv_share][n_ctx][d]
   const __half* v;
   int n_ctx;              // allocated rows per sequence
