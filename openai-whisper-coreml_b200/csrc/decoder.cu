@@ -457,6 +457,12 @@ __global__ void __launch_bounds__(kSkThreads) logits_gemm_kernel(SkinnyDesc p, i
     float acc[MT][4];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
+    unsigned char mk4[4];   // logit-filter classes of this lane's 4 rows of the group: fetched now, used in the epilogue
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = g * 128 + lane + 32 * i;
+      mk4[i] = (p.mask && n < p.N) ? __ldg(p.mask + n) : 0;
+    }
     auto mma_block = [&](const uint4& wa, const uint4& wb, int blk) {
       const uint32_t a0[4] = {wa.x, wb.x, wa.y, wb.y}, a1[4] = {wa.z, wb.z, wa.w, wb.w};
 #pragma unroll
@@ -513,7 +519,7 @@ __global__ void __launch_bounds__(kSkThreads) logits_gemm_kernel(SkinnyDesc p, i
         float x = -INFINITY;
         if (n < p.N) {
           x = red[rr * RS + b];
-          const unsigned char mk = p.mask ? p.mask[n] : 0;
+          const unsigned char mk = mk4[i];
           if (mk == 1 || (mk == 2 && first)) x = -INFINITY;
           if (p.out) reinterpret_cast<float*>(p.out)[(size_t)b * p.N + n] = x;
         }
@@ -563,7 +569,11 @@ static cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cud
   return cudaLaunchKernelEx(&cfg, kern, arg);
 }
 
-int skinny_logits_ctas(int N) { return ((N + 15) / 16 + 7) / 8; }
+int skinny_logits_ctas(int N) { return ((N + 15) / 16 + 7) / 8; }   // 128-row groups (= partials per sequence) of the LOGITS mode
+int logits_groups(int Mb, int N, int K) {
+  (void)Mb, (void)K;
+  return skinny_logits_ctas(N);
+}
 
 int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches) {
   if (d.Mb < 1 || d.Mb > 40 || d.K % 128 != 0 || d.N < 16) {
@@ -1017,13 +1027,31 @@ __global__ void __launch_bounds__(256) step_finish_kernel(FinishDesc p) {
       s_tok = __ldcg(trow + c + 1);
     }
   }
-  // everything that does not depend on the sampled token is fetched in one batch: the logits partials of this sequence
-  float4 rec[4];
+  // the logits partials of this sequence: each thread folds its records into an online (max, argmax, sum-exp)
+  float best = -INFINITY, se = 0.f;
+  int arg = 0x7fffffff;
+  if (p.sample) {
+    for (int i0 = tid; i0 < p.n_part; i0 += 256 * 4) {
+      float4 rec[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int i = tid + j * 256;
-    rec[j] = make_float4(-INFINITY, __int_as_float(0x7fffffff), 0.f, 0.f);
-    if (p.sample && i < p.n_part) rec[j] = __ldcg(reinterpret_cast<const float4*>(p.part_logits + ((size_t)b * p.n_part + i) * 4));
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * 256;
+        rec[j] = make_float4(-INFINITY, __int_as_float(0x7fffffff), 0.f, 0.f);
+        if (i < p.n_part) rec[j] = __ldcg(reinterpret_cast<const float4*>(p.part_logits + ((size_t)b * p.n_part + i) * 4));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float m = rec[j].x;
+        const int a = __float_as_int(rec[j].y);
+        if (m > best) {
+          se = se * expf(best - m) + rec[j].z;   // best = -inf first: se is 0
+          best = m, arg = a;
+        } else if (m > -INFINITY) {
+          se += rec[j].z * expf(m - best);
+          if (m == best && a < arg) arg = a;
+        }
+      }
+    }
   }
   __syncthreads();
   const int cur = s_cur;
@@ -1035,39 +1063,31 @@ __global__ void __launch_bounds__(256) step_finish_kernel(FinishDesc p) {
     pe_v[j] = (np < p.n_ctx && c < p.d) ? __ldg(p.pos_emb + (size_t)np * p.d + c) : 0.f;
   }
   if (p.sample) {
-    float best = -INFINITY;
-    int arg = 0x7fffffff;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int a = __float_as_int(rec[j].y);
-      if (rec[j].x > best || (rec[j].x == best && a < arg)) best = rec[j].x, arg = a;
-    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
-      if (ov > best || (ov == best && oi < arg)) best = ov, arg = oi;
+      const float om = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, se, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      const float nm = fmaxf(best, om);
+      se = (best > -INFINITY ? se * expf(best - nm) : 0.f) + (om > -INFINITY ? os * expf(om - nm) : 0.f);
+      if (om > best || (om == best && oa < arg)) arg = oa;
+      best = nm;
     }
-    if (lane == 0) s_val[warp] = best, s_idx[warp] = arg;
-    __syncthreads();
-    best = s_val[0], arg = s_idx[0];
-#pragma unroll
-    for (int w = 1; w < 8; ++w)
-      if (s_val[w] > best || (s_val[w] == best && s_idx[w] < arg)) best = s_val[w], arg = s_idx[w];
-    float se = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (rec[j].x > -INFINITY) se += rec[j].z * expf(rec[j].x - best);
-    se = warp_sum(se);
-    if (lane == 0) s_sum[warp] = se;
+    if (lane == 0) s_val[warp] = best, s_idx[warp] = arg, s_sum[warp] = se;
     __syncthreads();
     if (tid == 0) {
-      float tot = 0.f;
-      for (int w = 0; w < 8; ++w) tot += s_sum[w];
-      const float logprob = -logf(tot);   // the chosen logit is the maximum
+      float M = s_val[0], S = s_sum[0];
+      int A = s_idx[0];
+      for (int w = 1; w < 8; ++w) {
+        const float om = s_val[w];
+        const float nm = fmaxf(M, om);
+        S = (M > -INFINITY ? S * expf(M - nm) : 0.f) + (om > -INFINITY ? s_sum[w] * expf(om - nm) : 0.f);
+        if (om > M || (om == M && s_idx[w] < A)) A = s_idx[w];
+        M = nm;
+      }
+      const float logprob = -logf(S);   // the chosen logit is the maximum
       const bool ended = prev_tok == p.eot;
       if (!ended) p.sum_logprob[b] = slp_old + logprob;
-      const int next = ended ? p.eot : arg;
+      const int next = ended ? p.eot : A;
       trow[cur + 1] = next;
       p.done[b] = next == p.eot;
       s_tok = next;

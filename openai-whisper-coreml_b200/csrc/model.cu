@@ -377,7 +377,8 @@ static int step_finish(wb_handle* h, const StepOpts& o, int sample) {
   const size_t b0 = o.b0;
   FinishDesc f{};
   f.Mb = o.Mb, f.V = D.n_vocab, f.d = D.n_text_state, f.n_ctx = D.n_text_ctx, f.sample = sample;
-  f.part_logits = h->part_logits + b0 * h->n_logit_ctas * 4, f.n_part = h->n_logit_ctas, f.eot = o.eot;
+  f.n_part = logits_groups(o.Mb, D.n_vocab, D.n_text_state);
+  f.part_logits = h->part_logits + b0 * h->n_logit_ctas * 4, f.eot = o.eot;
   f.tokens = h->tokens + b0 * h->tokens_ld, f.tokens_ld = h->tokens_ld;
   f.sum_logprob = h->sum_logprob + b0, f.done = h->done + b0, f.tok_emb = h->tok_emb, f.pos_emb = h->dec_pos;
   f.x = h->xdec + b0 * D.n_text_state, f.state = step_state(h, o);

@@ -99,7 +99,8 @@ struct SkinnyDesc {
   const DecodeState* state;
 };
 int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches);
-int skinny_logits_ctas(int N);   // number of CTAs (= partials per sequence) of the LOGITS mode
+int skinny_logits_ctas(int N);   // upper bound on the row groups (= partials per sequence) of the LOGITS mode
+int logits_groups(int Mb, int N, int K);   // actual number of row groups for this shape
 
 // one query per (sequence, head) against rows [0, n_rows) of K/V [B][n_ctx][d] fp16 -> out16 [Mb][d] fp16
 struct AttnDecodeDesc {
