@@ -666,6 +666,7 @@ int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches) 
 // fp16 hi + lo parts (two MMAs each) so that only K and V themselves are fp16-rounded; fp32 online softmax in the log2 domain.
 constexpr int kHaStageRows = 128;
 constexpr int kHaThreads = 288;
+constexpr int kHaMaxCluster = 8;                   // heads per sequence the fused output projection supports (portable cluster size)
 constexpr int kHaTileBytes = kHaStageRows * 128;   // one K (or V) stage tile: 128 rows x 64 halves
 
 struct HeadAttnArgs {
@@ -676,10 +677,59 @@ struct HeadAttnArgs {
   const __half* wq;        //   [d][d]
   const float* bq;         //   [d]
   __half* out16;
+  // fused output projection (launched as one cluster per sequence, one CTA per head): xres[b] += concat_h(o_h) Wo^T + bo.
+  // The heads exchange their 64 outputs through distributed shared memory; CTA h then owns columns h*64..h*64+63.
+  const __half* wo;        //   [d][d], or null: write the head outputs to out16 instead
+  const float* bo;         //   [d]
+  float* xres;             //   residual stream [Mb][d], updated in place
   const DecodeState* state;
   int d, n_rows_fixed, kv_share, n_stages;
   int l2_prefetch_tiles;   // cross attention: stage tiles beyond the ring requested into L2 while q is still being computed
 };
+
+// 8 weight rows x d of a [.][d] fp16 matrix against one fp32 vector in shared memory: lane l owns the 16-byte chunks
+// l, l+32, ... of every row. Used by the fused query projection (prologue) and the fused output projection (epilogue) of
+// attn_decode_head_kernel; the rows are requested in two halves so that the first can be in flight across a barrier.
+template <int NJW>
+__device__ __forceinline__ void head_rows_load(uint4 (&w)[4][NJW], const __half* wbase, int d, int lane) {
+  const int n_chunks = d >> 3;
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int j = 0; j < NJW; ++j) {
+      const int c = lane + 32 * j;
+      w[r][j] = c < n_chunks ? ptx::ldg_nc_16(wbase + (size_t)r * d + c * 8) : make_uint4(0, 0, 0, 0);
+    }
+}
+template <int NJW>
+__device__ __forceinline__ float head_rows_dot(const uint4 (&w0)[4][NJW], const uint4 (&w1)[4][NJW], const float* s_vec, int lane) {
+  float acc[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+#pragma unroll
+  for (int j = 0; j < NJW; ++j) {
+    const int c = lane + 32 * j;
+    const float4 x0 = *reinterpret_cast<const float4*>(s_vec + c * 8), x1 = *reinterpret_cast<const float4*>(s_vec + c * 8 + 4);
+    const float xs8[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const uint4 wv = r < 4 ? w0[r][j] : w1[r - 4][j];
+      const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 wf = __half22float2(wh[e]);
+        acc[r] = fmaf(wf.x, xs8[2 * e], acc[r]);
+        acc[r] = fmaf(wf.y, xs8[2 * e + 1], acc[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) acc[r] = warp_sum(acc[r]);
+  float mine = 0.f;   // lane r (< 8) keeps the dot product of row r
+#pragma unroll
+  for (int r = 0; r < 8; ++r) mine = lane == r ? acc[r] : mine;
+  return mine;
+}
 
 template <int NJW>   // ceil(d / 256): 16-byte weight chunks per lane and row in the fused query projection
 __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head_kernel(const __grid_constant__ CUtensorMap tmK,
@@ -687,6 +737,7 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8];
   __shared__ __align__(16) float s_x[NJW * 256];   // normalised residual row (fused query projection)
+  __shared__ __align__(16) float s_a[NJW * 256];   // all heads' outputs of this sequence (fused output projection; written by the cluster)
   __shared__ float s_q[64], s_red[16];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -740,17 +791,11 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
       // Saves a whole kernel of the latency chain per layer. The weight rows of this warp (8 of the 64) and the LayerNorm
       // affine do not depend on the previous kernel and are requested before griddepcontrol.wait; meanwhile the producer
       // warp is already streaming K/V.
-      const int d = a.d, n_chunks = d >> 3;
+      const int d = a.d;
       const int ct = tid;                                   // 256 compute threads: columns ct, ct+256, ...
       const __half* wbase = a.wq + (size_t)(h * 64 + warp * 8) * d;
       uint4 w0[4][NJW];
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int j = 0; j < NJW; ++j) {
-          const int c = lane + 32 * j;
-          w0[r][j] = c < n_chunks ? ptx::ldg_nc_16(wbase + (size_t)r * d + c * 8) : make_uint4(0, 0, 0, 0);
-        }
+      head_rows_load<NJW>(w0, wbase, d, lane);
       float gv[NJW], bv[NJW];
 #pragma unroll
       for (int j = 0; j < NJW; ++j) {
@@ -761,13 +806,7 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
       const float bias = lane < 8 ? __ldg(a.bq + h * 64 + warp * 8 + lane) : 0.f;
       ptx::grid_dep_sync();                                 // x comes from the previous kernel
       uint4 w1[4][NJW];
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int j = 0; j < NJW; ++j) {
-          const int c = lane + 32 * j;
-          w1[r][j] = c < n_chunks ? ptx::ldg_nc_16(wbase + (size_t)(4 + r) * d + c * 8) : make_uint4(0, 0, 0, 0);
-        }
+      head_rows_load<NJW>(w1, wbase + (size_t)4 * d, d, lane);
       float xv[NJW], sum = 0.f, sq = 0.f;
 #pragma unroll
       for (int j = 0; j < NJW; ++j) {
@@ -789,35 +828,12 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
         if (c < NJW * 256) s_x[c] = c < d ? (xv[j] - mean) * rstd * gv[j] + bv[j] : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      float accq[8];
-#pragma unroll
-      for (int r = 0; r < 8; ++r) accq[r] = 0.f;
-#pragma unroll
-      for (int j = 0; j < NJW; ++j) {
-        const int c = lane + 32 * j;
-        const float4 x0 = *reinterpret_cast<const float4*>(s_x + c * 8), x1 = *reinterpret_cast<const float4*>(s_x + c * 8 + 4);
-        const float xs8[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const uint4 wv = r < 4 ? w0[r][j] : w1[r - 4][j];
-          const __half2* wh = reinterpret_cast<const __half2*>(&wv);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 wf = __half22float2(wh[e]);
-            accq[r] = fmaf(wf.x, xs8[2 * e], accq[r]);
-            accq[r] = fmaf(wf.y, xs8[2 * e + 1], accq[r]);
-          }
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < 8; ++r) accq[r] = warp_sum(accq[r]);
-      float mine = 0.f;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) mine = lane == r ? accq[r] : mine;
+      const float mine = head_rows_dot<NJW>(w0, w1, s_x, lane);
       if (lane < 8) s_q[warp * 8 + lane] = mine + bias;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       qsrc = s_q;
     } else {
+      if (fixed) ptx::grid_dep_sync();                      // q comes from the previous kernel
       qsrc = nullptr;
     }
     // q as B fragments (replicated over the 8 n columns), hi + lo fp16 parts, pre-scaled into the log2 domain
@@ -904,6 +920,20 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
   }
   __syncthreads();   // all stages consumed; reuse the ring for the cross-warp merge: [8][68] floats
   float* red = reinterpret_cast<float*>(smem);
+  const bool fuse_out = a.wo != nullptr;
+  // fused output projection: this warp's first four weight rows, its bias and the old residual values are requested now,
+  // so that their latency is covered by the merge and the cluster exchange
+  uint4 wo0[4][NJW];
+  float bias_o = 0.f, x_old = 0.f;
+  const __half* wobase = nullptr;
+  if (fuse_out && warp < 8) {
+    wobase = a.wo + (size_t)(h * 64 + warp * 8) * a.d;
+    head_rows_load<NJW>(wo0, wobase, a.d, lane);
+    if (lane < 8) {
+      bias_o = __ldg(a.bo + h * 64 + warp * 8 + lane);
+      x_old = __ldcg(a.xres + (size_t)b * a.d + h * 64 + warp * 8 + lane);
+    }
+  }
   if (warp < 8) {
     float L = l_run;
     L += __shfl_xor_sync(0xffffffffu, L, 4);
@@ -931,7 +961,26 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
       L += wgt * red[w * 68 + 65];
       A += wgt * red[w * 68 + tid];
     }
-    a.out16[(size_t)b * a.d + h * 64 + tid] = __float2half_rn(A / L);
+    if (!fuse_out) {
+      a.out16[(size_t)b * a.d + h * 64 + tid] = __float2half_rn(A / L);
+    } else {
+      // push this head's output into the s_a of every CTA of the cluster (one CTA per head, cluster rank == h)
+      const float val = A / L;
+      const uint32_t local = ptx::smem_u32(s_a + h * 64 + tid);
+      const int n_cta = (int)gridDim.x;
+      for (int r = 0; r < n_cta; ++r) ptx::st_cluster_f32(ptx::mapa(local, (uint32_t)r), val);
+    }
+  }
+  if (fuse_out) {
+    if (tid < NJW * 256 - a.d && a.d + tid < NJW * 256) s_a[a.d + tid] = 0.f;   // chunk padding beyond d (never written by a peer)
+    ptx::cluster_arrive_release();
+    ptx::cluster_wait_acquire();   // every head's outputs have landed in s_a; no remote access after this point
+    if (warp < 8) {
+      uint4 wo1[4][NJW];
+      head_rows_load<NJW>(wo1, wobase + (size_t)4 * a.d, a.d, lane);
+      const float mine = head_rows_dot<NJW>(wo0, wo1, s_a, lane);
+      if (lane < 8) a.xres[(size_t)b * a.d + h * 64 + warp * 8 + lane] = x_old + (mine + bias_o);
+    }
   }
   trace.end();
 }
@@ -943,7 +992,12 @@ static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int
   if (rc) return rc;
   rc = gemm_get_tmap(p.tmaps, p.v, p.d, p.n_ctx, nslab, p.d, (long long)p.n_ctx * p.d, kHaStageRows, &tmV);
   if (rc) return rc;
-  HeadAttnArgs a{p.q, p.x, p.ln_g, p.ln_b, p.wq, p.bq, p.out16, p.state, p.d, p.n_rows_fixed, p.kv_share, 3, 0};   // L2 prefetch measured slightly negative in-step: off
+  const bool fuse_out = p.wo != nullptr;
+  if (fuse_out && (p.n_head > kHaMaxCluster || !p.xres || !p.bo)) {
+    set_error("attn_decode: fused output projection needs n_head <= %d (one cluster per sequence)", kHaMaxCluster);
+    return -1;
+  }
+  HeadAttnArgs a{p.q, p.x, p.ln_g, p.ln_b, p.wq, p.bq, p.out16, p.wo, p.bo, p.xres, p.state, p.d, p.n_rows_fixed, p.kv_share, 3, 0};   // L2 prefetch measured slightly negative in-step: off
   const int ctas = p.n_head * p.Mb;
   if (p.n_rows_fixed <= 0 || ctas > 296) a.n_stages = 2;          // self attention: few rows; big grids: 3 CTAs per SM
   static int stages_env = -1;
@@ -961,10 +1015,19 @@ static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int
   const size_t smem = (size_t)a.n_stages * 2 * kHaTileBytes + 1024;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p.n_head, p.Mb), cfg.blockDim = dim3(kHaThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at, cfg.numAttrs = use_pdl() ? 1 : 0;
+  cudaLaunchAttribute at[2];
+  int n_at = 0;
+  if (fuse_out) {   // one cluster per sequence, one CTA per head (portable size)
+    at[n_at].id = cudaLaunchAttributeClusterDimension;
+    at[n_at].val.clusterDim.x = (unsigned)p.n_head, at[n_at].val.clusterDim.y = 1, at[n_at].val.clusterDim.z = 1;
+    ++n_at;
+  }
+  if (use_pdl()) {
+    at[n_at].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n_at].val.programmaticStreamSerializationAllowed = 1;
+    ++n_at;
+  }
+  cfg.attrs = at, cfg.numAttrs = n_at;
   cudaError_t le = cudaSuccess;
 #define WB_HA_CASE(J)                                                                                                     \
   case J: {                                                                                                               \
@@ -972,6 +1035,12 @@ static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int
     if (smem > smem_set) {                                                                                                \
       WB_CUDA_OK(cudaFuncSetAttribute(attn_decode_head_kernel<J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       smem_set = smem;                                                                                                    \
+    }                                                                                                                     \
+    if (fuse_out && getenv("WB_DEBUG_CLUSTERS")) {                                                                        \
+      int nc = -1;                                                                                                        \
+      cudaOccupancyMaxActiveClusters(&nc, attn_decode_head_kernel<J>, &cfg);                                              \
+      fprintf(stderr, "[wb] attn_decode cluster=%d smem=%zu stages=%d fixed=%d: max active clusters %d (grid %d)\n",      \
+              p.n_head, smem, a.n_stages, p.n_rows_fixed, nc, p.Mb);                                                      \
     }                                                                                                                     \
     le = cudaLaunchKernelEx(&cfg, attn_decode_head_kernel<J>, tmK, tmV, a);                                               \
   } break;
@@ -987,12 +1056,402 @@ static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int
   return 0;
 }
 
+// Off by default: measured on B200 (base.en, 32 sequences) the cluster launch keeps the attention CTAs from starting under
+// their predecessor, which costs what the saved kernel gains (WB_FUSE_OUT=1 enables it for cross attention).
+int attn_decode_can_fuse_out(int n_head) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("WB_FUSE_OUT");
+    env = e ? atoi(e) : 0;
+  }
+  return n_head <= kHaMaxCluster ? env : 0;
+}
+
 int launch_attn_decode(const AttnDecodeDesc& p, cudaStream_t st, int64_t* launches) {
   if (p.d % 64 != 0 || p.d / 64 != p.n_head || p.d > 1280 || p.kv_share < 1) {
     set_error("attn_decode: unsupported d=%d heads=%d", p.d, p.n_head);
     return -1;
   }
   return launch_attn_decode_head(p, st, launches);
+}
+
+// ---- self-attention block in one kernel: LayerNorm + QKV + cache append + attention + output projection + residual -----------------
+// For models with n_head <= 8. Grid (head, group of kSbG sequences), launched as one thread-block cluster per group: CTA h
+//   1. normalises the group's rows of the residual stream (fp32 LayerNorm -> fp16, as the skinny GEMM's input stage),
+//   2. multiplies them with the 192 rows of Wqkv that belong to head h (q, k, v: 64 each; one 16-row strip per warp, weights
+//      streamed once with 16-byte loads straight into mma.sync A fragments; the sequences are the 8 MMA columns),
+//   3. appends k, v (fp16) to the cache and attends over the cached rows plus the new one (three warps per sequence,
+//      16-byte K/V loads, fp32 online softmax in the log2 domain),
+//   4. pushes its 64 attention outputs per sequence into the shared memory of every CTA of the cluster (DSMEM), and after
+//      the cluster barrier owns columns h*64..h*64+63 of  x += attn Wo^T + bo  (strip x K-third per warp).
+// Replaces three kernels of the latency chain (QKV GEMM, attention, output projection) with one. The footprint is kept small
+// (64 CTAs at 32 sequences, ~36 KB shared memory, <= 96 registers) so that the CTAs of the following cross-attention kernel
+// are resident and streaming K/V while this one runs.
+constexpr int kSbG = 4;             // sequences per CTA
+constexpr int kSbThreads = 384;     // 12 warps
+constexpr int kSbWarps = kSbThreads / 32;
+
+struct SelfBlockArgs {
+  float* x;                 // [Mb][d] residual stream, updated in place
+  const float* ln_g;
+  const float* ln_b;
+  const __half* wqkv;       // [3d][d]
+  const float* bqkv;        // [3d]
+  const __half* wo;         // [d][d]
+  const float* bo;          // [d]
+  __half* kcache;           // [Mb][n_ctx][d]
+  __half* vcache;
+  int Mb, d, n_ctx;
+  const DecodeState* state;
+};
+
+struct SbPartial {   // online-softmax state of one lane / warp over the 8 columns it owns
+  float m, l, o[8];
+};
+__device__ __forceinline__ void sb_merge_shfl(SbPartial& p, int off) {
+  const float m2 = __shfl_xor_sync(0xffffffffu, p.m, off), l2 = __shfl_xor_sync(0xffffffffu, p.l, off);
+  const float M = fmaxf(p.m, m2);
+  const float w1 = p.m == -INFINITY ? 0.f : exp2f(p.m - M), w2 = m2 == -INFINITY ? 0.f : exp2f(m2 - M);
+  p.l = p.l * w1 + l2 * w2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float o2 = __shfl_xor_sync(0xffffffffu, p.o[i], off);
+    p.o[i] = p.o[i] * w1 + o2 * w2;
+  }
+  p.m = M;
+}
+__device__ __forceinline__ void sb_row(SbPartial& p, float score, const float (&v)[8]) {
+  const float mn = fmaxf(p.m, score);
+  const float corr = exp2f(p.m - mn), pr = exp2f(score - mn);   // p.m = -inf: corr = 0
+  p.l = p.l * corr + pr;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) p.o[i] = p.o[i] * corr + pr * v[i];
+  p.m = mn;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 t = __half22float2(h[e]);
+    f[2 * e] = t.x, f[2 * e + 1] = t.y;
+  }
+}
+
+__global__ void __maxnreg__(96) self_block_kernel(SelfBlockArgs a) {
+  extern __shared__ __align__(16) unsigned char sb_smem[];
+  TraceScope trace(a.state, 210);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 2, tq = lane & 3;
+  const int h = blockIdx.x, b0 = blockIdx.y * kSbG;
+  const int d = a.d, nblk = d >> 5;
+  const int XS = d * 2 + 64;                                   // bytes per activation row; (XS/16) % 8 == 4 -> conflict-free LDS.128
+  unsigned char* xs = sb_smem;                                 // [8][XS] fp16 LayerNorm(x) rows (slots >= kSbG stay zero)
+  unsigned char* sa = xs + 8 * XS;                             // [8][XS] fp16 attention outputs of all heads (written by the cluster)
+  float* s_g = reinterpret_cast<float*>(sa + 8 * XS);          // [d] LayerNorm gamma
+  float* s_b = s_g + d;                                        // [d] beta
+  float* s_qkv = s_b + d;                                      // [3][kSbG][64] q, k, v of this head (fp32)
+  float* s_part = s_qkv + 3 * kSbG * 64;                       // [kSbG][3][66] attention partials of the three warps of a sequence
+  float* s_red = s_part + kSbG * 3 * 66;                       // [3][kSbG][64] output-projection partials of the three K-thirds
+
+  // ---- before the wait: everything that does not depend on the previous kernel -------------------------------------------------
+  // warp w owns strip w of this head's 192 QKV rows: part = w / 4 (q, k, v), rows (w % 4) * 16 .. + 15 of the head
+  const int part = warp >> 2, strip = warp & 3;
+  const int row_lo = part * d + h * 64 + strip * 16 + grp;     // Wqkv row of accumulator rows grp / grp + 8
+  const __half* wrow0 = a.wqkv + (size_t)row_lo * d + tq * 8;
+  const __half* wrow1 = wrow0 + (size_t)8 * d;
+  constexpr int kPre = 8;
+  uint4 pwa[kPre], pwb[kPre];
+#pragma unroll
+  for (int u = 0; u < kPre; ++u) {
+    const int blk = u < nblk ? u : 0;
+    pwa[u] = ptx::ldg_nc_16(wrow0 + blk * 32);
+    pwb[u] = ptx::ldg_nc_16(wrow1 + blk * 32);
+  }
+  const float bias_lo = __ldg(a.bqkv + row_lo), bias_hi = __ldg(a.bqkv + row_lo + 8);
+  for (int i = tid * 4; i < d; i += kSbThreads * 4) {
+    *reinterpret_cast<float4*>(s_g + i) = __ldg(reinterpret_cast<const float4*>(a.ln_g + i));
+    *reinterpret_cast<float4*>(s_b + i) = __ldg(reinterpret_cast<const float4*>(a.ln_b + i));
+  }
+  for (int i = tid; i < (8 - kSbG) * XS / 16; i += kSbThreads) {   // zero the padding slots of both activation tiles
+    *reinterpret_cast<uint4*>(xs + kSbG * XS + i * 16) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(sa + kSbG * XS + i * 16) = make_uint4(0, 0, 0, 0);
+  }
+  ptx::grid_dep_launch();
+  ptx::grid_dep_sync();
+  __syncthreads();
+  trace.mark(3);
+  const int pos = ld_state(&a.state->cur_len);                 // cache row of the token this step consumes
+
+  // ---- 1. LayerNorm: warp s normalises row b0 + s (fp32 statistics, two passes over registers) ----------------------------------
+  if (warp < kSbG) {
+    const int b = b0 + warp;
+    __half* xr = reinterpret_cast<__half*>(xs + warp * XS);
+    const int n4 = d >> 2;
+    float4 v[4];
+    float sum = 0.f, sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = (c < n4 && b < a.Mb) ? ld_x4(a.x + (size_t)b * d + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    sum = warp_sum(sum), sq = warp_sum(sq);
+    const float mean = sum / (float)d;
+    const float rstd = b < a.Mb ? rsqrtf(fmaxf(sq / (float)d - mean * mean, 0.f) + 1e-5f) : 0.f;
+    const float ab = b < a.Mb ? 1.f : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = lane + 32 * i;
+      if (c < n4) {
+        const float4 g = *reinterpret_cast<const float4*>(s_g + c * 4), bb = *reinterpret_cast<const float4*>(s_b + c * 4);
+        const __half2 h0 = __floats2half2_rn((v[i].x - mean) * rstd * g.x + ab * bb.x, (v[i].y - mean) * rstd * g.y + ab * bb.y);
+        const __half2 h1 = __floats2half2_rn((v[i].z - mean) * rstd * g.z + ab * bb.z, (v[i].w - mean) * rstd * g.w + ab * bb.w);
+        uint2 u;
+        u.x = *reinterpret_cast<const uint32_t*>(&h0), u.y = *reinterpret_cast<const uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(xr + c * 4) = u;
+      }
+    }
+  }
+  __syncthreads();
+  trace.mark(4);
+
+  // ---- 2. QKV for head h: D[16 weight rows][8 sequence slots] per warp over the whole K ---------------------------------------
+  {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const unsigned char* xl = xs + grp * XS + tq * 16;
+#pragma unroll
+    for (int u = 0; u < kPre; ++u) {
+      if (u < nblk) {
+        const uint32_t a0[4] = {pwa[u].x, pwb[u].x, pwa[u].y, pwb[u].y}, a1[4] = {pwa[u].z, pwb[u].z, pwa[u].w, pwb[u].w};
+        const uint4 xb = *reinterpret_cast<const uint4*>(xl + u * 64);
+        const uint32_t bf0[2] = {xb.x, xb.y}, bf1[2] = {xb.z, xb.w};
+        ptx::mma_16816(acc, a0, bf0);
+        ptx::mma_16816(acc, a1, bf1);
+      }
+    }
+    for (int blk = kPre; blk < nblk; blk += 8) {
+      uint4 wa[8], wb[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int bb = blk + u < nblk ? blk + u : blk;
+        wa[u] = ptx::ldg_nc_16(wrow0 + bb * 32);
+        wb[u] = ptx::ldg_nc_16(wrow1 + bb * 32);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (blk + u < nblk) {
+          const uint32_t a0[4] = {wa[u].x, wb[u].x, wa[u].y, wb[u].y}, a1[4] = {wa[u].z, wb[u].z, wa[u].w, wb[u].w};
+          const uint4 xb = *reinterpret_cast<const uint4*>(xl + (blk + u) * 64);
+          const uint32_t bf0[2] = {xb.x, xb.y}, bf1[2] = {xb.z, xb.w};
+          ptx::mma_16816(acc, a0, bf0);
+          ptx::mma_16816(acc, a1, bf1);
+        }
+      }
+    }
+    // accumulator (row grp / grp+8, sequence slots 2tq, 2tq+1): + bias -> s_qkv; k and v also go to the cache (fp16)
+    if (2 * tq < kSbG) {
+      const int c_lo = strip * 16 + grp, c_hi = c_lo + 8;     // column inside the head
+      const float v00 = acc[0] + bias_lo, v01 = acc[1] + bias_lo, v10 = acc[2] + bias_hi, v11 = acc[3] + bias_hi;
+      float* dst = s_qkv + part * kSbG * 64;
+      dst[(2 * tq) * 64 + c_lo] = v00, dst[(2 * tq + 1) * 64 + c_lo] = v01;
+      dst[(2 * tq) * 64 + c_hi] = v10, dst[(2 * tq + 1) * 64 + c_hi] = v11;
+      if (part > 0) {
+        __half* cache = part == 1 ? a.kcache : a.vcache;
+        const int bA = b0 + 2 * tq, bB = bA + 1;
+        if (bA < a.Mb) {
+          __half* r = cache + ((size_t)bA * a.n_ctx + pos) * d + h * 64;
+          r[c_lo] = __float2half_rn(v00), r[c_hi] = __float2half_rn(v10);
+        }
+        if (bB < a.Mb) {
+          __half* r = cache + ((size_t)bB * a.n_ctx + pos) * d + h * 64;
+          r[c_lo] = __float2half_rn(v01), r[c_hi] = __float2half_rn(v11);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  trace.mark(5);
+
+  // ---- 3. attention: warps 3s .. 3s+2 share sequence slot s; lane = (row sub-index 0..3, 16-byte column chunk 0..7) -----------------
+  {
+    const int s = warp / 3, sub = warp - s * 3;
+    const int b = b0 + s;
+    const int rsub = lane >> 3, cc = lane & 7;
+    const float sl = 0.125f * kLog2e;   // (d_head^-0.25)^2 = 1/8 exactly; log2 domain
+    float qv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qv[i] = s_qkv[s * 64 + cc * 8 + i] * sl;
+    SbPartial p;
+    p.m = -INFINITY, p.l = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p.o[i] = 0.f;
+    if (b < a.Mb) {                                            // warp-uniform
+      const int per = (pos + 2) / 3;                           // cached rows [0, pos) in three contiguous ranges
+      const int r_begin = sub * per;
+      const int r_end = pos < r_begin + per ? pos : r_begin + per;
+      const __half* kb = a.kcache + (size_t)b * a.n_ctx * d + h * 64 + cc * 8;
+      const __half* vb = a.vcache + (size_t)b * a.n_ctx * d + h * 64 + cc * 8;
+      for (int r0 = r_begin; r0 < r_end; r0 += 32) {
+        uint4 kq[8], vq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = r0 + j * 4 + rsub;
+          const int rc = r < r_end ? r : r_begin;              // clamped: the value is discarded below
+          kq[j] = ptx::ldg_nc_16(kb + (size_t)rc * d);
+          vq[j] = ptx::ldg_nc_16(vb + (size_t)rc * d);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float kf[8], vf[8];
+          unpack8(kq[j], kf);
+          float dot = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dot = fmaf(qv[i], kf[i], dot);
+          dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+          dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+          dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+          if (r0 + j * 4 + rsub < r_end) {
+            unpack8(vq[j], vf);
+            sb_row(p, dot, vf);
+          }
+        }
+      }
+      if (sub == 0) {   // the new row: k, v as the cache holds them (fp16-rounded), taken from shared memory
+        float kf[8], vf[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          kf[i] = __half2float(__float2half_rn(s_qkv[(kSbG + s) * 64 + cc * 8 + i]));
+          vf[i] = __half2float(__float2half_rn(s_qkv[(2 * kSbG + s) * 64 + cc * 8 + i]));
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dot = fmaf(qv[i], kf[i], dot);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+        if (rsub == 0) sb_row(p, dot, vf);
+      }
+    }
+    sb_merge_shfl(p, 8);
+    sb_merge_shfl(p, 16);
+    if (rsub == 0) {
+      float* dst = s_part + (s * 3 + sub) * 66;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dst[cc * 8 + i] = p.o[i];
+      if (cc == 0) dst[64] = p.m, dst[65] = p.l;
+    }
+  }
+  // this warp's slice of the output projection: strip (warp % 4) of the head's 64 output columns, K-third warp / 4.
+  // Requested now so that the latency is covered by the merge and the cluster exchange.
+  const int ostrip = warp & 3, kthird = warp >> 2;
+  const int ob0 = (kthird * nblk) / 3, ob1 = ((kthird + 1) * nblk) / 3;
+  constexpr int kOB = 6;                                       // blocks per K-third: ceil(16 / 3)
+  uint4 owa[kOB], owb[kOB];
+  {
+    const __half* orow0 = a.wo + (size_t)(h * 64 + ostrip * 16 + grp) * d + tq * 8;
+    const __half* orow1 = orow0 + (size_t)8 * d;
+#pragma unroll
+    for (int u = 0; u < kOB; ++u) {
+      const int blk = ob0 + u < ob1 ? ob0 + u : ob0;
+      owa[u] = ptx::ldg_nc_16(orow0 + blk * 32);
+      owb[u] = ptx::ldg_nc_16(orow1 + blk * 32);
+    }
+  }
+  // epilogue mapping: thread -> (sequence slot, output column); old residual and bias requested now as well
+  const int es = tid >> 6, ec = tid & 63;
+  float x_old = 0.f, bias_o = 0.f;
+  if (tid < kSbG * 64) {
+    bias_o = __ldg(a.bo + h * 64 + ec);
+    if (b0 + es < a.Mb) x_old = __ldcg(a.x + (size_t)(b0 + es) * d + h * 64 + ec);
+  }
+  __syncthreads();
+  trace.mark(6);
+  if (tid < kSbG * 64) {   // merge the three partials of (slot es, column ec) and push the result into every CTA of the cluster
+    const float* pp = s_part + es * 3 * 66;
+    const float m0 = pp[64], m1 = pp[66 + 64], m2 = pp[132 + 64];
+    const float M = fmaxf(m0, fmaxf(m1, m2));
+    const float w0 = m0 == -INFINITY ? 0.f : exp2f(m0 - M), w1 = m1 == -INFINITY ? 0.f : exp2f(m1 - M),
+                w2 = m2 == -INFINITY ? 0.f : exp2f(m2 - M);
+    const float L = w0 * pp[65] + w1 * pp[66 + 65] + w2 * pp[132 + 65];
+    const float A = w0 * pp[ec] + w1 * pp[66 + ec] + w2 * pp[132 + ec];
+    const __half r = __float2half_rn(L > 0.f ? A / L : 0.f);
+    const uint32_t local = ptx::smem_u32(sa + es * XS + (h * 64 + ec) * 2);
+    const int n_cta = (int)gridDim.x;
+    for (int c = 0; c < n_cta; ++c) ptx::st_cluster_u16(ptx::mapa(local, (uint32_t)c), __half_as_ushort(r));
+  }
+  ptx::cluster_arrive_release();
+  ptx::cluster_wait_acquire();   // every head's outputs have landed in sa; no remote access after this point
+  trace.mark(7);
+
+  // ---- 4. output projection for columns h*64 .. h*64+63 ------------------------------------------------------------------------------
+  {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const unsigned char* al = sa + grp * XS + tq * 16;
+#pragma unroll
+    for (int u = 0; u < kOB; ++u) {
+      if (ob0 + u < ob1) {
+        const uint32_t a0[4] = {owa[u].x, owb[u].x, owa[u].y, owb[u].y}, a1[4] = {owa[u].z, owb[u].z, owa[u].w, owb[u].w};
+        const uint4 xb = *reinterpret_cast<const uint4*>(al + (ob0 + u) * 64);
+        const uint32_t bf0[2] = {xb.x, xb.y}, bf1[2] = {xb.z, xb.w};
+        ptx::mma_16816(acc, a0, bf0);
+        ptx::mma_16816(acc, a1, bf1);
+      }
+    }
+    if (2 * tq < kSbG) {
+      float* dst = s_red + kthird * kSbG * 64;
+      const int c_lo = ostrip * 16 + grp, c_hi = c_lo + 8;
+      dst[(2 * tq) * 64 + c_lo] = acc[0], dst[(2 * tq + 1) * 64 + c_lo] = acc[1];
+      dst[(2 * tq) * 64 + c_hi] = acc[2], dst[(2 * tq + 1) * 64 + c_hi] = acc[3];
+    }
+  }
+  __syncthreads();
+  if (tid < kSbG * 64 && b0 + es < a.Mb) {
+    const float v = (s_red[tid] + s_red[kSbG * 64 + tid]) + s_red[2 * kSbG * 64 + tid];
+    a.x[(size_t)(b0 + es) * d + h * 64 + ec] = x_old + (v + bias_o);
+  }
+  trace.end();
+}
+
+int self_block_supported(int n_head, int d) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("WB_SELF_BLOCK");
+    env = (e && e[0] == '0') ? 0 : 1;
+  }
+  return env && n_head >= 1 && n_head <= kHaMaxCluster && d == n_head * 64;
+}
+
+int launch_self_block(const SelfBlockDesc& p, cudaStream_t st, int64_t* launches) {
+  if (!self_block_supported(p.n_head, p.d) || p.Mb < 1) {
+    set_error("self_block: unsupported shape d=%d heads=%d Mb=%d", p.d, p.n_head, p.Mb);
+    return -1;
+  }
+  SelfBlockArgs a{p.x, p.ln_g, p.ln_b, p.wqkv, p.bqkv, p.wo, p.bo, p.kcache, p.vcache, p.Mb, p.d, p.n_ctx, p.state};
+  const int XS = p.d * 2 + 64;
+  const size_t smem = (size_t)16 * XS + (size_t)2 * p.d * 4 + (size_t)(3 * kSbG * 64 + kSbG * 3 * 66 + 3 * kSbG * 64) * 4;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    WB_CUDA_OK(cudaFuncSetAttribute(self_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.n_head, (p.Mb + kSbG - 1) / kSbG), cfg.blockDim = dim3(kSbThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int n_at = 0;
+  at[n_at].id = cudaLaunchAttributeClusterDimension;
+  at[n_at].val.clusterDim.x = (unsigned)p.n_head, at[n_at].val.clusterDim.y = 1, at[n_at].val.clusterDim.z = 1;
+  ++n_at;
+  if (use_pdl()) {
+    at[n_at].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n_at].val.programmaticStreamSerializationAllowed = 1;
+    ++n_at;
+  }
+  cfg.attrs = at, cfg.numAttrs = n_at;
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, self_block_kernel, a);
+  if (launches) *launches += 1;
+  WB_CUDA_OK(le);
+  return 0;
 }
 
 // ---- end of step: sample (optional), embed the next token, advance -------------------------------------------------------------

@@ -400,30 +400,41 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
   const size_t cross_off = (b0 / o.beams) * (size_t)D.n_audio_ctx * d;
   for (int l = 0; l < D.n_text_layer; ++l) {
     const LayerW& L = h->dec[l];
-    SkinnyDesc s{};
-    s.Mb = Mb, s.state = state;
-    // self attention: LN + fused QKV, K/V appended to the cache by the epilogue
-    s.N = 3 * d, s.K = d, s.w = L.wqkv, s.bias = L.bqkv, s.in_mode = SKINNY_IN_LN, s.in = xdec, s.ln_g = L.ln1_g,
-    s.ln_b = L.ln1_b, s.out_mode = SKINNY_OUT_QKV, s.q32 = q32, s.kcache = h->selfK[l] + self_off, s.vcache = h->selfV[l] + self_off,
-    s.n_ctx = D.n_text_ctx;
-    WB_TRY(launch_skinny_gemm(s, st, &h->launches));
     AttnDecodeDesc a{};
     a.Mb = Mb, a.d = d, a.n_head = H, a.q = q32, a.k = h->selfK[l] + self_off, a.v = h->selfV[l] + self_off;
     a.n_ctx = D.n_text_ctx, a.n_rows_fixed = 0, a.kv_share = 1, a.state = state, a.out16 = a16, a.tmaps = h->gemm;
-    WB_TRY(launch_attn_decode(a, st, &h->launches));
     SkinnyDesc so{};
     so.Mb = Mb, so.state = state, so.N = d, so.K = d, so.w = L.wo, so.bias = L.bo, so.in_mode = SKINNY_IN_F16, so.in = a16;
     so.out_mode = SKINNY_OUT_RESID, so.out = xdec;
-    WB_TRY(launch_skinny_gemm(so, st, &h->launches));
+    if (self_block_supported(H, d)) {
+      // n_head <= 8: LN + QKV + cache append + attention + output projection + residual in one cluster kernel
+      SelfBlockDesc sb{};
+      sb.Mb = Mb, sb.d = d, sb.n_head = H, sb.n_ctx = D.n_text_ctx, sb.x = xdec, sb.ln_g = L.ln1_g, sb.ln_b = L.ln1_b;
+      sb.wqkv = L.wqkv, sb.bqkv = L.bqkv, sb.wo = L.wo, sb.bo = L.bo;
+      sb.kcache = h->selfK[l] + self_off, sb.vcache = h->selfV[l] + self_off, sb.state = state;
+      WB_TRY(launch_self_block(sb, st, &h->launches));
+    } else {
+      // LN + fused QKV (K/V appended to the cache by the epilogue), attention, output projection
+      SkinnyDesc s{};
+      s.Mb = Mb, s.state = state;
+      s.N = 3 * d, s.K = d, s.w = L.wqkv, s.bias = L.bqkv, s.in_mode = SKINNY_IN_LN, s.in = xdec, s.ln_g = L.ln1_g,
+      s.ln_b = L.ln1_b, s.out_mode = SKINNY_OUT_QKV, s.q32 = q32, s.kcache = h->selfK[l] + self_off, s.vcache = h->selfV[l] + self_off,
+      s.n_ctx = D.n_text_ctx;
+      WB_TRY(launch_skinny_gemm(s, st, &h->launches));
+      WB_TRY(launch_attn_decode(a, st, &h->launches));
+      WB_TRY(launch_skinny_gemm(so, st, &h->launches));
+    }
     // cross attention: LayerNorm + query projection fused into the attention kernel (one kernel less per layer)
     AttnDecodeDesc c = a;
     c.k = h->crossK[l] + cross_off, c.v = h->crossV[l] + cross_off, c.n_ctx = D.n_audio_ctx, c.n_rows_fixed = D.n_audio_ctx;
     c.kv_share = o.beams;
     c.q = nullptr, c.x = xdec, c.ln_g = L.lnc_g, c.ln_b = L.lnc_b, c.wq = L.wq_c, c.bq = L.bq_c;
+    const bool fuse_out_c = attn_decode_can_fuse_out(H) != 0;
+    if (fuse_out_c) c.wo = L.wo_c, c.bo = L.bo_c, c.xres = xdec;
     WB_TRY(launch_attn_decode(c, st, &h->launches));
     SkinnyDesc sc = so;
     sc.w = L.wo_c, sc.bias = L.bo_c;
-    WB_TRY(launch_skinny_gemm(sc, st, &h->launches));
+    if (!fuse_out_c) WB_TRY(launch_skinny_gemm(sc, st, &h->launches));
     // MLP
     SkinnyDesc m1{};
     m1.Mb = Mb, m1.state = state, m1.N = 4 * d, m1.K = d, m1.w = L.w1, m1.bias = L.b1, m1.gelu = 1;
@@ -1206,6 +1217,8 @@ int wb_profile_cross_attention(wb_handle* h, int32_t B, int32_t reps, float* avg
     const int l = ((i % D.n_text_layer) + D.n_text_layer) % D.n_text_layer;
     c.k = h->crossK[l], c.v = h->crossV[l];
     c.ln_g = h->dec[l].lnc_g, c.ln_b = h->dec[l].lnc_b, c.wq = h->dec[l].wq_c, c.bq = h->dec[l].bq_c;
+    if (attn_decode_can_fuse_out(D.n_text_head))   // as the product runs it; the projection lands in a scratch buffer here
+      c.wo = h->dec[l].wo_c, c.bo = h->dec[l].bo_c, c.xres = h->q32;
     WB_TRY(launch_attn_decode(c, h->stream, &h->launches));
   }
   WB_CUDA_OK(cudaEventRecord(h->ev[1], h->stream));

@@ -155,6 +155,27 @@ __device__ __forceinline__ uint4 ldg_nc_16(const void* p) {   // streaming 16-by
                : "l"(p));
   return r;
 }
+// ---- thread-block clusters: distributed shared memory ---------------------------------------------------------------------
+// shared::cluster address of the same variable in the CTA with the given rank of this cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_u16(uint32_t cluster_addr, unsigned short v) {
+  asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(cluster_addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
 __device__ __forceinline__ void grid_dep_sync() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
