@@ -685,6 +685,7 @@ struct HeadAttnArgs {
   const DecodeState* state;
   int d, n_rows_fixed, kv_share, n_stages;
   int l2_prefetch_tiles;   // cross attention: stage tiles beyond the ring requested into L2 while q is still being computed
+  int pdl_late;            // release the dependent kernel after the main loop instead of at entry
 };
 
 // 8 weight rows x d of a [.][d] fp16 matrix against one fp32 vector in shared memory: lane l owns the 16-byte chunks
@@ -756,7 +757,7 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
     ptx::fence_mbar_init();
   }
   __syncthreads();
-  ptx::grid_dep_launch();
+  if (!a.pdl_late) ptx::grid_dep_launch();
   if (!fixed) ptx::grid_dep_sync();   // self attention: the row count and the newest K/V row come from the previous kernel
   const int n_rows = fixed ? a.n_rows_fixed : ld_state(&a.state->cur_len) + 1;
   const int n_tiles = (n_rows + kHaStageRows - 1) / kHaStageRows;
@@ -774,6 +775,9 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
         }
       }
       for (int t = 0; t < n_tiles; ++t) {
+        // pdl_late = k > 1: the dependent kernel is released when the producer reaches the k-th tile from the end, so that
+        // its launch latency runs under the last tiles of the stream (any thread of the CTA can issue the release)
+        if (a.pdl_late > 1 && t == (n_tiles > a.pdl_late ? n_tiles - a.pdl_late : 0)) ptx::grid_dep_launch();
         const int s = t % n_stages;
         const uint32_t ph = (uint32_t)(t / n_stages) & 1u;
         ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -919,6 +923,7 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
     }
   }
   __syncthreads();   // all stages consumed; reuse the ring for the cross-warp merge: [8][68] floats
+  if (a.pdl_late == 1) ptx::grid_dep_launch();
   float* red = reinterpret_cast<float*>(smem);
   const bool fuse_out = a.wo != nullptr;
   // fused output projection: this warp's first four weight rows, its bias and the old residual values are requested now,
@@ -997,7 +1002,13 @@ static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int
     set_error("attn_decode: fused output projection needs n_head <= %d (one cluster per sequence)", kHaMaxCluster);
     return -1;
   }
-  HeadAttnArgs a{p.q, p.x, p.ln_g, p.ln_b, p.wq, p.bq, p.out16, p.wo, p.bo, p.xres, p.state, p.d, p.n_rows_fixed, p.kv_share, 3, 0};   // L2 prefetch measured slightly negative in-step: off
+  HeadAttnArgs a{p.q, p.x, p.ln_g, p.ln_b, p.wq, p.bq, p.out16, p.wo, p.bo, p.xres, p.state, p.d, p.n_rows_fixed, p.kv_share, 3, 0, 0};   // L2 prefetch measured slightly negative in-step: off
+  static int pdl_xa = -1;
+  if (pdl_xa < 0) {
+    const char* e = getenv("WB_PDL_XA");
+    pdl_xa = e ? atoi(e) : 1;
+  }
+  a.pdl_late = (p.n_rows_fixed > 0 && p.pdl_late_ok) ? pdl_xa : 0;
   const int ctas = p.n_head * p.Mb;
   if (p.n_rows_fixed <= 0 || ctas > 296) a.n_stages = 2;          // self attention: few rows; big grids: 3 CTAs per SM
   static int stages_env = -1;
@@ -1087,7 +1098,6 @@ int launch_attn_decode(const AttnDecodeDesc& p, cudaStream_t st, int64_t* launch
 // Replaces three kernels of the latency chain (QKV GEMM, attention, output projection) with one. The footprint is kept small
 // (64 CTAs at 32 sequences, ~36 KB shared memory, <= 96 registers) so that the CTAs of the following cross-attention kernel
 // are resident and streaming K/V while this one runs.
-constexpr int kSbG = 4;             // sequences per CTA
 constexpr int kSbThreads = 384;     // 12 warps
 constexpr int kSbWarps = kSbThreads / 32;
 
@@ -1102,6 +1112,7 @@ struct SelfBlockArgs {
   __half* kcache;           // [Mb][n_ctx][d]
   __half* vcache;
   int Mb, d, n_ctx;
+  int pdl_point;            // where the dependent kernel may start: 0 at entry, 1 after the wait, 2 after QKV, 3 after attention
   const DecodeState* state;
 };
 
@@ -1137,7 +1148,9 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   }
 }
 
+template <int kSbG>   // sequences per CTA (2 or 4): 12 / kSbG warps share a sequence in the attention phase
 __global__ void __maxnreg__(96) self_block_kernel(SelfBlockArgs a) {
+  constexpr int WPS = kSbWarps / kSbG;
   extern __shared__ __align__(16) unsigned char sb_smem[];
   TraceScope trace(a.state, 210);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1150,8 +1163,8 @@ __global__ void __maxnreg__(96) self_block_kernel(SelfBlockArgs a) {
   float* s_g = reinterpret_cast<float*>(sa + 8 * XS);          // [d] LayerNorm gamma
   float* s_b = s_g + d;                                        // [d] beta
   float* s_qkv = s_b + d;                                      // [3][kSbG][64] q, k, v of this head (fp32)
-  float* s_part = s_qkv + 3 * kSbG * 64;                       // [kSbG][3][66] attention partials of the three warps of a sequence
-  float* s_red = s_part + kSbG * 3 * 66;                       // [3][kSbG][64] output-projection partials of the three K-thirds
+  float* s_part = s_qkv + 3 * kSbG * 64;                       // [kSbG][WPS][66] attention partials of the warps of a sequence
+  float* s_red = s_part + kSbG * WPS * 66;                       // [3][kSbG][64] output-projection partials of the three K-thirds
 
   // ---- before the wait: everything that does not depend on the previous kernel -------------------------------------------------
   // warp w owns strip w of this head's 192 QKV rows: part = w / 4 (q, k, v), rows (w % 4) * 16 .. + 15 of the head
@@ -1168,6 +1181,35 @@ __global__ void __maxnreg__(96) self_block_kernel(SelfBlockArgs a) {
     pwb[u] = ptx::ldg_nc_16(wrow1 + blk * 32);
   }
   const float bias_lo = __ldg(a.bqkv + row_lo), bias_hi = __ldg(a.bqkv + row_lo + 8);
+  // L2 hints for what is loaded later: the rest of this warp's QKV strip, its slice of Wo, and the cached K/V rows of the
+  // group (the row count may be one step stale before the wait: it is only a hint)
+#pragma unroll
+  for (int u = kPre; u < 16; u += 2) {
+    if (u < nblk) {
+      ptx::prefetch_l2(wrow0 + u * 32);
+      ptx::prefetch_l2(wrow1 + u * 32);
+    }
+  }
+  {
+    const int ostrip_h = warp & 3, kthird_h = warp >> 2;
+    const int hb0 = (kthird_h * nblk) / 3, hb1 = ((kthird_h + 1) * nblk) / 3;
+    const __half* orow = a.wo + (size_t)(h * 64 + ostrip_h * 16 + grp) * d + tq * 8;
+#pragma unroll
+    for (int u = 0; u < 6; u += 2) {
+      if (hb0 + u < hb1) {
+        ptx::prefetch_l2(orow + (hb0 + u) * 32);
+        ptx::prefetch_l2(orow + (size_t)8 * d + (hb0 + u) * 32);
+      }
+    }
+    const int n_hint = ld_state(&a.state->cur_len) + 1;
+    const int total = n_hint > 0 ? kSbG * 2 * n_hint : 0;
+    for (int i = tid; i < total; i += kSbThreads) {
+      const int sq = i / (2 * n_hint), rem = i - sq * 2 * n_hint;
+      const int kv = rem / n_hint, rr = rem - kv * n_hint;
+      if (b0 + sq < a.Mb && rr < a.n_ctx)
+        ptx::prefetch_l2((kv ? a.vcache : a.kcache) + ((size_t)(b0 + sq) * a.n_ctx + rr) * d + h * 64);
+    }
+  }
   for (int i = tid * 4; i < d; i += kSbThreads * 4) {
     *reinterpret_cast<float4*>(s_g + i) = __ldg(reinterpret_cast<const float4*>(a.ln_g + i));
     *reinterpret_cast<float4*>(s_b + i) = __ldg(reinterpret_cast<const float4*>(a.ln_b + i));
@@ -1176,8 +1218,12 @@ __global__ void __maxnreg__(96) self_block_kernel(SelfBlockArgs a) {
     *reinterpret_cast<uint4*>(xs + kSbG * XS + i * 16) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4*>(sa + kSbG * XS + i * 16) = make_uint4(0, 0, 0, 0);
   }
-  ptx::grid_dep_launch();
+  // The dependent kernel is the cross attention, whose CTAs start streaming K/V the moment they are resident: released too
+  // early, that stream competes with the latency-bound loads of this kernel and of its predecessor (measured: the step is
+  // slower with everything released at entry than with no programmatic launch at all).
+  if (a.pdl_point == 0) ptx::grid_dep_launch();
   ptx::grid_dep_sync();
+  if (a.pdl_point == 1) ptx::grid_dep_launch();
   __syncthreads();
   trace.mark(3);
   const int pos = ld_state(&a.state->cur_len);                 // cache row of the token this step consumes
@@ -1271,11 +1317,12 @@ __global__ void __maxnreg__(96) self_block_kernel(SelfBlockArgs a) {
     }
   }
   __syncthreads();
+  if (a.pdl_point == 2) ptx::grid_dep_launch();
   trace.mark(5);
 
-  // ---- 3. attention: warps 3s .. 3s+2 share sequence slot s; lane = (row sub-index 0..3, 16-byte column chunk 0..7) -----------------
+  // ---- 3. attention: warps WPS*s .. WPS*s+WPS-1 share sequence slot s; lane = (row sub-index 0..3, 16-byte column chunk 0..7) -----------------
   {
-    const int s = warp / 3, sub = warp - s * 3;
+    const int s = warp / WPS, sub = warp - s * WPS;
     const int b = b0 + s;
     const int rsub = lane >> 3, cc = lane & 7;
     const float sl = 0.125f * kLog2e;   // (d_head^-0.25)^2 = 1/8 exactly; log2 domain
@@ -1287,7 +1334,7 @@ __global__ void __maxnreg__(96) self_block_kernel(SelfBlockArgs a) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) p.o[i] = 0.f;
     if (b < a.Mb) {                                            // warp-uniform
-      const int per = (pos + 2) / 3;                           // cached rows [0, pos) in three contiguous ranges
+      const int per = (pos + WPS - 1) / WPS;                   // cached rows [0, pos) in WPS contiguous ranges
       const int r_begin = sub * per;
       const int r_end = pos < r_begin + per ? pos : r_begin + per;
       const __half* kb = a.kcache + (size_t)b * a.n_ctx * d + h * 64 + cc * 8;
@@ -1336,7 +1383,7 @@ __global__ void __maxnreg__(96) self_block_kernel(SelfBlockArgs a) {
     sb_merge_shfl(p, 8);
     sb_merge_shfl(p, 16);
     if (rsub == 0) {
-      float* dst = s_part + (s * 3 + sub) * 66;
+      float* dst = s_part + (s * WPS + sub) * 66;
 #pragma unroll
       for (int i = 0; i < 8; ++i) dst[cc * 8 + i] = p.o[i];
       if (cc == 0) dst[64] = p.m, dst[65] = p.l;
@@ -1366,15 +1413,21 @@ __global__ void __maxnreg__(96) self_block_kernel(SelfBlockArgs a) {
     if (b0 + es < a.Mb) x_old = __ldcg(a.x + (size_t)(b0 + es) * d + h * 64 + ec);
   }
   __syncthreads();
+  if (a.pdl_point == 3) ptx::grid_dep_launch();
   trace.mark(6);
-  if (tid < kSbG * 64) {   // merge the three partials of (slot es, column ec) and push the result into every CTA of the cluster
-    const float* pp = s_part + es * 3 * 66;
-    const float m0 = pp[64], m1 = pp[66 + 64], m2 = pp[132 + 64];
-    const float M = fmaxf(m0, fmaxf(m1, m2));
-    const float w0 = m0 == -INFINITY ? 0.f : exp2f(m0 - M), w1 = m1 == -INFINITY ? 0.f : exp2f(m1 - M),
-                w2 = m2 == -INFINITY ? 0.f : exp2f(m2 - M);
-    const float L = w0 * pp[65] + w1 * pp[66 + 65] + w2 * pp[132 + 65];
-    const float A = w0 * pp[ec] + w1 * pp[66 + ec] + w2 * pp[132 + ec];
+  if (tid < kSbG * 64) {   // merge the partials of (slot es, column ec) and push the result into every CTA of the cluster
+    const float* pp = s_part + es * WPS * 66;
+    float M = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < WPS; ++j) M = fmaxf(M, pp[j * 66 + 64]);
+    float L = 0.f, A = 0.f;
+#pragma unroll
+    for (int j = 0; j < WPS; ++j) {
+      const float mj = pp[j * 66 + 64];
+      const float wj = mj == -INFINITY ? 0.f : exp2f(mj - M);
+      L += wj * pp[j * 66 + 65];
+      A += wj * pp[j * 66 + ec];
+    }
     const __half r = __float2half_rn(L > 0.f ? A / L : 0.f);
     const uint32_t local = ptx::smem_u32(sa + es * XS + (h * 64 + ec) * 2);
     const int n_cta = (int)gridDim.x;
@@ -1427,16 +1480,25 @@ int launch_self_block(const SelfBlockDesc& p, cudaStream_t st, int64_t* launches
     set_error("self_block: unsupported shape d=%d heads=%d Mb=%d", p.d, p.n_head, p.Mb);
     return -1;
   }
-  SelfBlockArgs a{p.x, p.ln_g, p.ln_b, p.wqkv, p.bqkv, p.wo, p.bo, p.kcache, p.vcache, p.Mb, p.d, p.n_ctx, p.state};
+  static int pdl_point = -1, G = 0;
+  if (pdl_point < 0) {
+    const char* e = getenv("WB_PDL_SB");
+    pdl_point = e ? atoi(e) : 2;
+    e = getenv("WB_SB_G");
+    G = (e && atoi(e) == 2) ? 2 : 4;
+  }
+  SelfBlockArgs a{p.x, p.ln_g, p.ln_b, p.wqkv, p.bqkv, p.wo, p.bo, p.kcache, p.vcache, p.Mb, p.d, p.n_ctx, pdl_point, p.state};
   const int XS = p.d * 2 + 64;
-  const size_t smem = (size_t)16 * XS + (size_t)2 * p.d * 4 + (size_t)(3 * kSbG * 64 + kSbG * 3 * 66 + 3 * kSbG * 64) * 4;
+  const int wps = kSbWarps / G;
+  const size_t smem = (size_t)16 * XS + (size_t)2 * p.d * 4 + (size_t)(3 * G * 64 + G * wps * 66 + 3 * G * 64) * 4;
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    WB_CUDA_OK(cudaFuncSetAttribute(self_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WB_CUDA_OK(cudaFuncSetAttribute(self_block_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WB_CUDA_OK(cudaFuncSetAttribute(self_block_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(p.n_head, (p.Mb + kSbG - 1) / kSbG), cfg.blockDim = dim3(kSbThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cfg.gridDim = dim3(p.n_head, (p.Mb + G - 1) / G), cfg.blockDim = dim3(kSbThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
   cudaLaunchAttribute at[2];
   int n_at = 0;
   at[n_at].id = cudaLaunchAttributeClusterDimension;
@@ -1448,7 +1510,415 @@ int launch_self_block(const SelfBlockDesc& p, cudaStream_t st, int64_t* launches
     ++n_at;
   }
   cfg.attrs = at, cfg.numAttrs = n_at;
-  const cudaError_t le = cudaLaunchKernelEx(&cfg, self_block_kernel, a);
+  const cudaError_t le = G == 2 ? cudaLaunchKernelEx(&cfg, self_block_kernel<2>, a) : cudaLaunchKernelEx(&cfg, self_block_kernel<4>, a);
+  if (launches) *launches += 1;
+  WB_CUDA_OK(le);
+  return 0;
+}
+
+// ---- everything after cross attention in one kernel: output projection + residual + LayerNorm + MLP (GELU) + residual ---------------
+// For d = 384 / 512. Grid (C, groups of 8 sequences), one thread-block cluster of C CTAs per group (C = 16 for d = 512: non-portable
+// size, C = 8 otherwise). The 8 sequences of a group are the 8 columns of every mma.sync; weights stream once per group with
+// 16-byte loads straight into A fragments. CTA r of a cluster
+//   0. multiplies the cross-attention outputs a16 with rows r*OC .. of Wo (OC = d/C output columns), adds bias and the old
+//      residual, and pushes this slice of x' into the shared memory of all C CTAs (DSMEM all-gather),
+//   1. normalises the 8 rows of x' (every CTA needs the whole rows), fp32 statistics -> fp16,
+//   2. computes its HS = 4d/C hidden units h = gelu(W1[r*HS ..] LN(x') + b1) -> fp16 in shared memory,
+//   3. multiplies them with the matching K-slice of W2: a partial [8][d] of the MLP output,
+//   4. after the second cluster barrier sums the C partials of its own OC columns in rank order (remote shared-memory reads,
+//      deterministic), adds b2 and x' and writes x.
+// Replaces three kernels of the latency chain (cross-attention output projection, MLP1, MLP2).
+constexpr int kPbThreads = 256;
+
+struct PostBlockArgs {
+  float* x;                 // [Mb][d] residual stream, updated in place
+  const __half* a16;        // [Mb][d] cross-attention outputs
+  const __half* wo;         // [d][d]
+  const float* bo;
+  const float* ln_g;
+  const float* ln_b;
+  const __half* w1;         // [4d][d]
+  const float* b1;
+  const __half* w2;         // [d][4d]
+  const float* b2;
+  int Mb;
+  int pdl_point;            // where the dependent kernel may start: 0 at entry, 1 after phase 0, 2 after phase 2, 3 after phase 3
+  int hints_after_wait;
+  const DecodeState* state;
+};
+
+template <int D, int C>
+struct PbCfg {
+  static constexpr int OC = D / C, HS = 4 * D / C, NBLK = D / 32;
+  static constexpr int S0 = OC / 16, KS0 = 8 / S0, NB0 = NBLK / KS0;                 // phase 0: strips, K split, blocks per unit
+  static constexpr int SB = HS / 16, KSB = (SB % 8 == 0) ? 1 : 2, NBU = NBLK / KSB;  // phase 2
+  static constexpr int UPW = SB * KSB / 8;                                           //   units per warp
+  static constexpr int SCW = D / 16 / 8, NBC = HS / 32;                              // phase 3: strips per warp, blocks per strip
+  static constexpr int XS = D * 2 + 64, HSS = HS * 2 + 64, PS = D + 4;               // row strides: bytes, bytes, floats
+  static constexpr int RED = (KS0 * 8 * OC > KSB * 8 * HS) ? KS0 * 8 * OC : KSB * 8 * HS;
+  static constexpr size_t smem_used = (size_t)2 * 8 * XS + (size_t)8 * HSS + ((size_t)8 * D + 8 * PS + RED + 2 * D + HS) * 4;
+  // Requested size: more than half of an SM's shared memory, so that two CTAs of this kernel never share an SM. Released
+  // while the cross attention still occupies most SMs, the clusters were otherwise packed two CTAs per SM onto the few free
+  // ones and every weight-streaming phase took twice as long (per-SM L2 bandwidth).
+  static constexpr size_t smem = smem_used > (size_t)118 * 1024 ? smem_used : (size_t)118 * 1024;
+  static_assert(OC % 16 == 0 && HS % 32 == 0 && NBLK % KS0 == 0 && NBLK % KSB == 0 && (SB * KSB) % 8 == 0 && (D / 16) % 8 == 0, "shape");
+  static_assert(NB0 <= 8 && OC * 8 <= 2 * kPbThreads, "shape");
+};
+
+// one warp: acc += W[16 rows][blocks blk0 .. blk0+NB) x B tile (8 slots); NB <= 8 blocks requested at once
+template <int NB>
+__device__ __forceinline__ void pb_load(uint4 (&wa)[NB], uint4 (&wb)[NB], const __half* wrow0, const __half* wrow1, int blk0) {
+#pragma unroll
+  for (int u = 0; u < NB; ++u) {
+    wa[u] = ptx::ldg_nc_16(wrow0 + (blk0 + u) * 32);
+    wb[u] = ptx::ldg_nc_16(wrow1 + (blk0 + u) * 32);
+  }
+}
+template <int NB>
+__device__ __forceinline__ void pb_mma(float (&acc)[4], const uint4 (&wa)[NB], const uint4 (&wb)[NB], const unsigned char* bl, int bblk0) {
+#pragma unroll
+  for (int u = 0; u < NB; ++u) {
+    const uint32_t a0[4] = {wa[u].x, wb[u].x, wa[u].y, wb[u].y}, a1[4] = {wa[u].z, wb[u].z, wa[u].w, wb[u].w};
+    const uint4 xb = *reinterpret_cast<const uint4*>(bl + (bblk0 + u) * 64);
+    const uint32_t bf0[2] = {xb.x, xb.y}, bf1[2] = {xb.z, xb.w};
+    ptx::mma_16816(acc, a0, bf0);
+    ptx::mma_16816(acc, a1, bf1);
+  }
+}
+
+template <int D, int C>
+__global__ void __maxnreg__(128) post_block_kernel(PostBlockArgs a) {
+  using Cfg = PbCfg<D, C>;
+  constexpr int OC = Cfg::OC, HS = Cfg::HS, XS = Cfg::XS, HSS = Cfg::HSS, PS = Cfg::PS;
+  extern __shared__ __align__(16) unsigned char pb_smem[];
+  TraceScope trace(a.state, 220);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 2, tq = lane & 3;
+  const int r = blockIdx.x, b0 = blockIdx.y * 8;                // cluster rank, first sequence of the group
+  unsigned char* as16 = pb_smem;                                // [8][XS] fp16 cross-attention outputs
+  unsigned char* xs = as16 + 8 * XS;                            // [8][XS] fp16 LayerNorm(x')
+  unsigned char* hs = xs + 8 * XS;                              // [8][HSS] fp16 hidden slice
+  float* xp = reinterpret_cast<float*>(hs + 8 * HSS);           // [8][D] x' (all-gathered from the cluster)
+  float* s_part = xp + 8 * D;                                   // [8][PS] MLP2 partial (read by the cluster)
+  float* s_red = s_part + 8 * PS;                               // K-split partials of phases 0 and 2
+  float* s_g = s_red + Cfg::RED;                                // [D]
+  float* s_b = s_g + D;                                         // [D]
+  float* s_b1 = s_b + D;                                        // [HS]
+
+  // ---- before the wait ---------------------------------------------------------------------------------------------------------------
+  const int strip0 = warp % Cfg::S0, kp0 = warp / Cfg::S0;
+  const bool act0 = warp < Cfg::S0 * Cfg::KS0;
+  uint4 wa0[Cfg::NB0], wb0[Cfg::NB0];
+  {
+    const __half* w0 = a.wo + (size_t)(r * OC + strip0 * 16 + grp) * D + tq * 8;
+    pb_load<Cfg::NB0>(wa0, wb0, w0, w0 + (size_t)8 * D, act0 ? kp0 * Cfg::NB0 : 0);
+  }
+  for (int i = tid * 4; i < D; i += kPbThreads * 4) {
+    *reinterpret_cast<float4*>(s_g + i) = __ldg(reinterpret_cast<const float4*>(a.ln_g + i));
+    *reinterpret_cast<float4*>(s_b + i) = __ldg(reinterpret_cast<const float4*>(a.ln_b + i));
+  }
+  for (int i = tid; i < HS; i += kPbThreads) s_b1[i] = __ldg(a.b1 + r * HS + i);
+  // L2 hints for this CTA's slices of W1 (HS rows x D) and W2 (D rows x HS), 128-byte lines. When this kernel is released
+  // while the cross attention is still streaming, hints given before the wait are evicted again by that stream (measured:
+  // phases 2 and 3 take twice as long), so they are given after the wait in that case.
+  auto weight_hints = [&]() {
+    for (int i = tid; i < HS * (D / 64); i += kPbThreads) {
+      const int row = i / (D / 64), seg = i - row * (D / 64);
+      ptx::prefetch_l2(a.w1 + (size_t)(r * HS + row) * D + seg * 64);
+    }
+    for (int i = tid; i < D * (HS / 64); i += kPbThreads) {
+      const int row = i / (HS / 64), seg = i - row * (HS / 64);
+      ptx::prefetch_l2(a.w2 + (size_t)row * (4 * D) + r * HS + seg * 64);
+    }
+  };
+  if (!a.hints_after_wait) weight_hints();
+  float bias_o[2], b2v[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int i = tid + j * kPbThreads;
+    const int col = i % OC;
+    bias_o[j] = i < OC * 8 ? __ldg(a.bo + r * OC + col) : 0.f;
+    b2v[j] = i < OC * 8 ? __ldg(a.b2 + r * OC + col) : 0.f;
+  }
+  if (a.pdl_point == 0) ptx::grid_dep_launch();
+  ptx::grid_dep_sync();
+  trace.mark(3);
+  if (a.hints_after_wait) weight_hints();
+
+  // ---- 0. x' slice = x + a16 Wo[r*OC ..]^T + bo, pushed to every CTA of the cluster ---------------------------------------------------
+  for (int i = tid; i < 8 * (D / 8); i += kPbThreads) {          // a16 rows of the group -> as16
+    const int slot = i / (D / 8), c = i - slot * (D / 8);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (b0 + slot < a.Mb) v = __ldcg(reinterpret_cast<const uint4*>(a.a16 + (size_t)(b0 + slot) * D) + c);
+    *reinterpret_cast<uint4*>(as16 + slot * XS + c * 16) = v;
+  }
+  float x_old[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int i = tid + j * kPbThreads;
+    const int slot = i / OC, col = i - slot * OC;
+    x_old[j] = (i < OC * 8 && b0 + slot < a.Mb) ? __ldcg(a.x + (size_t)(b0 + slot) * D + r * OC + col) : 0.f;
+  }
+  __syncthreads();
+  if (act0) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    pb_mma<Cfg::NB0>(acc, wa0, wb0, as16 + grp * XS + tq * 16, kp0 * Cfg::NB0);
+    float* dst = s_red + kp0 * 8 * OC;
+    const int c_lo = strip0 * 16 + grp, c_hi = c_lo + 8;
+    dst[(2 * tq) * OC + c_lo] = acc[0], dst[(2 * tq + 1) * OC + c_lo] = acc[1];
+    dst[(2 * tq) * OC + c_hi] = acc[2], dst[(2 * tq + 1) * OC + c_hi] = acc[3];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int i = tid + j * kPbThreads;
+    if (i < OC * 8) {
+      const int slot = i / OC, col = i - slot * OC;
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < Cfg::KS0; ++k) v += s_red[k * 8 * OC + i];
+      v = x_old[j] + (v + bias_o[j]);
+      const uint32_t local = ptx::smem_u32(xp + slot * D + r * OC + col);
+#pragma unroll
+      for (int c = 0; c < C; ++c) ptx::st_cluster_f32(ptx::mapa(local, (uint32_t)c), v);
+    }
+  }
+  // weights never depend on activations: the first batch of phase 2 is requested before the barrier and the LayerNorm
+  constexpr int NBb = Cfg::NBU > 8 ? 8 : Cfg::NBU;               // blocks per batch
+  uint4 wa2[NBb], wb2[NBb];
+  {
+    const int strip = warp % Cfg::SB, kp = warp / Cfg::SB;
+    const __half* w0 = a.w1 + (size_t)(r * HS + strip * 16 + grp) * D + tq * 8;
+    pb_load<NBb>(wa2, wb2, w0, w0 + (size_t)8 * D, kp * Cfg::NBU);
+  }
+  ptx::cluster_arrive_release();
+  ptx::cluster_wait_acquire();
+  if (a.pdl_point == 1) ptx::grid_dep_launch();
+  trace.mark(4);
+
+  // ---- 1. LayerNorm of x' (warp w: row w) ---------------------------------------------------------------------------------------------
+  {
+    const bool live = b0 + warp < a.Mb;
+    const float* xr = xp + warp * D;
+    __half* dst = reinterpret_cast<__half*>(xs + warp * XS);
+    constexpr int N4 = D / 4;
+    float4 v[4];
+    float sum = 0.f, sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < N4 ? *reinterpret_cast<const float4*>(xr + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    sum = warp_sum(sum), sq = warp_sum(sq);
+    const float mean = sum / (float)D;
+    const float rstd = live ? rsqrtf(fmaxf(sq / (float)D - mean * mean, 0.f) + 1e-5f) : 0.f;
+    const float ab = live ? 1.f : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = lane + 32 * i;
+      if (c < N4) {
+        const float4 g = *reinterpret_cast<const float4*>(s_g + c * 4), bb = *reinterpret_cast<const float4*>(s_b + c * 4);
+        const __half2 h0 = __floats2half2_rn((v[i].x - mean) * rstd * g.x + ab * bb.x, (v[i].y - mean) * rstd * g.y + ab * bb.y);
+        const __half2 h1 = __floats2half2_rn((v[i].z - mean) * rstd * g.z + ab * bb.z, (v[i].w - mean) * rstd * g.w + ab * bb.w);
+        uint2 u;
+        u.x = *reinterpret_cast<const uint32_t*>(&h0), u.y = *reinterpret_cast<const uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(dst + c * 4) = u;
+      }
+    }
+  }
+  __syncthreads();
+  trace.mark(5);
+
+  // ---- 2. hidden slice: h = gelu(W1[r*HS ..] LN(x') + b1) -------------------------------------------------------------------------------
+  constexpr int NPAIR = Cfg::SCW * Cfg::NBC;                     // phase 3: (strip, block) pairs of this warp
+  const __half* w2base = a.w2 + (size_t)grp * (4 * D) + r * HS + tq * 8;
+  auto load_pairs = [&](uint4 (&wa)[8], uint4 (&wb)[8], int p0) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int p = p0 + u < NPAIR ? p0 + u : NPAIR - 1;
+      const int si = p / Cfg::NBC, blk = p % Cfg::NBC;
+      const __half* w0 = w2base + (size_t)((warp + 8 * si) * 16) * (4 * D) + blk * 32;
+      wa[u] = ptx::ldg_nc_16(w0);
+      wb[u] = ptx::ldg_nc_16(w0 + (size_t)8 * (4 * D));
+    }
+  };
+  uint4 wa3[8], wb3[8];
+#pragma unroll
+  for (int ui = 0; ui < Cfg::UPW; ++ui) {
+    const int u = warp + 8 * ui;
+    const int strip = u % Cfg::SB, kp = u / Cfg::SB;
+    const __half* w0 = a.w1 + (size_t)(r * HS + strip * 16 + grp) * D + tq * 8;
+    const __half* w1r = w0 + (size_t)8 * D;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int bb = 0; bb < Cfg::NBU; bb += NBb) {
+      if (ui == 0 && bb == 0) {
+        pb_mma<NBb>(acc, wa2, wb2, xs + grp * XS + tq * 16, kp * Cfg::NBU);
+      } else {
+        uint4 wa[NBb], wb[NBb];
+        pb_load<NBb>(wa, wb, w0, w1r, kp * Cfg::NBU + bb);
+        pb_mma<NBb>(acc, wa, wb, xs + grp * XS + tq * 16, kp * Cfg::NBU + bb);
+      }
+    }
+    if (ui == Cfg::UPW - 1) load_pairs(wa3, wb3, 0);             // first batch of phase 3, in flight across the GELU pass
+    float* dst = s_red + kp * 8 * HS;
+    const int c_lo = strip * 16 + grp, c_hi = c_lo + 8;
+    dst[(2 * tq) * HS + c_lo] = acc[0], dst[(2 * tq + 1) * HS + c_lo] = acc[1];
+    dst[(2 * tq) * HS + c_hi] = acc[2], dst[(2 * tq + 1) * HS + c_hi] = acc[3];
+  }
+  __syncthreads();
+  for (int i = tid; i < 8 * HS; i += kPbThreads) {
+    const int slot = i / HS, j = i - slot * HS;
+    float v = s_b1[j];
+#pragma unroll
+    for (int k = 0; k < Cfg::KSB; ++k) v += s_red[k * 8 * HS + i];
+    reinterpret_cast<__half*>(hs + slot * HSS)[j] = __float2half_rn(gelu_erf(v));
+  }
+  __syncthreads();
+  if (a.pdl_point == 2) ptx::grid_dep_launch();
+  trace.mark(6);
+
+  // ---- 3. partial MLP output over this CTA's hidden slice: strips warp, warp+8, ... of all D output rows --------------------------------
+  {
+    float acc[Cfg::SCW][4];
+#pragma unroll
+    for (int si = 0; si < Cfg::SCW; ++si) acc[si][0] = acc[si][1] = acc[si][2] = acc[si][3] = 0.f;
+    const unsigned char* hl = hs + grp * HSS + tq * 16;
+#pragma unroll
+    for (int p0 = 0; p0 < NPAIR; p0 += 8) {
+      if (p0 > 0) load_pairs(wa3, wb3, p0);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (p0 + u < NPAIR) {
+          const int si = (p0 + u) / Cfg::NBC, blk = (p0 + u) % Cfg::NBC;
+          const uint32_t a0[4] = {wa3[u].x, wb3[u].x, wa3[u].y, wb3[u].y}, a1[4] = {wa3[u].z, wb3[u].z, wa3[u].w, wb3[u].w};
+          const uint4 xb = *reinterpret_cast<const uint4*>(hl + blk * 64);
+          const uint32_t bf0[2] = {xb.x, xb.y}, bf1[2] = {xb.z, xb.w};
+          ptx::mma_16816(acc[si], a0, bf0);
+          ptx::mma_16816(acc[si], a1, bf1);
+        }
+      }
+    }
+#pragma unroll
+    for (int si = 0; si < Cfg::SCW; ++si) {
+      const int c_lo = (warp + 8 * si) * 16 + grp, c_hi = c_lo + 8;
+      s_part[(2 * tq) * PS + c_lo] = acc[si][0], s_part[(2 * tq + 1) * PS + c_lo] = acc[si][1];
+      s_part[(2 * tq) * PS + c_hi] = acc[si][2], s_part[(2 * tq + 1) * PS + c_hi] = acc[si][3];
+    }
+  }
+  ptx::cluster_arrive_release();
+  ptx::cluster_wait_acquire();
+  if (a.pdl_point == 3) ptx::grid_dep_launch();
+  trace.mark(7);
+
+  // ---- 4. x = x' + b2 + sum over the cluster of the partials (rank order), own OC columns -----------------------------------------------
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int i = tid + j * kPbThreads;
+    if (i < OC * 8) {
+      const int slot = i / OC, col = i - slot * OC;
+      const uint32_t local = ptx::smem_u32(s_part + slot * PS + r * OC + col);
+      float pv[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) pv[c] = ptx::ld_cluster_f32(ptx::mapa(local, (uint32_t)c));
+      float v = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) v += pv[c];
+      if (b0 + slot < a.Mb) a.x[(size_t)(b0 + slot) * D + r * OC + col] = xp[slot * D + r * OC + col] + (v + b2v[j]);
+    }
+  }
+  ptx::cluster_arrive_release();   // no CTA may exit (and free its shared memory) while a peer still reads its partial
+  ptx::cluster_wait_acquire();
+  trace.end();
+}
+
+// cluster size the post block uses for width d (0: unsupported)
+static int post_block_cluster(int d) {
+  static int c512 = -1;
+  if (d == 384) return 8;
+  if (d != 512) return 0;
+  if (c512 < 0) {   // 16 CTAs per cluster is a non-portable size: ask whether this device schedules it
+    c512 = 8;
+    const char* e = getenv("WB_POST_CLUSTER");
+    const int want = e ? atoi(e) : 16;
+    if (want == 16 &&
+        cudaFuncSetAttribute(post_block_kernel<512, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+        cudaFuncSetAttribute(post_block_kernel<512, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PbCfg<512, 16>::smem) == cudaSuccess) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(16, 1), cfg.blockDim = dim3(kPbThreads), cfg.dynamicSmemBytes = PbCfg<512, 16>::smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 16, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+      cfg.attrs = at, cfg.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, post_block_kernel<512, 16>, &cfg) == cudaSuccess && nc >= 1) c512 = 16;
+    }
+    cudaGetLastError();
+  }
+  return c512;
+}
+
+int post_block_supported(int n_head, int d) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("WB_POST_BLOCK");
+    env = (e && e[0] == '0') ? 0 : 1;
+  }
+  return env && d == n_head * 64 && (d == 384 || d == 512);
+}
+
+template <int D, int C>
+static cudaError_t launch_post_block_t(const PostBlockArgs& a, int n_groups, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(post_block_kernel<D, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PbCfg<D, C>::smem);
+    if (e != cudaSuccess) return e;
+    if (C > 8) {
+      e = cudaFuncSetAttribute(post_block_kernel<D, C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (e != cudaSuccess) return e;
+    }
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(C, n_groups), cfg.blockDim = dim3(kPbThreads), cfg.dynamicSmemBytes = PbCfg<D, C>::smem, cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int n_at = 0;
+  at[n_at].id = cudaLaunchAttributeClusterDimension;
+  at[n_at].val.clusterDim.x = C, at[n_at].val.clusterDim.y = 1, at[n_at].val.clusterDim.z = 1;
+  ++n_at;
+  if (use_pdl()) {
+    at[n_at].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n_at].val.programmaticStreamSerializationAllowed = 1;
+    ++n_at;
+  }
+  cfg.attrs = at, cfg.numAttrs = n_at;
+  return cudaLaunchKernelEx(&cfg, post_block_kernel<D, C>, a);
+}
+
+int launch_post_block(const PostBlockDesc& p, cudaStream_t st, int64_t* launches) {
+  const int C = post_block_supported(p.n_head, p.d) ? post_block_cluster(p.d) : 0;
+  if (!C || p.Mb < 1) {
+    set_error("post_block: unsupported shape d=%d heads=%d Mb=%d", p.d, p.n_head, p.Mb);
+    return -1;
+  }
+  static int pdl_point = -1, hints_late = 0;
+  if (pdl_point < 0) {
+    const char* e = getenv("WB_PDL_PB");
+    pdl_point = e ? atoi(e) : 3;
+    e = getenv("WB_PB_HINTS_LATE");
+    hints_late = e ? atoi(e) : 0;
+  }
+  PostBlockArgs a{p.x, p.a16, p.wo, p.bo, p.ln_g, p.ln_b, p.w1, p.b1, p.w2, p.b2, p.Mb, pdl_point, hints_late, p.state};
+  const int n_groups = (p.Mb + 7) / 8;
+  cudaError_t le;
+  if (p.d == 384)
+    le = launch_post_block_t<384, 8>(a, n_groups, st);
+  else if (C == 16)
+    le = launch_post_block_t<512, 16>(a, n_groups, st);
+  else
+    le = launch_post_block_t<512, 8>(a, n_groups, st);
   if (launches) *launches += 1;
   WB_CUDA_OK(le);
   return 0;

@@ -430,8 +430,17 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
     c.kv_share = o.beams;
     c.q = nullptr, c.x = xdec, c.ln_g = L.lnc_g, c.ln_b = L.lnc_b, c.wq = L.wq_c, c.bq = L.bq_c;
     const bool fuse_out_c = attn_decode_can_fuse_out(H) != 0;
+    c.pdl_late_ok = (!fuse_out_c && post_block_supported(H, d)) ? 1 : 0;
     if (fuse_out_c) c.wo = L.wo_c, c.bo = L.bo_c, c.xres = xdec;
     WB_TRY(launch_attn_decode(c, st, &h->launches));
+    if (!fuse_out_c && post_block_supported(H, d)) {
+      // d = 384 / 512: output projection + residual + LayerNorm + MLP + residual in one cluster kernel
+      PostBlockDesc pb{};
+      pb.Mb = Mb, pb.d = d, pb.n_head = H, pb.x = xdec, pb.a16 = a16, pb.wo = L.wo_c, pb.bo = L.bo_c, pb.ln_g = L.ln2_g, pb.ln_b = L.ln2_b;
+      pb.w1 = L.w1, pb.b1 = L.b1, pb.w2 = L.w2, pb.b2 = L.b2, pb.state = state;
+      WB_TRY(launch_post_block(pb, st, &h->launches));
+      continue;
+    }
     SkinnyDesc sc = so;
     sc.w = L.wo_c, sc.bias = L.bo_c;
     if (!fuse_out_c) WB_TRY(launch_skinny_gemm(sc, st, &h->launches));

@@ -122,6 +122,7 @@ struct AttnDecodeDesc {
   const __half* wo;       // [d][d] or null
   const float* bo;        // [d]
   float* xres;            // [Mb][d] residual stream
+  int pdl_late_ok;        // the successor is a block kernel that gains nothing from starting before this one's main loop ends
   GemmContext* tmaps;     // tensor-map cache
 };
 int launch_attn_decode(const AttnDecodeDesc& d, cudaStream_t st, int64_t* launches);
@@ -144,6 +145,25 @@ struct SelfBlockDesc {
 };
 int self_block_supported(int n_head, int d);
 int launch_self_block(const SelfBlockDesc& d, cudaStream_t st, int64_t* launches);
+
+// everything after cross attention in one cluster kernel (d = 384 / 512, 8 sequences per cluster):
+// x' = x + a16 wo^T + bo;  x = x' + w2 gelu(w1 LN(x') + b1) + b2
+struct PostBlockDesc {
+  int Mb, d, n_head;
+  float* x;               // [Mb][d] residual stream, updated in place
+  const __half* a16;      // [Mb][d] cross-attention outputs
+  const __half* wo;
+  const float* bo;
+  const float* ln_g;
+  const float* ln_b;
+  const __half* w1;       // [4d][d]
+  const float* b1;
+  const __half* w2;       // [d][4d]
+  const float* b2;
+  const DecodeState* state;
+};
+int post_block_supported(int n_head, int d);
+int launch_post_block(const PostBlockDesc& d, cudaStream_t st, int64_t* launches);
 
 struct FinishDesc {
   int Mb, V, d, n_ctx;

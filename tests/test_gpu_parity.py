@@ -262,6 +262,32 @@ def test_wider_models_two_layers(wbm, ref, oracle_logmel, d, heads, vocab):
     w.close()
 
 
+@pytest.mark.parametrize("B", [1, 5, 11])
+def test_base_width_block_kernels(wbm, ref, oracle_logmel, B):
+    """d = 512 / 8 heads (BASELINE config 3's width) with 2 layers: the decoder runs as cluster kernels there (self block:
+    groups of 4 sequences; post block: groups of 8, 16 CTAs per cluster). Batch sizes that leave ragged groups."""
+    dims = ref.ModelDims(80, 1500, 512, 8, 2, 51864, 448, 512, 8, 2)
+    weights = ref.random_weights(dims, seed=3)
+    oracle = ref.WhisperRef(dims, weights)
+    wd = wbm.ModelDims(*[getattr(dims, f) for f in dims.__dataclass_fields__])
+    w = wbm.Whisper(wd, weights=weights, max_batch=B)
+    audio = np.stack([ref.synth_audio(700 + i, "noise") for i in range(B)])
+    xa_ref = oracle.encode(torch.from_numpy(np.stack([oracle_logmel(a) for a in audio])).float())
+    w.encode(audio.astype(np.float32))
+    toks = torch.randint(0, 50000, (B, 9), generator=torch.Generator().manual_seed(B))
+    want = oracle.decoder_logits(toks, xa_ref)
+    got = torch.from_numpy(w.decoder_logits(toks.numpy()))
+    assert (got - want).abs().max().item() <= TOL_ABS and _rel(got, want) <= TOL_REL
+    opts_ref = ref.DecodeOptions.default_for(dims, sample_len=40)
+    tok_ref, slp_ref, _ = oracle.greedy(xa_ref, opts_ref)
+    tok, _, slp = w.greedy(B, wbm.DecodeOptions.default_for(wd, sample_len=40))
+    n = tok_ref.shape[1]
+    mism = (torch.from_numpy(tok[:, :n].astype(np.int64)) != tok_ref).any(0).nonzero()
+    assert mism.numel() == 0, f"first divergence at position {int(mism[0])}"
+    assert np.allclose(slp, slp_ref.numpy(), rtol=2e-3, atol=5e-2)
+    w.close()
+
+
 def test_whisper_decode_language_id(wbm, ref, oracle_logmel, capsys):
     """Whisper.decode(audioFeatures:) (Whisper.swift:33-40) on the multilingual vocabulary."""
     dims = ref.DIMS["tiny"]
