@@ -575,6 +575,321 @@ int logits_groups(int Mb, int N, int K) {
   return skinny_logits_ctas(N);
 }
 
+// ---- logits on the tensor cores: final LayerNorm + tied-embedding GEMM, swap-AB, tcgen05 + TMA ---------------------------------------
+// logits[b][n] = LN(x[b]) . E[n]: the vocabulary is the M dimension (128 embedding rows per tile = one partial group), the
+// sequences are N (NB = 16 / 32 / 48 columns). The [V][d] matrix is the only operand of the step that is bandwidth-bound
+// (V*d*2 = 53 MB for base.en): it streams through a TMA ring (128 rows x 64 k per stage, 128-byte swizzle, rows past V
+// zero-filled) that starts filling before the previous kernel has finished; the normalised activations are written once into
+// shared memory in the same swizzled K-major layout; one thread issues tcgen05.mma (M128 N=NB K16) into a double-buffered
+// TMEM accumulator; eight epilogue warps read it back (one vocabulary row per thread, half of the columns per warp), apply the
+// logit filters, and reduce (max, argmax, sum-exp) per sequence over the 128 rows through a padded shared-memory transpose
+// (the sequences of a warp are unrolled so that their shuffle chains overlap). Persistent: one CTA per SM.
+constexpr int kLtThreads = 320;   // warp 0: TMA producer, warp 1: TMEM + MMA issuer, warps 2-9: LayerNorm, then epilogue
+constexpr int kLtStageBytes = 128 * 64 * 2;
+
+struct LogitsTcArgs {
+  SkinnyDesc p;
+  int n_groups, n_stages;
+};
+
+template <int NB>
+__global__ void __launch_bounds__(kLtThreads, 1) logits_tc_kernel(const __grid_constant__ CUtensorMap tmW, LogitsTcArgs a) {
+  constexpr int kBufStride = NB <= 32 ? 32 : 64;               // TMEM columns per accumulator buffer
+  constexpr int kTmemCols = 2 * kBufStride;
+  constexpr int RS = NB + 1;                                   // padded row of the transpose buffer
+  extern __shared__ unsigned char lt_dyn[];
+  const SkinnyDesc& p = a.p;
+  TraceScope trace(p.state, 142);
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(lt_dyn) + 1023) & ~(uintptr_t)1023);
+  const int nkb = p.K >> 6, n_stages = a.n_stages;
+  unsigned char* ring = smem;                                            // [n_stages][128 rows][128 B]
+  unsigned char* xb = ring + (size_t)n_stages * kLtStageBytes;           // [nkb][NB rows][128 B] LayerNorm(x), swizzled
+  float* red = reinterpret_cast<float*>(xb + (size_t)nkb * NB * 128);    // [128][RS]
+  float* sg = red + 128 * RS;                                            // [K] LayerNorm gamma, beta
+  float* sb = sg + p.K;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sb + p.K);                // [n_stages]
+  uint64_t* empty = full + 8;
+  uint64_t* tfull = empty + 8;                                           // [2]
+  uint64_t* tempty = tfull + 2;                                          // [2]
+  uint64_t* bready = tempty + 2;                                         // activations written
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bready + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    ptx::prefetch_tensormap(&tmW);
+    for (int s = 0; s < n_stages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull[i], 1);
+      ptx::mbar_init(&tempty[i], 8);
+    }
+    ptx::mbar_init(bready, 256);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, kTmemCols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  ptx::grid_dep_launch();
+
+  if (warp == 0) {
+    // ---- TMA producer: the embedding matrix does not depend on the previous kernel, so the ring fills during its tail -----------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x) {
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % n_stages;
+          const uint32_t ph = (it / n_stages) & 1u;
+          ptx::mbar_wait(&empty[s], ph ^ 1u);
+          ptx::mbar_arrive_expect_tx(&full[s], kLtStageBytes);
+          ptx::tma_load_3d(ring + (size_t)s * kLtStageBytes, &tmW, &full[s], kb * 64, g * 128, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer ----------------------------------------------------------------------------------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(128, NB);
+      ptx::mbar_wait(bready, 0);
+      ptx::tc_fence_after();
+      const uint32_t xb_addr = ptx::smem_u32(xb);
+      uint32_t it = 0, lt = 0;
+      for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x, ++lt) {
+        const uint32_t buf = lt & 1u, tph = (lt >> 1) & 1u;
+        ptx::mbar_wait(&tempty[buf], tph ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * kBufStride;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % n_stages;
+          const uint32_t ph = (it / n_stages) & 1u;
+          ptx::mbar_wait(&full[s], ph);
+          ptx::tc_fence_after();
+          const uint64_t adesc = ptx::umma_desc_sw128_kmajor(ptx::smem_u32(ring + (size_t)s * kLtStageBytes));
+          const uint64_t bdesc = ptx::umma_desc_sw128_kmajor(xb_addr + (uint32_t)kb * NB * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ptx::umma_f16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          ptx::umma_commit(&empty[s]);
+        }
+        ptx::umma_commit(&tfull[buf]);
+      }
+    }
+  } else {
+    // ---- warps 2-9: LayerNorm of the residual stream into the swizzled B tiles, then the epilogue of every group -------------------------
+    const int et = tid - 64, ewarp = warp - 2;                 // 0..255, 0..7
+    for (int i = et * 4; i < p.K; i += 256 * 4) {
+      *reinterpret_cast<float4*>(sg + i) = __ldg(reinterpret_cast<const float4*>(p.ln_g + i));
+      *reinterpret_cast<float4*>(sb + i) = __ldg(reinterpret_cast<const float4*>(p.ln_b + i));
+    }
+    ptx::grid_dep_sync();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    trace.mark(3);
+    {
+      const int sub = et & 7;
+      for (int r = et >> 3; r < NB; r += 32) {                 // 8 threads per row, 32 rows per pass (trip count warp-uniform)
+        const bool act = r < p.Mb;
+        const float* src = reinterpret_cast<const float*>(p.in) + (size_t)(act ? r : 0) * p.K;
+        float sm = 0.f, q = 0.f;
+        float4 v[16];
+        for (int c0 = 0; c0 < p.K; c0 += 512) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = c0 + (sub + 8 * i) * 4;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < p.K) v[i] = ld_x4(src + c);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            sm += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+          }
+        }
+        sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        sm += __shfl_xor_sync(0xffffffffu, sm, 4);
+        q += __shfl_xor_sync(0xffffffffu, q, 4);
+        const float mean = sm / (float)p.K;
+        const float var = fmaxf(q / (float)p.K - mean * mean, 0.f);
+        const float rstd = act ? rsqrtf(var + 1e-5f) : 0.f;
+        const float ab = act ? 1.f : 0.f;
+        for (int c0 = 0; c0 < p.K; c0 += 512) {
+          if (p.K > 512) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int c = c0 + (sub + 8 * i) * 4;
+              if (c < p.K) v[i] = ld_x4(src + c);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = c0 + (sub + 8 * i) * 4;
+            if (c < p.K) {
+              const float4 gm = *reinterpret_cast<const float4*>(sg + c), bb = *reinterpret_cast<const float4*>(sb + c);
+              __half2 h0 = __floats2half2_rn((v[i].x - mean) * rstd * gm.x + ab * bb.x, (v[i].y - mean) * rstd * gm.y + ab * bb.y);
+              __half2 h1 = __floats2half2_rn((v[i].z - mean) * rstd * gm.z + ab * bb.z, (v[i].w - mean) * rstd * gm.w + ab * bb.w);
+              uint2 u;
+              u.x = *reinterpret_cast<uint32_t*>(&h0), u.y = *reinterpret_cast<uint32_t*>(&h1);
+              // element (row r, column c) of the K-major SWIZZLE_128B tile kt = c / 64: 16-byte chunk index xor (r & 7)
+              const int kt = c >> 6, kk = c & 63;
+              unsigned char* dst = xb + (size_t)kt * NB * 128 + r * 128 + ((((kk >> 3) ^ (r & 7)) << 4) | ((kk & 7) << 1));
+              *reinterpret_cast<uint2*>(dst) = u;
+            }
+          }
+        }
+      }
+    }
+    ptx::fence_proxy_async();                                  // generic-proxy writes -> visible to the tensor-core (async) proxy
+    ptx::mbar_arrive(bready);
+    trace.mark(4);
+    const bool first = ld_state(&p.state->cur_len) + 1 == p.n_initial;
+    const int q4 = warp & 3, half = ewarp >> 2;                // TMEM lane quadrant this warp may read; its half of the columns
+    const int j_lo = half * (NB / 2), j_hi = j_lo + NB / 2;
+    constexpr int kSeqPerWarp = (NB + 7) / 8;
+    uint32_t lt = 0;
+    for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x, ++lt) {
+      const uint32_t buf = lt & 1u, tph = (lt >> 1) & 1u;
+      const int row = q4 * 32 + lane, n = g * 128 + row;
+      const unsigned char mk = (p.mask && n < p.N) ? __ldg(p.mask + n) : 0;
+      const bool dead = n >= p.N || mk == 1 || (mk == 2 && first);
+      ptx::mbar_wait(&tfull[buf], tph);
+      ptx::tc_fence_after();
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(tmem_base + buf * kBufStride + ((uint32_t)(q4 * 32) << 16), v);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < NB && j >= j_lo && j < j_hi) red[row * RS + j] = dead ? -INFINITY : __uint_as_float(v[j]);
+      if (NB > 32) {
+        ptx::tmem_ld_32x32(tmem_base + buf * kBufStride + ((uint32_t)(q4 * 32) << 16) + 32u, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (32 + j < NB && 32 + j >= j_lo && 32 + j < j_hi) red[row * RS + 32 + j] = dead ? -INFINITY : __uint_as_float(v[j]);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[buf]);           // the accumulator buffer is free for the group after next
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // warp per sequence (b = ewarp, ewarp + 8, ...): optional store, group-local (max, argmax, sum-exp); unrolled over the
+      // sequences of this warp so that the independent shuffle chains overlap
+      float xv[kSeqPerWarp][4], best[kSeqPerWarp], se[kSeqPerWarp];
+      int arg[kSeqPerWarp];
+#pragma unroll
+      for (int jb = 0; jb < kSeqPerWarp; ++jb) {
+        const int b = ewarp + 8 * jb;
+        best[jb] = -INFINITY, arg[jb] = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = lane + 32 * i, nn = g * 128 + rr;
+          float x = -INFINITY;
+          if (nn < p.N && b < p.Mb) {
+            x = red[rr * RS + b];
+            if (p.out) reinterpret_cast<float*>(p.out)[(size_t)b * p.N + nn] = x;
+          }
+          xv[jb][i] = x;
+          if (x > best[jb]) best[jb] = x, arg[jb] = nn;        // ascending n: first maximum wins
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int jb = 0; jb < kSeqPerWarp; ++jb) {
+          const float ov = __shfl_xor_sync(0xffffffffu, best[jb], o);
+          const int oi = __shfl_xor_sync(0xffffffffu, arg[jb], o);
+          if (ov > best[jb] || (ov == best[jb] && oi < arg[jb])) best[jb] = ov, arg[jb] = oi;
+        }
+      }
+#pragma unroll
+      for (int jb = 0; jb < kSeqPerWarp; ++jb) {
+        se[jb] = 0.f;
+        if (best[jb] > -INFINITY) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) se[jb] += expf(xv[jb][i] - best[jb]);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int jb = 0; jb < kSeqPerWarp; ++jb) se[jb] += __shfl_xor_sync(0xffffffffu, se[jb], o);
+      }
+#pragma unroll
+      for (int jb = 0; jb < kSeqPerWarp; ++jb) {
+        const int b = ewarp + 8 * jb;
+        if (lane == 0 && b < p.Mb)
+          *reinterpret_cast<float4*>(p.part_logits + ((size_t)b * a.n_groups + g) * 4) = make_float4(best[jb], __int_as_float(arg[jb]), se[jb], 0.f);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // red is rewritten by the next group
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+  trace.end();
+}
+
+static int launch_logits_tc(const SkinnyDesc& d, cudaStream_t st, int64_t* launches) {
+  const int NB = d.Mb <= 16 ? 16 : (d.Mb <= 32 ? 32 : 48);
+  const int nkb = d.K / 64, n_groups = skinny_logits_ctas(d.N);
+  CUtensorMap tmW;
+  const int rc = gemm_get_tmap(d.tmaps, d.w, d.K, d.N, 1, d.K, (long long)d.N * d.K, 128, &tmW);
+  if (rc) return rc;
+  const size_t fixed = (size_t)nkb * NB * 128 + (size_t)128 * (NB + 1) * 4 + (size_t)2 * d.K * 4 + 256 + 1024;
+  int n_stages = (int)(((size_t)200 * 1024 - fixed) / kLtStageBytes);
+  n_stages = n_stages > 8 ? 8 : n_stages;
+  if (n_stages < 2) {
+    set_error("logits GEMM: K=%d too wide for the shared-memory ring", d.K);
+    return -1;
+  }
+  const size_t smem = fixed + (size_t)n_stages * kLtStageBytes;
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  LogitsTcArgs a{d, n_groups, n_stages};
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(n_groups < n_sm ? n_groups : n_sm), cfg.blockDim = dim3(kLtThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at, cfg.numAttrs = use_pdl() ? 1 : 0;
+  cudaError_t le = cudaSuccess;
+#define WB_LT_CASE(N_)                                                                                                 \
+  case N_: {                                                                                                           \
+    static size_t smem_set = 0;                                                                                        \
+    if (smem > smem_set) {                                                                                             \
+      WB_CUDA_OK(cudaFuncSetAttribute(logits_tc_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      smem_set = smem;                                                                                                 \
+    }                                                                                                                  \
+    le = cudaLaunchKernelEx(&cfg, logits_tc_kernel<N_>, tmW, a);                                                       \
+  } break;
+  switch (NB) {
+    WB_LT_CASE(16) WB_LT_CASE(32) WB_LT_CASE(48)
+  }
+#undef WB_LT_CASE
+  if (launches) *launches += 1;
+  WB_CUDA_OK(le);
+  return 0;
+}
+
+static bool use_logits_tc() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WB_LOGITS_TC");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches) {
   if (d.Mb < 1 || d.Mb > 40 || d.K % 128 != 0 || d.N < 16) {
     set_error("skinny_gemm: unsupported shape Mb=%d N=%d K=%d", d.Mb, d.N, d.K);
@@ -589,6 +904,7 @@ int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches) 
       set_error("logits GEMM: LayerNorm input with K <= %d required", kSkKC);
       return -1;
     }
+    if (use_logits_tc() && d.tmaps && d.K % 64 == 0 && d.Mb <= 48) return launch_logits_tc(d, st, launches);
     const int n_groups = skinny_logits_ctas(d.N);
     const int MTl = (d.Mb + 7) / 8;
     const size_t sm = (size_t)MTl * 8 * (d.K * 2 + 64) + (size_t)128 * (MTl * 8 + 1) * 4 + 16 + (size_t)2 * d.K * 4;

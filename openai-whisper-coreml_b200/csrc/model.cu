@@ -461,6 +461,7 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
     lg.in = xdec, lg.ln_g = h->lnf_g, lg.ln_b = h->lnf_b, lg.out_mode = SKINNY_OUT_LOGITS;
     lg.out = o.store_logits ? h->logits + b0 * (size_t)D.n_vocab : nullptr, lg.mask = o.sample ? h->mask : nullptr, lg.n_initial = o.n_initial;
     lg.part_logits = h->part_logits + b0 * h->n_logit_ctas * 4;
+    lg.tmaps = h->gemm;
     WB_TRY(launch_skinny_gemm(lg, st, &h->launches));
   }
   if (o.no_finish) return 0;

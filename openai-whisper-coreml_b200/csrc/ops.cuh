@@ -96,6 +96,7 @@ struct SkinnyDesc {
   const unsigned char* mask;   // [N]: 1 = suppressed, 2 = suppressed at the first sampled position only; may be null
   int n_initial;
   float* part_logits;
+  GemmContext* tmaps;          // LOGITS: tensor-map cache (tcgen05 path); null selects the mma.sync kernel
   const DecodeState* state;
 };
 int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches);
