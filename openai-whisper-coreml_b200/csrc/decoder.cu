@@ -982,7 +982,7 @@ int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches) 
 // fp16 hi + lo parts (two MMAs each) so that only K and V themselves are fp16-rounded; fp32 online softmax in the log2 domain.
 constexpr int kHaStageRows = 128;
 constexpr int kHaThreads = 288;
-constexpr int kHaMaxCluster = 8;                   // heads per sequence the fused output projection supports (portable cluster size)
+constexpr int kHaMaxCluster = 8;                   // portable thread-block cluster size: the self block runs one CTA per head
 constexpr int kHaTileBytes = kHaStageRows * 128;   // one K (or V) stage tile: 128 rows x 64 halves
 
 struct HeadAttnArgs {
@@ -993,11 +993,6 @@ struct HeadAttnArgs {
   const __half* wq;        //   [d][d]
   const float* bq;         //   [d]
   __half* out16;
-  // fused output projection (launched as one cluster per sequence, one CTA per head): xres[b] += concat_h(o_h) Wo^T + bo.
-  // The heads exchange their 64 outputs through distributed shared memory; CTA h then owns columns h*64..h*64+63.
-  const __half* wo;        //   [d][d], or null: write the head outputs to out16 instead
-  const float* bo;         //   [d]
-  float* xres;             //   residual stream [Mb][d], updated in place
   const DecodeState* state;
   int d, n_rows_fixed, kv_share, n_stages;
   int l2_prefetch_tiles;   // cross attention: stage tiles beyond the ring requested into L2 while q is still being computed
@@ -1005,8 +1000,8 @@ struct HeadAttnArgs {
 };
 
 // 8 weight rows x d of a [.][d] fp16 matrix against one fp32 vector in shared memory: lane l owns the 16-byte chunks
-// l, l+32, ... of every row. Used by the fused query projection (prologue) and the fused output projection (epilogue) of
-// attn_decode_head_kernel; the rows are requested in two halves so that the first can be in flight across a barrier.
+// l, l+32, ... of every row. Used by the fused query projection (prologue) of
+// attn_decode_head_kernel; the rows are requested in two halves so that the first can be in flight across the wait.
 template <int NJW>
 __device__ __forceinline__ void head_rows_load(uint4 (&w)[4][NJW], const __half* wbase, int d, int lane) {
   const int n_chunks = d >> 3;
@@ -1054,7 +1049,6 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8];
   __shared__ __align__(16) float s_x[NJW * 256];   // normalised residual row (fused query projection)
-  __shared__ __align__(16) float s_a[NJW * 256];   // all heads' outputs of this sequence (fused output projection; written by the cluster)
   __shared__ float s_q[64], s_red[16];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1241,20 +1235,6 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
   __syncthreads();   // all stages consumed; reuse the ring for the cross-warp merge: [8][68] floats
   if (a.pdl_late == 1) ptx::grid_dep_launch();
   float* red = reinterpret_cast<float*>(smem);
-  const bool fuse_out = a.wo != nullptr;
-  // fused output projection: this warp's first four weight rows, its bias and the old residual values are requested now,
-  // so that their latency is covered by the merge and the cluster exchange
-  uint4 wo0[4][NJW];
-  float bias_o = 0.f, x_old = 0.f;
-  const __half* wobase = nullptr;
-  if (fuse_out && warp < 8) {
-    wobase = a.wo + (size_t)(h * 64 + warp * 8) * a.d;
-    head_rows_load<NJW>(wo0, wobase, a.d, lane);
-    if (lane < 8) {
-      bias_o = __ldg(a.bo + h * 64 + warp * 8 + lane);
-      x_old = __ldcg(a.xres + (size_t)b * a.d + h * 64 + warp * 8 + lane);
-    }
-  }
   if (warp < 8) {
     float L = l_run;
     L += __shfl_xor_sync(0xffffffffu, L, 4);
@@ -1282,26 +1262,7 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
       L += wgt * red[w * 68 + 65];
       A += wgt * red[w * 68 + tid];
     }
-    if (!fuse_out) {
-      a.out16[(size_t)b * a.d + h * 64 + tid] = __float2half_rn(A / L);
-    } else {
-      // push this head's output into the s_a of every CTA of the cluster (one CTA per head, cluster rank == h)
-      const float val = A / L;
-      const uint32_t local = ptx::smem_u32(s_a + h * 64 + tid);
-      const int n_cta = (int)gridDim.x;
-      for (int r = 0; r < n_cta; ++r) ptx::st_cluster_f32(ptx::mapa(local, (uint32_t)r), val);
-    }
-  }
-  if (fuse_out) {
-    if (tid < NJW * 256 - a.d && a.d + tid < NJW * 256) s_a[a.d + tid] = 0.f;   // chunk padding beyond d (never written by a peer)
-    ptx::cluster_arrive_release();
-    ptx::cluster_wait_acquire();   // every head's outputs have landed in s_a; no remote access after this point
-    if (warp < 8) {
-      uint4 wo1[4][NJW];
-      head_rows_load<NJW>(wo1, wobase + (size_t)4 * a.d, a.d, lane);
-      const float mine = head_rows_dot<NJW>(wo0, wo1, s_a, lane);
-      if (lane < 8) a.xres[(size_t)b * a.d + h * 64 + warp * 8 + lane] = x_old + (mine + bias_o);
-    }
+    a.out16[(size_t)b * a.d + h * 64 + tid] = __float2half_rn(A / L);
   }
   trace.end();
 }
@@ -1313,12 +1274,7 @@ static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int
   if (rc) return rc;
   rc = gemm_get_tmap(p.tmaps, p.v, p.d, p.n_ctx, nslab, p.d, (long long)p.n_ctx * p.d, kHaStageRows, &tmV);
   if (rc) return rc;
-  const bool fuse_out = p.wo != nullptr;
-  if (fuse_out && (p.n_head > kHaMaxCluster || !p.xres || !p.bo)) {
-    set_error("attn_decode: fused output projection needs n_head <= %d (one cluster per sequence)", kHaMaxCluster);
-    return -1;
-  }
-  HeadAttnArgs a{p.q, p.x, p.ln_g, p.ln_b, p.wq, p.bq, p.out16, p.wo, p.bo, p.xres, p.state, p.d, p.n_rows_fixed, p.kv_share, 3, 0, 0};   // L2 prefetch measured slightly negative in-step: off
+  HeadAttnArgs a{p.q, p.x, p.ln_g, p.ln_b, p.wq, p.bq, p.out16, p.state, p.d, p.n_rows_fixed, p.kv_share, 3, 0, 0};   // L2 prefetch measured slightly negative in-step: off
   static int pdl_xa = -1;
   if (pdl_xa < 0) {
     const char* e = getenv("WB_PDL_XA");
@@ -1342,19 +1298,10 @@ static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int
   const size_t smem = (size_t)a.n_stages * 2 * kHaTileBytes + 1024;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p.n_head, p.Mb), cfg.blockDim = dim3(kHaThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
-  cudaLaunchAttribute at[2];
-  int n_at = 0;
-  if (fuse_out) {   // one cluster per sequence, one CTA per head (portable size)
-    at[n_at].id = cudaLaunchAttributeClusterDimension;
-    at[n_at].val.clusterDim.x = (unsigned)p.n_head, at[n_at].val.clusterDim.y = 1, at[n_at].val.clusterDim.z = 1;
-    ++n_at;
-  }
-  if (use_pdl()) {
-    at[n_at].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[n_at].val.programmaticStreamSerializationAllowed = 1;
-    ++n_at;
-  }
-  cfg.attrs = at, cfg.numAttrs = n_at;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at, cfg.numAttrs = use_pdl() ? 1 : 0;
   cudaError_t le = cudaSuccess;
 #define WB_HA_CASE(J)                                                                                                     \
   case J: {                                                                                                               \
@@ -1362,12 +1309,6 @@ static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int
     if (smem > smem_set) {                                                                                                \
       WB_CUDA_OK(cudaFuncSetAttribute(attn_decode_head_kernel<J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       smem_set = smem;                                                                                                    \
-    }                                                                                                                     \
-    if (fuse_out && getenv("WB_DEBUG_CLUSTERS")) {                                                                        \
-      int nc = -1;                                                                                                        \
-      cudaOccupancyMaxActiveClusters(&nc, attn_decode_head_kernel<J>, &cfg);                                              \
-      fprintf(stderr, "[wb] attn_decode cluster=%d smem=%zu stages=%d fixed=%d: max active clusters %d (grid %d)\n",      \
-              p.n_head, smem, a.n_stages, p.n_rows_fixed, nc, p.Mb);                                                      \
     }                                                                                                                     \
     le = cudaLaunchKernelEx(&cfg, attn_decode_head_kernel<J>, tmK, tmV, a);                                               \
   } break;
@@ -1381,17 +1322,6 @@ static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int
   if (launches) *launches += 1;
   WB_CUDA_OK(le);
   return 0;
-}
-
-// Off by default: measured on B200 (base.en, 32 sequences) the cluster launch keeps the attention CTAs from starting under
-// their predecessor, which costs what the saved kernel gains (WB_FUSE_OUT=1 enables it for cross attention).
-int attn_decode_can_fuse_out(int n_head) {
-  static int env = -1;
-  if (env < 0) {
-    const char* e = getenv("WB_FUSE_OUT");
-    env = e ? atoi(e) : 0;
-  }
-  return n_head <= kHaMaxCluster ? env : 0;
 }
 
 int launch_attn_decode(const AttnDecodeDesc& p, cudaStream_t st, int64_t* launches) {

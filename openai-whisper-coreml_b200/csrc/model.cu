@@ -429,11 +429,9 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
     c.k = h->crossK[l] + cross_off, c.v = h->crossV[l] + cross_off, c.n_ctx = D.n_audio_ctx, c.n_rows_fixed = D.n_audio_ctx;
     c.kv_share = o.beams;
     c.q = nullptr, c.x = xdec, c.ln_g = L.lnc_g, c.ln_b = L.lnc_b, c.wq = L.wq_c, c.bq = L.bq_c;
-    const bool fuse_out_c = attn_decode_can_fuse_out(H) != 0;
-    c.pdl_late_ok = (!fuse_out_c && post_block_supported(H, d)) ? 1 : 0;
-    if (fuse_out_c) c.wo = L.wo_c, c.bo = L.bo_c, c.xres = xdec;
+    c.pdl_late_ok = post_block_supported(H, d) ? 1 : 0;
     WB_TRY(launch_attn_decode(c, st, &h->launches));
-    if (!fuse_out_c && post_block_supported(H, d)) {
+    if (post_block_supported(H, d)) {
       // d = 384 / 512: output projection + residual + LayerNorm + MLP + residual in one cluster kernel
       PostBlockDesc pb{};
       pb.Mb = Mb, pb.d = d, pb.n_head = H, pb.x = xdec, pb.a16 = a16, pb.wo = L.wo_c, pb.bo = L.bo_c, pb.ln_g = L.ln2_g, pb.ln_b = L.ln2_b;
@@ -443,7 +441,7 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
     }
     SkinnyDesc sc = so;
     sc.w = L.wo_c, sc.bias = L.bo_c;
-    if (!fuse_out_c) WB_TRY(launch_skinny_gemm(sc, st, &h->launches));
+    WB_TRY(launch_skinny_gemm(sc, st, &h->launches));
     // MLP
     SkinnyDesc m1{};
     m1.Mb = Mb, m1.state = state, m1.N = 4 * d, m1.K = d, m1.w = L.w1, m1.bias = L.b1, m1.gelu = 1;
@@ -1227,8 +1225,6 @@ int wb_profile_cross_attention(wb_handle* h, int32_t B, int32_t reps, float* avg
     const int l = ((i % D.n_text_layer) + D.n_text_layer) % D.n_text_layer;
     c.k = h->crossK[l], c.v = h->crossV[l];
     c.ln_g = h->dec[l].lnc_g, c.ln_b = h->dec[l].lnc_b, c.wq = h->dec[l].wq_c, c.bq = h->dec[l].bq_c;
-    if (attn_decode_can_fuse_out(D.n_text_head))   // as the product runs it; the projection lands in a scratch buffer here
-      c.wo = h->dec[l].wo_c, c.bo = h->dec[l].bo_c, c.xres = h->q32;
     WB_TRY(launch_attn_decode(c, h->stream, &h->launches));
   }
   WB_CUDA_OK(cudaEventRecord(h->ev[1], h->stream));

@@ -119,15 +119,10 @@ struct AttnDecodeDesc {
   int kv_share;           // sequences per K/V slab (beam search: beams of one chunk share the cross K/V); >= 1
   const DecodeState* state;
   __half* out16;          // [Mb][d]
-  // fused output projection (n_head <= 8: one thread-block cluster per sequence): xres[b] += attn[b] wo^T + bo instead of out16
-  const __half* wo;       // [d][d] or null
-  const float* bo;        // [d]
-  float* xres;            // [Mb][d] residual stream
   int pdl_late_ok;        // the successor is a block kernel that gains nothing from starting before this one's main loop ends
   GemmContext* tmaps;     // tensor-map cache
 };
 int launch_attn_decode(const AttnDecodeDesc& d, cudaStream_t st, int64_t* launches);
-int attn_decode_can_fuse_out(int n_head);   // whether the fused output projection is available for this head count
 
 // whole self-attention block of a decoder layer in one kernel (n_head <= 8; one cluster per group of 4 sequences):
 // x += Wo attn(LN(x) Wqkv^T + bqkv against the self-attention cache, new k/v appended at state->cur_len) + bo
