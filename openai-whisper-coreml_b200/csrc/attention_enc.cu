@@ -6,6 +6,8 @@
 // K/V tiles double-buffered in shared memory with cp.async; S = Q K^T and O += P V on mma.sync m16n8k16 (fp16 in,
 // fp32 accumulate); online softmax in registers with quad shuffles. Input is the fused QKV GEMM output
 // [B*T][3d] (q | k | v), output [B*T][d] fp16.
+#include <cuda.h>
+
 #include "ops.cuh"
 #include "ptx.cuh"
 
@@ -155,14 +157,252 @@ __global__ void __launch_bounds__(kAttThreads, 2) encoder_attention_kernel(const
   }
 }
 
-int launch_encoder_attention(const __half* qkv, int B, int T, int n_head, __half* out, cudaStream_t st, int64_t* launches) {
+// ---- the same attention on the tensor cores of sm_100a: tcgen05 + TMEM + TMA ------------------------------------------------------------
+// One CTA = 256 queries (two 128-row tiles) of one (chunk, head), one CTA per SM, 384 threads in three warpgroups:
+//   warp 0     TMA producer: the two Q tiles once, then [128 keys][64] K and V boxes of the fused QKV matrix through a 3-stage
+//              ring (128-byte swizzle; rows past T are zero-filled by the TMA unit). K/V are read once per 256 queries.
+//   warp 1     MMA issuer (+ TMEM allocation, all 512 columns): per key tile and query tile w, S_w = Q_w K^T (4 x tcgen05.mma
+//              M128 N128 K16, K-major operands) and PV_w = P_w V (8 x M128 N64 K16: P K-major from shared memory, V MN-major —
+//              rows are keys, the 64 head columns contiguous, exactly as the QKV GEMM wrote them). S_w(j+1) is issued as soon
+//              as the softmax warpgroup has S_w(j) in registers, so the tensor pipe works under the exponentials.
+//   warps 4-7 / 8-11   softmax warpgroup of query tile 0 / 1, one query row per thread (TMEM lane = row): the whole S row with
+//              one burst of tcgen05.ld (128 registers; setmaxnreg moves the register budget from warpgroup 0 to these two),
+//              row maximum, exp2 in the log2 domain, P as fp16 into the swizzled K-major A tiles, fence.proxy.async; after the
+//              PV MMA  O = O * corr + PV  in registers (the output accumulator never needs rescaling in TMEM).
+constexpr int kEtThreads = 384;
+constexpr int kEtTile = 128 * 128;                       // bytes of one [128 rows][64 halves] tile
+constexpr int kEtStages = 3;
+constexpr int kEtSmem = kEtTile * (2 + 2 * kEtStages + 4) + 256;   // Q0 Q1, ring of (K, V), P0 P1 (2 k-tiles each), barriers
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kEtThreads, 1) encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, int T, int d,
+                                                                            __half* __restrict__ out) {
+  extern __shared__ __align__(1024) unsigned char et_dyn[];   // no static shared memory in this kernel: the window starts 1024-aligned
+  unsigned char* smem = et_dyn;
+  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();           // SWIZZLE_128B tiles need it
+  unsigned char* sQ = smem;                                   // [2][tile]
+  unsigned char* ring = sQ + 2 * kEtTile;                     // [stages][K tile | V tile]
+  unsigned char* sP = ring + 2 * kEtStages * kEtTile;         // [2 query tiles][2 k-tiles][128 rows][128 B]
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(sP + 4 * kEtTile);
+  uint64_t* kv_full = q_full + 1;                             // [stages]
+  uint64_t* kv_empty = kv_full + kEtStages;                   // [stages]
+  uint64_t* s_full = kv_empty + kEtStages;                    // [2] S_w(j) is in TMEM
+  uint64_t* s_free = s_full + 2;                              // [2] S_w(j) is in registers: the buffer may be overwritten
+  uint64_t* p_full = s_free + 2;                              // [2] P_w(j) is in shared memory, PV_w(j-1) has been read
+  uint64_t* pv_full = p_full + 2;                             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_full + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int n_kv = (T + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tmQKV);
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < kEtStages; ++i) {
+      ptx::mbar_init(&kv_full[i], 1);
+      ptx::mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&s_free[i], 128);
+      ptx::mbar_init(&p_full[i], 128);
+      ptx::mbar_init(&pv_full[i], 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0 && lane == 0) {
+      ptx::mbar_arrive_expect_tx(q_full, 2 * kEtTile);
+      ptx::tma_load_3d(sQ, &tmQKV, q_full, h * 64, q0, b);
+      ptx::tma_load_3d(sQ + kEtTile, &tmQKV, q_full, h * 64, q0 + 128, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % kEtStages;
+        ptx::mbar_wait(&kv_empty[s], (((uint32_t)(j / kEtStages)) & 1u) ^ 1u);
+        ptx::mbar_arrive_expect_tx(&kv_full[s], 2 * kEtTile);
+        ptx::tma_load_3d(ring + s * 2 * kEtTile, &tmQKV, &kv_full[s], d + h * 64, j * 128, b);
+        ptx::tma_load_3d(ring + s * 2 * kEtTile + kEtTile, &tmQKV, &kv_full[s], 2 * d + h * 64, j * 128, b);
+      }
+    } else if (warp == 1 && lane == 0) {
+      constexpr uint32_t idesc_s = ptx::umma_idesc_f16(128, 128);
+      constexpr uint32_t idesc_pv = ptx::umma_idesc_f16(128, 64) | (1u << 16);   // B (= V) is MN-major
+      ptx::mbar_wait(q_full, 0);
+      auto issue_s = [&](int j, int w) {
+        const int s = j % kEtStages;
+        const uint64_t qdesc = ptx::umma_desc_sw128_kmajor(ptx::smem_u32(sQ + w * kEtTile));
+        const uint64_t kdesc = ptx::umma_desc_sw128_kmajor(ptx::smem_u32(ring + s * 2 * kEtTile));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          ptx::umma_f16(tmem_base + w * 128, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k != 0);
+        ptx::umma_commit(&s_full[w]);
+      };
+      ptx::mbar_wait(&kv_full[0], 0);
+      ptx::tc_fence_after();
+      issue_s(0, 0);
+      issue_s(0, 1);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % kEtStages;
+        if (j + 1 < n_kv) {   // S(j+1) runs on the tensor pipe while the softmax warpgroups work on S(j)
+          ptx::mbar_wait(&kv_full[(j + 1) % kEtStages], ((uint32_t)((j + 1) / kEtStages)) & 1u);
+          for (int w = 0; w < 2; ++w) {
+            ptx::mbar_wait(&s_free[w], (uint32_t)j & 1u);
+            ptx::tc_fence_after();
+            issue_s(j + 1, w);
+          }
+        }
+        const uint64_t vdesc = ptx::umma_desc_sw128_kmajor(ptx::smem_u32(ring + s * 2 * kEtTile + kEtTile));
+        for (int w = 0; w < 2; ++w) {
+          ptx::mbar_wait(&p_full[w], (uint32_t)j & 1u);
+          ptx::tc_fence_after();
+          const uint64_t pdesc0 = ptx::umma_desc_sw128_kmajor(ptx::smem_u32(sP + (2 * w) * kEtTile));
+          const uint64_t pdesc1 = ptx::umma_desc_sw128_kmajor(ptx::smem_u32(sP + (2 * w + 1) * kEtTile));
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            // A: 16 keys = 32 bytes along K inside a 64-key swizzle atom (+2), next atom for k >= 4; B (MN-major): 16 key rows = 2048 bytes (+128)
+            const uint64_t pd = (k < 4 ? pdesc0 : pdesc1) + (uint64_t)(2 * (k & 3));
+            ptx::umma_f16(tmem_base + 256 + w * 64, pd, vdesc + (uint64_t)(128 * k), idesc_pv, k != 0);
+          }
+          ptx::umma_commit(&pv_full[w]);
+        }
+        ptx::umma_commit(&kv_empty[s]);
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int w = (warp >> 2) - 1;                           // query tile of this warpgroup
+    const int q4 = warp & 3;                                 // TMEM lane quadrant of this warp
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    const uint32_t tmem_s = tmem_base + w * 128 + lane_off, tmem_pv = tmem_base + 256 + w * 64 + lane_off;
+    const float c = 0.125f * 1.44269504088896340736f;        // (d_head^-0.25)^2 = 1/8, log2 domain
+    float m = -INFINITY, l = 0.f;
+    float o[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+    unsigned char* prow = sP + (2 * w) * kEtTile + row * 128;
+    for (int j = 0; j < n_kv; ++j) {
+      const int valid = T - j * 128;                         // keys of this tile that exist (>= 128: all)
+      ptx::mbar_wait(&s_full[w], (uint32_t)j & 1u);
+      ptx::tc_fence_after();
+      uint32_t v[128];
+#pragma unroll
+      for (int hc = 0; hc < 4; ++hc) ptx::tmem_ld_32x32(tmem_s + hc * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[hc * 32]));
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&s_free[w]);                          // the MMA warp may overwrite S_w with the next tile's scores
+      if (valid < 128) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i >= valid) v[i] = 0xff800000u;                // -inf: exp2 gives an exact 0
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 128; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(v[i])), mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(v[i + 2])), mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
+      }
+      const float m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+      const float mc = m_new * c;
+      const float corr = ex2_approx(m * c - mc);             // m = -inf: 0
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int hc = 0; hc < 4; ++hc) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(v[hc * 32 + i]), c, -mc));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(v[hc * 32 + i + 1]), c, -mc));
+          sum0 += p0, sum1 += p1;
+          const __half2 hp = __floats2half2_rn(p0, p1);
+          pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+        }
+        // 32 keys = four 16-byte chunks of k-tile hc / 2, chunk index xor (row & 7) (SWIZZLE_128B, K-major)
+        unsigned char* pt = prow + (hc >> 1) * kEtTile;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int chunk = (hc & 1) * 4 + ch;
+          *reinterpret_cast<uint4*>(pt + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+        }
+      }
+      l = l * corr + (sum0 + sum1);
+      m = m_new;
+      ptx::fence_proxy_async();                              // P: generic-proxy writes -> tensor-core (async) proxy
+      ptx::mbar_arrive(&p_full[w]);
+      ptx::mbar_wait(&pv_full[w], (uint32_t)j & 1u);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int hc = 0; hc < 2; ++hc) {
+        uint32_t pv[32];
+        ptx::tmem_ld_32x32(tmem_pv + hc * 32, pv);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[hc * 32 + i] = fmaf(o[hc * 32 + i], corr, __uint_as_float(pv[i]));
+      }
+      ptx::tc_fence_before();
+    }
+    const int q = q0 + w * 128 + row;
+    if (q < T) {
+      const float inv = 1.f / l;
+      __half* dst = out + ((size_t)b * T + q) * d + h * 64;
+#pragma unroll
+      for (int i = 0; i < 64; i += 8) {
+        const __half2 h0 = __floats2half2_rn(o[i] * inv, o[i + 1] * inv), h1 = __floats2half2_rn(o[i + 2] * inv, o[i + 3] * inv);
+        const __half2 h2 = __floats2half2_rn(o[i + 4] * inv, o[i + 5] * inv), h3 = __floats2half2_rn(o[i + 6] * inv, o[i + 7] * inv);
+        uint4 u;
+        u.x = *reinterpret_cast<const uint32_t*>(&h0), u.y = *reinterpret_cast<const uint32_t*>(&h1);
+        u.z = *reinterpret_cast<const uint32_t*>(&h2), u.w = *reinterpret_cast<const uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(dst + i) = u;
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int launch_encoder_attention(GemmContext* tmaps, const __half* qkv, int B, int T, int n_head, __half* out, cudaStream_t st, int64_t* launches) {
+  static int use_tc = -1;
+  if (use_tc < 0) {
+    const char* e = getenv("WB_ENC_ATTN_TC");
+    use_tc = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int d = n_head * kAttD;
+  dim3 grid((T + kAttBM - 1) / kAttBM, n_head, B);
+  if (use_tc && tmaps) {
+    grid.x = (T + 255) / 256;
+    CUtensorMap tm;
+    const int rc = gemm_get_tmap(tmaps, qkv, 3 * d, T, B, 3 * d, (long long)T * 3 * d, 128, &tm);
+    if (rc) return rc;
+    static bool attr_tc = false;
+    if (!attr_tc) {
+      WB_CUDA_OK(cudaFuncSetAttribute(encoder_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEtSmem));
+      attr_tc = true;
+    }
+    encoder_attention_tc_kernel<<<grid, kEtThreads, kEtSmem, st>>>(tm, T, d, out);
+    if (launches) *launches += 1;
+    WB_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     WB_CUDA_OK(cudaFuncSetAttribute(encoder_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem));
     attr_set = true;
   }
-  dim3 grid((T + kAttBM - 1) / kAttBM, n_head, B);
-  encoder_attention_kernel<<<grid, kAttThreads, kAttSmem, st>>>(qkv, T, n_head * kAttD, out);
+  encoder_attention_kernel<<<grid, kAttThreads, kAttSmem, st>>>(qkv, T, d, out);
   if (launches) *launches += 1;
   WB_CUDA_OK(cudaGetLastError());
   return 0;

@@ -336,7 +336,7 @@ static int encoder_forward(wb_handle* h, int B) {
     const LayerW& L = h->enc[l];
     WB_TRY(launch_layernorm(h->xenc, L.ln1_g, L.ln1_b, M, d, h->h16, nullptr, st, &h->launches));
     WB_TRY(plain_gemm(h, h->h16, M, L.wqkv, 3 * d, d, L.bqkv, 0, nullptr, h->qkv16, nullptr));
-    WB_TRY(launch_encoder_attention(h->qkv16, B, T, D.n_audio_head, h->att16, st, &h->launches));
+    WB_TRY(launch_encoder_attention(h->gemm, h->qkv16, B, T, D.n_audio_head, h->att16, st, &h->launches));
     WB_TRY(plain_gemm(h, h->att16, M, L.wo, d, d, L.bo, 0, h->xenc, nullptr, h->xenc));
     WB_TRY(launch_layernorm(h->xenc, L.ln2_g, L.ln2_b, M, d, h->h16, nullptr, st, &h->launches));
     WB_TRY(plain_gemm(h, h->h16, M, L.w1, 4 * d, d, L.b1, 1, nullptr, h->mlp16, nullptr));
@@ -1252,7 +1252,7 @@ int wb_op_layernorm(wb_handle* h, const float* x, const float* gamma, const floa
 int wb_op_attention(wb_handle* h, const void* qkv_f16, int32_t B, int32_t T, int32_t n_head, void* out_f16) {
   if (!h || !qkv_f16 || !out_f16) return WB_ERR_ARG;
   WB_CUDA_OK(cudaSetDevice(h->device));
-  return launch_encoder_attention((const __half*)qkv_f16, B, T, n_head, (__half*)out_f16, h->stream, &h->launches);
+  return launch_encoder_attention(h->gemm, (const __half*)qkv_f16, B, T, n_head, (__half*)out_f16, h->stream, &h->launches);
 }
 
 // ---- legacy f64 symbol (stft/src/lib.rs:110-122; bridge.h:11) --------------------------------------------------------------------

@@ -59,7 +59,8 @@ int launch_fill_random(void* ptr, size_t n, int is_f16, float scale, float offse
 
 // ---- encoder attention (attention_enc.cu) ---------------------------------------------------------------------------------
 // qkv fp16 [B*T][3d] (q | k | v, head h at columns h*64) -> out fp16 [B*T][d]; softmax(q k^T / 8) v, non-causal
-int launch_encoder_attention(const __half* qkv, int B, int T, int n_head, __half* out, cudaStream_t st, int64_t* launches);
+// tmaps != null: tcgen05 kernel (TMA-fed, S and PV accumulators in TMEM); null: the mma.sync kernel
+int launch_encoder_attention(GemmContext* tmaps, const __half* qkv, int B, int T, int n_head, __half* out, cudaStream_t st, int64_t* launches);
 
 // ---- decoder step (decoder.cu) ---------------------------------------------------------------------------------------------
 struct DecodeState {      // lives in device memory; read by every kernel of a step (CUDA-graph friendly)
