@@ -139,6 +139,8 @@ struct wb_handle {
   cudaStream_t sub_stream[kMaxSub];
   cudaEvent_t sub_ev[kMaxSub], fork_ev;
   cudaGraphExec_t g_step[kMaxSub], g_sample[kMaxSub];
+  cudaGraphExec_t g_sample_n[kMaxSub];   // several sampling steps in one graph (fewer graph launches, dependent launch across steps)
+  int sample_n;                          // steps per g_sample_n graph
   int64_t nodes_step, nodes_sample;
   std::string graph_key;
 
@@ -481,17 +483,19 @@ static void destroy_graphs(wb_handle* h) {
   for (int i = 0; i < wb_handle::kMaxSub; ++i) {
     if (h->g_step[i]) cudaGraphExecDestroy(h->g_step[i]);
     if (h->g_sample[i]) cudaGraphExecDestroy(h->g_sample[i]);
-    h->g_step[i] = h->g_sample[i] = nullptr;
+    if (h->g_sample_n[i]) cudaGraphExecDestroy(h->g_sample_n[i]);
+    h->g_step[i] = h->g_sample[i] = h->g_sample_n[i] = nullptr;
   }
   h->graph_key.clear();
 }
 
-static int capture(wb_handle* h, const StepOpts& o, cudaGraphExec_t* out, int64_t* nodes) {
+static int capture(wb_handle* h, const StepOpts& o, cudaGraphExec_t* out, int64_t* nodes, int n_steps = 1) {
   cudaGraph_t g;
   const int64_t before = h->launches;
   cudaStream_t st = step_stream(h, o);
   WB_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-  const int rc = decode_step(h, o);
+  int rc = 0;
+  for (int k = 0; k < n_steps && rc == 0; ++k) rc = decode_step(h, o);
   const cudaError_t e = cudaStreamEndCapture(st, &g);
   *nodes = h->launches - before;
   h->launches = before;
@@ -540,7 +544,8 @@ int wb_create(const wb_dims* dims, int32_t max_batch, int32_t max_beams, int32_t
   h->dims = *dims, h->max_batch = max_batch, h->max_beams = max_beams, h->device = device;
   h->Mb_max = max_batch * max_beams;
   h->launches = 0, h->weights_ready = false, h->enc_batch = 0;
-  for (int i = 0; i < wb_handle::kMaxSub; ++i) h->g_step[i] = h->g_sample[i] = nullptr, h->sub_stream[i] = nullptr;
+  for (int i = 0; i < wb_handle::kMaxSub; ++i) h->g_step[i] = h->g_sample[i] = h->g_sample_n[i] = nullptr, h->sub_stream[i] = nullptr;
+  h->sample_n = 1;
   h->nodes_step = h->nodes_sample = 0;
   h->own_stream = stream == nullptr;
   if (h->own_stream)
@@ -905,11 +910,17 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
     samp[i] = o;
   }
 
+  // the host looks at the EOT flags every `interval` steps anyway: that many steps go into one graph
+  const int interval = opts->eot_check_interval > 0 ? opts->eot_check_interval : 8;
+  int multi = interval;
+  if (const char* e = getenv("WB_GRAPH_STEPS")) multi = atoi(e);
+  multi = multi < 1 ? 1 : (multi > 32 ? 32 : multi);
   char key[128];
-  snprintf(key, sizeof(key), "B%d i%d e%d s%d", B, n_init, opts->eot, nsb);
+  snprintf(key, sizeof(key), "B%d i%d e%d s%d m%d", B, n_init, opts->eot, nsb, multi);
   const bool use_graph = getenv("WB_NO_GRAPH") == nullptr;
   if (use_graph && h->graph_key != key) {
     destroy_graphs(h);
+    h->sample_n = multi;
     for (int i = 0; i < nsb; ++i) {
       // one eager pass of each variant first: sets function attributes and faults in code outside of capture
       WB_TRY(reset_decode_state(h, plain[i]));
@@ -918,6 +929,10 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
       WB_CUDA_OK(cudaStreamSynchronize(step_stream(h, plain[i])));
       WB_TRY(capture(h, plain[i], &h->g_step[i], &h->nodes_step));
       WB_TRY(capture(h, samp[i], &h->g_sample[i], &h->nodes_sample));
+      if (h->sample_n > 1) {
+        int64_t nodes_n = 0;
+        WB_TRY(capture(h, samp[i], &h->g_sample_n[i], &nodes_n, h->sample_n));
+      }
     }
     h->graph_key = key;
     // the eager passes wrote tokens and log-probs: restore
@@ -941,19 +956,20 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
       }
     }
   }
-  const int interval = opts->eot_check_interval > 0 ? opts->eot_check_interval : 8;
   int steps = 0;
-  for (int s = 0; s < opts->sample_len; ++s) {
+  for (int s = 0; s < opts->sample_len;) {
+    const int n = (use_graph && multi > 1 && s + multi <= opts->sample_len && (s % interval) + multi <= interval) ? multi : 1;
     for (int i = 0; i < nsb; ++i) {
       if (use_graph) {
-        WB_CUDA_OK(cudaGraphLaunch(h->g_sample[i], step_stream(h, samp[i])));
-        h->launches += h->nodes_sample;
+        WB_CUDA_OK(cudaGraphLaunch(n > 1 ? h->g_sample_n[i] : h->g_sample[i], step_stream(h, samp[i])));
+        h->launches += h->nodes_sample * n;
       } else {
         WB_TRY(decode_step(h, samp[i]));
       }
     }
-    ++steps;
-    if ((s + 1) % interval == 0 && s + 1 < opts->sample_len) {
+    s += n;
+    steps += n;
+    if (s % interval == 0 && s < opts->sample_len) {
       for (int i = 0; i < nsb; ++i)
         WB_CUDA_OK(cudaMemcpyAsync(h->h_done + plain[i].b0, h->done + plain[i].b0, sizeof(int32_t) * plain[i].Mb, cudaMemcpyDeviceToHost,
                                    step_stream(h, plain[i])));
