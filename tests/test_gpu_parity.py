@@ -369,6 +369,30 @@ def test_beam_search_matches_oracle(wbm, ref, small_dims, small_dims_ml, oracle_
     w.close()
 
 
+def test_beam_search_on_block_kernels(wbm, ref, oracle_logmel):
+    """Beam search at base width (d = 512): the decoder step runs as the cluster kernels with chunks x beams sequences
+    (groups of 4 / 8 that straddle chunks), the cross K/V shared per chunk and the self K/V cache re-indexed every step."""
+    dims = ref.ModelDims(80, 1500, 512, 8, 2, 51864, 448, 512, 8, 2)
+    weights = ref.random_weights(dims, seed=5)
+    oracle = ref.WhisperRef(dims, weights)
+    pd = wbm.ModelDims(*[getattr(dims, f) for f in dims.__dataclass_fields__])
+    B, beam = 3, 5
+    w = wbm.Whisper(pd, weights=weights, max_batch=B, max_beams=beam)
+    audio = np.stack([ref.synth_audio(800 + i, "noise") for i in range(B)])
+    xa_ref = oracle.encode(torch.from_numpy(np.stack([oracle_logmel(a) for a in audio])).float())
+    w.encode(audio.astype(np.float32), return_features=False)
+    opts_ref = ref.DecodeOptions.default_for(dims, sample_len=9)
+    want_tokens, want_scores = oracle.beam_search(xa_ref, opts_ref, beam_size=beam)
+    o = wbm.DecodeOptions.default_for(pd, sample_len=9)
+    o.beam_size = beam
+    tok, lens, slp = w.decode_tokens(B, o)
+    for b in range(B):
+        n = len(want_tokens[b])
+        assert tok[b, :n].tolist() == want_tokens[b], (b, tok[b].tolist(), want_tokens[b])
+        assert abs(float(slp[b]) - want_scores[b]) <= 0.05
+    w.close()
+
+
 def test_error_paths(tiny, wbm):
     w, _ = tiny
     lib = wbm.load_library()
