@@ -52,6 +52,11 @@ typedef struct wb_decode_opts {
   int32_t n_suppress_begin;
   int32_t beam_size;             /* 0 or 1 = greedy; 2..7 = beam search, patience 1 (needs max_beams >= beam_size)  */
   int32_t eot_check_interval;    /* how often (in steps) the host polls "all sequences ended"; 0 = default (8)      */
+  /* upstream ApplyTimestampRules (DecodingOptions.without_timestamps = False, upstream's own default): greedy only.   */
+  int32_t timestamps;            /* 0 = off (the prompt then ends with <|notimestamps|>)                            */
+  int32_t timestamp_begin;       /* first timestamp token <|0.00|>: 50363 (.en) / 50364 (multilingual)              */
+  int32_t no_timestamps;         /* <|notimestamps|>: 50362 / 50363; never sampled when the rules are on            */
+  int32_t max_initial_timestamp_index; /* first timestamp <= this many 0.02 s steps (upstream: 50); < 0 = no limit  */
 } wb_decode_opts;
 
 typedef struct wb_handle wb_handle;

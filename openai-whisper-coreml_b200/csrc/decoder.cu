@@ -592,7 +592,7 @@ struct LogitsTcArgs {
   int n_groups, n_stages;
 };
 
-template <int NB>
+template <int NB, bool TS>   // TS: upstream ApplyTimestampRules among the logit filters (compiled out otherwise)
 __global__ void __launch_bounds__(kLtThreads, 1) logits_tc_kernel(const __grid_constant__ CUtensorMap tmW, LogitsTcArgs a) {
   constexpr int kBufStride = NB <= 32 ? 32 : 64;               // TMEM columns per accumulator buffer
   constexpr int kTmemCols = 2 * kBufStride;
@@ -746,6 +746,14 @@ __global__ void __launch_bounds__(kLtThreads, 1) logits_tc_kernel(const __grid_c
     ptx::mbar_arrive(bready);
     trace.mark(4);
     const bool first = ld_state(&p.state->cur_len) + 1 == p.n_initial;
+    // timestamp rules: per-sequence state of this step (written by the previous finish kernel) into shared memory
+    int4* s_ts = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(tmem_slot) + 31) & ~(uintptr_t)15);
+    constexpr bool ts_on = TS;
+    if (ts_on) {
+      if (et < NB) s_ts[et] = et < p.Mb ? __ldcg(p.ts_state + et) : make_int4(0, 0, 0, 0);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    const int g_straddle = (ts_on && (p.ts_begin & 127)) ? (p.ts_begin >> 7) : -1;   // group with text and timestamp rows
     const int q4 = warp & 3, half = ewarp >> 2;                // TMEM lane quadrant this warp may read; its half of the columns
     const int j_lo = half * (NB / 2), j_hi = j_lo + NB / 2;
     constexpr int kSeqPerWarp = (NB + 7) / 8;
@@ -760,67 +768,84 @@ __global__ void __launch_bounds__(kLtThreads, 1) logits_tc_kernel(const __grid_c
       uint32_t v[32];
       ptx::tmem_ld_32x32(tmem_base + buf * kBufStride + ((uint32_t)(q4 * 32) << 16), v);
       ptx::tmem_ld_wait();
+      const bool is_ts = n >= p.ts_begin, below_eot = n < p.eot, late = first && n > p.ts_last_allowed;
+      auto dead_for = [&](int j) {   // static filters, then the timestamp rules of sequence j
+        if (!ts_on) return dead;
+        const int4 st = s_ts[j];
+        const bool dyn = is_ts ? ((st.x & 1) || n < st.y || late) : (first || ((st.x & 2) && below_eot));
+        return dead || dyn;
+      };
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (j < NB && j >= j_lo && j < j_hi) red[row * RS + j] = dead ? -INFINITY : __uint_as_float(v[j]);
+        if (j < NB && j >= j_lo && j < j_hi) red[row * RS + j] = dead_for(j) ? -INFINITY : __uint_as_float(v[j]);
       if (NB > 32) {
         ptx::tmem_ld_32x32(tmem_base + buf * kBufStride + ((uint32_t)(q4 * 32) << 16) + 32u, v);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (32 + j < NB && 32 + j >= j_lo && 32 + j < j_hi) red[row * RS + 32 + j] = dead ? -INFINITY : __uint_as_float(v[j]);
+          if (32 + j < NB && 32 + j >= j_lo && 32 + j < j_hi) red[row * RS + 32 + j] = dead_for(32 + j) ? -INFINITY : __uint_as_float(v[j]);
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[buf]);           // the accumulator buffer is free for the group after next
       asm volatile("bar.sync 1, 256;" ::: "memory");
       // warp per sequence (b = ewarp, ewarp + 8, ...): optional store, group-local (max, argmax, sum-exp); unrolled over the
-      // sequences of this warp so that the independent shuffle chains overlap
-      float xv[kSeqPerWarp][4], best[kSeqPerWarp], se[kSeqPerWarp];
-      int arg[kSeqPerWarp];
-#pragma unroll
-      for (int jb = 0; jb < kSeqPerWarp; ++jb) {
-        const int b = ewarp + 8 * jb;
-        best[jb] = -INFINITY, arg[jb] = 0x7fffffff;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = lane + 32 * i, nn = g * 128 + rr;
-          float x = -INFINITY;
-          if (nn < p.N && b < p.Mb) {
-            x = red[rr * RS + b];
-            if (p.out) reinterpret_cast<float*>(p.out)[(size_t)b * p.N + nn] = x;
-          }
-          xv[jb][i] = x;
-          if (x > best[jb]) best[jb] = x, arg[jb] = nn;        // ascending n: first maximum wins
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+      // sequences of this warp so that the independent shuffle chains overlap. `cls`: 0 = every row of the group,
+      // 1 / 2 = only its text / timestamp rows (the group that straddles ts_begin is reduced once per class)
+      auto reduce_group = [&](int cls, float* dst_base, int dst_stride, int dst_index) {
+        float xv[kSeqPerWarp][4], best[kSeqPerWarp], se[kSeqPerWarp];
+        int arg[kSeqPerWarp];
 #pragma unroll
         for (int jb = 0; jb < kSeqPerWarp; ++jb) {
-          const float ov = __shfl_xor_sync(0xffffffffu, best[jb], o);
-          const int oi = __shfl_xor_sync(0xffffffffu, arg[jb], o);
-          if (ov > best[jb] || (ov == best[jb] && oi < arg[jb])) best[jb] = ov, arg[jb] = oi;
+          const int b = ewarp + 8 * jb;
+          best[jb] = -INFINITY, arg[jb] = 0x7fffffff;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = lane + 32 * i, nn = g * 128 + rr;
+            float x = -INFINITY;
+            if (nn < p.N && b < p.Mb) {
+              x = red[rr * RS + b];
+              if (cls != 2 && p.out) reinterpret_cast<float*>(p.out)[(size_t)b * p.N + nn] = x;
+              if ((cls == 1 && nn >= p.ts_begin) || (cls == 2 && nn < p.ts_begin)) x = -INFINITY;
+            }
+            xv[jb][i] = x;
+            if (x > best[jb]) best[jb] = x, arg[jb] = nn;      // ascending n: first maximum wins
+          }
         }
-      }
 #pragma unroll
-      for (int jb = 0; jb < kSeqPerWarp; ++jb) {
-        se[jb] = 0.f;
-        if (best[jb] > -INFINITY) {
+        for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) se[jb] += expf(xv[jb][i] - best[jb]);
+          for (int jb = 0; jb < kSeqPerWarp; ++jb) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best[jb], o);
+            const int oi = __shfl_xor_sync(0xffffffffu, arg[jb], o);
+            if (ov > best[jb] || (ov == best[jb] && oi < arg[jb])) best[jb] = ov, arg[jb] = oi;
+          }
         }
-      }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+        for (int jb = 0; jb < kSeqPerWarp; ++jb) {
+          se[jb] = 0.f;
+          if (best[jb] > -INFINITY) {
 #pragma unroll
-        for (int jb = 0; jb < kSeqPerWarp; ++jb) se[jb] += __shfl_xor_sync(0xffffffffu, se[jb], o);
-      }
+            for (int i = 0; i < 4; ++i) se[jb] += expf(xv[jb][i] - best[jb]);
+          }
+        }
 #pragma unroll
-      for (int jb = 0; jb < kSeqPerWarp; ++jb) {
-        const int b = ewarp + 8 * jb;
-        if (lane == 0 && b < p.Mb)
-          *reinterpret_cast<float4*>(p.part_logits + ((size_t)b * a.n_groups + g) * 4) = make_float4(best[jb], __int_as_float(arg[jb]), se[jb], 0.f);
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int jb = 0; jb < kSeqPerWarp; ++jb) se[jb] += __shfl_xor_sync(0xffffffffu, se[jb], o);
+        }
+#pragma unroll
+        for (int jb = 0; jb < kSeqPerWarp; ++jb) {
+          const int b = ewarp + 8 * jb;
+          if (lane == 0 && b < p.Mb)
+            *reinterpret_cast<float4*>(dst_base + ((size_t)b * dst_stride + dst_index) * 4) = make_float4(best[jb], __int_as_float(arg[jb]), se[jb], 0.f);
+        }
+      };
+      if (g == g_straddle) {
+        reduce_group(1, p.part_logits, a.n_groups, g);
+        reduce_group(2, p.part_extra, 1, 0);
+      } else {
+        reduce_group(0, p.part_logits, a.n_groups, g);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");          // red is rewritten by the next group
     }
@@ -840,7 +865,7 @@ static int launch_logits_tc(const SkinnyDesc& d, cudaStream_t st, int64_t* launc
   CUtensorMap tmW;
   const int rc = gemm_get_tmap(d.tmaps, d.w, d.K, d.N, 1, d.K, (long long)d.N * d.K, 128, &tmW);
   if (rc) return rc;
-  const size_t fixed = (size_t)nkb * NB * 128 + (size_t)128 * (NB + 1) * 4 + (size_t)2 * d.K * 4 + 256 + 1024;
+  const size_t fixed = (size_t)nkb * NB * 128 + (size_t)128 * (NB + 1) * 4 + (size_t)2 * d.K * 4 + 1280 + 1024;   // + barriers and rule states + alignment slack
   int n_stages = (int)(((size_t)200 * 1024 - fixed) / kLtStageBytes);
   n_stages = n_stages > 8 ? 8 : n_stages;
   if (n_stages < 2) {
@@ -867,10 +892,12 @@ static int launch_logits_tc(const SkinnyDesc& d, cudaStream_t st, int64_t* launc
   case N_: {                                                                                                           \
     static size_t smem_set = 0;                                                                                        \
     if (smem > smem_set) {                                                                                             \
-      WB_CUDA_OK(cudaFuncSetAttribute(logits_tc_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      WB_CUDA_OK(cudaFuncSetAttribute(logits_tc_kernel<N_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      WB_CUDA_OK(cudaFuncSetAttribute(logits_tc_kernel<N_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       smem_set = smem;                                                                                                 \
     }                                                                                                                  \
-    le = cudaLaunchKernelEx(&cfg, logits_tc_kernel<N_>, tmW, a);                                                       \
+    le = d.ts_state ? cudaLaunchKernelEx(&cfg, logits_tc_kernel<N_, true>, tmW, a)                                     \
+                    : cudaLaunchKernelEx(&cfg, logits_tc_kernel<N_, false>, tmW, a);                                   \
   } break;
   switch (NB) {
     WB_LT_CASE(16) WB_LT_CASE(32) WB_LT_CASE(48)
@@ -905,6 +932,10 @@ int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches) 
       return -1;
     }
     if (use_logits_tc() && d.tmaps && d.K % 64 == 0 && d.Mb <= 48) return launch_logits_tc(d, st, launches);
+    if (d.ts_state) {
+      set_error("logits GEMM: the timestamp rules are implemented by the tcgen05 kernel only (Mb <= 48, K %% 64 == 0)");
+      return -1;
+    }
     const int n_groups = skinny_logits_ctas(d.N);
     const int MTl = (d.Mb + 7) / 8;
     const size_t sm = (size_t)MTl * 8 * (d.K * 2 + 64) + (size_t)128 * (MTl * 8 + 1) * 4 + 16 + (size_t)2 * d.K * 4;
@@ -2174,9 +2205,30 @@ int launch_post_block(const PostBlockDesc& p, cudaStream_t st, int64_t* launches
 // Upstream DecodingTask with temperature 0: the logit filters were applied in the logits GEMM epilogue;
 // here argmax over the CTA partials, sum_logprobs += logprob * (previous token != eot), sequences that ended keep
 // emitting eot. Then x[b] = token_embedding[next] + positional_embedding[cur_len + 1] for the next step.
+// online (max, argmax, sum-exp) accumulator over partial records
+struct LseAcc {
+  float best, se;
+  int arg;
+};
+__device__ __forceinline__ void lse_fold(LseAcc& a, float m, int idx, float z) {
+  if (m > a.best) {
+    a.se = a.se * expf(a.best - m) + z;   // best = -inf first: se is 0
+    a.best = m, a.arg = idx;
+  } else if (m > -INFINITY) {
+    a.se += z * expf(m - a.best);
+    if (m == a.best && idx < a.arg) a.arg = idx;
+  }
+}
+__device__ __forceinline__ void lse_merge(LseAcc& a, float om, int oa, float os) {
+  const float nm = fmaxf(a.best, om);
+  a.se = (a.best > -INFINITY ? a.se * expf(a.best - nm) : 0.f) + (om > -INFINITY ? os * expf(om - nm) : 0.f);
+  if (om > a.best || (om == a.best && oa < a.arg)) a.arg = oa;
+  a.best = nm;
+}
+
 __global__ void __launch_bounds__(256) step_finish_kernel(FinishDesc p) {
-  __shared__ float s_val[8], s_sum[8];
-  __shared__ int s_idx[8];
+  __shared__ float s_val[2][8], s_sum[2][8];
+  __shared__ int s_idx[2][8];
   __shared__ int s_tok, s_cur;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   TraceScope trace(p.state, 300 + p.sample);
@@ -2202,9 +2254,11 @@ __global__ void __launch_bounds__(256) step_finish_kernel(FinishDesc p) {
       s_tok = __ldcg(trow + c + 1);
     }
   }
-  // the logits partials of this sequence: each thread folds its records into an online (max, argmax, sum-exp)
-  float best = -INFINITY, se = 0.f;
-  int arg = 0x7fffffff;
+  // the logits partials of this sequence: each thread folds its records into online (max, argmax, sum-exp) accumulators,
+  // one for the text rows and (timestamp rules) one for the timestamp rows: groups >= ts_group0 and the extra record
+  const bool ts_on = p.ts_state != nullptr;
+  const int ts_group0 = ts_on ? p.ts_group0 : 0x7fffffff;
+  LseAcc acc[2] = {{-INFINITY, 0.f, 0x7fffffff}, {-INFINITY, 0.f, 0x7fffffff}};
   if (p.sample) {
     for (int i0 = tid; i0 < p.n_part; i0 += 256 * 4) {
       float4 rec[4];
@@ -2216,16 +2270,16 @@ __global__ void __launch_bounds__(256) step_finish_kernel(FinishDesc p) {
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float m = rec[j].x;
-        const int a = __float_as_int(rec[j].y);
-        if (m > best) {
-          se = se * expf(best - m) + rec[j].z;   // best = -inf first: se is 0
-          best = m, arg = a;
-        } else if (m > -INFINITY) {
-          se += rec[j].z * expf(m - best);
-          if (m == best && a < arg) arg = a;
-        }
+        const int i = i0 + j * 256;
+        if (i >= ts_group0)
+          lse_fold(acc[1], rec[j].x, __float_as_int(rec[j].y), rec[j].z);
+        else
+          lse_fold(acc[0], rec[j].x, __float_as_int(rec[j].y), rec[j].z);
       }
+    }
+    if (ts_on && tid == 0 && (p.ts_begin & 127)) {   // timestamp rows of the group that straddles ts_begin
+      const float4 r = __ldcg(reinterpret_cast<const float4*>(p.part_extra + (size_t)b * 4));
+      lse_fold(acc[1], r.x, __float_as_int(r.y), r.z);
     }
   }
   __syncthreads();
@@ -2238,34 +2292,59 @@ __global__ void __launch_bounds__(256) step_finish_kernel(FinishDesc p) {
     pe_v[j] = (np < p.n_ctx && c < p.d) ? __ldg(p.pos_emb + (size_t)np * p.d + c) : 0.f;
   }
   if (p.sample) {
+    const int n_cls = ts_on ? 2 : 1;
+    for (int k = 0; k < n_cls; ++k) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float om = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, se, o);
-      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
-      const float nm = fmaxf(best, om);
-      se = (best > -INFINITY ? se * expf(best - nm) : 0.f) + (om > -INFINITY ? os * expf(om - nm) : 0.f);
-      if (om > best || (om == best && oa < arg)) arg = oa;
-      best = nm;
+      for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, acc[k].best, o), os = __shfl_xor_sync(0xffffffffu, acc[k].se, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, acc[k].arg, o);
+        lse_merge(acc[k], om, oa, os);
+      }
+      if (lane == 0) s_val[k][warp] = acc[k].best, s_idx[k][warp] = acc[k].arg, s_sum[k][warp] = acc[k].se;
     }
-    if (lane == 0) s_val[warp] = best, s_idx[warp] = arg, s_sum[warp] = se;
     __syncthreads();
     if (tid == 0) {
-      float M = s_val[0], S = s_sum[0];
-      int A = s_idx[0];
-      for (int w = 1; w < 8; ++w) {
-        const float om = s_val[w];
-        const float nm = fmaxf(M, om);
-        S = (M > -INFINITY ? S * expf(M - nm) : 0.f) + (om > -INFINITY ? s_sum[w] * expf(om - nm) : 0.f);
-        if (om > M || (om == M && s_idx[w] < A)) A = s_idx[w];
-        M = nm;
+      LseAcc t[2];
+      for (int k = 0; k < n_cls; ++k) {
+        t[k] = LseAcc{s_val[k][0], s_sum[k][0], s_idx[k][0]};
+        for (int w = 1; w < 8; ++w) lse_merge(t[k], s_val[k][w], s_idx[k][w], s_sum[k][w]);
       }
-      const float logprob = -logf(S);   // the chosen logit is the maximum
+      float logprob;
+      int A;
+      if (!ts_on) {
+        A = t[0].arg;
+        logprob = -logf(t[0].se);   // the chosen logit is the maximum
+      } else {
+        // upstream ApplyTimestampRules, last rule: if the probability mass over the timestamps is above every text token,
+        // the text tokens are suppressed:  logsumexp(ts) > max(text)  <=>  M_ts + log S_ts > M_text
+        const float lse_ts = t[1].best > -INFINITY ? t[1].best + logf(t[1].se) : -INFINITY;
+        if (lse_ts > t[0].best) {
+          A = t[1].arg;
+          logprob = -logf(t[1].se);
+        } else {
+          const bool text = t[0].best >= t[1].best;   // equal logits: the lower index (text) wins, as argmax does
+          A = text ? t[0].arg : t[1].arg;
+          LseAcc all = t[0];
+          lse_merge(all, t[1].best, t[1].arg, t[1].se);
+          logprob = -logf(all.se);
+        }
+      }
       const bool ended = prev_tok == p.eot;
       if (!ended) p.sum_logprob[b] = slp_old + logprob;
       const int next = ended ? p.eot : A;
       trow[cur + 1] = next;
       p.done[b] = next == p.eot;
       s_tok = next;
+      if (ts_on) {   // rule state of the next step: sampled tokens are positions n_initial .. cur + 1
+        int4 st = p.ts_state[b];
+        const int len = cur + 2 - p.n_initial;
+        const bool last_ts = next >= p.ts_begin;
+        const bool penult_ts = len < 2 || prev_tok >= p.ts_begin;
+        if (last_ts) st.z = next;                            // the newest timestamp of the sequence
+        st.x = (last_ts && penult_ts ? 1 : 0) | (last_ts && !penult_ts ? 2 : 0);
+        st.y = st.z ? ((last_ts && !penult_ts) ? st.z : st.z + 1) : 0;
+        p.ts_state[b] = st;
+      }
     }
     __syncthreads();
   }

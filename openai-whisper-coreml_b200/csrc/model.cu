@@ -125,7 +125,8 @@ struct wb_handle {
   int32_t *top_idx, *beam_src;
   int32_t* tokens;
   int tokens_ld;
-  float *xdec, *q32, *logits, *sum_logprob, *part_logits;
+  float *xdec, *q32, *logits, *sum_logprob, *part_logits, *part_extra;
+  int4* ts_state;   // timestamp-rule state per sequence (FinishDesc)
   __half *dmlp16, *a16;
   int32_t* done;
   unsigned char* mask;
@@ -286,6 +287,8 @@ static void layout_workspace(wb_handle* h) {
   h->mask = A.take<unsigned char>((size_t)D.n_vocab);
   h->n_logit_ctas = skinny_logits_ctas(D.n_vocab);
   h->part_logits = A.take<float>(Mb * (size_t)h->n_logit_ctas * 4);
+  h->part_extra = A.take<float>(Mb * (size_t)4);
+  h->ts_state = A.take<int4>(Mb);
   h->state = A.take<DecodeState>(wb_handle::kMaxSub);
   h->trace = getenv("WB_TRACE") ? A.take<unsigned long long>(65536 * 8) : nullptr;
 }
@@ -369,6 +372,8 @@ struct StepOpts {
   int no_finish;      // beam search: the host picks the next tokens between the logits and the finish kernel
   int b0;             // first sequence of this sub-batch (Mb sequences starting at b0)
   int sub;            // sub-batch index: selects the stream and the DecodeState
+  int timestamps;     // upstream ApplyTimestampRules among the logit filters (sampling steps only)
+  int ts_begin, ts_last_allowed;
 };
 
 static cudaStream_t step_stream(wb_handle* h, const StepOpts& o) { return o.sub > 0 ? h->sub_stream[o.sub] : h->stream; }
@@ -384,6 +389,10 @@ static int step_finish(wb_handle* h, const StepOpts& o, int sample) {
   f.tokens = h->tokens + b0 * h->tokens_ld, f.tokens_ld = h->tokens_ld;
   f.sum_logprob = h->sum_logprob + b0, f.done = h->done + b0, f.tok_emb = h->tok_emb, f.pos_emb = h->dec_pos;
   f.x = h->xdec + b0 * D.n_text_state, f.state = step_state(h, o);
+  if (sample && o.timestamps) {
+    f.ts_state = h->ts_state + b0, f.part_extra = h->part_extra + b0 * 4;
+    f.ts_begin = o.ts_begin, f.ts_group0 = (o.ts_begin + 127) / 128, f.n_initial = o.n_initial;
+  }
   return launch_step_finish(f, step_stream(h, o), &h->launches);
 }
 
@@ -462,6 +471,11 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
     lg.out = o.store_logits ? h->logits + b0 * (size_t)D.n_vocab : nullptr, lg.mask = o.sample ? h->mask : nullptr, lg.n_initial = o.n_initial;
     lg.part_logits = h->part_logits + b0 * h->n_logit_ctas * 4;
     lg.tmaps = h->gemm;
+    lg.ts_begin = 0x7fffffff, lg.ts_last_allowed = 0x7fffffff, lg.eot = o.eot;
+    if (o.sample && o.timestamps) {
+      lg.ts_state = h->ts_state + b0, lg.part_extra = h->part_extra + b0 * 4;
+      lg.ts_begin = o.ts_begin, lg.ts_last_allowed = o.ts_last_allowed;
+    }
     WB_TRY(launch_skinny_gemm(lg, st, &h->launches));
   }
   if (o.no_finish) return 0;
@@ -876,6 +890,12 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
     set_error("wb_decode: bad options (n_initial=%d sample_len=%d n_text_ctx=%d)", n_init, opts->sample_len, D.n_text_ctx);
     return WB_ERR_ARG;
   }
+  const bool ts_on = opts->timestamps != 0;
+  if (ts_on && (opts->timestamp_begin <= opts->eot || opts->timestamp_begin >= D.n_vocab || opts->no_timestamps < 0 ||
+                opts->no_timestamps >= D.n_vocab || B > 48)) {
+    set_error("wb_decode: timestamp rules need eot < timestamp_begin < n_vocab, a valid no_timestamps token and <= 48 sequences");
+    return WB_ERR_ARG;
+  }
   cudaStream_t st = h->stream;
   // token rows: sot sequence, then eot padding
   std::vector<int32_t> rows((size_t)B * h->tokens_ld, opts->eot);
@@ -883,6 +903,7 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
     for (int i = 0; i < n_init; ++i) rows[(size_t)b * h->tokens_ld + i] = opts->initial_tokens[i];
   // logit filters as a per-token mask: 1 = SuppressTokens (every step), 2 = SuppressBlank (first sampled position only)
   std::vector<unsigned char> mask(D.n_vocab, 0);
+  if (ts_on) mask[opts->no_timestamps] = 1;   // ApplyTimestampRules: <|notimestamps|> is never sampled
   for (int i = 0; i < opts->n_suppress_begin; ++i)
     if (opts->suppress_begin[i] >= 0 && opts->suppress_begin[i] < D.n_vocab) mask[opts->suppress_begin[i]] = 2;
   for (int i = 0; i < opts->n_suppress; ++i)
@@ -891,6 +912,7 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
   WB_CUDA_OK(cudaMemcpyAsync(h->mask, mask.data(), mask.size(), cudaMemcpyHostToDevice, st));
   WB_CUDA_OK(cudaMemsetAsync(h->sum_logprob, 0, sizeof(float) * B, st));
   WB_CUDA_OK(cudaMemsetAsync(h->done, 0, sizeof(int32_t) * B, st));
+  WB_CUDA_OK(cudaMemsetAsync(h->ts_state, 0, sizeof(int4) * B, st));
   WB_CUDA_OK(cudaStreamSynchronize(st));   // `rows` / `mask` are pageable host memory
 
   // sub-batches: the chunks are decoded as up to 4 independent groups on their own streams, so the latency-bound GEMM
@@ -905,6 +927,8 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
     StepOpts o{};
     o.b0 = i * per, o.Mb = (B - o.b0) < per ? (B - o.b0) : per, o.sub = i;
     o.beams = 1, o.store_logits = 0, o.sample = 0, o.n_initial = n_init, o.eot = opts->eot;
+    o.timestamps = ts_on ? 1 : 0, o.ts_begin = opts->timestamp_begin;
+    o.ts_last_allowed = opts->max_initial_timestamp_index >= 0 ? opts->timestamp_begin + opts->max_initial_timestamp_index : 0x7fffffff;
     plain[i] = o;
     o.sample = 1;
     samp[i] = o;
@@ -916,7 +940,8 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
   if (const char* e = getenv("WB_GRAPH_STEPS")) multi = atoi(e);
   multi = multi < 1 ? 1 : (multi > 32 ? 32 : multi);
   char key[128];
-  snprintf(key, sizeof(key), "B%d i%d e%d s%d m%d", B, n_init, opts->eot, nsb, multi);
+  snprintf(key, sizeof(key), "B%d i%d e%d s%d m%d t%d.%d.%d", B, n_init, opts->eot, nsb, multi, ts_on ? 1 : 0,
+           ts_on ? opts->timestamp_begin : 0, ts_on ? opts->max_initial_timestamp_index : 0);
   const bool use_graph = getenv("WB_NO_GRAPH") == nullptr;
   if (use_graph && h->graph_key != key) {
     destroy_graphs(h);
@@ -939,6 +964,7 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
     WB_CUDA_OK(cudaMemcpyAsync(h->tokens, rows.data(), rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     WB_CUDA_OK(cudaMemsetAsync(h->sum_logprob, 0, sizeof(float) * B, st));
     WB_CUDA_OK(cudaMemsetAsync(h->done, 0, sizeof(int32_t) * B, st));
+    WB_CUDA_OK(cudaMemsetAsync(h->ts_state, 0, sizeof(int4) * B, st));
     WB_CUDA_OK(cudaStreamSynchronize(st));
   }
 
@@ -1018,6 +1044,10 @@ static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int3
   }
   if (n_init < 1 || opts->sample_len < 1 || total > D.n_text_ctx || !opts->initial_tokens) {
     set_error("wb_decode: bad options");
+    return WB_ERR_ARG;
+  }
+  if (opts->timestamps) {
+    set_error("wb_decode: the timestamp rules are implemented for greedy decoding only");
     return WB_ERR_ARG;
   }
   cudaStream_t st = h->stream;

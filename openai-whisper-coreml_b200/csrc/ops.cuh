@@ -97,6 +97,13 @@ struct SkinnyDesc {
   const unsigned char* mask;   // [N]: 1 = suppressed, 2 = suppressed at the first sampled position only; may be null
   int n_initial;
   float* part_logits;
+  // LOGITS, timestamp rules (upstream ApplyTimestampRules; null = off): per-sequence rule state written by the finish kernel
+  // {x: bit0 = timestamps forbidden, bit1 = text below eot forbidden; y: timestamps below y forbidden}; rows >= ts_begin
+  // are timestamps; at the first sampled position only timestamps <= ts_last_allowed are allowed. The group that straddles
+  // ts_begin reports its text rows in its partial and its timestamp rows in part_extra[b].
+  const int4* ts_state;
+  int ts_begin, ts_last_allowed, eot;
+  float* part_extra;           // [Mb][4]
   GemmContext* tmaps;          // LOGITS: tensor-map cache (tcgen05 path); null selects the mma.sync kernel
   const DecodeState* state;
 };
@@ -175,6 +182,11 @@ struct FinishDesc {
   const __half* tok_emb;
   const float* pos_emb;
   float* x;                   // [Mb][d] residual stream of the next step
+  // timestamp rules (null = off): partial groups >= ts_group0 (and part_extra) are timestamp rows; the probability-mass rule
+  // and the rule state for the next step are evaluated here
+  int4* ts_state;
+  const float* part_extra;
+  int ts_begin, ts_group0, n_initial;
   DecodeState* state;
 };
 int launch_step_finish(const FinishDesc& d, cudaStream_t st, int64_t* launches);

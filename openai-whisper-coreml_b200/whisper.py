@@ -42,7 +42,9 @@ class _DecodeOpts(ctypes.Structure):
                 ("sample_len", ctypes.c_int32), ("eot", ctypes.c_int32),
                 ("suppress", ctypes.POINTER(ctypes.c_int32)), ("n_suppress", ctypes.c_int32),
                 ("suppress_begin", ctypes.POINTER(ctypes.c_int32)), ("n_suppress_begin", ctypes.c_int32),
-                ("beam_size", ctypes.c_int32), ("eot_check_interval", ctypes.c_int32)]
+                ("beam_size", ctypes.c_int32), ("eot_check_interval", ctypes.c_int32),
+                ("timestamps", ctypes.c_int32), ("timestamp_begin", ctypes.c_int32), ("no_timestamps", ctypes.c_int32),
+                ("max_initial_timestamp_index", ctypes.c_int32)]
 
 
 @dataclass(frozen=True)
@@ -86,19 +88,26 @@ class DecodeOptions:
     suppress_begin: Sequence[int] = field(default_factory=list)
     beam_size: int = 0
     eot_check_interval: int = 8
+    timestamps: bool = False                 # upstream ApplyTimestampRules (DecodingOptions.without_timestamps = False); greedy only
+    timestamp_begin: int = 0                 # <|0.00|>
+    no_timestamps: int = 0                   # <|notimestamps|>
+    max_initial_timestamp_index: int = 50    # upstream max_initial_timestamp = 1.0 s; < 0: no limit
 
     @staticmethod
-    def default_for(dims: ModelDims, sample_len: int = 224, language: int = 0) -> "DecodeOptions":
+    def default_for(dims: ModelDims, sample_len: int = 224, language: int = 0, without_timestamps: bool = True) -> "DecodeOptions":
         if dims.is_multilingual:
             eot, sot, lang0, translate, transcribe, sot_lm, sot_prev, no_speech, no_ts = (
                 50257, 50258, 50259, 50358, 50359, 50360, 50361, 50362, 50363)
-            init = [sot, lang0 + language, transcribe, no_ts]
+            init = [sot, lang0 + language, transcribe]
         else:
             eot, sot, translate, transcribe, sot_lm, sot_prev, no_speech, no_ts = (
                 50256, 50257, 50357, 50358, 50359, 50360, 50361, 50362)
-            init = [sot, no_ts]
+            init = [sot]
+        if without_timestamps:
+            init.append(no_ts)
         suppress = sorted({sot, sot_prev, sot_lm, translate, transcribe, no_speech})
-        return DecodeOptions(init, eot, sample_len, suppress, [220, eot])
+        return DecodeOptions(init, eot, sample_len, suppress, [220, eot], timestamps=not without_timestamps,
+                             timestamp_begin=no_ts + 1, no_timestamps=no_ts)
 
 
 _HF_RULES = (("layers.", "blocks."), (".encoder_attn_layer_norm.", ".cross_attn_ln."), (".self_attn_layer_norm.", ".attn_ln."),
@@ -363,7 +372,8 @@ class Whisper:
         supb = np.asarray(list(o.suppress_begin), dtype=np.int32)
         c = _DecodeOpts(init.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), init.size, o.sample_len, o.eot,
                         sup.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), sup.size,
-                        supb.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), supb.size, o.beam_size, o.eot_check_interval)
+                        supb.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), supb.size, o.beam_size, o.eot_check_interval,
+                        1 if o.timestamps else 0, o.timestamp_begin, o.no_timestamps, o.max_initial_timestamp_index)
         return c, (init, sup, supb)
 
     def greedy(self, B: int, opts: DecodeOptions):

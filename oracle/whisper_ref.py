@@ -294,6 +294,8 @@ class WhisperRef:
                 logits[:, list(opts.suppress_begin)] = float("-inf")
             if len(opts.suppress):
                 logits[:, list(opts.suppress)] = float("-inf")
+            if opts.timestamps:
+                logits = apply_timestamp_rules(logits, tokens, sample_begin, v, opts.max_initial_timestamp_index)
             all_logits.append(logits)
             nxt = logits.argmax(dim=-1)
             logprobs = F.log_softmax(logits.float(), dim=-1)
@@ -400,18 +402,55 @@ class DecodeOptions:
     sample_len: int = 224                      # upstream default n_text_ctx // 2
     suppress: Sequence[int] = field(default_factory=list)         # SuppressTokens (every step)
     suppress_begin: Sequence[int] = field(default_factory=list)   # SuppressBlank (first sampled position only)
+    timestamps: bool = False                   # ApplyTimestampRules (upstream: unless without_timestamps)
+    max_initial_timestamp_index: Optional[int] = 50   # upstream max_initial_timestamp = 1.0 s / 0.02 s per timestamp token
 
     @staticmethod
-    def default_for(dims: ModelDims, sample_len: int = 224, language: int = 0) -> "DecodeOptions":
-        """Upstream defaults with `without_timestamps=True`. The non-speech symbol list needs the tokenizer vocab,
-        which is not available offline; the special tokens upstream always suppresses are included."""
+    def default_for(dims: ModelDims, sample_len: int = 224, language: int = 0, without_timestamps: bool = True) -> "DecodeOptions":
+        """Upstream defaults. The non-speech symbol list needs the tokenizer vocab, which is not available offline; the
+        special tokens upstream always suppresses are included. `without_timestamps=False` is upstream's own default:
+        no <|notimestamps|> in the prompt and ApplyTimestampRules among the logit filters."""
         v = Vocab.for_dims(dims)
         if dims.is_multilingual:
-            init = [v.sot, v.lang0 + language, v.transcribe, v.no_timestamps]
+            init = [v.sot, v.lang0 + language, v.transcribe]
         else:
-            init = [v.sot, v.no_timestamps]
+            init = [v.sot]
+        if without_timestamps:
+            init.append(v.no_timestamps)
         suppress = sorted({v.sot, v.sot_prev, v.sot_lm, v.translate, v.transcribe, v.no_speech})
-        return DecodeOptions(init, sample_len, suppress, [220, v.eot])
+        return DecodeOptions(init, sample_len, suppress, [220, v.eot], timestamps=not without_timestamps)
+
+
+def apply_timestamp_rules(logits: torch.Tensor, tokens: torch.Tensor, sample_begin: int, vocab: "Vocab",
+                          max_initial_timestamp_index: Optional[int]) -> torch.Tensor:
+    """Restatement of upstream whisper/decoding.py ApplyTimestampRules.apply (the version with the non-decreasing rule of
+    openai/whisper PR 914): logits [B,V] of the next position given tokens [B,t] (prompt included). Pinned in
+    tests/test_oracle_whisper.py against transformers' WhisperTimeStampLogitsProcessor, an independent implementation."""
+    logits = logits.clone()
+    ts_begin = vocab.timestamp_begin
+    logits[:, vocab.no_timestamps] = float("-inf")           # handled by without_timestamps
+    for k in range(tokens.shape[0]):                         # timestamps appear in pairs, except directly before EOT
+        seq = tokens[k, sample_begin:].tolist()
+        last_was_timestamp = len(seq) >= 1 and seq[-1] >= ts_begin
+        penultimate_was_timestamp = len(seq) < 2 or seq[-2] >= ts_begin
+        if last_was_timestamp:
+            if penultimate_was_timestamp:                    # has to be non-timestamp
+                logits[k, ts_begin:] = float("-inf")
+            else:                                            # cannot be normal text tokens
+                logits[k, :vocab.eot] = float("-inf")
+        stamps = [t for t in seq if t >= ts_begin]
+        if stamps:                                           # timestamps shouldn't decrease; segments have nonzero length
+            last = stamps[-1] if (last_was_timestamp and not penultimate_was_timestamp) else stamps[-1] + 1
+            logits[k, ts_begin:last] = float("-inf")
+    if tokens.shape[1] == sample_begin:                      # first position: a timestamp, at most max_initial_timestamp
+        logits[:, :ts_begin] = float("-inf")
+        if max_initial_timestamp_index is not None:
+            logits[:, ts_begin + max_initial_timestamp_index + 1:] = float("-inf")
+    logprobs = F.log_softmax(logits.float(), dim=-1)         # probability mass over timestamps above every text token: timestamp
+    for k in range(tokens.shape[0]):
+        if logprobs[k, ts_begin:].logsumexp(dim=-1) > logprobs[k, :ts_begin].max():
+            logits[k, :ts_begin] = float("-inf")
+    return logits
 
 
 # ---- independent cross-check: map these weights into transformers' Whisper ------------------------------------------

@@ -393,6 +393,42 @@ def test_beam_search_on_block_kernels(wbm, ref, oracle_logmel):
     w.close()
 
 
+@pytest.mark.parametrize("name,B,text_scale", [("tiny.en", 3, 1.0), ("tiny.en", 3, 1.8), ("tiny", 2, 1.8)])
+def test_greedy_with_timestamp_rules_matches_oracle(wbm, ref, oracle_logmel, name, B, text_scale):
+    """Upstream's default decoding (without_timestamps=False): ApplyTimestampRules among the logit filters — first token a
+    timestamp <= 1 s, timestamps in pairs and non-decreasing, timestamp probability mass above every text token forces a
+    timestamp. With seeded random weights the mass of the 1501 timestamp logits always wins (text_scale 1.0: a timestamp
+    whenever one is allowed); scaling the text rows of the embedding makes the mass rule fall either way from step to step."""
+    dims = ref.DIMS[name]
+    v = ref.Vocab.for_dims(dims)
+    weights = ref.random_weights(dims, seed=11)
+    weights["decoder.token_embedding.weight"][:v.eot] *= text_scale
+    oracle = ref.WhisperRef(dims, weights)
+    w = wbm.Whisper(name, weights=weights, max_batch=B)
+    audio = np.stack([ref.synth_audio(900 + i, "noise") for i in range(B)])
+    xa_ref = oracle.encode(torch.from_numpy(np.stack([oracle_logmel(a) for a in audio])).float())
+    w.encode(audio.astype(np.float32), return_features=False)
+    opts_ref = ref.DecodeOptions.default_for(dims, sample_len=48, without_timestamps=False)
+    tok_ref, slp_ref, _ = oracle.greedy(xa_ref, opts_ref)
+    o = wbm.DecodeOptions.default_for(wbm.DIMS[name], sample_len=48, without_timestamps=False)
+    tok, lens, slp = w.greedy(B, o)
+    n = tok_ref.shape[1]
+    mism = (torch.from_numpy(tok[:, :n].astype(np.int64)) != tok_ref).any(0).nonzero()
+    assert mism.numel() == 0, f"first divergence at position {int(mism[0])}: {tok[:, :n].tolist()} vs {tok_ref.tolist()}"
+    assert np.allclose(slp, slp_ref.numpy(), rtol=2e-3, atol=5e-2)
+    body = tok_ref[:, len(opts_ref.initial_tokens):]
+    assert (body[:, 0] >= v.timestamp_begin).all() and (body[:, 0] <= v.timestamp_begin + 50).all()   # the rules did act
+    assert (body >= v.timestamp_begin).any(1).all() and (body < v.eot).any()                            # both classes sampled
+    # the same handle without the rules afterwards: nothing of the rule state leaks (bit-identical to a fresh handle)
+    o2 = wbm.DecodeOptions.default_for(wbm.DIMS[name], sample_len=8)
+    g, _, gs = w.greedy(B, o2)
+    w2 = wbm.Whisper(name, weights=weights, max_batch=B)
+    w2.encode(audio.astype(np.float32), return_features=False)
+    g2, _, gs2 = w2.greedy(B, o2)
+    assert np.array_equal(g, g2) and np.array_equal(gs, gs2)
+    w.close(), w2.close()
+
+
 def test_error_paths(tiny, wbm):
     w, _ = tiny
     lib = wbm.load_library()

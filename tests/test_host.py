@@ -38,6 +38,13 @@ def test_default_decode_options_match_oracle(wbm, ref, name):
     assert list(o.initial_tokens) == list(r.initial_tokens)
     assert list(o.suppress) == list(r.suppress) and list(o.suppress_begin) == list(r.suppress_begin)
     assert o.eot == ref.Vocab.for_dims(ref.DIMS[name]).eot and o.sample_len == r.sample_len == 224
+    # upstream's own default (without_timestamps=False): no <|notimestamps|> in the prompt, timestamp rules on
+    ot = wbm.DecodeOptions.default_for(wbm.DIMS[name], without_timestamps=False)
+    rt = ref.DecodeOptions.default_for(ref.DIMS[name], without_timestamps=False)
+    v = ref.Vocab.for_dims(ref.DIMS[name])
+    assert list(ot.initial_tokens) == list(rt.initial_tokens) == list(r.initial_tokens)[:-1]
+    assert ot.timestamps and rt.timestamps and not o.timestamps and not r.timestamps
+    assert (ot.timestamp_begin, ot.no_timestamps, ot.max_initial_timestamp_index) == (v.timestamp_begin, v.no_timestamps, rt.max_initial_timestamp_index)
 
 
 def test_generate_spectrogram_validates_length(wbm):

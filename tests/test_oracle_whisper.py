@@ -108,3 +108,33 @@ def test_beam_finds_at_least_greedy_likelihood(ref, small_dims):
     _, slp, _ = model.greedy(xa, opts)
     _, bs = model.beam_search(xa, opts, beam_size=4)
     assert bs[0] >= float(slp[0]) - 1e-4
+
+
+@pytest.mark.parametrize("multilingual", [False, True])
+def test_timestamp_rules_match_hf_logits_processor(ref, multilingual):
+    """The oracle's ApplyTimestampRules restatement against transformers' WhisperTimeStampLogitsProcessor (an independent
+    implementation of the same upstream rules) on random logits and token histories that exercise every branch: first
+    position, text after a timestamp pair, single timestamp, timestamp mass above / below the best text token."""
+    from types import SimpleNamespace
+    from transformers.generation.logits_process import WhisperTimeStampLogitsProcessor
+
+    dims = ref.DIMS["tiny" if multilingual else "tiny.en"]
+    v = ref.Vocab.for_dims(dims)
+    V, ts = dims.n_vocab, v.timestamp_begin
+    g = torch.Generator().manual_seed(7 + int(multilingual))
+    begin = 3 if multilingual else 1
+    cfg = SimpleNamespace(no_timestamps_token_id=v.no_timestamps, eos_token_id=v.eot, bos_token_id=v.eot, max_initial_timestamp_index=50)
+    hf = WhisperTimeStampLogitsProcessor(cfg, begin_index=begin)
+    prompt = list(range(v.sot, v.sot + begin))
+    histories = [[], [ts + 3], [ts + 3, 100], [ts + 3, 100, 200, ts + 40], [ts + 3, 100, ts + 40, ts + 40],
+                 [ts, 11, 12, ts + 7, ts + 7, 13], [500, 600], [ts + 1499]]
+    for hist in histories:
+        for boost in (0.0, 12.0):                           # boost: put the probability mass on the timestamps
+            tokens = torch.tensor([prompt + hist, prompt + hist], dtype=torch.long)
+            logits = torch.randn(2, V, generator=g) * 3.0
+            logits[1, ts:] += boost
+            want = hf(tokens, logits)
+            got = ref.apply_timestamp_rules(logits, tokens, begin, v, 50)
+            assert torch.equal(torch.isinf(got), torch.isinf(want)), (hist, boost)
+            assert torch.equal(got[~torch.isinf(got)], want[~torch.isinf(want)])
+            assert torch.equal(got.argmax(-1), want.argmax(-1))
