@@ -58,6 +58,31 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float erf_abs = fmaf(-p * t, __expf(-z * z), 1.0f);
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
+// The same formula on a pair of values: packed fp32 arithmetic (FFMA2 / FMUL2 halve the instruction count) and single-MUFU
+// reciprocal / exp2 (rcp.approx, ex2.approx: ~1 ulp, far below the fp16 rounding of the stored result). The GELU epilogue
+// issues more instructions per tile than the tile's MMAs take cycles, so this is what paces the MLP1 and conv GEMMs.
+__device__ __forceinline__ float2 gelu_erf_fast2(float2 x) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 z = __fmul2_rn(ax, make_float2(0.70710678118654752440f, 0.70710678118654752440f));
+  const float2 dn = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), z, make_float2(1.0f, 1.0f));
+  float2 t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(dn.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(dn.y));
+  float2 p = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
+  p = __ffma2_rn(p, t, make_float2(1.421413741f, 1.421413741f));
+  p = __ffma2_rn(p, t, make_float2(-0.284496736f, -0.284496736f));
+  p = __ffma2_rn(p, t, make_float2(0.254829592f, 0.254829592f));
+  // exp(-z^2) = exp2(-z^2 * log2(e))
+  const float2 w = __fmul2_rn(__fmul2_rn(z, z), make_float2(-1.44269504088896340736f, -1.44269504088896340736f));
+  float2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(w.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(w.y));
+  const float2 pt = __fmul2_rn(p, t);
+  const float2 erf_abs = __ffma2_rn(make_float2(-pt.x, -pt.y), e, make_float2(1.0f, 1.0f));
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  // 0.5 x (1 + sign(x) erf_abs) = hx + |hx| erf_abs
+  return __ffma2_rn(make_float2(fabsf(hx.x), fabsf(hx.y)), erf_abs, hx);
+}
 
 // Persistent: one CTA per SM loops over output tiles (n fastest, so the CTAs running at the same time share A tiles in
 // L2). The TMA->MMA shared-memory ring runs continuously across tiles; the fp32 accumulator is double-buffered in TMEM
@@ -178,7 +203,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           }
           if (ep.gelu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
+            for (int j = 0; j < 32; j += 2) {
+              const float2 g = gelu_erf_fast2(make_float2(f[j], f[j + 1]));
+              f[j] = g.x, f[j + 1] = g.y;
+            }
           }
           if (ep.res_mode) {
             const float* rp = ep.res + (ep.res_mode == 1 ? crow * ep.ldc : (long long)t * ep.N) + nb;
