@@ -392,7 +392,7 @@ int launch_encoder_attention(GemmContext* tmaps, const __half* qkv, int B, int T
     CUtensorMap tm;
     const int rc = gemm_get_tmap(tmaps, qkv, 3 * d, T, B, 3 * d, (long long)T * 3 * d, 128, &tm);
     if (rc) return rc;
-    static bool attr_tc = false;
+    static bool attr_tc_dev[kMaxDevices] = {}; bool& attr_tc = attr_tc_dev[current_device_slot()];
     if (!attr_tc) {
       WB_CUDA_OK(cudaFuncSetAttribute(encoder_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEtSmem));
       attr_tc = true;
@@ -402,7 +402,7 @@ int launch_encoder_attention(GemmContext* tmaps, const __half* qkv, int B, int T
     WB_CUDA_OK(cudaGetLastError());
     return 0;
   }
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {}; bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
     WB_CUDA_OK(cudaFuncSetAttribute(encoder_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem));
     attr_set = true;

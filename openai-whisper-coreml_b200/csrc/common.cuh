@@ -29,6 +29,15 @@ const char* get_error();
     }                                                                                      \
   } while (0)
 
+// Per-kernel launch attributes (dynamic shared-memory limit, non-portable cluster size) are per device: the "already set"
+// caches of the launchers are indexed by the current device, so one process may hold handles on several GPUs.
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d < 0 || d >= kMaxDevices) ? 0 : d;
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

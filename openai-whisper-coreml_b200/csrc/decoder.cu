@@ -890,7 +890,7 @@ static int launch_logits_tc(const SkinnyDesc& d, cudaStream_t st, int64_t* launc
   cudaError_t le = cudaSuccess;
 #define WB_LT_CASE(N_)                                                                                                 \
   case N_: {                                                                                                           \
-    static size_t smem_set = 0;                                                                                        \
+    static size_t smem_set_dev[kMaxDevices] = {}; size_t& smem_set = smem_set_dev[current_device_slot()];                                                                                        \
     if (smem > smem_set) {                                                                                             \
       WB_CUDA_OK(cudaFuncSetAttribute(logits_tc_kernel<N_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       WB_CUDA_OK(cudaFuncSetAttribute(logits_tc_kernel<N_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -950,7 +950,7 @@ int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches) 
     cudaError_t le2 = cudaSuccess;
 #define WB_LG_CASE(M)                                                                                                 \
   case M: {                                                                                                           \
-    static size_t smem_set = 0;                                                                                       \
+    static size_t smem_set_dev[kMaxDevices] = {}; size_t& smem_set = smem_set_dev[current_device_slot()];                                                                                       \
     if (sm > smem_set) {                                                                                              \
       WB_CUDA_OK(cudaFuncSetAttribute(logits_gemm_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
       smem_set = sm;                                                                                                  \
@@ -985,7 +985,7 @@ int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches) 
   cudaError_t le = cudaSuccess;
 #define WB_SK_CASE(M)                                                                                             \
   case M: {                                                                                                       \
-    static size_t smem_set = 0;                                                                                   \
+    static size_t smem_set_dev[kMaxDevices] = {}; size_t& smem_set = smem_set_dev[current_device_slot()];                                                                                   \
     if (smem > smem_set) {                                                                                        \
       WB_CUDA_OK(cudaFuncSetAttribute(skinny_gemm_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       smem_set = smem;                                                                                            \
@@ -1336,7 +1336,7 @@ static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int
   cudaError_t le = cudaSuccess;
 #define WB_HA_CASE(J)                                                                                                     \
   case J: {                                                                                                               \
-    static size_t smem_set = 0;                                                                                           \
+    static size_t smem_set_dev[kMaxDevices] = {}; size_t& smem_set = smem_set_dev[current_device_slot()];                                                                                           \
     if (smem > smem_set) {                                                                                                \
       WB_CUDA_OK(cudaFuncSetAttribute(attn_decode_head_kernel<J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       smem_set = smem;                                                                                                    \
@@ -1768,7 +1768,7 @@ int launch_self_block(const SelfBlockDesc& p, cudaStream_t st, int64_t* launches
   const int XS = p.d * 2 + 64;
   const int wps = kSbWarps / G;
   const size_t smem = (size_t)16 * XS + (size_t)2 * p.d * 4 + (size_t)(3 * G * 64 + G * wps * 66 + 3 * G * 64) * 4;
-  static size_t smem_set = 0;
+  static size_t smem_set_dev[kMaxDevices] = {}; size_t& smem_set = smem_set_dev[current_device_slot()];
   if (smem > smem_set) {
     WB_CUDA_OK(cudaFuncSetAttribute(self_block_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WB_CUDA_OK(cudaFuncSetAttribute(self_block_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -2113,7 +2113,13 @@ __global__ void __maxnreg__(128) post_block_kernel(PostBlockArgs a) {
 
 // cluster size the post block uses for width d (0: unsupported)
 static int post_block_cluster(int d) {
-  static int c512 = -1;
+  static int c512_dev[kMaxDevices];
+  static bool c512_init = false;
+  if (!c512_init) {
+    for (int i = 0; i < kMaxDevices; ++i) c512_dev[i] = -1;
+    c512_init = true;
+  }
+  int& c512 = c512_dev[current_device_slot()];
   if (d == 384) return 8;
   if (d != 512) return 0;
   if (c512 < 0) {   // 16 CTAs per cluster is a non-portable size: ask whether this device schedules it
@@ -2148,7 +2154,7 @@ int post_block_supported(int n_head, int d) {
 
 template <int D, int C>
 static cudaError_t launch_post_block_t(const PostBlockArgs& a, int n_groups, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {}; bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(post_block_kernel<D, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PbCfg<D, C>::smem);
     if (e != cudaSuccess) return e;

@@ -331,7 +331,7 @@ static int launch_tc(GemmContext* ctx, const GemmDesc& d, const GemmEpi& ep, cud
     ctx->cache[key] = tmB;
   }
   auto kern = gemm_tc_kernel<BN>;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {}; bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
     WB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
     attr_set = true;

@@ -429,6 +429,21 @@ def test_greedy_with_timestamp_rules_matches_oracle(wbm, ref, oracle_logmel, nam
     w.close(), w2.close()
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_handles_on_two_devices_in_one_process(wbm, ref):
+    """One process, one handle per GPU (the launch-attribute caches of the kernels are per device): same tokens on both."""
+    dims = ref.DIMS["tiny.en"]
+    weights = ref.random_weights(dims, seed=0)
+    audio = np.stack([ref.synth_audio(40 + i, "noise") for i in range(2)]).astype(np.float32)
+    o = wbm.DecodeOptions.default_for(wbm.DIMS["tiny.en"], sample_len=12)
+    res = []
+    for dev in (0, 1):
+        w = wbm.Whisper("tiny.en", weights=weights, max_batch=2, device=dev)
+        res.append(w.transcribe(audio, o))
+        w.close()
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][2], res[1][2])
+
+
 def test_error_paths(tiny, wbm):
     w, _ = tiny
     lib = wbm.load_library()
