@@ -444,6 +444,29 @@ def test_handles_on_two_devices_in_one_process(wbm, ref):
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][2], res[1][2])
 
 
+def test_thirty_six_sequences_tiny(wbm, ref, oracle_logmel):
+    """33..48 sequences: the logits kernel runs with 48 MMA columns (two TMEM loads per row), the block kernels with ragged
+    last groups (36 = 9 x 4 = 4 x 8 + 4). Features are set directly so that the oracle only has to run the decoder."""
+    dims = ref.DIMS["tiny.en"]
+    weights = ref.random_weights(dims, seed=2)
+    oracle = ref.WhisperRef(dims, weights)
+    B = 36
+    w = wbm.Whisper("tiny.en", weights=weights, max_batch=B)
+    xa = torch.randn(B, 1500, dims.n_audio_state, generator=torch.Generator().manual_seed(9)) * 0.7
+    w.set_audio_features(xa.numpy())
+    toks = torch.randint(0, 50000, (B, 3), generator=torch.Generator().manual_seed(4))
+    want = oracle.decoder_logits(toks, xa)
+    got = torch.from_numpy(w.decoder_logits(toks.numpy()))
+    assert (got - want).abs().max().item() <= TOL_ABS and _rel(got, want) <= TOL_REL
+    tok_ref, slp_ref, _ = oracle.greedy(xa, ref.DecodeOptions.default_for(dims, sample_len=10))
+    tok, _, slp = w.greedy(B, wbm.DecodeOptions.default_for(wbm.DIMS["tiny.en"], sample_len=10))
+    n = tok_ref.shape[1]
+    bad = (torch.from_numpy(tok[:, :n].astype(np.int64)) != tok_ref).any(1).sum().item()
+    assert bad == 0, f"{bad} of {B} sequences diverge from the oracle"
+    assert np.allclose(slp, slp_ref.numpy(), rtol=2e-3, atol=5e-2)
+    w.close()
+
+
 def test_error_paths(tiny, wbm):
     w, _ = tiny
     lib = wbm.load_library()
