@@ -81,3 +81,26 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "whisper_ref" not in txt and "logmel_ref" not in txt and "oracle/" not in txt.replace("oracle/ ", ""), f
+
+
+def test_struct_layouts_match_the_header(wbm, tmp_path):
+    """The ctypes mirrors of wb_dims / wb_decode_opts have exactly the layout a C compiler gives the header's structs
+    (what a Swift / cgo / JNI binding generated from include/whisper_b200.h would see): sizes and every field offset."""
+    from importlib import import_module
+    mod = import_module("openai-whisper-coreml_b200.whisper")
+    fields = {"wb_dims": [n for n, _ in mod._Dims._fields_], "wb_decode_opts": [n for n, _ in mod._DecodeOpts._fields_]}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "whisper_b200.h"', 'int main(void) {']
+    for st, names in fields.items():
+        lines.append(f'  printf("{st} %zu\\n", sizeof({st}));')
+        for n in names:
+            lines.append(f'  printf("{st}.{n} %zu\\n", offsetof({st}, {n}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for st, cls in (("wb_dims", mod._Dims), ("wb_decode_opts", mod._DecodeOpts)):
+        assert int(got[st]) == ctypes.sizeof(cls), st
+        for n in fields[st]:
+            assert int(got[f"{st}.{n}"]) == getattr(cls, n).offset, (st, n)
