@@ -98,6 +98,14 @@ int wb_init_random_weights(wb_handle* h, uint64_t seed);
 int wb_weight_arena(wb_handle* h, void** device_ptr, size_t* bytes);
 /* Mark weights as present after the arena was filled externally (e.g. by the broadcast). */
 int wb_weights_mark_loaded(wb_handle* h);
+/* Read a tensor back as host fp32 in its upstream layout (the inverse of wb_set_weight; fp16-stored tensors return their
+ * rounded values). Makes device-generated weights (wb_init_random_weights) visible to a checker. */
+int wb_get_weight(wb_handle* h, const char* name, float* data, size_t numel);
+/* Enumerate the tensors of the model: count, then (name, element count) by index in sorted-name order. */
+int wb_weight_count(const wb_handle* h);
+int wb_weight_info(const wb_handle* h, int32_t index, char* name_out, size_t name_cap, size_t* numel);
+/* Position-weighted 64-bit checksum of the packed arena, computed on the device (ranks compare it after the broadcast). */
+int wb_weights_checksum(wb_handle* h, uint64_t* out);
 
 /* ---- log-mel ------------------------------------------------------------------------------------------------------
  * Replaces `generateSpectrogram(audio:)` (Whisper/Whisper/stft.swift:8-19) for B clips of f32 PCM: audio [B][480000]
@@ -127,7 +135,8 @@ int wb_decoder_logits(wb_handle* h, const int32_t* tokens, int32_t B, int32_t t,
 int wb_decoder_logits_f32tok(wb_handle* h, const float* tokens, int32_t B, int32_t t, float* logits);
 
 /* Replaces `Whisper.decode(audioFeatures:)` (Whisper.swift:33-40): one decoder call on [sot], arg-max over the 99
- * language logits [lang0, lang0+99) with Swift `max(by:)` tie-breaking (last maximal element). sot/lang0 default to
+ * language logits [lang0, lang0+99) with Swift `max(by:)` tie-breaking (the first maximal element: `max(by:)` replaces
+ * its running result only on a strict increase, so NaN never wins either). sot/lang0 default to
  * 50258/50259 (Whisper.swift:35,37) when passed as 0. lang_idx [B] in 0..98. */
 int wb_detect_language(wb_handle* h, int32_t B, int32_t sot, int32_t lang0, int32_t* lang_idx);
 

@@ -17,6 +17,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -544,23 +546,26 @@ static int select_device(int device) {
   return 0;
 }
 
-int wb_create(const wb_dims* dims, int32_t max_batch, int32_t max_beams, int32_t device, void* stream, wb_handle** out) {
-  if (!dims || !out || max_batch < 1 || max_beams < 1 || max_batch * max_beams > 40) {
-    set_error("wb_create: bad argument");
-    return WB_ERR_ARG;
-  }
-  if (check_dims(*dims)) {
-    set_error("wb_create: unsupported model dimensions");
-    return WB_ERR_ARG;
-  }
-  WB_TRY(select_device(device));
-  wb_handle* h = new wb_handle();
-  h->dims = *dims, h->max_batch = max_batch, h->max_beams = max_beams, h->device = device;
-  h->Mb_max = max_batch * max_beams;
-  h->launches = 0, h->weights_ready = false, h->enc_batch = 0;
-  for (int i = 0; i < wb_handle::kMaxSub; ++i) h->g_step[i] = h->g_sample[i] = h->g_sample_n[i] = nullptr, h->sub_stream[i] = nullptr;
-  h->sample_n = 1;
-  h->nodes_step = h->nodes_sample = 0;
+// Releases whatever a (possibly half-constructed) handle owns; every member is null / zero until it is created.
+static void free_handle(wb_handle* h) {
+  if (!h) return;
+  destroy_graphs(h);
+  if (h->gemm) gemm_context_destroy(h->gemm);
+  for (int i = 0; i < 4; ++i)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (int i = 1; i < wb_handle::kMaxSub; ++i)
+    if (h->sub_stream[i]) cudaStreamDestroy(h->sub_stream[i]);
+  for (int i = 0; i < wb_handle::kMaxSub; ++i)
+    if (h->sub_ev[i]) cudaEventDestroy(h->sub_ev[i]);
+  if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+  if (h->h_done) cudaFreeHost(h->h_done);
+  if (h->arena.base) cudaFree(h->arena.base);
+  if (h->ws.base) cudaFree(h->ws.base);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+static int create_impl(wb_handle* h, void* stream) {
   h->own_stream = stream == nullptr;
   if (h->own_stream)
     WB_CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -571,11 +576,11 @@ int wb_create(const wb_dims* dims, int32_t max_batch, int32_t max_beams, int32_t
   layout_weights(h);
   h->arena.size = (h->arena.off + 255) & ~(size_t)255;
   if (cudaMalloc(&h->arena.base, h->arena.size) != cudaSuccess) {
+    h->arena.base = nullptr;
     set_error("wb_create: cudaMalloc(%zu) for weights failed", h->arena.size);
-    delete h;
     return WB_ERR_NOMEM;
   }
-  WB_CUDA_OK(cudaMemset(h->arena.base, 0, h->arena.size));
+  WB_CUDA_OK(cudaMemsetAsync(h->arena.base, 0, h->arena.size, h->stream));
   h->arena.measure = false, h->arena.off = 0;
   layout_weights(h);
   // workspace
@@ -583,25 +588,50 @@ int wb_create(const wb_dims* dims, int32_t max_batch, int32_t max_beams, int32_t
   layout_workspace(h);
   h->ws.size = (h->ws.off + 255) & ~(size_t)255;
   if (cudaMalloc(&h->ws.base, h->ws.size) != cudaSuccess) {
+    h->ws.base = nullptr;
     set_error("wb_create: cudaMalloc(%zu) for workspace failed", h->ws.size);
-    cudaFree(h->arena.base);
-    delete h;
     return WB_ERR_NOMEM;
   }
-  WB_CUDA_OK(cudaMemset(h->ws.base, 0, h->ws.size));
+  WB_CUDA_OK(cudaMemsetAsync(h->ws.base, 0, h->ws.size, h->stream));
   h->ws.measure = false, h->ws.off = 0;
   layout_workspace(h);
-  LogmelTables<float>* t = new LogmelTables<float>();
-  build_logmel_tables<float>(*t);
-  WB_CUDA_OK(cudaMemcpy(h->tab32, t, sizeof(*t), cudaMemcpyHostToDevice));
-  delete t;
+  {
+    std::unique_ptr<LogmelTables<float>> t(new LogmelTables<float>());
+    build_logmel_tables<float>(*t);
+    WB_CUDA_OK(cudaMemcpyAsync(h->tab32, t.get(), sizeof(*t), cudaMemcpyHostToDevice, h->stream));
+    WB_CUDA_OK(cudaStreamSynchronize(h->stream));   // `t` is pageable host memory
+  }
   h->gemm = gemm_context_create();
   WB_CUDA_OK(cudaMallocHost(&h->h_done, sizeof(int32_t) * h->Mb_max));
   for (int i = 0; i < 4; ++i) WB_CUDA_OK(cudaEventCreate(&h->ev[i]));
   for (int i = 1; i < wb_handle::kMaxSub; ++i) WB_CUDA_OK(cudaStreamCreateWithFlags(&h->sub_stream[i], cudaStreamNonBlocking));
   for (int i = 0; i < wb_handle::kMaxSub; ++i) WB_CUDA_OK(cudaEventCreateWithFlags(&h->sub_ev[i], cudaEventDisableTiming));
   WB_CUDA_OK(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
-  memset(h->timings, 0, sizeof(h->timings));
+  // everything above (the zero fill the bqkv key-bias slice, the melT pad rows and x1 row 0 rely on, the tables) is complete
+  // on the device before the handle is handed out, whatever stream later work uses
+  WB_CUDA_OK(cudaDeviceSynchronize());
+  return WB_OK;
+}
+
+int wb_create(const wb_dims* dims, int32_t max_batch, int32_t max_beams, int32_t device, void* stream, wb_handle** out) {
+  if (!dims || !out || max_batch < 1 || max_beams < 1 || max_batch * max_beams > kMaxSequences) {
+    set_error("wb_create: bad argument (max_batch * max_beams must be in [1, %d])", kMaxSequences);
+    return WB_ERR_ARG;
+  }
+  if (check_dims(*dims)) {
+    set_error("wb_create: unsupported model dimensions");
+    return WB_ERR_ARG;
+  }
+  WB_TRY(select_device(device));
+  wb_handle* h = new wb_handle();   // value-initialised: every pointer null, every counter zero
+  h->dims = *dims, h->max_batch = max_batch, h->max_beams = max_beams, h->device = device;
+  h->Mb_max = max_batch * max_beams;
+  h->sample_n = 1;
+  const int rc = create_impl(h, stream);
+  if (rc != WB_OK) {
+    free_handle(h);
+    return rc;
+  }
   *out = h;
   return WB_OK;
 }
@@ -610,18 +640,7 @@ int wb_destroy(wb_handle* h) {
   if (!h) return WB_ERR_ARG;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  destroy_graphs(h);
-  gemm_context_destroy(h->gemm);
-  for (int i = 0; i < 4; ++i) cudaEventDestroy(h->ev[i]);
-  for (int i = 1; i < wb_handle::kMaxSub; ++i)
-    if (h->sub_stream[i]) cudaStreamDestroy(h->sub_stream[i]);
-  for (int i = 0; i < wb_handle::kMaxSub; ++i) cudaEventDestroy(h->sub_ev[i]);
-  cudaEventDestroy(h->fork_ev);
-  cudaFreeHost(h->h_done);
-  cudaFree(h->arena.base);
-  cudaFree(h->ws.base);
-  if (h->own_stream) cudaStreamDestroy(h->stream);
-  delete h;
+  free_handle(h);
   return WB_OK;
 }
 
@@ -669,6 +688,10 @@ int wb_weights_commit(wb_handle* h) {
       set_error("wb_weights_commit: tensor '%s' was never set", kv.first.c_str());
       return WB_ERR_STATE;
     }
+  // wb_set_weight copies from pageable memory on the legacy stream, which does not order against the handle's
+  // non-blocking stream: make every copy land before anything can read the arena
+  WB_CUDA_OK(cudaSetDevice(h->device));
+  WB_CUDA_OK(cudaDeviceSynchronize());
   h->weights_ready = true;
   return WB_OK;
 }
@@ -698,6 +721,7 @@ int wb_init_random_weights(wb_handle* h, uint64_t seed) {
     }
   WB_CUDA_OK(cudaStreamSynchronize(h->stream));
   WB_CUDA_OK(cudaMemcpy(h->enc_pos, pos.data(), pos.size() * sizeof(float), cudaMemcpyHostToDevice));
+  WB_CUDA_OK(cudaDeviceSynchronize());
   h->weights_ready = true;
   return WB_OK;
 }
@@ -712,7 +736,70 @@ int wb_weight_arena(wb_handle* h, void** device_ptr, size_t* bytes) {
 int wb_weights_mark_loaded(wb_handle* h) {
   if (!h) return WB_ERR_ARG;
   for (auto& kv : h->wmap) kv.second.set = true;
+  WB_CUDA_OK(cudaSetDevice(h->device));
+  WB_CUDA_OK(cudaDeviceSynchronize());   // the external fill (e.g. an NCCL broadcast on another stream) has landed
   h->weights_ready = true;
+  return WB_OK;
+}
+
+int wb_get_weight(wb_handle* h, const char* name, float* data, size_t numel) {
+  if (!h || !name || !data) return WB_ERR_ARG;
+  auto it = h->wmap.find(name);
+  if (it == h->wmap.end()) {
+    set_error("wb_get_weight: unknown tensor '%s'", name);
+    return WB_ERR_ARG;
+  }
+  const WEntry& e = it->second;
+  if (numel != e.numel) {
+    set_error("wb_get_weight: '%s' holds %zu elements, caller asked for %zu", name, e.numel, numel);
+    return WB_ERR_ARG;
+  }
+  WB_CUDA_OK(cudaSetDevice(h->device));
+  WB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (e.kind == WK_F32) {
+    WB_CUDA_OK(cudaMemcpy(data, e.dst, numel * sizeof(float), cudaMemcpyDeviceToHost));
+    return WB_OK;
+  }
+  std::vector<__half> tmp(numel);
+  WB_CUDA_OK(cudaMemcpy(tmp.data(), e.dst, numel * sizeof(__half), cudaMemcpyDeviceToHost));
+  if (e.kind == WK_F16) {
+    for (size_t i = 0; i < numel; ++i) data[i] = __half2float(tmp[i]);
+  } else {   // device [out][3][in] -> upstream [out][in][3]
+    const size_t ci = e.conv_in;
+    for (size_t o = 0; o < (size_t)e.conv_out; ++o)
+      for (size_t c = 0; c < ci; ++c)
+        for (size_t t = 0; t < 3; ++t) data[(o * ci + c) * 3 + t] = __half2float(tmp[(o * 3 + t) * ci + c]);
+  }
+  return WB_OK;
+}
+
+int wb_weight_count(const wb_handle* h) { return h ? (int)h->wmap.size() : -1; }
+
+int wb_weight_info(const wb_handle* h, int32_t index, char* name_out, size_t name_cap, size_t* numel) {
+  if (!h || index < 0 || (size_t)index >= h->wmap.size() || !name_out || name_cap == 0) return WB_ERR_ARG;
+  std::vector<std::string> names;
+  names.reserve(h->wmap.size());
+  for (auto& kv : h->wmap) names.push_back(kv.first);
+  std::sort(names.begin(), names.end());
+  const std::string& nm = names[index];
+  if (nm.size() + 1 > name_cap) {
+    set_error("wb_weight_info: name buffer too small (%zu needed)", nm.size() + 1);
+    return WB_ERR_ARG;
+  }
+  memcpy(name_out, nm.c_str(), nm.size() + 1);
+  if (numel) *numel = h->wmap.at(nm).numel;
+  return WB_OK;
+}
+
+int wb_weights_checksum(wb_handle* h, uint64_t* out) {
+  if (!h || !out) return WB_ERR_ARG;
+  WB_CUDA_OK(cudaSetDevice(h->device));
+  unsigned long long* acc = reinterpret_cast<unsigned long long*>(h->gmax);   // scratch word of the workspace
+  WB_TRY(launch_checksum64(h->arena.base, h->arena.size, acc, h->stream, &h->launches));
+  unsigned long long v = 0;
+  WB_CUDA_OK(cudaMemcpyAsync(&v, acc, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  *out = (uint64_t)v;
   return WB_OK;
 }
 
@@ -873,29 +960,61 @@ int wb_detect_language(wb_handle* h, int32_t B, int32_t sot, int32_t lang0, int3
                                cudaMemcpyDeviceToHost, h->stream));
   WB_CUDA_OK(cudaStreamSynchronize(h->stream));
   for (int b = 0; b < B; ++b) {
-    // Swift `max { $0.element < $1.element }` keeps the LAST maximal element on ties (Whisper.swift:38)
+    // Swift `max { $0.element < $1.element }` (Whisper.swift:38) replaces its running result only on a strict increase
+    // (`if areInIncreasingOrder(result, e) { result = e }`): the FIRST maximal element wins ties, NaN never replaces
     int best = 0;
     for (int i = 1; i < 99; ++i)
-      if (!(conf[b * 99 + i] < conf[b * 99 + best])) best = i;
+      if (conf[b * 99 + best] < conf[b * 99 + i]) best = i;
     lang_idx[b] = best;
   }
   return WB_OK;
 }
 
+// Option checks shared by the greedy and the beam path (pointer / count consistency, lengths, vocabulary ranges)
+static int validate_decode_opts(const wb_handle* h, int32_t B, const wb_decode_opts* opts) {
+  const wb_dims& D = h->dims;
+  const int n_init = opts->n_initial, total = n_init + opts->sample_len;
+  if (n_init < 1 || opts->sample_len < 1 || total > D.n_text_ctx || !opts->initial_tokens) {
+    set_error("wb_decode: bad options (n_initial=%d sample_len=%d: need n_initial >= 1, sample_len >= 1, n_initial + sample_len <= n_text_ctx=%d)",
+              n_init, opts->sample_len, D.n_text_ctx);
+    return WB_ERR_ARG;
+  }
+  if (opts->n_suppress < 0 || opts->n_suppress_begin < 0 || (opts->n_suppress > 0 && !opts->suppress) ||
+      (opts->n_suppress_begin > 0 && !opts->suppress_begin)) {
+    set_error("wb_decode: suppress / suppress_begin count without a list");
+    return WB_ERR_ARG;
+  }
+  if (opts->eot < 0 || opts->eot >= D.n_vocab) {
+    set_error("wb_decode: eot %d outside the vocabulary (%d)", opts->eot, D.n_vocab);
+    return WB_ERR_ARG;
+  }
+  for (int i = 0; i < n_init; ++i)
+    if (opts->initial_tokens[i] < 0 || opts->initial_tokens[i] >= D.n_vocab) {
+      set_error("wb_decode: initial token %d outside the vocabulary (%d)", opts->initial_tokens[i], D.n_vocab);
+      return WB_ERR_ARG;
+    }
+  if (opts->beam_size < 0 || opts->beam_size > 7) {
+    set_error("wb_decode: beam_size %d out of range [0, 7]", opts->beam_size);
+    return WB_ERR_ARG;
+  }
+  if (opts->timestamps) {
+    if (opts->beam_size > 1) {
+      set_error("wb_decode: the timestamp rules are implemented for greedy decoding only");
+      return WB_ERR_ARG;
+    }
+    if (opts->timestamp_begin <= opts->eot || opts->timestamp_begin >= D.n_vocab || opts->no_timestamps < 0 ||
+        opts->no_timestamps >= D.n_vocab || B > 48) {
+      set_error("wb_decode: timestamp rules need eot < timestamp_begin < n_vocab, a valid no_timestamps token and <= 48 sequences");
+      return WB_ERR_ARG;
+    }
+  }
+  return 0;
+}
+
 static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, int32_t* tokens_out, int32_t* lens, float* sum_logprob) {
   const wb_dims& D = h->dims;
   const int n_init = opts->n_initial, total = n_init + opts->sample_len;
-  if (n_init < 1 || opts->sample_len < 1 || total > D.n_text_ctx || opts->n_suppress < 0 || opts->n_suppress_begin < 0 ||
-      !opts->initial_tokens || (opts->n_suppress && !opts->suppress) || (opts->n_suppress_begin && !opts->suppress_begin)) {
-    set_error("wb_decode: bad options (n_initial=%d sample_len=%d n_text_ctx=%d)", n_init, opts->sample_len, D.n_text_ctx);
-    return WB_ERR_ARG;
-  }
   const bool ts_on = opts->timestamps != 0;
-  if (ts_on && (opts->timestamp_begin <= opts->eot || opts->timestamp_begin >= D.n_vocab || opts->no_timestamps < 0 ||
-                opts->no_timestamps >= D.n_vocab || B > 48)) {
-    set_error("wb_decode: timestamp rules need eot < timestamp_begin < n_vocab, a valid no_timestamps token and <= 48 sequences");
-    return WB_ERR_ARG;
-  }
   cudaStream_t st = h->stream;
   // token rows: sot sequence, then eot padding
   std::vector<int32_t> rows((size_t)B * h->tokens_ld, opts->eot);
@@ -1038,16 +1157,8 @@ static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int3
   const wb_dims& D = h->dims;
   const int beam = opts->beam_size, Mb = B * beam, K = beam + 1;
   const int n_init = opts->n_initial, total = n_init + opts->sample_len, eot = opts->eot;
-  if (beam > h->max_beams || beam > 7 || Mb > h->Mb_max || h->selfK_alt.empty()) {
+  if (beam > h->max_beams || Mb > h->Mb_max || h->selfK_alt.empty()) {
     set_error("wb_decode: beam_size %d exceeds the handle's max_beams %d (or 7), or batch*beam %d exceeds %d", beam, h->max_beams, Mb, h->Mb_max);
-    return WB_ERR_ARG;
-  }
-  if (n_init < 1 || opts->sample_len < 1 || total > D.n_text_ctx || !opts->initial_tokens) {
-    set_error("wb_decode: bad options");
-    return WB_ERR_ARG;
-  }
-  if (opts->timestamps) {
-    set_error("wb_decode: the timestamp rules are implemented for greedy decoding only");
     return WB_ERR_ARG;
   }
   cudaStream_t st = h->stream;
@@ -1210,7 +1321,11 @@ static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int3
 int wb_decode(wb_handle* h, int32_t B, const wb_decode_opts* opts, int32_t* tokens_out, int32_t* lens, float* sum_logprob) {
   WB_TRY(check_batch(h, B));
   WB_TRY(need_features(h, B));
-  if (!opts || !tokens_out) return WB_ERR_ARG;
+  if (!opts || !tokens_out) {
+    set_error("wb_decode: null options or output");
+    return WB_ERR_ARG;
+  }
+  WB_TRY(validate_decode_opts(h, B, opts));
   if (opts->beam_size > 1) return decode_beam(h, B, opts, tokens_out, lens, sum_logprob);
   return decode_greedy(h, B, opts, tokens_out, lens, sum_logprob);
 }
@@ -1302,13 +1417,63 @@ int wb_op_attention(wb_handle* h, const void* qkv_f16, int32_t B, int32_t T, int
 }
 
 // ---- legacy f64 symbol (stft/src/lib.rs:110-122; bridge.h:11) --------------------------------------------------------------------
+// Per-device state of the legacy path: the f64 tables (like the crate's lazy_static GENERATOR, lib.rs:11-13) and the
+// scratch buffers, created once under a lock and reused by later calls (grown when a larger batch arrives).
+struct LegacyState {
+  std::mutex mu;
+  LogmelTables<double>* tab = nullptr;
+  double *audio = nullptr, *logspec = nullptr, *out = nullptr;
+  unsigned long long* gmax = nullptr;
+  int cap = 0;   // clips the scratch buffers hold
+};
+static LegacyState g_legacy[wb::kMaxDevices];
+
+static int legacy_prepare(LegacyState& L, int B) {
+  if (!L.tab) {
+    std::unique_ptr<LogmelTables<double>> t(new LogmelTables<double>());
+    build_logmel_tables<double>(*t);
+    LogmelTables<double>* dptr = nullptr;
+    WB_CUDA_OK(cudaMalloc(&dptr, sizeof(*t)));
+    if (cudaMemcpy(dptr, t.get(), sizeof(*t), cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaFree(dptr);
+      set_error("wb_generate_spectrogram_f64: table upload failed");
+      return WB_ERR_CUDA;
+    }
+    L.tab = dptr;
+  }
+  if (B > L.cap) {
+    cudaFree(L.audio), cudaFree(L.logspec), cudaFree(L.out), cudaFree(L.gmax);
+    L.audio = L.logspec = L.out = nullptr, L.gmax = nullptr, L.cap = 0;
+    const size_t na = (size_t)B * WB_N_SAMPLES_PADDED, no = (size_t)B * WB_N_MELS * WB_N_FRAMES;
+    if (cudaMalloc(&L.audio, na * 8) != cudaSuccess || cudaMalloc(&L.logspec, no * 8) != cudaSuccess ||
+        cudaMalloc(&L.out, no * 8) != cudaSuccess || cudaMalloc(&L.gmax, 8 * (size_t)B) != cudaSuccess) {
+      cudaFree(L.audio), cudaFree(L.logspec), cudaFree(L.out), cudaFree(L.gmax);
+      L.audio = L.logspec = L.out = nullptr, L.gmax = nullptr;
+      cudaGetLastError();
+      set_error("wb_generate_spectrogram_f64: cudaMalloc failed");
+      return WB_ERR_NOMEM;
+    }
+    L.cap = B;
+  }
+  return 0;
+}
+
 int wb_generate_spectrogram_f64(double* audio, int32_t B, double* output) {
   if (!audio || !output || B < 1) {
     set_error("wb_generate_spectrogram_f64: bad argument");
     return WB_ERR_ARG;
   }
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    set_error("no CUDA device available (this library has no CPU fallback)");
+    return WB_ERR_CUDA;
+  }
   const char* dev_env = getenv("WB_DEVICE");
-  WB_TRY(select_device(dev_env ? atoi(dev_env) : 0));
+  const int dev = dev_env ? atoi(dev_env) : 0;
+  if (dev < 0 || dev >= n_dev || dev >= wb::kMaxDevices) {
+    set_error("WB_DEVICE=%d out of range (%d visible)", dev, n_dev);
+    return WB_ERR_ARG;
+  }
   // the in-place reflection of the two 200-sample pads (lib.rs:34-40) is part of the contract: do it on the host buffer
   for (int b = 0; b < B; ++b) {
     double* a = audio + (size_t)b * WB_N_SAMPLES_PADDED;
@@ -1317,44 +1482,35 @@ int wb_generate_spectrogram_f64(double* audio, int32_t B, double* output) {
       a[WB_N_SAMPLES + 200 + i] = a[200 + (WB_N_SAMPLES - 2) - i];
     }
   }
-  static LogmelTables<double>* dtab = nullptr;   // per-process, device-resident (like the crate's lazy_static GENERATOR)
-  static int dtab_device = -1;
-  int cur = 0;
-  cudaGetDevice(&cur);
-  if (!dtab || dtab_device != cur) {
-    LogmelTables<double>* t = new LogmelTables<double>();
-    build_logmel_tables<double>(*t);
-    LogmelTables<double>* dptr = nullptr;
-    WB_CUDA_OK(cudaMalloc(&dptr, sizeof(*t)));
-    WB_CUDA_OK(cudaMemcpy(dptr, t, sizeof(*t), cudaMemcpyHostToDevice));
-    delete t;
-    dtab = dptr, dtab_device = cur;
-  }
-  double *d_audio = nullptr, *d_log = nullptr, *d_out = nullptr;
-  unsigned long long* d_max = nullptr;
-  const size_t na = (size_t)B * WB_N_SAMPLES_PADDED, no = (size_t)B * WB_N_MELS * WB_N_FRAMES;
+  int caller_dev = 0;
+  const bool have_caller_dev = cudaGetDevice(&caller_dev) == cudaSuccess;   // restored on every exit path
+  LegacyState& L = g_legacy[dev];
   int rc = WB_OK;
-  cudaStream_t st = nullptr;
-  do {
-    if (cudaMalloc(&d_audio, na * 8) != cudaSuccess || cudaMalloc(&d_log, no * 8) != cudaSuccess ||
-        cudaMalloc(&d_out, no * 8) != cudaSuccess || cudaMalloc(&d_max, 8 * (size_t)B) != cudaSuccess) {
-      set_error("wb_generate_spectrogram_f64: cudaMalloc failed");
-      rc = WB_ERR_NOMEM;
-      break;
-    }
-    if (cudaMemcpy(d_audio, audio, na * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
-      set_error("wb_generate_spectrogram_f64: H2D copy failed");
-      rc = WB_ERR_CUDA;
-      break;
-    }
-    rc = launch_logmel<double>(d_audio, WB_N_SAMPLES_PADDED, 200, B, dtab, d_log, d_max, d_out, nullptr, st, nullptr);
-    if (rc) break;
-    if (cudaMemcpy(output, d_out, no * 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
-      set_error("wb_generate_spectrogram_f64: D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
-      rc = WB_ERR_CUDA;
-    }
-  } while (0);
-  cudaFree(d_audio), cudaFree(d_log), cudaFree(d_out), cudaFree(d_max);
+  {
+    std::lock_guard<std::mutex> lock(L.mu);   // the reference's lazy_static is thread-safe; calls on one device serialise here
+    do {
+      if (cudaSetDevice(dev) != cudaSuccess) {
+        set_error("wb_generate_spectrogram_f64: cudaSetDevice(%d) failed", dev);
+        rc = WB_ERR_CUDA;
+        break;
+      }
+      rc = legacy_prepare(L, B);
+      if (rc) break;
+      const size_t na = (size_t)B * WB_N_SAMPLES_PADDED, no = (size_t)B * WB_N_MELS * WB_N_FRAMES;
+      if (cudaMemcpy(L.audio, audio, na * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("wb_generate_spectrogram_f64: H2D copy failed");
+        rc = WB_ERR_CUDA;
+        break;
+      }
+      rc = launch_logmel<double>(L.audio, WB_N_SAMPLES_PADDED, 200, B, L.tab, L.logspec, L.gmax, L.out, nullptr, nullptr, nullptr);
+      if (rc) break;
+      if (cudaMemcpy(output, L.out, no * 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        set_error("wb_generate_spectrogram_f64: D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = WB_ERR_CUDA;
+      }
+    } while (0);
+  }
+  if (have_caller_dev) cudaSetDevice(caller_dev);
   return rc;
 }
 

@@ -5,6 +5,8 @@
 
 namespace wb {
 
+constexpr int kMaxSequences = 40;   // decoder rows per handle (chunks x beams): 5 MMA column tiles of 8 in the skinny GEMMs
+
 // ---- log-mel (logmel.cu) ---------------------------------------------------------------------------------------------
 template <typename T>
 struct LogmelTables;
@@ -56,6 +58,7 @@ int launch_f32_to_f16(const float* in, __half* out, size_t n, cudaStream_t st, i
 int launch_f16_to_f32(const __half* in, float* out, size_t n, cudaStream_t st, int64_t* launches);
 int launch_fill_random(void* ptr, size_t n, int is_f16, float scale, float offset, uint64_t seed, cudaStream_t st,
                        int64_t* launches);
+int launch_checksum64(const void* ptr, size_t bytes, unsigned long long* acc, cudaStream_t st, int64_t* launches);
 
 // ---- encoder attention (attention_enc.cu) ---------------------------------------------------------------------------------
 // qkv fp16 [B*T][3d] (q | k | v, head h at columns h*64) -> out fp16 [B*T][d]; softmax(q k^T / 8) v, non-causal

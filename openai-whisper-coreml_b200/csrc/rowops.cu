@@ -119,4 +119,24 @@ int launch_fill_random(void* ptr, size_t n, int is_f16, float scale, float offse
   return 0;
 }
 
+// Position-weighted 64-bit checksum of a byte range (size a multiple of 4): sum over 32-bit words w_i of w_i * (2i + 1)
+// mod 2^64. Integer adds commute, so the value does not depend on the order the atomics land in. Used to verify that
+// every rank holds the same weight arena after the load-time broadcast.
+__global__ void checksum64_kernel(const uint32_t* __restrict__ words, size_t n, unsigned long long* __restrict__ acc) {
+  unsigned long long s = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    s += (unsigned long long)words[i] * (2ull * i + 1ull);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(acc, s);
+}
+int launch_checksum64(const void* ptr, size_t bytes, unsigned long long* acc, cudaStream_t st, int64_t* launches) {
+  WB_CUDA_OK(cudaMemsetAsync(acc, 0, sizeof(*acc), st));
+  const size_t n = bytes / 4;
+  if (n) checksum64_kernel<<<148 * 4, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(ptr), n, acc);
+  if (launches) *launches += 1;
+  WB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace wb

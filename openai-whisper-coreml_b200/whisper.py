@@ -157,6 +157,10 @@ _SYMBOLS = {
     "wb_init_random_weights": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64]),
     "wb_weight_arena": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
     "wb_weights_mark_loaded": (ctypes.c_int, [ctypes.c_void_p]),
+    "wb_get_weight": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "wb_weight_count": (ctypes.c_int, [ctypes.c_void_p]),
+    "wb_weight_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
+    "wb_weights_checksum": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]),
     "wb_logmel": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
     "wb_logmel_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
     "wb_encode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
@@ -300,6 +304,32 @@ class Whisper:
     def mark_weights_loaded(self) -> None:
         _check(self._lib.wb_weights_mark_loaded(self._h), "wb_weights_mark_loaded")
 
+    def weight_names(self) -> Dict[str, int]:
+        """Upstream state-dict name -> element count of every tensor of the model."""
+        out: Dict[str, int] = {}
+        buf = ctypes.create_string_buffer(256)
+        n = ctypes.c_size_t()
+        for i in range(int(self._lib.wb_weight_count(self._h))):
+            _check(self._lib.wb_weight_info(self._h, i, buf, 256, ctypes.byref(n)), "wb_weight_info")
+            out[buf.value.decode()] = int(n.value)
+        return out
+
+    def get_weight(self, name: str) -> np.ndarray:
+        """Reads a tensor back as flat host fp32 in its upstream layout (fp16-stored tensors return their rounded values)."""
+        n = self.weight_names()[name]
+        a = np.empty(n, dtype=np.float32)
+        _check(self._lib.wb_get_weight(self._h, name.encode(), _ptr(a), n), f"wb_get_weight({name})")
+        return a
+
+    def state_dict(self) -> Dict[str, np.ndarray]:
+        """Every tensor as the device holds it (flat fp32): makes device-generated weights visible to a checker."""
+        return {k: self.get_weight(k) for k in self.weight_names()}
+
+    def weights_checksum(self) -> int:
+        v = ctypes.c_uint64()
+        _check(self._lib.wb_weights_checksum(self._h, ctypes.byref(v)), "wb_weights_checksum")
+        return int(v.value)
+
     # ---- Whisper.encode (Whisper.swift:23-31) ------------------------------------------------------------------------
     def _as_batch(self, audio) -> np.ndarray:
         a = np.asarray(audio)
@@ -376,8 +406,9 @@ class Whisper:
                         1 if o.timestamps else 0, o.timestamp_begin, o.no_timestamps, o.max_initial_timestamp_index)
         return c, (init, sup, supb)
 
-    def greedy(self, B: int, opts: DecodeOptions):
-        """Greedy decode of the resident features: (tokens [B, n_init+sample_len], lens [B], sum_logprob [B])."""
+    def decode_tokens(self, B: int, opts: DecodeOptions):
+        """wb_decode on the resident features: greedy (beam_size <= 1) or beam search (beam_size > 1; per chunk the best
+        candidate by sum_logprob / length). Returns (tokens [B, n_init+sample_len], lens [B], sum_logprob [B])."""
         c, keep = self._opts(opts)
         total = len(opts.initial_tokens) + opts.sample_len
         tokens = np.empty((B, total), dtype=np.int32)
@@ -386,10 +417,16 @@ class Whisper:
         _check(self._lib.wb_decode(self._h, B, ctypes.byref(c), _ptr(tokens), _ptr(lens), _ptr(slp)), "wb_decode")
         return tokens, lens, slp
 
-    def decode_tokens(self, B: int, opts: DecodeOptions):
-        """Greedy (beam_size <= 1) or beam-search (beam_size > 1, needs max_beams >= beam_size at construction) decode of
-        the resident features. Beam search returns, per chunk, the best candidate by sum_logprob / length."""
-        return self.greedy(B, opts)
+    def greedy(self, B: int, opts: DecodeOptions):
+        """Greedy decode of the resident features (rejects beam options: use decode_tokens / beam_search for those)."""
+        if opts.beam_size > 1:
+            raise ValueError("greedy() was given beam_size > 1; use decode_tokens() or beam_search()")
+        return self.decode_tokens(B, opts)
+
+    def beam_search(self, B: int, opts: DecodeOptions, beam_size: int = 5):
+        """Beam-search decode (upstream BeamSearchDecoder, patience 1); needs max_beams >= beam_size at construction."""
+        import dataclasses
+        return self.decode_tokens(B, dataclasses.replace(opts, beam_size=beam_size))
 
     def transcribe(self, audio, opts: Optional[DecodeOptions] = None):
         a = self._as_batch(audio)

@@ -390,10 +390,17 @@ class WhisperRef:
 
 def language_argmax(logits: torch.Tensor, lang0: int = 50259) -> torch.Tensor:
     """Whisper.swift:37-38: `(50259...50357).map{...}.enumerated().max{ $0.element < $1.element }`.
-    Swift's `max(by:)` returns the LAST maximal element on ties."""
+    Swift's `Sequence.max(by:)` replaces its running result only when `areInIncreasingOrder(result, e)` holds, i.e. on a
+    strict increase: the FIRST maximal element wins ties (all-equal logits -> index 0, "en"), and a NaN never replaces
+    the running result."""
     conf = logits[..., lang0:lang0 + 99].float()
-    rev = torch.flip(conf, dims=[-1])
-    return 98 - rev.argmax(dim=-1)
+    best = torch.zeros(conf.shape[:-1], dtype=torch.long)
+    cur = conf[..., 0].clone()
+    for i in range(1, 99):
+        take = cur < conf[..., i]
+        best = torch.where(take, torch.full_like(best, i), best)
+        cur = torch.where(take, conf[..., i], cur)
+    return best
 
 
 @dataclass

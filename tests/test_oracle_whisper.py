@@ -59,14 +59,20 @@ def test_kv_cache_equals_uncached(small, ref, oracle_logmel):
     assert (full - step).abs().max() <= 1e-4
 
 
-def test_language_argmax_is_last_max(ref):
-    """Whisper.swift:38 `max { $0.element < $1.element }` returns the LAST maximal element."""
+def test_language_argmax_is_first_max(ref):
+    """Whisper.swift:38 `max { $0.element < $1.element }`: Swift's Sequence.max(by:) replaces its running result only on a
+    strict increase, so the FIRST maximal element wins ties and NaN never replaces it (all-equal logits print "en")."""
     lg = torch.zeros(1, 51865)
+    assert int(ref.language_argmax(lg)[0]) == 0
     lg[0, 50259 + 4] = 3.0
     lg[0, 50259 + 17] = 3.0
-    assert int(ref.language_argmax(lg)[0]) == 17
+    assert int(ref.language_argmax(lg)[0]) == 4
     lg[0, 50259 + 98] = 5.0
     assert int(ref.language_argmax(lg)[0]) == 98
+    lg[0, 50259 + 50] = float("nan")
+    assert int(ref.language_argmax(lg)[0]) == 98
+    lg2 = torch.full((1, 51865), float("nan"))
+    assert int(ref.language_argmax(lg2)[0]) == 0
 
 
 def test_eot_forcing_and_logprob_mask(ref, small_dims):
