@@ -59,3 +59,44 @@ def broadcast_weights(whisper, device, src: int = 0, group=None) -> int:
     torch.cuda.synchronize(device)
     whisper.mark_weights_loaded()
     return nbytes
+
+
+def verify_ranks(whisper, device, rank: int, world_size: int, group=None) -> int:
+    """After the broadcast: all-gathers the 64-bit checksum of every rank's weight arena and raises unless they agree.
+    Returns the number of ranks verified. (A broken broadcast would otherwise still decode — to different tokens.)"""
+    import torch
+    import torch.distributed as dist
+
+    mine = whisper.weights_checksum()
+    t = torch.tensor([mine & 0x7fffffff, (mine >> 31) & 0x7fffffff, mine >> 62], dtype=torch.int64, device=device)
+    every = [torch.empty_like(t) for _ in range(world_size)]
+    dist.all_gather(every, t, group=group)
+    vals = [int(e[0]) | (int(e[1]) << 31) | (int(e[2]) << 62) for e in every]
+    if any(v != vals[0] for v in vals):
+        raise RuntimeError(f"weight arenas differ across ranks after the broadcast: {[hex(v) for v in vals]}")
+    return world_size
+
+
+def transcribe_windows_sharded(whisper, windows, opts, rank: int, world_size: int, device=None, group=None):
+    """BASELINE config 5 as a job: `windows` [n, 480000] (every rank holds, or can produce, the same array) are partitioned
+    contiguously over the ranks (60 windows on 8 GPUs -> 8,8,8,8,7,7,7,7), each rank transcribes its block `max_batch` at
+    a time, and the token rows are all-gathered (the only exchange, a few KB). Returns (tokens [n, L], lens [n]) on every
+    rank. With world_size == 1 no process group is needed."""
+    import numpy as np
+    import torch
+
+    n = int(windows.shape[0])
+    s, e = partition(n, world_size)[rank]
+    L = len(opts.initial_tokens) + opts.sample_len
+    toks = np.zeros((e - s, L), dtype=np.int32)
+    lens = np.zeros((e - s,), dtype=np.int32)
+    for i in range(s, e, whisper.max_batch):
+        j = min(e, i + whisper.max_batch)
+        t, l, _ = whisper.transcribe(windows[i:j], opts)
+        toks[i - s:j - s] = t
+        lens[i - s:j - s] = l
+    if world_size == 1:
+        return toks, lens
+    dev = device if device is not None else torch.device("cpu")
+    all_t, all_l = gather_tokens(torch.from_numpy(toks).to(dev), torch.from_numpy(lens).to(dev), n, world_size, rank, group=group)
+    return all_t.cpu().numpy(), all_l.cpu().numpy()
