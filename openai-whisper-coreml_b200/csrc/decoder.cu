@@ -23,6 +23,22 @@ namespace wb {
 
 constexpr float kLog2e = 1.44269504088896340736f;
 
+// L2 residency policy of the decode step (ptx.cuh): 1 = weights evict_last + cross-attention K/V stream evict_first, 0 = no
+// hints. Set per device by decoder_set_l2_mode() (env WB_L2_POLICY, default 1).
+__constant__ int c_l2_mode = 1;
+__device__ __forceinline__ uint64_t weight_policy() { return ptx::l2_policy(c_l2_mode ? 1 : 0); }
+__device__ __forceinline__ uint64_t stream_policy() { return ptx::l2_policy(c_l2_mode ? 2 : 0); }
+__device__ __forceinline__ void weight_prefetch_l2(const void* p) {
+  if (c_l2_mode)
+    ptx::prefetch_l2_evict_last(p);
+  else
+    ptx::prefetch_l2(p);
+}
+int decoder_set_l2_mode(int mode) {
+  WB_CUDA_OK(cudaMemcpyToSymbol(c_l2_mode, &mode, sizeof(int)));
+  return 0;
+}
+
 // Everything that changes from kernel to kernel inside a decode step (residual stream, q, attention outputs, partials,
 // tokens, DecodeState) is read through L2 (.cg): with programmatic dependent launch a kernel can share an SM — and its L1 —
 // with its still-running predecessor, so L1 may hold lines the predecessor fetched before another SM rewrote them.
@@ -103,12 +119,13 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
   const int nblk0 = KC0 / 32;
   const int pb0 = (kslice * nblk0) / KS, pb1 = ((kslice + 1) * nblk0) / KS;
   constexpr int kPre = 8;
+  const uint64_t wpol = weight_policy();
   uint4 pwa[kPre], pwb[kPre];
 #pragma unroll
   for (int u = 0; u < kPre; ++u) {
     const int blk = (pb0 + u < pb1) ? pb0 + u : pb0;
-    pwa[u] = ptx::ldg_nc_16(wrow0 + blk * 32);
-    pwb[u] = ptx::ldg_nc_16(wrow1 + blk * 32);
+    pwa[u] = ptx::ldg_nc_16(wrow0 + blk * 32, wpol);
+    pwb[u] = ptx::ldg_nc_16(wrow1 + blk * 32, wpol);
   }
   // constants (bias, LayerNorm affine) are staged in shared memory before the wait as well: keeping their global loads
   // out of the input stage and of the epilogue matters — interleaved with shared-memory stores the compiler cannot batch
@@ -251,8 +268,8 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
       uint4 wa[8], wb[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        wa[u] = ptx::ldg_nc_16(wrow0 + kc0 + (blk + u) * 32);
-        wb[u] = ptx::ldg_nc_16(wrow1 + kc0 + (blk + u) * 32);
+        wa[u] = ptx::ldg_nc_16(wrow0 + kc0 + (blk + u) * 32, wpol);
+        wb[u] = ptx::ldg_nc_16(wrow1 + kc0 + (blk + u) * 32, wpol);
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -271,8 +288,8 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyArgs a) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int bb = (blk + u < blk1) ? blk + u : blk;
-        wa[u] = ptx::ldg_nc_16(wrow0 + kc0 + bb * 32);
-        wb[u] = ptx::ldg_nc_16(wrow1 + kc0 + bb * 32);
+        wa[u] = ptx::ldg_nc_16(wrow0 + kc0 + bb * 32, wpol);
+        wb[u] = ptx::ldg_nc_16(wrow1 + kc0 + bb * 32, wpol);
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -380,12 +397,13 @@ __global__ void __launch_bounds__(kSkThreads) logits_gemm_kernel(SkinnyDesc p, i
   int g = blockIdx.x;
   const __half* wrow0 = row_ptr(g, 0);
   const __half* wrow1 = row_ptr(g, 1);
+  const uint64_t wpol = weight_policy();
   uint4 pwa[kPre], pwb[kPre];
 #pragma unroll
   for (int u = 0; u < kPre; ++u) {
     const int blk = u < nblk ? u : 0;
-    pwa[u] = ptx::ldg_nc_16(wrow0 + blk * 32);
-    pwb[u] = ptx::ldg_nc_16(wrow1 + blk * 32);
+    pwa[u] = ptx::ldg_nc_16(wrow0 + blk * 32, wpol);
+    pwb[u] = ptx::ldg_nc_16(wrow1 + blk * 32, wpol);
   }
   for (int i = tid * 4; i < p.K; i += kSkThreads * 4) {
     *reinterpret_cast<float4*>(sg + i) = __ldg(reinterpret_cast<const float4*>(p.ln_g + i));
@@ -481,8 +499,8 @@ __global__ void __launch_bounds__(kSkThreads) logits_gemm_kernel(SkinnyDesc p, i
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int bb = blk + u < nblk ? blk + u : blk;
-        wa[u] = ptx::ldg_nc_16(wrow0 + bb * 32);
-        wb[u] = ptx::ldg_nc_16(wrow1 + bb * 32);
+        wa[u] = ptx::ldg_nc_16(wrow0 + bb * 32, wpol);
+        wb[u] = ptx::ldg_nc_16(wrow1 + bb * 32, wpol);
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u)
@@ -495,8 +513,8 @@ __global__ void __launch_bounds__(kSkThreads) logits_gemm_kernel(SkinnyDesc p, i
 #pragma unroll
       for (int u = 0; u < kPre; ++u) {
         const int blk = u < nblk ? u : 0;
-        pwa[u] = ptx::ldg_nc_16(wrow0 + blk * 32);
-        pwb[u] = ptx::ldg_nc_16(wrow1 + blk * 32);
+        pwa[u] = ptx::ldg_nc_16(wrow0 + blk * 32, wpol);
+        pwb[u] = ptx::ldg_nc_16(wrow1 + blk * 32, wpol);
       }
     }
     // accumulators -> red[row in group][sequence]
@@ -638,6 +656,7 @@ __global__ void __launch_bounds__(kLtThreads, 1) logits_tc_kernel(const __grid_c
   if (warp == 0) {
     // ---- TMA producer: the embedding matrix does not depend on the previous kernel, so the ring fills during its tail -----------------
     if (lane == 0) {
+      const uint64_t wpol = weight_policy();
       uint32_t it = 0;
       for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x) {
         for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -645,7 +664,7 @@ __global__ void __launch_bounds__(kLtThreads, 1) logits_tc_kernel(const __grid_c
           const uint32_t ph = (it / n_stages) & 1u;
           ptx::mbar_wait(&empty[s], ph ^ 1u);
           ptx::mbar_arrive_expect_tx(&full[s], kLtStageBytes);
-          ptx::tma_load_3d(ring + (size_t)s * kLtStageBytes, &tmW, &full[s], kb * 64, g * 128, 0);
+          ptx::tma_load_3d(ring + (size_t)s * kLtStageBytes, &tmW, &full[s], kb * 64, g * 128, 0, wpol);
         }
       }
     }
@@ -1034,14 +1053,14 @@ struct HeadAttnArgs {
 // l, l+32, ... of every row. Used by the fused query projection (prologue) of
 // attn_decode_head_kernel; the rows are requested in two halves so that the first can be in flight across the wait.
 template <int NJW>
-__device__ __forceinline__ void head_rows_load(uint4 (&w)[4][NJW], const __half* wbase, int d, int lane) {
+__device__ __forceinline__ void head_rows_load(uint4 (&w)[4][NJW], const __half* wbase, int d, int lane, uint64_t wpol) {
   const int n_chunks = d >> 3;
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int j = 0; j < NJW; ++j) {
       const int c = lane + 32 * j;
-      w[r][j] = c < n_chunks ? ptx::ldg_nc_16(wbase + (size_t)r * d + c * 8) : make_uint4(0, 0, 0, 0);
+      w[r][j] = c < n_chunks ? ptx::ldg_nc_16(wbase + (size_t)r * d + c * 8, wpol) : make_uint4(0, 0, 0, 0);
     }
 }
 template <int NJW>
@@ -1108,6 +1127,7 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
   if (warp == 8) {
     if (lane == 0) {
       const int slab = b / a.kv_share;
+      const uint64_t kvpol = fixed ? stream_policy() : ptx::l2_policy(0);   // cross K/V: read once per step
       if (fixed) {   // the producer of a cross-attention CTA runs ahead of q: pull the tiles after the ring into L2 meanwhile
         const int pf_end = n_stages + a.l2_prefetch_tiles < n_tiles ? n_stages + a.l2_prefetch_tiles : n_tiles;
         for (int t = n_stages; t < pf_end; ++t) {
@@ -1124,8 +1144,8 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
         ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
         ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * kHaTileBytes);
         unsigned char* dk = smem + (size_t)s * 2 * kHaTileBytes;
-        ptx::tma_load_3d(dk, &tmK, &full_bar[s], h * 64, t * kHaStageRows, slab);
-        ptx::tma_load_3d(dk + kHaTileBytes, &tmV, &full_bar[s], h * 64, t * kHaStageRows, slab);
+        ptx::tma_load_3d(dk, &tmK, &full_bar[s], h * 64, t * kHaStageRows, slab, kvpol);
+        ptx::tma_load_3d(dk + kHaTileBytes, &tmV, &full_bar[s], h * 64, t * kHaStageRows, slab, kvpol);
       }
     }
   } else {
@@ -1140,7 +1160,8 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
       const int ct = tid;                                   // 256 compute threads: columns ct, ct+256, ...
       const __half* wbase = a.wq + (size_t)(h * 64 + warp * 8) * d;
       uint4 w0[4][NJW];
-      head_rows_load<NJW>(w0, wbase, d, lane);
+      const uint64_t wpol = weight_policy();
+      head_rows_load<NJW>(w0, wbase, d, lane, wpol);
       float gv[NJW], bv[NJW];
 #pragma unroll
       for (int j = 0; j < NJW; ++j) {
@@ -1151,7 +1172,7 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
       const float bias = lane < 8 ? __ldg(a.bq + h * 64 + warp * 8 + lane) : 0.f;
       ptx::grid_dep_sync();                                 // x comes from the previous kernel
       uint4 w1[4][NJW];
-      head_rows_load<NJW>(w1, wbase + (size_t)4 * d, d, lane);
+      head_rows_load<NJW>(w1, wbase + (size_t)4 * d, d, lane, wpol);
       float xv[NJW], sum = 0.f, sq = 0.f;
 #pragma unroll
       for (int j = 0; j < NJW; ++j) {
@@ -1450,12 +1471,13 @@ __global__ void __maxnreg__(96) self_block_kernel(SelfBlockArgs a) {
   const __half* wrow0 = a.wqkv + (size_t)row_lo * d + tq * 8;
   const __half* wrow1 = wrow0 + (size_t)8 * d;
   constexpr int kPre = 8;
+  const uint64_t wpol = weight_policy();
   uint4 pwa[kPre], pwb[kPre];
 #pragma unroll
   for (int u = 0; u < kPre; ++u) {
     const int blk = u < nblk ? u : 0;
-    pwa[u] = ptx::ldg_nc_16(wrow0 + blk * 32);
-    pwb[u] = ptx::ldg_nc_16(wrow1 + blk * 32);
+    pwa[u] = ptx::ldg_nc_16(wrow0 + blk * 32, wpol);
+    pwb[u] = ptx::ldg_nc_16(wrow1 + blk * 32, wpol);
   }
   const float bias_lo = __ldg(a.bqkv + row_lo), bias_hi = __ldg(a.bqkv + row_lo + 8);
   // L2 hints for what is loaded later: the rest of this warp's QKV strip, its slice of Wo, and the cached K/V rows of the
@@ -1463,8 +1485,8 @@ __global__ void __maxnreg__(96) self_block_kernel(SelfBlockArgs a) {
 #pragma unroll
   for (int u = kPre; u < 16; u += 2) {
     if (u < nblk) {
-      ptx::prefetch_l2(wrow0 + u * 32);
-      ptx::prefetch_l2(wrow1 + u * 32);
+      weight_prefetch_l2(wrow0 + u * 32);
+      weight_prefetch_l2(wrow1 + u * 32);
     }
   }
   {
@@ -1474,8 +1496,8 @@ __global__ void __maxnreg__(96) self_block_kernel(SelfBlockArgs a) {
 #pragma unroll
     for (int u = 0; u < 6; u += 2) {
       if (hb0 + u < hb1) {
-        ptx::prefetch_l2(orow + (hb0 + u) * 32);
-        ptx::prefetch_l2(orow + (size_t)8 * d + (hb0 + u) * 32);
+        weight_prefetch_l2(orow + (hb0 + u) * 32);
+        weight_prefetch_l2(orow + (size_t)8 * d + (hb0 + u) * 32);
       }
     }
     const int n_hint = ld_state(&a.state->cur_len) + 1;
@@ -1558,8 +1580,8 @@ __global__ void __maxnreg__(96) self_block_kernel(SelfBlockArgs a) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int bb = blk + u < nblk ? blk + u : blk;
-        wa[u] = ptx::ldg_nc_16(wrow0 + bb * 32);
-        wb[u] = ptx::ldg_nc_16(wrow1 + bb * 32);
+        wa[u] = ptx::ldg_nc_16(wrow0 + bb * 32, wpol);
+        wb[u] = ptx::ldg_nc_16(wrow1 + bb * 32, wpol);
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -1625,9 +1647,12 @@ __global__ void __maxnreg__(96) self_block_kernel(SelfBlockArgs a) {
           kq[j] = ptx::ldg_nc_16(kb + (size_t)rc * d);
           vq[j] = ptx::ldg_nc_16(vb + (size_t)rc * d);
         }
+        // the 8 scores of this lane group first (independent chains), then ONE rescale of the running state for the batch:
+        // a per-row online update serialises max -> exp2 -> accumulate eight times over
+        float dots[8], bm = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float kf[8], vf[8];
+          float kf[8];
           unpack8(kq[j], kf);
           float dot = 0.f;
 #pragma unroll
@@ -1635,10 +1660,25 @@ __global__ void __maxnreg__(96) self_block_kernel(SelfBlockArgs a) {
           dot += __shfl_xor_sync(0xffffffffu, dot, 1);
           dot += __shfl_xor_sync(0xffffffffu, dot, 2);
           dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-          if (r0 + j * 4 + rsub < r_end) {
+          dots[j] = (r0 + j * 4 + rsub < r_end) ? dot : -INFINITY;
+          bm = fmaxf(bm, dots[j]);
+        }
+        if (bm > -INFINITY) {                                  // uniform over the 8 lanes that share a row group
+          const float mn = fmaxf(p.m, bm);
+          const float corr = exp2f(p.m - mn);                  // p.m = -inf: 0
+          p.l *= corr;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) p.o[i] *= corr;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float pr = exp2f(dots[j] - mn);              // masked rows: exp2(-inf) = 0
+            float vf[8];
             unpack8(vq[j], vf);
-            sb_row(p, dot, vf);
+            p.l += pr;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) p.o[i] = fmaf(pr, vf[i], p.o[i]);
           }
+          p.m = mn;
         }
       }
       if (sub == 0) {   // the new row: k, v as the cache holds them (fp16-rounded), taken from shared memory
@@ -1678,8 +1718,8 @@ __global__ void __maxnreg__(96) self_block_kernel(SelfBlockArgs a) {
 #pragma unroll
     for (int u = 0; u < kOB; ++u) {
       const int blk = ob0 + u < ob1 ? ob0 + u : ob0;
-      owa[u] = ptx::ldg_nc_16(orow0 + blk * 32);
-      owb[u] = ptx::ldg_nc_16(orow1 + blk * 32);
+      owa[u] = ptx::ldg_nc_16(orow0 + blk * 32, wpol);
+      owb[u] = ptx::ldg_nc_16(orow1 + blk * 32, wpol);
     }
   }
   // epilogue mapping: thread -> (sequence slot, output column); old residual and bias requested now as well
@@ -1844,11 +1884,11 @@ struct PbCfg {
 
 // one warp: acc += W[16 rows][blocks blk0 .. blk0+NB) x B tile (8 slots); NB <= 8 blocks requested at once
 template <int NB>
-__device__ __forceinline__ void pb_load(uint4 (&wa)[NB], uint4 (&wb)[NB], const __half* wrow0, const __half* wrow1, int blk0) {
+__device__ __forceinline__ void pb_load(uint4 (&wa)[NB], uint4 (&wb)[NB], const __half* wrow0, const __half* wrow1, int blk0, uint64_t wpol) {
 #pragma unroll
   for (int u = 0; u < NB; ++u) {
-    wa[u] = ptx::ldg_nc_16(wrow0 + (blk0 + u) * 32);
-    wb[u] = ptx::ldg_nc_16(wrow1 + (blk0 + u) * 32);
+    wa[u] = ptx::ldg_nc_16(wrow0 + (blk0 + u) * 32, wpol);
+    wb[u] = ptx::ldg_nc_16(wrow1 + (blk0 + u) * 32, wpol);
   }
 }
 template <int NB>
@@ -1885,10 +1925,11 @@ __global__ void __maxnreg__(128) post_block_kernel(PostBlockArgs a) {
   // ---- before the wait ---------------------------------------------------------------------------------------------------------------
   const int strip0 = warp % Cfg::S0, kp0 = warp / Cfg::S0;
   const bool act0 = warp < Cfg::S0 * Cfg::KS0;
+  const uint64_t wpol = weight_policy();
   uint4 wa0[Cfg::NB0], wb0[Cfg::NB0];
   {
     const __half* w0 = a.wo + (size_t)(r * OC + strip0 * 16 + grp) * D + tq * 8;
-    pb_load<Cfg::NB0>(wa0, wb0, w0, w0 + (size_t)8 * D, act0 ? kp0 * Cfg::NB0 : 0);
+    pb_load<Cfg::NB0>(wa0, wb0, w0, w0 + (size_t)8 * D, act0 ? kp0 * Cfg::NB0 : 0, wpol);
   }
   for (int i = tid * 4; i < D; i += kPbThreads * 4) {
     *reinterpret_cast<float4*>(s_g + i) = __ldg(reinterpret_cast<const float4*>(a.ln_g + i));
@@ -1901,11 +1942,11 @@ __global__ void __maxnreg__(128) post_block_kernel(PostBlockArgs a) {
   auto weight_hints = [&]() {
     for (int i = tid; i < HS * (D / 64); i += kPbThreads) {
       const int row = i / (D / 64), seg = i - row * (D / 64);
-      ptx::prefetch_l2(a.w1 + (size_t)(r * HS + row) * D + seg * 64);
+      weight_prefetch_l2(a.w1 + (size_t)(r * HS + row) * D + seg * 64);
     }
     for (int i = tid; i < D * (HS / 64); i += kPbThreads) {
       const int row = i / (HS / 64), seg = i - row * (HS / 64);
-      ptx::prefetch_l2(a.w2 + (size_t)row * (4 * D) + r * HS + seg * 64);
+      weight_prefetch_l2(a.w2 + (size_t)row * (4 * D) + r * HS + seg * 64);
     }
   };
   if (!a.hints_after_wait) weight_hints();
@@ -1966,7 +2007,7 @@ __global__ void __maxnreg__(128) post_block_kernel(PostBlockArgs a) {
   {
     const int strip = warp % Cfg::SB, kp = warp / Cfg::SB;
     const __half* w0 = a.w1 + (size_t)(r * HS + strip * 16 + grp) * D + tq * 8;
-    pb_load<NBb>(wa2, wb2, w0, w0 + (size_t)8 * D, kp * Cfg::NBU);
+    pb_load<NBb>(wa2, wb2, w0, w0 + (size_t)8 * D, kp * Cfg::NBU, wpol);
   }
   ptx::cluster_arrive_release();
   ptx::cluster_wait_acquire();
@@ -2017,8 +2058,8 @@ __global__ void __maxnreg__(128) post_block_kernel(PostBlockArgs a) {
       const int p = p0 + u < NPAIR ? p0 + u : NPAIR - 1;
       const int si = p / Cfg::NBC, blk = p % Cfg::NBC;
       const __half* w0 = w2base + (size_t)((warp + 8 * si) * 16) * (4 * D) + blk * 32;
-      wa[u] = ptx::ldg_nc_16(w0);
-      wb[u] = ptx::ldg_nc_16(w0 + (size_t)8 * (4 * D));
+      wa[u] = ptx::ldg_nc_16(w0, wpol);
+      wb[u] = ptx::ldg_nc_16(w0 + (size_t)8 * (4 * D), wpol);
     }
   };
   uint4 wa3[8], wb3[8];
@@ -2035,7 +2076,7 @@ __global__ void __maxnreg__(128) post_block_kernel(PostBlockArgs a) {
         pb_mma<NBb>(acc, wa2, wb2, xs + grp * XS + tq * 16, kp * Cfg::NBU);
       } else {
         uint4 wa[NBb], wb[NBb];
-        pb_load<NBb>(wa, wb, w0, w1r, kp * Cfg::NBU + bb);
+        pb_load<NBb>(wa, wb, w0, w1r, kp * Cfg::NBU + bb, wpol);
         pb_mma<NBb>(acc, wa, wb, xs + grp * XS + tq * 16, kp * Cfg::NBU + bb);
       }
     }

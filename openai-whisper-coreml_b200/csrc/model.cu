@@ -602,6 +602,10 @@ static int create_impl(wb_handle* h, void* stream) {
     WB_CUDA_OK(cudaStreamSynchronize(h->stream));   // `t` is pageable host memory
   }
   h->gemm = gemm_context_create();
+  {
+    const char* e = getenv("WB_L2_POLICY");
+    WB_TRY(decoder_set_l2_mode(e ? atoi(e) : 1));
+  }
   WB_CUDA_OK(cudaMallocHost(&h->h_done, sizeof(int32_t) * h->Mb_max));
   for (int i = 0; i < 4; ++i) WB_CUDA_OK(cudaEventCreate(&h->ev[i]));
   for (int i = 1; i < wb_handle::kMaxSub; ++i) WB_CUDA_OK(cudaStreamCreateWithFlags(&h->sub_stream[i], cudaStreamNonBlocking));

@@ -193,6 +193,8 @@ struct FinishDesc {
   DecodeState* state;
 };
 int launch_step_finish(const FinishDesc& d, cudaStream_t st, int64_t* launches);
+// L2 residency hints of the decode kernels on the current device: 1 = weights evict_last, cross K/V stream evict_first
+int decoder_set_l2_mode(int mode);
 
 // beam search support: per-row top-k (k <= 8) of the filtered logits with their log-softmax values, and the re-indexing
 // of the self-attention K/V cache by source beam (upstream rearrange_kv_cache)

@@ -155,6 +155,35 @@ __device__ __forceinline__ uint4 ldg_nc_16(const void* p) {   // streaming 16-by
                : "l"(p));
   return r;
 }
+// ---- L2 residency hints ---------------------------------------------------------------------------------------------------
+// A decode step streams ~590 MB of cross-attention K/V (read once per step) past ~100 MB of decoder weights (read every
+// step) through a 126 MB L2: weights are loaded with an evict_last policy and the K/V stream with evict_first, so that the
+// stream does not push the weights out between steps. kind: 0 = evict_normal, 1 = evict_last, 2 = evict_first.
+__device__ __forceinline__ uint64_t l2_policy(int kind) {
+  uint64_t p;
+  if (kind == 1)
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else if (kind == 2)
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 ldg_nc_16(const void* p, uint64_t policy) {   // streaming 16-byte load with an L2 policy
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(policy));
+  return r;
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
+
 // ---- thread-block clusters: distributed shared memory ---------------------------------------------------------------------
 // shared::cluster address of the same variable in the CTA with the given rank of this cluster
 __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t cta_rank) {
@@ -174,6 +203,7 @@ __device__ __forceinline__ float ld_cluster_f32(uint32_t cluster_addr) {
   return v;
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2_evict_last(const void* p) { asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {

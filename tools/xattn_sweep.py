@@ -1,14 +1,16 @@
 #!/usr/bin/env python3
-"""Times the KV-cache attention kernel alone (wb_profile_cross_attention) at the bench configuration."""
+"""Development: per-launch time of the KV-cache attention kernel alone for several batch sizes (CTAs = 8 x B at base.en):
+how much HBM bandwidth a given number of resident CTAs pulls with the ring depth WB_HA_STAGES."""
 import importlib, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 wbm = importlib.import_module("openai-whisper-coreml_b200")
 model = sys.argv[1] if len(sys.argv) > 1 else "base.en"
-B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
-w = wbm.Whisper(model, seed=0, max_batch=B)
-w.encode((np.random.default_rng(0).standard_normal((B, 480000)) * 0.1).astype(np.float32), return_features=False)
-ms, by = w.profile_cross_attention(B, 240)
-print(f"{model} B={B} env={ {k: v for k, v in os.environ.items() if k.startswith('WB_')} }: {ms*1e3:.2f} us/launch  {by/ms/1e6:.0f} GB/s  frac={by/ms/1e6/6541.5:.3f}")
+w = wbm.Whisper(model, seed=0, max_batch=32)
+audio = (np.random.default_rng(0).standard_normal((32, 480000)) * 0.1).astype(np.float32)
+w.encode(audio, return_features=False)
+for B in (1, 2, 4, 8, 12, 16, 18, 24, 32):
+    ms, by = w.profile_cross_attention(B, 240)
+    print(f"stages={os.environ.get('WB_HA_STAGES', 'default')} B={B:2d} ctas={B * w.dims.n_text_head:3d} us={ms * 1e3:7.2f} GB/s={by / ms / 1e6:8.1f} per-CTA GB/s={by / ms / 1e6 / (B * w.dims.n_text_head):6.1f}")
 w.close()
