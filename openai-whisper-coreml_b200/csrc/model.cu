@@ -411,6 +411,33 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
   __half* dmlp16 = h->dmlp16 + b0 * 4 * d;
   const size_t self_off = b0 * (size_t)D.n_text_ctx * d;
   const size_t cross_off = (b0 / o.beams) * (size_t)D.n_audio_ctx * d;
+  if (layer_block_supported(H, d)) {
+    // d = 384 / 512: one cluster kernel per layer boundary (post part of layer l-1 + self-attention block of layer l + the
+    // cross-attention query of layer l), and between two of them the KV-cache kernel as a pure stream: 2 launches per layer
+    for (int l = 0; l <= D.n_text_layer; ++l) {
+      LayerBlockDesc lb{};
+      lb.Mb = Mb, lb.d = d, lb.n_head = H, lb.n_ctx = D.n_text_ctx, lb.x = xdec, lb.state = state;
+      lb.has_post = l > 0, lb.has_self = l < D.n_text_layer;
+      if (lb.has_post) {
+        const LayerW& P = h->dec[l - 1];
+        lb.a16 = a16, lb.wo_c = P.wo_c, lb.bo_c = P.bo_c, lb.ln2_g = P.ln2_g, lb.ln2_b = P.ln2_b;
+        lb.w1 = P.w1, lb.b1 = P.b1, lb.w2 = P.w2, lb.b2 = P.b2;
+      }
+      if (lb.has_self) {
+        const LayerW& L = h->dec[l];
+        lb.ln1_g = L.ln1_g, lb.ln1_b = L.ln1_b, lb.wqkv = L.wqkv, lb.bqkv = L.bqkv, lb.wo = L.wo, lb.bo = L.bo;
+        lb.kcache = h->selfK[l] + self_off, lb.vcache = h->selfV[l] + self_off;
+        lb.lnc_g = L.lnc_g, lb.lnc_b = L.lnc_b, lb.wq_c = L.wq_c, lb.bq_c = L.bq_c, lb.q_out = q32;
+      }
+      WB_TRY(launch_layer_block(lb, st, &h->launches));
+      if (!lb.has_self) break;
+      AttnDecodeDesc c{};
+      c.Mb = Mb, c.d = d, c.n_head = H, c.q = q32, c.k = h->crossK[l] + cross_off, c.v = h->crossV[l] + cross_off;
+      c.n_ctx = D.n_audio_ctx, c.n_rows_fixed = D.n_audio_ctx, c.kv_share = o.beams, c.state = state, c.out16 = a16, c.tmaps = h->gemm;
+      c.pdl_late_ok = 1, c.stream_ok = 1;
+      WB_TRY(launch_attn_decode(c, st, &h->launches));
+    }
+  } else
   for (int l = 0; l < D.n_text_layer; ++l) {
     const LayerW& L = h->dec[l];
     AttnDecodeDesc a{};
@@ -1106,8 +1133,16 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
     }
   }
   int steps = 0;
+  // sub-batch i starts i * stagger microseconds late (again after every EOT poll, which re-aligns the streams)
+  int stagger_us = 0;
+  if (const char* e = getenv("WB_STAGGER_US")) stagger_us = atoi(e);
+  bool restagger = nsb > 1 && stagger_us > 0;
   for (int s = 0; s < opts->sample_len;) {
     const int n = (use_graph && multi > 1 && s + multi <= opts->sample_len && (s % interval) + multi <= interval) ? multi : 1;
+    if (restagger) {
+      for (int i = 1; i < nsb; ++i) WB_TRY(launch_delay((unsigned long long)i * stagger_us * 1000ull, step_stream(h, samp[i]), &h->launches));
+      restagger = false;
+    }
     for (int i = 0; i < nsb; ++i) {
       if (use_graph) {
         WB_CUDA_OK(cudaGraphLaunch(n > 1 ? h->g_sample_n[i] : h->g_sample[i], step_stream(h, samp[i])));
@@ -1126,6 +1161,7 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
       bool all = true;
       for (int b = 0; b < B; ++b) all = all && h->h_done[b];
       if (all) break;
+      restagger = nsb > 1 && stagger_us > 0;
     }
   }
   for (int i = 1; i < nsb; ++i) {   // join: everything after this point is ordered after every sub-batch
@@ -1385,11 +1421,15 @@ int wb_profile_cross_attention(wb_handle* h, int32_t B, int32_t reps, float* avg
   AttnDecodeDesc c{};
   c.Mb = B, c.d = D.n_text_state, c.n_head = D.n_text_head, c.q = nullptr, c.x = h->xdec;
   c.n_ctx = D.n_audio_ctx, c.n_rows_fixed = D.n_audio_ctx, c.kv_share = 1, c.state = h->state, c.out16 = h->a16, c.tmaps = h->gemm;
+  // the kernel exactly as the decode step runs it: queries from memory where the layer-boundary kernel projects them, the
+  // fused LayerNorm + query projection prologue otherwise
+  const bool q_from_memory = layer_block_supported(D.n_text_head, D.n_text_state) != 0;
+  if (q_from_memory) c.q = h->q32, c.x = nullptr, c.stream_ok = 1;
   for (int i = -3; i < reps; ++i) {   // 3 warm-up launches
     if (i == 0) WB_CUDA_OK(cudaEventRecord(h->ev[0], h->stream));
     const int l = ((i % D.n_text_layer) + D.n_text_layer) % D.n_text_layer;
     c.k = h->crossK[l], c.v = h->crossV[l];
-    c.ln_g = h->dec[l].lnc_g, c.ln_b = h->dec[l].lnc_b, c.wq = h->dec[l].wq_c, c.bq = h->dec[l].bq_c;
+    if (!q_from_memory) c.ln_g = h->dec[l].lnc_g, c.ln_b = h->dec[l].lnc_b, c.wq = h->dec[l].wq_c, c.bq = h->dec[l].bq_c;
     WB_TRY(launch_attn_decode(c, h->stream, &h->launches));
   }
   WB_CUDA_OK(cudaEventRecord(h->ev[1], h->stream));

@@ -131,6 +131,7 @@ struct AttnDecodeDesc {
   const DecodeState* state;
   __half* out16;          // [Mb][d]
   int pdl_late_ok;        // the successor is a block kernel that gains nothing from starting before this one's main loop ends
+  int stream_ok;          // cross attention between two layer-block kernels: may run as the persistent one-CTA-per-SM stream
   GemmContext* tmaps;     // tensor-map cache
 };
 int launch_attn_decode(const AttnDecodeDesc& d, cudaStream_t st, int64_t* launches);
@@ -172,6 +173,42 @@ struct PostBlockDesc {
 int post_block_supported(int n_head, int d);
 int launch_post_block(const PostBlockDesc& d, cudaStream_t st, int64_t* launches);
 
+// post part of the previous layer + self-attention block of this layer + this layer's cross-attention query in one cluster
+// kernel (d = 384 / 512; see layer_block_kernel). has_post = 0 for the first kernel of a step, has_self = 0 for the last.
+struct LayerBlockDesc {
+  int Mb, d, n_head, n_ctx;
+  int has_post, has_self;
+  float* x;               // [Mb][d] residual stream
+  // post part (previous layer)
+  const __half* a16;      // [Mb][d] cross-attention outputs
+  const __half* wo_c;
+  const float* bo_c;
+  const float* ln2_g;
+  const float* ln2_b;
+  const __half* w1;
+  const float* b1;
+  const __half* w2;
+  const float* b2;
+  // self part (this layer)
+  const float* ln1_g;
+  const float* ln1_b;
+  const __half* wqkv;
+  const float* bqkv;
+  const __half* wo;
+  const float* bo;
+  __half* kcache;
+  __half* vcache;
+  // cross-attention query (this layer)
+  const float* lnc_g;
+  const float* lnc_b;
+  const __half* wq_c;
+  const float* bq_c;
+  float* q_out;           // [Mb][d]
+  const DecodeState* state;
+};
+int layer_block_supported(int n_head, int d);
+int launch_layer_block(const LayerBlockDesc& d, cudaStream_t st, int64_t* launches);
+
 struct FinishDesc {
   int Mb, V, d, n_ctx;
   int sample;                 // 0: only embed the next (already present) token and advance
@@ -195,6 +232,7 @@ struct FinishDesc {
 int launch_step_finish(const FinishDesc& d, cudaStream_t st, int64_t* launches);
 // L2 residency hints of the decode kernels on the current device: 1 = weights evict_last, cross K/V stream evict_first
 int decoder_set_l2_mode(int mode);
+int launch_delay(unsigned long long ns, cudaStream_t st, int64_t* launches);
 
 // beam search support: per-row top-k (k <= 8) of the filtered logits with their log-softmax values, and the re-indexing
 // of the self-attention K/V cache by source beam (upstream rearrange_kv_cache)
