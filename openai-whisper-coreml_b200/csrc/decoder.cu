@@ -45,6 +45,27 @@ int decoder_set_l2_mode(int mode) {
 // Weights and the cross-attention K/V are constant during a decode and use the non-coherent path.
 __device__ __forceinline__ int ld_state(const int* p) { return __ldcg(p); }
 
+// Hand-off counters in DecodeState (q_ready / a_done): producers fence their data stores, synchronise, and one thread adds
+// with release semantics; a consumer thread polls with acquire semantics, then the rest of its CTA / warp is released by a
+// barrier and reads the data through L2. The poll is bounded so that a protocol bug cannot hang the device.
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void poll_at_least(const int* counter, int target, int* timeout_flag) {
+  unsigned int spins = 0;
+  while (ld_acquire_gpu(counter) < target) {
+    if (++spins > (1u << 24)) {   // tens of milliseconds: thousands of times longer than any legitimate wait
+      atomicExch(timeout_flag, 1);
+      break;
+    }
+  }
+}
+
 // Development tracing: block (0,0) thread 0 of every decode kernel stamps %globaltimer at entry and exit (WB_TRACE=1).
 __device__ __forceinline__ unsigned long long globaltimer() {
   unsigned long long t;
@@ -58,7 +79,7 @@ struct TraceScope {
       unsigned long long* tr = st->trace;
       if (tr) {
         const int i = atomicAdd(const_cast<int*>(&st->trace_n), 1);
-        if (i < 65536) {
+        if (i < 16384) {
           rec = tr + (size_t)i * 8;
           rec[0] = (unsigned long long)id;
           rec[1] = globaltimer();
@@ -1324,12 +1345,109 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
 // attn_decode_head_kernel, but ONE resident CTA per SM (9 warps, ~28K registers, the ring + 3 KB of shared memory): the cluster
 // kernels before and after it fit on the same SMs next to it, so they become resident — constants loaded, first weights in flight —
 // while this kernel streams, and this kernel's ring fills while they compute. The producer runs ahead across item boundaries.
+// Online-softmax state of one warp over the rows it owns (16 of every 128-row tile)
+struct AttnAcc {
+  float o[4][4];
+  float m_run, l_run;
+};
+// One warp, NT (1 or 2) K/V stage tiles at once: S = K q^T (q split into fp16 hi + lo, separate accumulator chains), ONE
+// running-max update for the NT x 16 rows, P V accumulated into the 4 output blocks. Two tiles per call halve the number of
+// dependent max -> exp2 -> rescale chains per byte streamed and give the tensor pipe 4 independent chains instead of 1.
+// sk[i]: shared-memory address of K tile i (V follows at + kHaTileBytes); row0[i]: global row of this warp's first row in tile i.
+// Requires row0[0] < n_rows (at least one live row), rows >= n_rows are masked (the TMA unit zero-filled them).
+template <int NT>
+__device__ __forceinline__ void attn_tiles(AttnAcc& A, const uint32_t (&qh)[4][2], const uint32_t (&ql)[4][2], const uint32_t (&sk)[NT],
+                                           const int (&row0)[NT], int n_rows, int warp, int lane) {
+  const int grp = lane >> 2, tq = lane & 3, mi = lane >> 3, r8 = lane & 7;
+  float ch[NT][4], cl[NT][4];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    ch[i][0] = ch[i][1] = ch[i][2] = ch[i][3] = 0.f;
+    cl[i][0] = cl[i][1] = cl[i][2] = cl[i][3] = 0.f;
+  }
+  const int Rk = warp * 16 + (mi & 1) * 8 + r8;       // tile row this lane addresses for ldmatrix (K)
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      uint32_t af[4];
+      ptx::ldmatrix_x4(af, sk[i] + Rk * 128 + (((kk * 2 + (mi >> 1)) ^ (Rk & 7)) << 4));
+      ptx::mma_16816(ch[i], af, qh[kk]);
+      ptx::mma_16816(cl[i], af, ql[kk]);
+    }
+  }
+  float s_lo[NT], s_hi[NT], tmax = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    s_lo[i] = (row0[i] + grp < n_rows) ? ch[i][0] + cl[i][0] : -INFINITY;
+    s_hi[i] = (row0[i] + grp + 8 < n_rows) ? ch[i][2] + cl[i][2] : -INFINITY;
+    tmax = fmaxf(tmax, fmaxf(s_lo[i], s_hi[i]));
+  }
+  tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 4));
+  tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 8));
+  tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 16));
+  if (tmax > A.m_run) {                                // warp-uniform (identical in every lane)
+    const float corr = exp2f(A.m_run - tmax);
+    A.m_run = tmax;
+    A.l_run *= corr;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) A.o[mt][0] *= corr, A.o[mt][1] *= corr, A.o[mt][2] *= corr, A.o[mt][3] *= corr;
+  }
+  const int Rv = warp * 16 + (mi >> 1) * 8 + r8;      // (V, transposed load)
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    const float p_lo = exp2f(s_lo[i] - A.m_run), p_hi = exp2f(s_hi[i] - A.m_run);
+    A.l_run += p_lo + p_hi;
+    const float e0 = __shfl_sync(0xffffffffu, p_lo, (2 * tq) * 4), e1 = __shfl_sync(0xffffffffu, p_lo, (2 * tq + 1) * 4);
+    const float e2 = __shfl_sync(0xffffffffu, p_hi, (2 * tq) * 4), e3 = __shfl_sync(0xffffffffu, p_hi, (2 * tq + 1) * 4);
+    const __half2 ph0 = __floats2half2_rn(e0, e1), ph1 = __floats2half2_rn(e2, e3);
+    const float2 f0 = __half22float2(ph0), f1 = __half22float2(ph1);
+    const __half2 pl0 = __floats2half2_rn(e0 - f0.x, e1 - f0.y), pl1 = __floats2half2_rn(e2 - f1.x, e3 - f1.y);
+    const uint32_t pbh[2] = {*reinterpret_cast<const uint32_t*>(&ph0), *reinterpret_cast<const uint32_t*>(&ph1)};
+    const uint32_t pbl[2] = {*reinterpret_cast<const uint32_t*>(&pl0), *reinterpret_cast<const uint32_t*>(&pl1)};
+    const uint32_t sv = sk[i] + kHaTileBytes;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      uint32_t af[4];
+      ptx::ldmatrix_x4_trans(af, sv + Rv * 128 + (((mt * 2 + (mi & 1)) ^ (Rv & 7)) << 4));
+      ptx::mma_16816(A.o[mt], af, pbh);
+      ptx::mma_16816(A.o[mt], af, pbl);
+    }
+  }
+}
+// q (64 fp32 values of one head) -> B fragments replicated over the 8 n columns, fp16 hi + lo parts, pre-scaled into the log2 domain
+__device__ __forceinline__ void attn_q_frags(uint32_t (&qh)[4][2], uint32_t (&ql)[4][2], const float* q64, bool from_global, int tq) {
+  const float sl = 0.125f * kLog2e;   // (d_head^-0.25)^2 = 1/8 exactly
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const float* qp = q64 + kk * 16 + 2 * tq;
+    float2 q0, q1;
+    if (from_global)
+      q0 = __ldcg(reinterpret_cast<const float2*>(qp)), q1 = __ldcg(reinterpret_cast<const float2*>(qp + 8));
+    else
+      q0 = *reinterpret_cast<const float2*>(qp), q1 = *reinterpret_cast<const float2*>(qp + 8);
+    const float v[4] = {q0.x * sl, q0.y * sl, q1.x * sl, q1.y * sl};
+    __half hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      hi[e] = __float2half_rn(v[e]);
+      lo[e] = __float2half_rn(v[e] - __half2float(hi[e]));
+    }
+    __half2 h0 = __halves2half2(hi[0], hi[1]), h1 = __halves2half2(hi[2], hi[3]);
+    __half2 l0 = __halves2half2(lo[0], lo[1]), l1 = __halves2half2(lo[2], lo[3]);
+    qh[kk][0] = *reinterpret_cast<uint32_t*>(&h0), qh[kk][1] = *reinterpret_cast<uint32_t*>(&h1);
+    ql[kk][0] = *reinterpret_cast<uint32_t*>(&l0), ql[kk][1] = *reinterpret_cast<uint32_t*>(&l1);
+  }
+}
+
 struct StreamAttnArgs {
   const float* q;          // [Mb][d] queries (fp32)
   __half* out16;           // [Mb][d]
   const DecodeState* state;
   int d, n_head, n_items, n_rows, kv_share, n_stages;
   int pdl_early;           // release the dependent kernel at entry (it only becomes resident; it waits for this kernel's completion itself)
+  int use_flags;           // 1: per-group hand-off counters in DecodeState (q_ready / a_done) instead of griddepcontrol.wait
+  int layer, n_layer, Mb;
 };
 
 __global__ void __maxnreg__(96) attn_stream_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -1374,87 +1492,58 @@ __global__ void __maxnreg__(96) attn_stream_kernel(const __grid_constant__ CUten
       }
     }
   } else {
-    const float sl = 0.125f * kLog2e;   // (d_head^-0.25)^2 = 1/8 exactly
-    ptx::grid_dep_sync();               // the queries come from the previous kernel
+    DecodeState* st = const_cast<DecodeState*>(a.state);
+    int q_target = 0;
+    if (a.use_flags) {
+      // the launch is only ordered after the START of the layer-block kernel (which itself started after the previous step's
+      // finish kernel completed, so cur_len is this step's); a group's queries are ready when all C = 2 * n_head CTAs of
+      // its cluster have counted in
+      q_target = 2 * a.n_head * (ld_state(&st->cur_len) * a.n_layer + a.layer + 1);
+    } else {
+      ptx::grid_dep_sync();             // the queries come from the previous kernel
+    }
     uint32_t it = 0, n_done = 0;
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++n_done) {
       const int h = item % a.n_head, b = item / a.n_head;
-      // q as B fragments (replicated over the 8 n columns), hi + lo fp16 parts, pre-scaled into the log2 domain
-      uint32_t qh[4][2], ql[4][2];
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const float* qp = a.q + (size_t)b * a.d + h * 64 + kk * 16 + 2 * tq;
-        const float2 q0 = __ldcg(reinterpret_cast<const float2*>(qp)), q1 = __ldcg(reinterpret_cast<const float2*>(qp + 8));
-        const float v[4] = {q0.x * sl, q0.y * sl, q1.x * sl, q1.y * sl};
-        __half hi[4], lo[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          hi[e] = __float2half_rn(v[e]);
-          lo[e] = __float2half_rn(v[e] - __half2float(hi[e]));
-        }
-        __half2 h0 = __halves2half2(hi[0], hi[1]), h1 = __halves2half2(hi[2], hi[3]);
-        __half2 l0 = __halves2half2(lo[0], lo[1]), l1 = __halves2half2(lo[2], lo[3]);
-        qh[kk][0] = *reinterpret_cast<uint32_t*>(&h0), qh[kk][1] = *reinterpret_cast<uint32_t*>(&h1);
-        ql[kk][0] = *reinterpret_cast<uint32_t*>(&l0), ql[kk][1] = *reinterpret_cast<uint32_t*>(&l1);
+      if (a.use_flags) {
+        if (lane == 0) poll_at_least(&st->q_ready[b >> 3], q_target, &st->spin_timeout);
+        __syncwarp();
       }
-      float o[4][4], m_run = -INFINITY, l_run = 0.f;
+      uint32_t qh[4][2], ql[4][2];
+      attn_q_frags(qh, ql, a.q + (size_t)b * a.d + h * 64, true, tq);
+      AttnAcc acc;
+      acc.m_run = -INFINITY, acc.l_run = 0.f;
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt) o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f;
-      for (int t = 0; t < n_tiles; ++t, ++it) {
-        const int s = it % n_stages;
-        const uint32_t ph = (it / n_stages) & 1u;
-        ptx::mbar_wait(&full_bar[s], ph);
-        const int row0 = t * kHaStageRows + warp * 16;       // first of this warp's 16 rows
-        if (row0 < n_rows) {                                 // warp-uniform
-          const uint32_t sk = ptx::smem_u32(smem + (size_t)s * 2 * kHaTileBytes);
-          const uint32_t sv = sk + kHaTileBytes;
-          float c[4] = {0.f, 0.f, 0.f, 0.f};
-          {
-            const int R = warp * 16 + (mi & 1) * 8 + r8;     // tile row this lane addresses for ldmatrix
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              uint32_t af[4];
-              ptx::ldmatrix_x4(af, sk + R * 128 + (((kk * 2 + (mi >> 1)) ^ (R & 7)) << 4));
-              ptx::mma_16816(c, af, qh[kk]);
-              ptx::mma_16816(c, af, ql[kk]);
-            }
-          }
-          const float s_lo = (row0 + grp < n_rows) ? c[0] : -INFINITY;
-          const float s_hi = (row0 + grp + 8 < n_rows) ? c[2] : -INFINITY;
-          float tmax = fmaxf(s_lo, s_hi);
-          tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 4));
-          tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 8));
-          tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 16));
-          if (tmax > m_run) {                                // warp-uniform (identical in every lane)
-            const float corr = exp2f(m_run - tmax);
-            m_run = tmax;
-            l_run *= corr;
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt) o[mt][0] *= corr, o[mt][1] *= corr, o[mt][2] *= corr, o[mt][3] *= corr;
-          }
-          const float p_lo = exp2f(s_lo - m_run), p_hi = exp2f(s_hi - m_run);
-          l_run += p_lo + p_hi;
-          const float e0 = __shfl_sync(0xffffffffu, p_lo, (2 * tq) * 4), e1 = __shfl_sync(0xffffffffu, p_lo, (2 * tq + 1) * 4);
-          const float e2 = __shfl_sync(0xffffffffu, p_hi, (2 * tq) * 4), e3 = __shfl_sync(0xffffffffu, p_hi, (2 * tq + 1) * 4);
-          const __half2 ph0 = __floats2half2_rn(e0, e1), ph1 = __floats2half2_rn(e2, e3);
-          const float2 f0 = __half22float2(ph0), f1 = __half22float2(ph1);
-          const __half2 pl0 = __floats2half2_rn(e0 - f0.x, e1 - f0.y), pl1 = __floats2half2_rn(e2 - f1.x, e3 - f1.y);
-          const uint32_t pbh[2] = {*reinterpret_cast<const uint32_t*>(&ph0), *reinterpret_cast<const uint32_t*>(&ph1)};
-          const uint32_t pbl[2] = {*reinterpret_cast<const uint32_t*>(&pl0), *reinterpret_cast<const uint32_t*>(&pl1)};
-          {
-            const int R = warp * 16 + (mi >> 1) * 8 + r8;
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt) {
-              uint32_t af[4];
-              ptx::ldmatrix_x4_trans(af, sv + R * 128 + (((mt * 2 + (mi & 1)) ^ (R & 7)) << 4));
-              ptx::mma_16816(o[mt], af, pbh);
-              ptx::mma_16816(o[mt], af, pbl);
-            }
-          }
+      for (int mt = 0; mt < 4; ++mt) acc.o[mt][0] = acc.o[mt][1] = acc.o[mt][2] = acc.o[mt][3] = 0.f;
+      int t = 0;
+      for (; t + 2 <= n_tiles; t += 2, it += 2) {            // two stage tiles per pass
+        const int s0 = it % n_stages, s1 = (it + 1) % n_stages;
+        ptx::mbar_wait(&full_bar[s0], (it / n_stages) & 1u);
+        ptx::mbar_wait(&full_bar[s1], ((it + 1) / n_stages) & 1u);
+        const int row0[2] = {t * kHaStageRows + warp * 16, (t + 1) * kHaStageRows + warp * 16};
+        if (row0[0] < n_rows) {                              // warp-uniform
+          const uint32_t sk[2] = {ptx::smem_u32(smem + (size_t)s0 * 2 * kHaTileBytes), ptx::smem_u32(smem + (size_t)s1 * 2 * kHaTileBytes)};
+          attn_tiles<2>(acc, qh, ql, sk, row0, n_rows, warp, lane);
         }
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&empty_bar[s]);
+        if (lane == 0) {
+          ptx::mbar_arrive(&empty_bar[s0]);
+          ptx::mbar_arrive(&empty_bar[s1]);
+        }
       }
+      for (; t < n_tiles; ++t, ++it) {                       // odd tile count: the last one alone
+        const int s0 = it % n_stages;
+        ptx::mbar_wait(&full_bar[s0], (it / n_stages) & 1u);
+        const int row0[1] = {t * kHaStageRows + warp * 16};
+        if (row0[0] < n_rows) {
+          const uint32_t sk[1] = {ptx::smem_u32(smem + (size_t)s0 * 2 * kHaTileBytes)};
+          attn_tiles<1>(acc, qh, ql, sk, row0, n_rows, warp, lane);
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty_bar[s0]);
+      }
+      const float m_run = acc.m_run, l_run = acc.l_run;
+      float (&o)[4][4] = acc.o;
       // cross-warp merge of the item (double-buffered scratch: one named barrier per item; the producer warp is not involved)
       float* red = s_red[n_done & 1u];
       float L = l_run;
@@ -1483,6 +1572,11 @@ __global__ void __maxnreg__(96) attn_stream_kernel(const __grid_constant__ CUten
           A += wgt * red[w * 68 + tid];
         }
         a.out16[(size_t)b * a.d + h * 64 + tid] = __float2half_rn(A / Ls);
+        if (a.use_flags) {
+          __threadfence();
+          asm volatile("bar.sync 2, 64;" ::: "memory");     // the 64 writers of this item
+          if (tid == 0) red_release_gpu_add(&st->a_done[b >> 3], 1);
+        }
       }
     }
   }
@@ -1512,7 +1606,7 @@ static int launch_attn_stream(const AttnDecodeDesc& p, cudaStream_t st, int64_t*
     e = getenv("WB_XS_EARLY");
     early = e ? atoi(e) : 1;
   }
-  StreamAttnArgs a{p.q, p.out16, p.state, p.d, p.n_head, p.n_head * p.Mb, p.n_rows_fixed, p.kv_share, stages, early};
+  StreamAttnArgs a{p.q, p.out16, p.state, p.d, p.n_head, p.n_head * p.Mb, p.n_rows_fixed, p.kv_share, stages, early, p.use_flags, p.layer, p.n_layer, p.Mb};
   const size_t smem = (size_t)stages * 2 * kHaTileBytes + 1024;
   static size_t smem_set_dev[kMaxDevices] = {};
   size_t& smem_set = smem_set_dev[current_device_slot()];
@@ -2515,7 +2609,9 @@ struct LayerBlockArgs {
   float* q_out;             // [Mb][d] cross-attention queries (global)
   int Mb, n_ctx, has_post, has_self;
   int pdl_point;            // where the dependent kernel may start: 0 at entry, 1 after the post part, 2 after QKV, 3 after attention
-  const DecodeState* state;
+  int use_flags, layer, n_layer;
+  int stagger_ns;           // first kernel of a step: group g starts g * stagger_ns late, so that the groups' attention streams do not coincide
+  DecodeState* state;
 };
 
 template <int D, int C>
@@ -2682,7 +2778,23 @@ __global__ void __maxnreg__(96) layer_block_kernel(LayerBlockArgs a) {
     }
   }
   if (a.pdl_point == 0) ptx::grid_dep_launch();
-  ptx::grid_dep_sync();
+  if (a.use_flags && a.has_post) {
+    // the previous layer's attention outputs of THIS group: (sequence, head) items counted in by the stream kernel. Everything
+    // else this kernel reads was written by its own cluster in the previous layer-block kernel (ordered by the same chain).
+    if (tid == 0) {
+      const int n_seq = a.Mb - b0 < 8 ? a.Mb - b0 : 8;
+      const int target = H * n_seq * (ld_state(&a.state->cur_len) * a.n_layer + a.layer);
+      poll_at_least(&a.state->a_done[blockIdx.y], target, &a.state->spin_timeout);
+    }
+    __syncthreads();
+  } else {
+    ptx::grid_dep_sync();
+    if (a.stagger_ns > 0 && blockIdx.y > 0) {
+      const unsigned long long t0 = globaltimer(), wait_ns = (unsigned long long)a.stagger_ns * blockIdx.y;
+      while (globaltimer() - t0 < wait_ns) {
+      }
+    }
+  }
   trace.mark(3);
 
   constexpr int NBq = NBLK > 8 ? 8 : NBLK;                       // blocks per batch of the full-K GEMMs (MLP1, QKV)
@@ -3027,6 +3139,11 @@ __global__ void __maxnreg__(96) layer_block_kernel(LayerBlockArgs a) {
     for (int k = 0; k < KP; ++k) v += s_red[k * 8 * OC + tid];
     a.q_out[(size_t)(b0 + e_slot) * D + r * OC + e_col] = v + bias_q;
   }
+  if (a.use_flags) {   // this CTA's columns of x'' and q are in global memory: count in (the stream waits for all C CTAs of the group)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) red_release_gpu_add(&a.state->q_ready[blockIdx.y], 1);
+  }
   trace.end();
 }
 
@@ -3042,8 +3159,10 @@ static int layer_block_cluster(int d) {
   int& c = c_dev[current_device_slot()][d == 512];
   if (c < 0) {
     c = 0;
+    // Off unless WB_LAYER_BLOCK=1: measured on B200 (base.en, 32 sequences) the two-launch-per-layer path runs 281 us per step
+    // against 273-275 us for self block + KV-cache kernel with the fused query projection + post block.
     const char* e = getenv("WB_LAYER_BLOCK");
-    if (!(e && e[0] == '0')) {
+    if (e && e[0] == '1') {
       const int want = d / 32;   // 2 * n_head: 16 / 12, both beyond the portable cluster size of 8
       cudaError_t e1, e2;
       cudaLaunchConfig_t cfg{};
@@ -3090,7 +3209,16 @@ int launch_layer_block(const LayerBlockDesc& p, cudaStream_t st, int64_t* launch
   a.w2 = p.w2, a.b2 = p.b2, a.ln1_g = p.ln1_g, a.ln1_b = p.ln1_b, a.wqkv = p.wqkv, a.bqkv = p.bqkv, a.wo = p.wo, a.bo = p.bo;
   a.kcache = p.kcache, a.vcache = p.vcache, a.lnc_g = p.lnc_g, a.lnc_b = p.lnc_b, a.wq_c = p.wq_c, a.bq_c = p.bq_c, a.q_out = p.q_out;
   a.Mb = p.Mb, a.n_ctx = p.n_ctx, a.has_post = p.has_post, a.has_self = p.has_self, a.state = p.state;
-  a.pdl_point = p.has_self ? pdl_self : pdl_last;
+  a.use_flags = p.use_flags, a.layer = p.layer, a.n_layer = p.n_layer;
+  static int stagger = -1;
+  if (stagger < 0) {
+    const char* e = getenv("WB_LB_STAGGER_NS");
+    stagger = e ? atoi(e) : 0;
+  }
+  a.stagger_ns = (p.use_flags && !p.has_post) ? stagger : 0;
+  // with the counters the dependents are released at entry (they only become resident and poll); the first kernel of a step
+  // releases after its wait, so that everything downstream starts after the previous step's finish kernel
+  a.pdl_point = p.use_flags ? (p.has_post ? 0 : 1) : (p.has_self ? pdl_self : pdl_last);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(C, (p.Mb + 7) / 8), cfg.blockDim = dim3(kLbThreads), cfg.stream = st;
   cfg.dynamicSmemBytes = p.d == 512 ? LbCfg<512, 16>::smem : LbCfg<384, 12>::smem;

@@ -378,6 +378,15 @@ struct StepOpts {
   int ts_begin, ts_last_allowed;
 };
 
+static bool use_handoff_flags() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WB_HANDOFF_FLAGS");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static cudaStream_t step_stream(wb_handle* h, const StepOpts& o) { return o.sub > 0 ? h->sub_stream[o.sub] : h->stream; }
 static DecodeState* step_state(wb_handle* h, const StepOpts& o) { return h->state + o.sub; }
 
@@ -418,6 +427,7 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
       LayerBlockDesc lb{};
       lb.Mb = Mb, lb.d = d, lb.n_head = H, lb.n_ctx = D.n_text_ctx, lb.x = xdec, lb.state = state;
       lb.has_post = l > 0, lb.has_self = l < D.n_text_layer;
+      lb.layer = l, lb.n_layer = D.n_text_layer, lb.use_flags = use_handoff_flags() && Mb <= 64;
       if (lb.has_post) {
         const LayerW& P = h->dec[l - 1];
         lb.a16 = a16, lb.wo_c = P.wo_c, lb.bo_c = P.bo_c, lb.ln2_g = P.ln2_g, lb.ln2_b = P.ln2_b;
@@ -434,7 +444,7 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
       AttnDecodeDesc c{};
       c.Mb = Mb, c.d = d, c.n_head = H, c.q = q32, c.k = h->crossK[l] + cross_off, c.v = h->crossV[l] + cross_off;
       c.n_ctx = D.n_audio_ctx, c.n_rows_fixed = D.n_audio_ctx, c.kv_share = o.beams, c.state = state, c.out16 = a16, c.tmaps = h->gemm;
-      c.pdl_late_ok = 1, c.stream_ok = 1;
+      c.pdl_late_ok = 1, c.stream_ok = 1, c.layer = l, c.n_layer = D.n_text_layer, c.use_flags = lb.use_flags;
       WB_TRY(launch_attn_decode(c, st, &h->launches));
     }
   } else
@@ -513,9 +523,9 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
 
 // cur_len = -1, then embed the token at position 0 (which advances cur_len to 0)
 static int reset_decode_state(wb_handle* h, const StepOpts& o) {
-  static const DecodeState k_init_untraced{-1, 0, 0, 0, nullptr};
+  static const DecodeState k_init_untraced{-1, 0, 0, 0, nullptr, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, 0, {0, 0, 0}};
   DecodeState init = k_init_untraced;
-  if (o.sub == 0) init.trace = h->trace;   // only the first sub-batch is traced
+  if (h->trace) init.trace = h->trace + (size_t)o.sub * 16384 * 8;   // a quarter of the trace buffer per sub-batch
   static thread_local DecodeState staged[wb_handle::kMaxSub];
   staged[o.sub] = init;                    // stays valid until the async copy has run
   WB_CUDA_OK(cudaMemcpyAsync(step_state(h, o), &staged[o.sub], sizeof(init), cudaMemcpyHostToDevice, step_stream(h, o)));
@@ -1392,15 +1402,16 @@ int wb_transcribe(wb_handle* h, const float* audio, int32_t B, const wb_decode_o
 int64_t wb_launch_count(const wb_handle* h) { return h ? h->launches : -1; }
 
 /* development: copy out the %globaltimer trace of the last decode (WB_TRACE=1); returns the number of records */
-int wb_debug_trace(wb_handle* h, unsigned long long* out, int max_records) {
-  if (!h || !h->trace || !out) return 0;
+int wb_debug_trace_sub(wb_handle* h, int sub, unsigned long long* out, int max_records) {
+  if (!h || !h->trace || !out || sub < 0 || sub >= wb_handle::kMaxSub) return 0;
   DecodeState st;
-  if (cudaMemcpy(&st, h->state, sizeof(st), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  if (cudaMemcpy(&st, h->state + sub, sizeof(st), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
   int n = st.trace_n < max_records ? st.trace_n : max_records;
-  n = n < 65536 ? n : 65536;
-  if (cudaMemcpy(out, h->trace, (size_t)n * 64, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  n = n < 16384 ? n : 16384;
+  if (cudaMemcpy(out, h->trace + (size_t)sub * 16384 * 8, (size_t)n * 64, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
   return n;
 }
+int wb_debug_trace(wb_handle* h, unsigned long long* out, int max_records) { return wb_debug_trace_sub(h, 0, out, max_records); }
 int wb_last_timings(const wb_handle* h, float out[4]) {
   if (!h || !out) return WB_ERR_ARG;
   for (int i = 0; i < 4; ++i) out[i] = h->timings[i];

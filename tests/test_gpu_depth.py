@@ -203,3 +203,17 @@ def test_language_id_tie_break_is_first_max(wbm, ref):
     assert w.detect_language(2).tolist() == [0, 0]
     assert w.decode(quiet=True) == ["en"]
     w.close()
+
+
+@pytest.mark.parametrize("env", [{"WB_LAYER_BLOCK": "1"}, {"WB_LAYER_BLOCK": "1", "WB_HANDOFF_FLAGS": "0"}, {"WB_SUBBATCHES": "2"}])
+def test_alternate_decode_paths_keep_parity(env):
+    """The decode paths that are not the default (the two-launch-per-layer cluster kernel + persistent attention stream, with
+    and without the per-group hand-off counters; two sub-batches on two streams) stay behind environment switches that are
+    read once per process: the oracle parity tests of the block-kernel widths run again in a child process with them set."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sel = "tests/test_gpu_parity.py::test_base_width_block_kernels tests/test_gpu_parity.py::test_thirty_six_sequences_tiny " \
+          "tests/test_gpu_parity.py::test_greedy_tokens_identical_to_oracle"
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", *sel.split()], cwd=root, env={**os.environ, **env},
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
