@@ -57,6 +57,16 @@ typedef struct wb_decode_opts {
   int32_t timestamp_begin;       /* first timestamp token <|0.00|>: 50363 (.en) / 50364 (multilingual)              */
   int32_t no_timestamps;         /* <|notimestamps|>: 50362 / 50363; never sampled when the rules are on            */
   int32_t max_initial_timestamp_index; /* first timestamp <= this many 0.02 s steps (upstream: 50); < 0 = no limit  */
+  /* upstream DecodingOptions.temperature / best_of (greedy path only). The draw is defined as Gumbel-max with a counter-
+   * based generator (see wb_transcribe_long), so that a CPU restatement sees the same noise: reproducible per seed.      */
+  float temperature;             /* 0 = arg-max; > 0: one draw from softmax(logits / temperature) per step            */
+  int32_t best_of;               /* temperature > 0: independent samples per chunk (<= max_beams, batch * best_of <=
+                                    the handle's sequence capacity); the best sum_logprob / length is returned; 0 = 1  */
+  uint64_t seed;                 /* generator key of this call                                                        */
+  /* upstream DecodingTask no_speech_probs: softmax of the UNFILTERED logits after <|startoftranscript|>.                */
+  int32_t no_speech;             /* <|nospeech|> token: 50361 (.en) / 50362 (multilingual)                            */
+  int32_t sot_index;             /* index of <|startoftranscript|> in initial_tokens (> 0 with a prompt)              */
+  float* no_speech_prob;         /* out [B], or null (then no_speech / sot_index are ignored)                         */
 } wb_decode_opts;
 
 typedef struct wb_handle wb_handle;
@@ -150,6 +160,69 @@ int wb_transcribe(wb_handle* h, const float* audio, int32_t B, const wb_decode_o
 /* Same with the audio already on the device (throughput path; device pointer, results to host). */
 int wb_transcribe_dev(wb_handle* h, const float* audio_dev, int32_t B, const wb_decode_opts* opts, int32_t* tokens_out,
                       int32_t* lens, float* sum_logprob);
+
+/* ---- long-form transcription ---------------------------------------------------------------
+ * The reference transcribes exactly one fixed 30 s window (Whisper/Whisper/ContentView.swift:57-62). For longer recordings
+ * "transcribe" means upstream openai-whisper `transcribe()` (whisper/transcribe.py), restated here: log-mel of the whole
+ * recording followed by 30 s of zeros with one global maximum; a 3000-frame window at `seek`; decode_with_fallback over a
+ * temperature schedule (compression-ratio and average-log-probability thresholds, no-speech override); the no-speech skip;
+ * segments cut at consecutive timestamp tokens; seek advanced to the last timestamp; the previous text as the next prompt
+ * unless the window needed a temperature above 0.5. Not restated: word_timestamps, clip_timestamps,
+ * hallucination_silence_threshold. One recording per call (the loop is sequential and data dependent); recordings shard
+ * across handles / GPUs. A window's prompt + sampled tokens are capped at n_text_ctx (upstream: n_text_ctx + 1).
+ *
+ * Token table for the compression-ratio rule and the empty-text test (the vocabulary is not part of the model): token id
+ * -> bytes, ids beyond the table (special tokens) decode to nothing. */
+typedef struct wb_tokenizer wb_tokenizer;
+wb_tokenizer* wb_tokenizer_create(const uint8_t* blob, const uint32_t* offsets /* [n_tokens + 1] */, int32_t n_tokens);
+/* upstream whisper/assets/{gpt2,multilingual}.tiktoken: lines of "base64(token bytes) rank" */
+wb_tokenizer* wb_tokenizer_load_tiktoken(const char* path);
+void wb_tokenizer_destroy(wb_tokenizer* t);
+int32_t wb_tokenizer_size(const wb_tokenizer* t);
+/* Upstream Tokenizer.decode before the UTF-8 step: concatenated bytes of the ids below drop_from (pass timestamp_begin to drop
+ * timestamps and special tokens). *len = total bytes; at most cap of them are written to out (out may be null). */
+int wb_tokenizer_decode(const wb_tokenizer* t, const int32_t* ids, int32_t n, int32_t drop_from, uint8_t* out, size_t cap, size_t* len);
+/* upstream whisper/utils.py compression_ratio of `raw.decode("utf-8", errors="replace").strip()`:
+ * len(utf8) / len(zlib.compress(utf8)); *stripped_len (optional) = len(utf8). */
+int wb_text_compression_ratio(const uint8_t* raw, size_t n, float* ratio, size_t* stripped_len);
+
+typedef struct wb_long_opts {
+  wb_decode_opts decode;           /* per-window options: initial_tokens = the sot sequence WITHOUT prompt, sot_index into it,
+                                      no_speech, timestamps (upstream default: on), suppress lists, sample_len (0 = n_text_ctx/2),
+                                      beam_size (temperature 0 only, without timestamps), best_of (temperature > 0), seed;
+                                      temperature and no_speech_prob are set by the loop                                     */
+  const float* temperatures;       /* fallback schedule; null = {0, 0.2, 0.4, 0.6, 0.8, 1.0}                                 */
+  int32_t n_temperatures;
+  float compression_ratio_threshold; /* upstream 2.4; NaN = rule off (also off without a tokenizer)                           */
+  float logprob_threshold;         /* upstream -1.0; NaN = off                                                               */
+  float no_speech_threshold;       /* upstream 0.6; NaN = off                                                                */
+  int32_t condition_on_previous_text; /* upstream True                                                                      */
+  const int32_t* initial_prompt;   /* tokenised initial_prompt (upstream: encode(" " + prompt.strip())), or null              */
+  int32_t n_initial_prompt;
+  int32_t sot_prev;                /* <|startofprev|>: 50360 (.en) / 50361 (multilingual)                                    */
+  const wb_tokenizer* tokenizer;   /* may be null                                                                            */
+  int32_t detect_language;         /* 1: arg-max language of the first window replaces initial_tokens[sot_index + 1]         */
+  int32_t lang0;                   /* first language token (50259), used with detect_language                                */
+  int32_t* detected_language;      /* out (optional): language index 0..98, or -1                                            */
+} wb_long_opts;
+
+typedef struct wb_segment {
+  int32_t seek;                    /* mel frame the window started at                                                        */
+  float start, end;                /* seconds                                                                                */
+  int32_t token_begin, n_tokens;   /* range in the returned token stream (timestamp tokens included); n_tokens = 0 for a
+                                      cleared segment (instantaneous or without text)                                        */
+  float temperature, avg_logprob, compression_ratio, no_speech_prob;   /* of the window's accepted decode                   */
+} wb_segment;
+
+/* pcm: n_samples of 16 kHz mono f32 (host). Fails with WB_ERR_ARG (and the needed counts in n_segments / n_tokens) when the
+ * output buffers are too small. */
+int wb_transcribe_long(wb_handle* h, const float* pcm, int64_t n_samples, const wb_long_opts* opts, wb_segment* segments,
+                       int32_t segment_cap, int32_t* n_segments, int32_t* tokens, int32_t token_cap, int32_t* n_tokens);
+/* The loop's front end alone: upstream log_mel_spectrogram(pcm, padding = 30 s of zeros)[:, frame0 : frame0 + 3000], one global
+ * maximum, reflection only at the start of the recording -> out [80][3000] f32 host (frames past the padded end are 0). */
+int wb_logmel_long(wb_handle* h, const float* pcm, int64_t n_samples, int64_t frame0, float* out);
+/* generator key the loop passes to wb_decode for window `seek` and schedule index i (for restatements / tests) */
+uint64_t wb_call_seed(uint64_t seed, int64_t seek, int32_t temperature_index);
 
 /* ---- introspection for tests / benchmarks ----------------------------------------------------------------------------- */
 /* Number of kernels this library launched on the handle since creation (graph replays count their nodes). */

@@ -8,8 +8,8 @@ plus the north-star extension Whisper.transcribe (greedy decode over a persisten
 All compute happens in libwhisper_b200.so (hand-written sm_100a CUDA). There is no CPU fallback: importing works
 anywhere, but every compute call raises if the library is missing or no CUDA device is present.
 """
-from .whisper import (DIMS, LANGUAGES, DecodeOptions, ModelDims, Whisper, WhisperB200Error, generateSpectrogram,
-                      hf_to_upstream_name, library_path, load_library, pad_or_trim, split_windows)
+from .whisper import (DIMS, LANGUAGES, DecodeOptions, ModelDims, Tokenizer, Whisper, WhisperB200Error, bytes_to_unicode,
+                      generateSpectrogram, hf_to_upstream_name, library_path, load_library, pad_or_trim, split_windows)
 
-__all__ = ["DIMS", "LANGUAGES", "DecodeOptions", "ModelDims", "Whisper", "WhisperB200Error", "generateSpectrogram",
+__all__ = ["DIMS", "LANGUAGES", "DecodeOptions", "ModelDims", "Tokenizer", "Whisper", "WhisperB200Error", "bytes_to_unicode", "generateSpectrogram",
            "hf_to_upstream_name", "library_path", "load_library", "pad_or_trim", "split_windows"]

@@ -51,7 +51,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc failed")
     if force or procs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-cudart", "static", "-o", LIB] + objs + ["-lpthread", "-ldl", "-lrt"]
+        cmd = [nvcc, "-shared", "-cudart", "static", "-o", LIB] + objs + ["-lpthread", "-ldl", "-lrt", "-lz"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

@@ -3349,7 +3349,11 @@ __global__ void __launch_bounds__(256) step_finish_kernel(FinishDesc p) {
       }
       float logprob;
       int A;
-      if (!ts_on) {
+      if (p.chosen) {
+        // temperature > 0: sample_rows_kernel drew the token from the filtered logits (mass rule included)
+        A = __ldcg(p.chosen + b);
+        logprob = __ldcg(p.chosen_logprob + b);
+      } else if (!ts_on) {
         A = t[0].arg;
         logprob = -logf(t[0].se);   // the chosen logit is the maximum
       } else {
@@ -3416,6 +3420,162 @@ __global__ void delay_kernel(unsigned long long ns) {
 int launch_delay(unsigned long long ns, cudaStream_t st, int64_t* launches) {
   if (ns > 1000000ull) ns = 1000000ull;
   delay_kernel<<<1, 1, 0, st>>>(ns);
+  if (launches) *launches += 1;
+  WB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---- temperature sampling (upstream GreedyDecoder.update with temperature > 0) ---------------------------------------------------------
+// Upstream draws `Categorical(logits = logits / temperature).sample()` from torch's global generator, which no other
+// implementation can reproduce; this library defines the draw as the Gumbel-max form of the same distribution with a
+// counter-based generator, so that a CPU restatement sees the same noise:
+//   token = argmax_v ( logit_v / T + g_v ),  g_v = -log(-log(u_v)),  u_v = (top 23 bits of r_v + 0.5) / 2^23,
+//   r_v = splitmix64(key + v),  key = splitmix64(seed ^ splitmix64((sample << 32) | position))
+// sample = index of the sequence within the call, position = index of the token being drawn. The log-probability that goes
+// into sum_logprobs is log_softmax(logits)[token] at temperature 1, as upstream.
+__host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+struct SampleBest {
+  float pv;    // perturbed value logit / T + g
+  float lg;    // the logit itself
+  int idx;
+};
+__device__ __forceinline__ void sample_take(SampleBest& a, float pv, float lg, int idx) {
+  if (pv > a.pv || (pv == a.pv && idx < a.idx)) a.pv = pv, a.lg = lg, a.idx = idx;
+}
+// One CTA per sequence over the stored, filtered logits row. Text rows [0, ts_begin) and timestamp rows [ts_begin, V) keep
+// separate (max, sum-exp, best perturbed) records so that the last timestamp rule (probability mass over the timestamps above
+// every text token -> text suppressed; upstream ApplyTimestampRules) is applied here; ts_begin >= V turns it off.
+__global__ void __launch_bounds__(256) sample_rows_kernel(const float* __restrict__ logits, int V, int ts_begin, float inv_temperature,
+                                                          unsigned long long seed, const DecodeState* state, int32_t* __restrict__ chosen,
+                                                          float* __restrict__ chosen_logprob) {
+  __shared__ float s_m[2][8], s_s[2][8], s_pv[2][8], s_lg[2][8];
+  __shared__ int s_ix[2][8];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* row = logits + (size_t)b * V;
+  const int position = ld_state(&state->cur_len) + 1;
+  const unsigned long long key = splitmix64(seed ^ splitmix64(((unsigned long long)b << 32) | (unsigned int)position));
+  float m[2] = {-INFINITY, -INFINITY}, ss[2] = {0.f, 0.f};
+  SampleBest best[2] = {{-INFINITY, -INFINITY, 0x7fffffff}, {-INFINITY, -INFINITY, 0x7fffffff}};
+  for (int i = tid; i < V; i += 256) {
+    const float x = row[i];
+    if (x == -INFINITY) continue;
+    const int c = i >= ts_begin ? 1 : 0;
+    if (x > m[c]) {
+      ss[c] = ss[c] * expf(m[c] - x) + 1.0f;
+      m[c] = x;
+    } else {
+      ss[c] += expf(x - m[c]);
+    }
+    const unsigned long long r = splitmix64(key + (unsigned long long)i);
+    const float u = ((float)(unsigned int)(r >> 41) + 0.5f) * (1.0f / 8388608.0f);   // 23 bits: strictly inside (0, 1) in fp32
+    const float g = -logf(-logf(u));
+    sample_take(best[c], x * inv_temperature + g, x, i);
+  }
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, m[c], o), os = __shfl_xor_sync(0xffffffffu, ss[c], o);
+      const float nm = fmaxf(m[c], om);
+      ss[c] = (m[c] > -INFINITY ? ss[c] * expf(m[c] - nm) : 0.f) + (om > -INFINITY ? os * expf(om - nm) : 0.f);
+      m[c] = nm;
+      const float opv = __shfl_xor_sync(0xffffffffu, best[c].pv, o), olg = __shfl_xor_sync(0xffffffffu, best[c].lg, o);
+      const int oix = __shfl_xor_sync(0xffffffffu, best[c].idx, o);
+      sample_take(best[c], opv, olg, oix);
+    }
+    if (lane == 0) s_m[c][warp] = m[c], s_s[c][warp] = ss[c], s_pv[c][warp] = best[c].pv, s_lg[c][warp] = best[c].lg, s_ix[c][warp] = best[c].idx;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float M[2], S[2];
+    SampleBest B2[2];
+    for (int c = 0; c < 2; ++c) {
+      M[c] = -INFINITY, S[c] = 0.f;
+      B2[c] = SampleBest{-INFINITY, -INFINITY, 0x7fffffff};
+      for (int w = 0; w < 8; ++w) M[c] = fmaxf(M[c], s_m[c][w]);
+      for (int w = 0; w < 8; ++w) {
+        S[c] += s_m[c][w] > -INFINITY ? s_s[c][w] * expf(s_m[c][w] - M[c]) : 0.f;
+        sample_take(B2[c], s_pv[c][w], s_lg[c][w], s_ix[c][w]);
+      }
+    }
+    const float lse_ts = M[1] > -INFINITY ? M[1] + logf(S[1]) : -INFINITY;
+    int tok;
+    float lp;
+    if (lse_ts > M[0]) {                      // timestamps only
+      tok = B2[1].idx, lp = B2[1].lg - lse_ts;
+    } else {
+      const float Mx = fmaxf(M[0], M[1]);
+      const float Sx = (M[0] > -INFINITY ? S[0] * expf(M[0] - Mx) : 0.f) + (M[1] > -INFINITY ? S[1] * expf(M[1] - Mx) : 0.f);
+      SampleBest all = B2[0];
+      sample_take(all, B2[1].pv, B2[1].lg, B2[1].idx);
+      tok = all.idx, lp = all.lg - (Mx + logf(Sx));
+    }
+    chosen[b] = tok, chosen_logprob[b] = lp;
+  }
+}
+int launch_sample_rows(const float* logits, int Mb, int V, int ts_begin, float temperature, unsigned long long seed, const DecodeState* state,
+                       int32_t* chosen, float* chosen_logprob, cudaStream_t st, int64_t* launches) {
+  if (!(temperature > 0.f)) {
+    set_error("sample_rows: temperature must be positive");
+    return -1;
+  }
+  sample_rows_kernel<<<Mb, 256, 0, st>>>(logits, V, ts_begin, 1.0f / temperature, seed, state, chosen, chosen_logprob);
+  if (launches) *launches += 1;
+  WB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// softmax(logits row)[token] per sequence (upstream no_speech_probs: the unfiltered logits at the <|startoftranscript|> position)
+__global__ void __launch_bounds__(256) row_token_prob_kernel(const float* __restrict__ logits, int V, int token, float* __restrict__ prob) {
+  __shared__ float s_m[8], s_s[8];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* row = logits + (size_t)b * V;
+  float m = -INFINITY, ss = 0.f;
+  for (int i = tid; i < V; i += 256) {
+    const float x = row[i];
+    if (x > m) {
+      ss = ss * expf(m - x) + 1.0f;
+      m = x;
+    } else if (x > -INFINITY) {
+      ss += expf(x - m);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, ss, o);
+    const float nm = fmaxf(m, om);
+    ss = (m > -INFINITY ? ss * expf(m - nm) : 0.f) + (om > -INFINITY ? os * expf(om - nm) : 0.f);
+    m = nm;
+  }
+  if (lane == 0) s_m[warp] = m, s_s[warp] = ss;
+  __syncthreads();
+  if (tid == 0) {
+    float M = -INFINITY, S = 0.f;
+    for (int w = 0; w < 8; ++w) M = fmaxf(M, s_m[w]);
+    for (int w = 0; w < 8; ++w) S += s_m[w] > -INFINITY ? s_s[w] * expf(s_m[w] - M) : 0.f;
+    prob[b] = expf(row[token] - M) / S;
+  }
+}
+int launch_row_token_prob(const float* logits, int Mb, int V, int token, float* prob, cudaStream_t st, int64_t* launches) {
+  if (token < 0 || token >= V) {
+    set_error("row_token_prob: token %d outside the vocabulary", token);
+    return -1;
+  }
+  row_token_prob_kernel<<<Mb, 256, 0, st>>>(logits, V, token, prob);
+  if (launches) *launches += 1;
+  WB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// state->cur_len = v (the no-speech probe re-runs the step of one prompt position: see decode_prompt in model.cu)
+__global__ void set_cur_len_kernel(DecodeState* state, int v) { state->cur_len = v; }
+int launch_set_cur_len(DecodeState* state, int v, cudaStream_t st, int64_t* launches) {
+  set_cur_len_kernel<<<1, 1, 0, st>>>(state, v);
   if (launches) *launches += 1;
   WB_CUDA_OK(cudaGetLastError());
   return 0;

@@ -43,7 +43,7 @@ struct OrderedMax<double> {
 template <typename T, int F, int NT>
 __global__ void __launch_bounds__(NT) logmel_kernel(const T* __restrict__ audio, size_t chunk_stride, int chunk_off,
                                                     const LogmelTables<T>* __restrict__ gtab, T* __restrict__ logspec,
-                                                    typename OrderedMax<T>::U* __restrict__ gmax) {
+                                                    typename OrderedMax<T>::U* __restrict__ gmax, long long stream_samples) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LogmelSmem<T, F>& sm = *reinterpret_cast<LogmelSmem<T, F>*>(smem_raw);
   const int tid = threadIdx.x;
@@ -58,7 +58,19 @@ __global__ void __launch_bounds__(NT) logmel_kernel(const T* __restrict__ audio,
   }
   // samples of this tile, reflection folded into the index map (lib.rs:34-40); padded coordinate p0 + s
   const int p0 = tile * F * WB_HOP;
-  for (int s = tid; s < tile_samples<F>(); s += NT) sm.region0[samp_index(s)] = clip[reflect_index(p0 + s)];
+  if (stream_samples < 0) {
+    for (int s = tid; s < tile_samples<F>(); s += NT) sm.region0[samp_index(s)] = clip[reflect_index(p0 + s)];
+  } else {
+    // stream mode (upstream whisper/audio.py log_mel_spectrogram on a whole recording followed by 30 s of zeros): item b holds
+    // frames [3000 b, 3000 b + 3000) of ONE signal of stream_samples samples; the reflection exists only at the start of the
+    // signal, everything past its end reads as zero (the appended zeros, and their reflection)
+    const long long i0 = (long long)b * WB_N_SAMPLES + p0 - 200;
+    for (int s = tid; s < tile_samples<F>(); s += NT) {
+      long long i = i0 + s;
+      if (i < 0) i = -i;
+      sm.region0[samp_index(s)] = i < stream_samples ? audio[i] : (T)0;
+    }
+  }
   __syncthreads();
 
   logmel_phase_a<T, F>(sm, tid);
@@ -86,7 +98,7 @@ __global__ void __launch_bounds__(NT) logmel_kernel(const T* __restrict__ audio,
   if (tid == 0) {
     T m = sm.red[0];
     for (int w = 1; w < NT / 32; ++w) m = sm.red[w] > m ? sm.red[w] : m;
-    atomicMax(&gmax[b], OrderedMax<T>::enc(m));
+    atomicMax(&gmax[stream_samples < 0 ? b : 0], OrderedMax<T>::enc(m));   // stream mode: one maximum for the whole signal
   }
 }
 
@@ -187,7 +199,7 @@ int launch_logmel(const T* audio, size_t chunk_stride, int chunk_off, int B, con
   auto kern = logmel_kernel<T, Cfg::F, Cfg::NT>;
   WB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fill_kernel<U><<<(B + 127) / 128, 128, 0, st>>>((U*)gmax, (U)0, B);
-  kern<<<dim3(WB_N_FRAMES / Cfg::F, B), Cfg::NT, smem, st>>>(audio, chunk_stride, chunk_off, dtab, logspec, (U*)gmax);
+  kern<<<dim3(WB_N_FRAMES / Cfg::F, B), Cfg::NT, smem, st>>>(audio, chunk_stride, chunk_off, dtab, logspec, (U*)gmax, -1ll);
   logmel_normalize_kernel<T><<<dim3(WB_N_FRAMES / kNormFrames, B), 256, 0, st>>>(logspec, (const U*)gmax, out, melT);
   if (launches) *launches += 3;
   WB_CUDA_OK(cudaGetLastError());
@@ -197,6 +209,58 @@ template int launch_logmel<float>(const float*, size_t, int, int, const LogmelTa
                                   __half*, cudaStream_t, int64_t*);
 template int launch_logmel<double>(const double*, size_t, int, int, const LogmelTables<double>*, double*, void*,
                                    double*, __half*, cudaStream_t, int64_t*);
+
+// ---- stream mode: the log-mel of a whole recording, then 3000-frame segments at arbitrary frame offsets ------------------------------
+// logspec [W][80][3000] unnormalised, one maximum for the whole signal (upstream normalises with the global maximum).
+int launch_logmel_stream(const float* audio, long long n_samples, int W, const LogmelTables<float>* dtab, float* logspec, void* gmax,
+                         cudaStream_t st, int64_t* launches) {
+  using Cfg = LogmelCfg<float>;
+  using U = OrderedMax<float>::U;
+  const size_t smem = sizeof(LogmelSmem<float, Cfg::F>);
+  auto kern = logmel_kernel<float, Cfg::F, Cfg::NT>;
+  WB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fill_kernel<U><<<1, 32, 0, st>>>((U*)gmax, (U)0, 1);
+  kern<<<dim3(WB_N_FRAMES / Cfg::F, W), Cfg::NT, smem, st>>>(audio, 0, 0, dtab, logspec, (U*)gmax, n_samples);
+  if (launches) *launches += 2;
+  WB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+// frames [frame0, frame0 + 3000) of the stream -> one normalised segment: out [80][3000] f32 (optional) and melT f16 [3002][80]
+// (optional); frames past the W windows are zero (upstream pad_or_trim of the mel segment)
+__global__ void __launch_bounds__(256) logmel_segment_kernel(const float* __restrict__ logspec, const unsigned int* __restrict__ gmax, int W,
+                                                             long long frame0, float* __restrict__ out, __half* __restrict__ melT) {
+  __shared__ __half tile[kNormFrames][WB_N_MELS + 2];
+  const int f0 = blockIdx.x * kNormFrames;
+  const float floor_v = OrderedMax<float>::dec(gmax[0]) - 8.0f;
+  for (int idx = threadIdx.x; idx < WB_N_MELS * kNormFrames; idx += 256) {
+    const int i = idx / kNormFrames, f = idx - i * kNormFrames;
+    const long long gf = frame0 + f0 + f;
+    const long long w = gf / WB_N_FRAMES;
+    float v = 0.f;
+    if (w < W) {
+      v = logspec[((size_t)w * WB_N_MELS + i) * WB_N_FRAMES + (int)(gf - w * WB_N_FRAMES)];
+      v = v > floor_v ? v : floor_v;
+      v = (v + 4.0f) / 4.0f;
+    }
+    if (out) out[(size_t)i * WB_N_FRAMES + f0 + f] = v;
+    if (melT) tile[f][i] = __float2half_rn(v);
+  }
+  if (melT) {
+    __syncthreads();
+    __half* dst = melT + ((size_t)1 + f0) * WB_N_MELS;
+    for (int idx = threadIdx.x; idx < WB_N_MELS * kNormFrames; idx += 256) {
+      const int f = idx / WB_N_MELS, i = idx - f * WB_N_MELS;
+      dst[idx] = tile[f][i];
+    }
+  }
+}
+int launch_logmel_segment(const float* logspec, const void* gmax, int W, long long frame0, float* out, __half* melT, cudaStream_t st,
+                          int64_t* launches) {
+  logmel_segment_kernel<<<WB_N_FRAMES / kNormFrames, 256, 0, st>>>(logspec, (const unsigned int*)gmax, W, frame0, out, melT);
+  if (launches) *launches += 1;
+  WB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 int launch_mel_transpose(const float* mel, int B, __half* melT, cudaStream_t st, int64_t* launches) {
   mel_transpose_kernel<<<dim3(WB_N_FRAMES / kNormFrames, B), 256, 0, st>>>(mel, melT);

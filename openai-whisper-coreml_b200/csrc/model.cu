@@ -15,6 +15,8 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <stdio.h>
+#include <zlib.h>
 
 #include <algorithm>
 #include <memory>
@@ -129,6 +131,11 @@ struct wb_handle {
   int tokens_ld;
   float *xdec, *q32, *logits, *sum_logprob, *part_logits, *part_extra;
   int4* ts_state;   // timestamp-rule state per sequence (FinishDesc)
+  int32_t* chosen;  // temperature sampling: drawn tokens / their log-probabilities / no-speech probabilities [Mb]
+  float *chosen_lp, *no_speech_prob;
+  // long-form (wb_transcribe_long): the whole recording and its unnormalised log-mel, allocated on demand
+  float *long_audio, *long_logspec;
+  size_t long_audio_cap, long_windows_cap;
   __half *dmlp16, *a16;
   int32_t* done;
   unsigned char* mask;
@@ -291,6 +298,9 @@ static void layout_workspace(wb_handle* h) {
   h->part_logits = A.take<float>(Mb * (size_t)h->n_logit_ctas * 4);
   h->part_extra = A.take<float>(Mb * (size_t)4);
   h->ts_state = A.take<int4>(Mb);
+  h->chosen = A.take<int32_t>(Mb);
+  h->chosen_lp = A.take<float>(Mb);
+  h->no_speech_prob = A.take<float>(Mb);
   h->state = A.take<DecodeState>(wb_handle::kMaxSub);
   h->trace = getenv("WB_TRACE") ? A.take<unsigned long long>(65536 * 8) : nullptr;
 }
@@ -376,6 +386,7 @@ struct StepOpts {
   int sub;            // sub-batch index: selects the stream and the DecodeState
   int timestamps;     // upstream ApplyTimestampRules among the logit filters (sampling steps only)
   int ts_begin, ts_last_allowed;
+  int use_chosen;     // the finish kernel takes the tokens sample_rows_kernel drew (temperature > 0)
 };
 
 static bool use_handoff_flags() {
@@ -404,6 +415,7 @@ static int step_finish(wb_handle* h, const StepOpts& o, int sample) {
     f.ts_state = h->ts_state + b0, f.part_extra = h->part_extra + b0 * 4;
     f.ts_begin = o.ts_begin, f.ts_group0 = (o.ts_begin + 127) / 128, f.n_initial = o.n_initial;
   }
+  if (sample && o.use_chosen) f.chosen = h->chosen + b0, f.chosen_logprob = h->chosen_lp + b0;
   return launch_step_finish(f, step_stream(h, o), &h->launches);
 }
 
@@ -598,6 +610,8 @@ static void free_handle(wb_handle* h) {
   if (h->h_done) cudaFreeHost(h->h_done);
   if (h->arena.base) cudaFree(h->arena.base);
   if (h->ws.base) cudaFree(h->ws.base);
+  if (h->long_audio) cudaFree(h->long_audio);
+  if (h->long_logspec) cudaFree(h->long_logspec);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1038,6 +1052,15 @@ static int validate_decode_opts(const wb_handle* h, int32_t B, const wb_decode_o
     set_error("wb_decode: beam_size %d out of range [0, 7]", opts->beam_size);
     return WB_ERR_ARG;
   }
+  if (!(opts->temperature >= 0.f) || opts->best_of < 0 || (opts->temperature > 0.f && opts->beam_size > 1)) {
+    set_error("wb_decode: temperature must be >= 0 (and 0 with beam search), best_of >= 0");
+    return WB_ERR_ARG;
+  }
+  if (opts->no_speech_prob &&
+      (opts->sot_index < 0 || opts->sot_index >= n_init || opts->no_speech < 0 || opts->no_speech >= D.n_vocab || opts->beam_size > 1)) {
+    set_error("wb_decode: no_speech_prob needs 0 <= sot_index < n_initial, a valid no_speech token and greedy / sampled decoding");
+    return WB_ERR_ARG;
+  }
   if (opts->timestamps) {
     if (opts->beam_size > 1) {
       set_error("wb_decode: the timestamp rules are implemented for greedy decoding only");
@@ -1048,6 +1071,24 @@ static int validate_decode_opts(const wb_handle* h, int32_t B, const wb_decode_o
       set_error("wb_decode: timestamp rules need eot < timestamp_begin < n_vocab, a valid no_timestamps token and <= 48 sequences");
       return WB_ERR_ARG;
     }
+  }
+  return 0;
+}
+
+// Upstream DecodingTask._main_loop `no_speech_probs`: softmax of the unfiltered logits at the <|startoftranscript|> position.
+// The prompt step that consumes that token runs with the logits GEMM; if it is also the first sampling step (the whole
+// prompt is [sot]), its state is rewound afterwards (the step updates the residual stream in place) and the token embedded
+// again, so that the sampling step runs from the same state with the logit filters.
+static int no_speech_probe_step(wb_handle* h, const StepOpts& plain, int no_speech, int pos, bool advance) {
+  const int V = h->dims.n_vocab;
+  StepOpts o = plain;
+  o.store_logits = 1, o.sample = 0, o.no_finish = advance ? 0 : 1;
+  WB_TRY(decode_step(h, o));
+  WB_TRY(launch_row_token_prob(h->logits + (size_t)plain.b0 * V, plain.Mb, V, no_speech, h->no_speech_prob + plain.b0, step_stream(h, plain),
+                               &h->launches));
+  if (!advance) {
+    WB_TRY(launch_set_cur_len(step_state(h, plain), pos - 1, step_stream(h, plain), &h->launches));
+    WB_TRY(step_finish(h, plain, 0));
   }
   return 0;
 }
@@ -1132,9 +1173,12 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
   WB_CUDA_OK(cudaEventRecord(h->fork_ev, st));
   for (int i = 1; i < nsb; ++i) WB_CUDA_OK(cudaStreamWaitEvent(h->sub_stream[i], h->fork_ev, 0));
   for (int i = 0; i < nsb; ++i) WB_TRY(reset_decode_state(h, plain[i]));
+  const bool probe = opts->no_speech_prob != nullptr;
   for (int k = 0; k + 1 < n_init; ++k) {
     for (int i = 0; i < nsb; ++i) {
-      if (use_graph) {
+      if (probe && k == opts->sot_index) {
+        WB_TRY(no_speech_probe_step(h, plain[i], opts->no_speech, k, true));
+      } else if (use_graph) {
         WB_CUDA_OK(cudaGraphLaunch(h->g_step[i], step_stream(h, plain[i])));
         h->launches += h->nodes_step;
       } else {
@@ -1142,6 +1186,8 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
       }
     }
   }
+  if (probe && opts->sot_index == n_init - 1)
+    for (int i = 0; i < nsb; ++i) WB_TRY(no_speech_probe_step(h, plain[i], opts->no_speech, n_init - 1, false));
   int steps = 0;
   // sub-batch i starts i * stagger microseconds late (again after every EOT poll, which re-aligns the streams)
   int stagger_us = 0;
@@ -1183,6 +1229,7 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
   WB_CUDA_OK(cudaMemcpyAsync(rows.data(), h->tokens, rows.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   std::vector<float> slp(B);
   WB_CUDA_OK(cudaMemcpyAsync(slp.data(), h->sum_logprob, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
+  if (probe) WB_CUDA_OK(cudaMemcpyAsync(opts->no_speech_prob, h->no_speech_prob, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
   WB_CUDA_OK(cudaStreamSynchronize(st));
   for (int b = 0; b < B; ++b) {
     const int32_t* r = &rows[(size_t)b * h->tokens_ld];
@@ -1195,6 +1242,102 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
     for (int i = 0; i < total; ++i) tokens_out[(size_t)b * total + i] = i < len ? r[i] : opts->eot;
     if (lens) lens[b] = len;
     if (sum_logprob) sum_logprob[b] = slp[b];
+  }
+  return WB_OK;
+}
+
+// Temperature > 0 (upstream GreedyDecoder with Categorical sampling, DecodingOptions.best_of, MaximumLikelihoodRanker): the step
+// stores the filtered logits, sample_rows_kernel draws per sequence, the finish kernel takes the drawn token. best_of samples
+// of a chunk are rows of the same batch that share the chunk's cross K/V. Runs eagerly: it is the fallback path of
+// wb_transcribe_long, taken only for windows whose arg-max decode failed the quality thresholds.
+static int decode_sampled(wb_handle* h, int32_t B, const wb_decode_opts* opts, int32_t* tokens_out, int32_t* lens, float* sum_logprob) {
+  const wb_dims& D = h->dims;
+  const int G = opts->best_of > 1 ? opts->best_of : 1, Mb = B * G, V = D.n_vocab;
+  const int n_init = opts->n_initial, total = n_init + opts->sample_len, eot = opts->eot;
+  const bool ts_on = opts->timestamps != 0;
+  if (G > h->max_beams || Mb > h->Mb_max || (ts_on && Mb > 48)) {
+    set_error("wb_decode: best_of %d exceeds the handle's max_beams %d, or batch * best_of %d exceeds %d (48 with timestamp rules)", G,
+              h->max_beams, Mb, h->Mb_max);
+    return WB_ERR_ARG;
+  }
+  cudaStream_t st = h->stream;
+  std::vector<int32_t> rows((size_t)Mb * h->tokens_ld, eot);
+  for (int b = 0; b < Mb; ++b)
+    for (int i = 0; i < n_init; ++i) rows[(size_t)b * h->tokens_ld + i] = opts->initial_tokens[i];
+  std::vector<unsigned char> mask(V, 0);
+  if (ts_on) mask[opts->no_timestamps] = 1;
+  for (int i = 0; i < opts->n_suppress_begin; ++i)
+    if (opts->suppress_begin[i] >= 0 && opts->suppress_begin[i] < V) mask[opts->suppress_begin[i]] = 2;
+  for (int i = 0; i < opts->n_suppress; ++i)
+    if (opts->suppress[i] >= 0 && opts->suppress[i] < V) mask[opts->suppress[i]] = 1;
+  WB_CUDA_OK(cudaMemcpyAsync(h->tokens, rows.data(), rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  WB_CUDA_OK(cudaMemcpyAsync(h->mask, mask.data(), mask.size(), cudaMemcpyHostToDevice, st));
+  WB_CUDA_OK(cudaMemsetAsync(h->sum_logprob, 0, sizeof(float) * Mb, st));
+  WB_CUDA_OK(cudaMemsetAsync(h->done, 0, sizeof(int32_t) * Mb, st));
+  WB_CUDA_OK(cudaMemsetAsync(h->ts_state, 0, sizeof(int4) * Mb, st));
+  WB_CUDA_OK(cudaStreamSynchronize(st));   // `rows` / `mask` are pageable host memory
+
+  StepOpts plain{};
+  plain.Mb = Mb, plain.beams = G, plain.n_initial = n_init, plain.eot = eot;
+  plain.timestamps = ts_on ? 1 : 0, plain.ts_begin = opts->timestamp_begin;
+  plain.ts_last_allowed = opts->max_initial_timestamp_index >= 0 ? opts->timestamp_begin + opts->max_initial_timestamp_index : 0x7fffffff;
+  StepOpts scored = plain, fin = plain;
+  scored.sample = 1, scored.store_logits = 1, scored.no_finish = 1;
+  fin.sample = 1, fin.use_chosen = 1;
+  WB_CUDA_OK(cudaEventRecord(h->ev[2], st));
+  WB_TRY(reset_decode_state(h, plain));
+  const bool probe = opts->no_speech_prob != nullptr;
+  for (int k = 0; k + 1 < n_init; ++k) {
+    if (probe && k == opts->sot_index)
+      WB_TRY(no_speech_probe_step(h, plain, opts->no_speech, k, true));
+    else
+      WB_TRY(decode_step(h, plain));
+  }
+  if (probe && opts->sot_index == n_init - 1) WB_TRY(no_speech_probe_step(h, plain, opts->no_speech, n_init - 1, false));
+  const int interval = opts->eot_check_interval > 0 ? opts->eot_check_interval : 8;
+  int steps = 0;
+  for (int s = 0; s < opts->sample_len; ++s) {
+    WB_TRY(decode_step(h, scored));
+    WB_TRY(launch_sample_rows(h->logits, Mb, V, ts_on ? opts->timestamp_begin : 0x7fffffff, opts->temperature, opts->seed, h->state, h->chosen,
+                              h->chosen_lp, st, &h->launches));
+    WB_TRY(step_finish(h, fin, 1));
+    ++steps;
+    if ((s + 1) % interval == 0 && s + 1 < opts->sample_len) {
+      WB_CUDA_OK(cudaMemcpyAsync(h->h_done, h->done, sizeof(int32_t) * Mb, cudaMemcpyDeviceToHost, st));
+      WB_CUDA_OK(cudaStreamSynchronize(st));
+      bool all = true;
+      for (int b = 0; b < Mb; ++b) all = all && h->h_done[b];
+      if (all) break;
+    }
+  }
+  WB_CUDA_OK(cudaEventRecord(h->ev[3], st));
+  h->timings[3] = (float)(steps + n_init - 1);
+  WB_CUDA_OK(cudaMemcpyAsync(rows.data(), h->tokens, rows.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  std::vector<float> slp(Mb), nsp(Mb, 0.f);
+  WB_CUDA_OK(cudaMemcpyAsync(slp.data(), h->sum_logprob, sizeof(float) * Mb, cudaMemcpyDeviceToHost, st));
+  if (probe) WB_CUDA_OK(cudaMemcpyAsync(nsp.data(), h->no_speech_prob, sizeof(float) * Mb, cudaMemcpyDeviceToHost, st));
+  WB_CUDA_OK(cudaStreamSynchronize(st));
+  for (int a = 0; a < B; ++a) {
+    // MaximumLikelihoodRanker without length penalty: sum_logprob / number of sampled tokens before the first eot
+    int best = -1, best_len = 0;
+    double best_score = 0.0;
+    for (int j = 0; j < G; ++j) {
+      const int32_t* r = &rows[(size_t)(a * G + j) * h->tokens_ld];
+      int len = total;
+      for (int i = n_init; i < total; ++i)
+        if (r[i] == eot) {
+          len = i + 1;
+          break;
+        }
+      const int n_text = (len < total || r[total - 1] == eot ? len - 1 : len) - n_init;   // tokens before the first eot
+      const double score = (double)slp[a * G + j] / (double)(n_text > 0 ? n_text : 1);
+      if (best < 0 || score > best_score) best = j, best_score = score, best_len = len;
+    }
+    const int32_t* r = &rows[(size_t)(a * G + best) * h->tokens_ld];
+    for (int i = 0; i < total; ++i) tokens_out[(size_t)a * total + i] = i < best_len ? r[i] : eot;
+    if (lens) lens[a] = best_len;
+    if (sum_logprob) sum_logprob[a] = slp[a * G + best];
+    if (probe) opts->no_speech_prob[a] = nsp[a * G + best];
   }
   return WB_OK;
 }
@@ -1377,6 +1520,7 @@ int wb_decode(wb_handle* h, int32_t B, const wb_decode_opts* opts, int32_t* toke
   }
   WB_TRY(validate_decode_opts(h, B, opts));
   if (opts->beam_size > 1) return decode_beam(h, B, opts, tokens_out, lens, sum_logprob);
+  if (opts->temperature > 0.f) return decode_sampled(h, B, opts, tokens_out, lens, sum_logprob);
   return decode_greedy(h, B, opts, tokens_out, lens, sum_logprob);
 }
 
@@ -1576,5 +1720,7 @@ void generate_spectrogram(double* audio, double* output) {
     abort();   // the reference panics across the FFI boundary (lib.rs .unwrap()); there is no status to return
   }
 }
+
+#include "longform.inc"
 
 }  // extern "C"

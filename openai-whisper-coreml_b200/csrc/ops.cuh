@@ -16,6 +16,12 @@ template <typename T>
 int launch_logmel(const T* audio, size_t chunk_stride, int chunk_off, int B, const LogmelTables<T>* dtab, T* logspec,
                   void* gmax, T* out, __half* melT, cudaStream_t st, int64_t* launches);
 int launch_mel_transpose(const float* mel, int B, __half* melT, cudaStream_t st, int64_t* launches);
+// stream mode (a whole recording followed by zeros, one global maximum): logspec [W][80][3000]; then one normalised 3000-frame
+// segment starting at any frame of the stream
+int launch_logmel_stream(const float* audio, long long n_samples, int W, const LogmelTables<float>* dtab, float* logspec, void* gmax,
+                         cudaStream_t st, int64_t* launches);
+int launch_logmel_segment(const float* logspec, const void* gmax, int W, long long frame0, float* out, __half* melT, cudaStream_t st,
+                          int64_t* launches);
 size_t logmel_tables_bytes_f32();
 size_t logmel_tables_bytes_f64();
 
@@ -239,9 +245,18 @@ struct FinishDesc {
   int4* ts_state;
   const float* part_extra;
   int ts_begin, ts_group0, n_initial;
+  // temperature > 0: the tokens drawn by sample_rows_kernel and their log-probabilities [Mb] (null: argmax of the partials)
+  const int32_t* chosen;
+  const float* chosen_logprob;
   DecodeState* state;
 };
 int launch_step_finish(const FinishDesc& d, cudaStream_t st, int64_t* launches);
+// Gumbel-max draw from softmax(logits / temperature) per sequence over the stored filtered logits [Mb][V] (timestamp mass rule
+// applied when ts_begin < V), with log_softmax(logits)[token]; and softmax(logits)[token] for one fixed token
+int launch_sample_rows(const float* logits, int Mb, int V, int ts_begin, float temperature, unsigned long long seed, const DecodeState* state,
+                       int32_t* chosen, float* chosen_logprob, cudaStream_t st, int64_t* launches);
+int launch_set_cur_len(DecodeState* state, int v, cudaStream_t st, int64_t* launches);
+int launch_row_token_prob(const float* logits, int Mb, int V, int token, float* prob, cudaStream_t st, int64_t* launches);
 // L2 residency hints of the decode kernels on the current device: 1 = weights evict_last, cross K/V stream evict_first
 int decoder_set_l2_mode(int mode);
 int launch_delay(unsigned long long ns, cudaStream_t st, int64_t* launches);

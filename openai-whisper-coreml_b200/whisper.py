@@ -44,7 +44,24 @@ class _DecodeOpts(ctypes.Structure):
                 ("suppress_begin", ctypes.POINTER(ctypes.c_int32)), ("n_suppress_begin", ctypes.c_int32),
                 ("beam_size", ctypes.c_int32), ("eot_check_interval", ctypes.c_int32),
                 ("timestamps", ctypes.c_int32), ("timestamp_begin", ctypes.c_int32), ("no_timestamps", ctypes.c_int32),
-                ("max_initial_timestamp_index", ctypes.c_int32)]
+                ("max_initial_timestamp_index", ctypes.c_int32),
+                ("temperature", ctypes.c_float), ("best_of", ctypes.c_int32), ("seed", ctypes.c_uint64),
+                ("no_speech", ctypes.c_int32), ("sot_index", ctypes.c_int32), ("no_speech_prob", ctypes.POINTER(ctypes.c_float))]
+
+
+class _LongOpts(ctypes.Structure):
+    _fields_ = [("decode", _DecodeOpts), ("temperatures", ctypes.POINTER(ctypes.c_float)), ("n_temperatures", ctypes.c_int32),
+                ("compression_ratio_threshold", ctypes.c_float), ("logprob_threshold", ctypes.c_float),
+                ("no_speech_threshold", ctypes.c_float), ("condition_on_previous_text", ctypes.c_int32),
+                ("initial_prompt", ctypes.POINTER(ctypes.c_int32)), ("n_initial_prompt", ctypes.c_int32),
+                ("sot_prev", ctypes.c_int32), ("tokenizer", ctypes.c_void_p), ("detect_language", ctypes.c_int32),
+                ("lang0", ctypes.c_int32), ("detected_language", ctypes.POINTER(ctypes.c_int32))]
+
+
+class _Segment(ctypes.Structure):
+    _fields_ = [("seek", ctypes.c_int32), ("start", ctypes.c_float), ("end", ctypes.c_float), ("token_begin", ctypes.c_int32),
+                ("n_tokens", ctypes.c_int32), ("temperature", ctypes.c_float), ("avg_logprob", ctypes.c_float),
+                ("compression_ratio", ctypes.c_float), ("no_speech_prob", ctypes.c_float)]
 
 
 @dataclass(frozen=True)
@@ -92,6 +109,12 @@ class DecodeOptions:
     timestamp_begin: int = 0                 # <|0.00|>
     no_timestamps: int = 0                   # <|notimestamps|>
     max_initial_timestamp_index: int = 50    # upstream max_initial_timestamp = 1.0 s; < 0: no limit
+    temperature: float = 0.0                 # > 0: Gumbel-max draw from softmax(logits / temperature) (whisper_b200.h)
+    best_of: int = 0                         # temperature > 0: samples per chunk, best sum_logprob / length wins
+    seed: int = 0
+    no_speech: int = -1                      # <|nospeech|>; with want_no_speech_prob the decode also returns its probability
+    sot_index: int = 0                       # index of <|startoftranscript|> in initial_tokens
+    sot_prev: int = 0                        # <|startofprev|> (long-form prompts)
 
     @staticmethod
     def default_for(dims: ModelDims, sample_len: int = 224, language: int = 0, without_timestamps: bool = True) -> "DecodeOptions":
@@ -107,7 +130,7 @@ class DecodeOptions:
             init.append(no_ts)
         suppress = sorted({sot, sot_prev, sot_lm, translate, transcribe, no_speech})
         return DecodeOptions(init, eot, sample_len, suppress, [220, eot], timestamps=not without_timestamps,
-                             timestamp_begin=no_ts + 1, no_timestamps=no_ts)
+                             timestamp_begin=no_ts + 1, no_timestamps=no_ts, no_speech=no_speech, sot_index=0, sot_prev=sot_prev)
 
 
 _HF_RULES = (("layers.", "blocks."), (".encoder_attn_layer_norm.", ".cross_attn_ln."), (".self_attn_layer_norm.", ".attn_ln."),
@@ -176,6 +199,19 @@ _SYMBOLS = {
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "wb_transcribe_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(_DecodeOpts),
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "wb_tokenizer_create": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]),
+    "wb_tokenizer_load_tiktoken": (ctypes.c_void_p, [ctypes.c_char_p]),
+    "wb_tokenizer_destroy": (None, [ctypes.c_void_p]),
+    "wb_tokenizer_size": (ctypes.c_int32, [ctypes.c_void_p]),
+    "wb_tokenizer_decode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                           ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
+    "wb_text_compression_ratio": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_float),
+                                                 ctypes.POINTER(ctypes.c_size_t)]),
+    "wb_transcribe_long": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(_LongOpts),
+                                          ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.c_void_p,
+                                          ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
+    "wb_call_seed": (ctypes.c_uint64, [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int32]),
+    "wb_logmel_long": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
     "wb_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "wb_last_timings": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "wb_sync": (ctypes.c_int, [ctypes.c_void_p]),
@@ -245,6 +281,125 @@ def generateSpectrogram(audio: Sequence[float]) -> np.ndarray:
     lib = load_library()
     _check(lib.wb_generate_spectrogram_f64(_ptr(buf), 1, _ptr(result)), "generate_spectrogram")
     return result
+
+
+def bytes_to_unicode() -> Dict[int, str]:
+    """GPT-2's reversible byte <-> printable-character map (the alphabet of vocab.json / merges.txt)."""
+    bs = list(range(ord("!"), ord("~") + 1)) + list(range(0xA1, 0xAC + 1)) + list(range(0xAE, 0xFF + 1))
+    cs = bs[:]
+    n = 0
+    for b in range(256):
+        if b not in bs:
+            bs.append(b)
+            cs.append(256 + n)
+            n += 1
+    return {b: chr(c) for b, c in zip(bs, cs)}
+
+
+_GPT2_PAT = r"""'s|'t|'re|'ve|'m|'ll|'d| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+"""
+
+
+class Tokenizer:
+    """Byte-level BPE vocabulary of Whisper (upstream whisper/tokenizer.py over tiktoken).
+
+    Detokenisation (token ids -> bytes -> text, compression ratio) lives behind the C ABI (wb_tokenizer_*), because the
+    long-form loop needs it natively; encoding (text -> ids, used only for prompts) is the published BPE merge loop here.
+    Sources: an upstream `.tiktoken` rank file, a transformers `vocab.json` (+ the byte map above), or a dict of ranks."""
+
+    def __init__(self, ranks: Dict[bytes, int]):
+        self._lib = load_library()
+        n = max(ranks.values()) + 1
+        table: List[bytes] = [b""] * n
+        for tok, r in ranks.items():
+            table[r] = tok
+        self.ranks = dict(ranks)
+        self.table = table
+        blob = b"".join(table)
+        offs = np.zeros(n + 1, dtype=np.uint32)
+        np.cumsum([len(t) for t in table], out=offs[1:])
+        buf = np.frombuffer(blob, dtype=np.uint8) if blob else np.zeros(1, dtype=np.uint8)
+        self._h = ctypes.c_void_p(self._lib.wb_tokenizer_create(_ptr(buf), _ptr(offs), n))
+        if not self._h:
+            raise WhisperB200Error("wb_tokenizer_create failed: " + (self._lib.wb_last_error() or b"").decode())
+
+    @classmethod
+    def from_tiktoken(cls, path: str) -> "Tokenizer":
+        import base64
+        ranks = {}
+        with open(path, "rb") as f:
+            for line in f:
+                if line.strip():
+                    tok, rank = line.split()
+                    ranks[base64.b64decode(tok)] = int(rank)
+        return cls(ranks)
+
+    @classmethod
+    def from_vocab_json(cls, path: str) -> "Tokenizer":
+        import json
+        inv = {c: b for b, c in bytes_to_unicode().items()}
+        with open(path, "r", encoding="utf-8") as f:
+            vocab = json.load(f)
+        ranks = {}
+        for tok, idx in vocab.items():
+            if all(ch in inv for ch in tok):            # special tokens (<|...|>) are not byte-level entries
+                ranks[bytes(inv[ch] for ch in tok)] = idx
+        return cls(ranks)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.wb_tokenizer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self) -> ctypes.c_void_p:
+        return self._h
+
+    def __len__(self) -> int:
+        return int(self._lib.wb_tokenizer_size(self._h))
+
+    def decode_bytes(self, ids: Sequence[int], drop_from: int = 1 << 30) -> bytes:
+        a = np.asarray(list(ids), dtype=np.int32)
+        n = ctypes.c_size_t(0)
+        _check(self._lib.wb_tokenizer_decode(self._h, _ptr(a) if a.size else None, a.size, drop_from, None, 0, ctypes.byref(n)),
+               "wb_tokenizer_decode")
+        out = np.zeros(max(1, n.value), dtype=np.uint8)
+        _check(self._lib.wb_tokenizer_decode(self._h, _ptr(a) if a.size else None, a.size, drop_from, _ptr(out), out.size,
+                                             ctypes.byref(n)), "wb_tokenizer_decode")
+        return out[:n.value].tobytes()
+
+    def decode(self, ids: Sequence[int], drop_from: int = 1 << 30) -> str:
+        return self.decode_bytes(ids, drop_from).decode("utf-8", errors="replace")
+
+    def compression_ratio(self, ids: Sequence[int], drop_from: int = 1 << 30) -> float:
+        raw = np.frombuffer(self.decode_bytes(ids, drop_from) or b"\0", dtype=np.uint8)
+        n = len(self.decode_bytes(ids, drop_from))
+        r = ctypes.c_float(0)
+        _check(self._lib.wb_text_compression_ratio(_ptr(raw), n, ctypes.byref(r), None), "wb_text_compression_ratio")
+        return float(r.value)
+
+    def encode(self, text: str) -> List[int]:
+        """tiktoken's encode_ordinary: GPT-2 pre-tokenisation, then lowest-rank-first merges per piece."""
+        import regex
+        out: List[int] = []
+        for piece in regex.findall(_GPT2_PAT, text):
+            parts = [bytes([b]) for b in piece.encode("utf-8")]
+            while len(parts) > 1:
+                best, at = None, -1
+                for i in range(len(parts) - 1):
+                    r = self.ranks.get(parts[i] + parts[i + 1])
+                    if r is not None and (best is None or r < best):
+                        best, at = r, i
+                if best is None:
+                    break
+                parts[at:at + 2] = [parts[at] + parts[at + 1]]
+            out.extend(self.ranks[p] for p in parts)
+        return out
 
 
 class Whisper:
@@ -403,7 +558,9 @@ class Whisper:
         c = _DecodeOpts(init.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), init.size, o.sample_len, o.eot,
                         sup.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), sup.size,
                         supb.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), supb.size, o.beam_size, o.eot_check_interval,
-                        1 if o.timestamps else 0, o.timestamp_begin, o.no_timestamps, o.max_initial_timestamp_index)
+                        1 if o.timestamps else 0, o.timestamp_begin, o.no_timestamps, o.max_initial_timestamp_index,
+                        float(o.temperature), int(o.best_of), int(o.seed) & 0xFFFFFFFFFFFFFFFF, int(o.no_speech), int(o.sot_index),
+                        ctypes.POINTER(ctypes.c_float)())
         return c, (init, sup, supb)
 
     def decode_tokens(self, B: int, opts: DecodeOptions):
@@ -416,6 +573,19 @@ class Whisper:
         slp = np.empty(B, dtype=np.float32)
         _check(self._lib.wb_decode(self._h, B, ctypes.byref(c), _ptr(tokens), _ptr(lens), _ptr(slp)), "wb_decode")
         return tokens, lens, slp
+
+    def decode_with_no_speech(self, B: int, opts: DecodeOptions):
+        """decode_tokens plus upstream's no_speech_probs: softmax of the unfiltered logits at opts.sot_index, at opts.no_speech.
+        Returns (tokens, lens, sum_logprob, no_speech_prob [B])."""
+        c, keep = self._opts(opts)
+        nsp = np.zeros(B, dtype=np.float32)
+        c.no_speech_prob = nsp.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+        total = len(opts.initial_tokens) + opts.sample_len
+        tokens = np.empty((B, total), dtype=np.int32)
+        lens = np.empty(B, dtype=np.int32)
+        slp = np.empty(B, dtype=np.float32)
+        _check(self._lib.wb_decode(self._h, B, ctypes.byref(c), _ptr(tokens), _ptr(lens), _ptr(slp)), "wb_decode")
+        return tokens, lens, slp, nsp
 
     def greedy(self, B: int, opts: DecodeOptions):
         """Greedy decode of the resident features (rejects beam options: use decode_tokens / beam_search for those)."""
@@ -450,6 +620,67 @@ class Whisper:
             toks.append(t)
             lens.append(l)
         return np.concatenate(toks, axis=0), np.concatenate(lens, axis=0)
+
+    def logmel_long(self, pcm, frame0: int = 0) -> np.ndarray:
+        """upstream log_mel_spectrogram(pcm, padding=N_SAMPLES)[:, frame0:frame0 + 3000] -> [80, 3000] f32."""
+        a = np.ascontiguousarray(np.asarray(pcm, dtype=np.float32).reshape(-1))
+        out = np.empty((N_MELS, N_FRAMES), dtype=np.float32)
+        _check(self._lib.wb_logmel_long(self._h, _ptr(a), a.shape[0], frame0, _ptr(out)), "wb_logmel_long")
+        return out
+
+    def transcribe_seek(self, pcm, opts: Optional[DecodeOptions] = None, *, temperatures: Optional[Sequence[float]] = None,
+                        compression_ratio_threshold: Optional[float] = 2.4, logprob_threshold: Optional[float] = -1.0,
+                        no_speech_threshold: Optional[float] = 0.6, condition_on_previous_text: bool = True,
+                        initial_prompt: Optional[Sequence[int]] = None, tokenizer: Optional["Tokenizer"] = None,
+                        detect_language: bool = False, max_segments: int = 0) -> dict:
+        """Upstream whisper `transcribe()` on one recording of any length (wb_transcribe_long: seek loop, temperature fallback,
+        thresholds, previous text as prompt). `opts` holds the per-window options (default: upstream's, timestamps on);
+        a threshold of None turns its rule off. Returns {"tokens", "segments": [dict], "language": index or None}."""
+        a = np.ascontiguousarray(np.asarray(pcm, dtype=np.float32).reshape(-1))
+        opts = opts or DecodeOptions.default_for(self.dims, without_timestamps=False)
+        c, keep = self._opts(opts)
+        lo = _LongOpts()
+        lo.decode = c
+        t = None
+        if temperatures is not None:
+            t = np.asarray(list(temperatures), dtype=np.float32)
+            lo.temperatures = t.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+            lo.n_temperatures = t.size
+        nan = float("nan")
+        lo.compression_ratio_threshold = nan if compression_ratio_threshold is None else compression_ratio_threshold
+        lo.logprob_threshold = nan if logprob_threshold is None else logprob_threshold
+        lo.no_speech_threshold = nan if no_speech_threshold is None else no_speech_threshold
+        lo.condition_on_previous_text = 1 if condition_on_previous_text else 0
+        ip = np.asarray(list(initial_prompt or []), dtype=np.int32)
+        if ip.size:
+            lo.initial_prompt = ip.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+            lo.n_initial_prompt = ip.size
+        lo.sot_prev = opts.sot_prev
+        lo.tokenizer = tokenizer.handle if tokenizer is not None else None
+        lo.detect_language = 1 if detect_language else 0
+        lo.lang0 = 50259
+        lang = ctypes.c_int32(-1)
+        lo.detected_language = ctypes.pointer(lang)
+        n_windows = a.shape[0] // N_SAMPLES + 2
+        seg_cap = max_segments or 64 * n_windows
+        tok_cap = 256 * n_windows + 256
+        segs = (_Segment * seg_cap)()
+        tokens = np.empty(tok_cap, dtype=np.int32)
+        n_seg, n_tok = ctypes.c_int32(0), ctypes.c_int32(0)
+        _check(self._lib.wb_transcribe_long(self._h, _ptr(a), a.shape[0], ctypes.byref(lo), segs, seg_cap, ctypes.byref(n_seg),
+                                            _ptr(tokens), tok_cap, ctypes.byref(n_tok)), "wb_transcribe_long")
+        out = []
+        for i in range(n_seg.value):
+            g = segs[i]
+            out.append({"id": i, "seek": g.seek, "start": g.start, "end": g.end,
+                        "tokens": tokens[g.token_begin:g.token_begin + g.n_tokens].tolist(), "temperature": g.temperature,
+                        "avg_logprob": g.avg_logprob, "compression_ratio": g.compression_ratio, "no_speech_prob": g.no_speech_prob})
+            if tokenizer is not None:
+                out[-1]["text"] = tokenizer.decode(out[-1]["tokens"], drop_from=opts.eot)
+        res = {"tokens": tokens[:n_tok.value].copy(), "segments": out, "language": lang.value if lang.value >= 0 else None}
+        if tokenizer is not None:
+            res["text"] = tokenizer.decode(res["tokens"].tolist(), drop_from=opts.eot)
+        return res
 
     def transcribe_dev(self, audio_dev_ptr: int, B: int, opts: DecodeOptions):
         c, keep = self._opts(opts)

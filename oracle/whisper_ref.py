@@ -521,3 +521,226 @@ def synth_audio(seed: int, kind: str = "noise", n: int = 480000) -> np.ndarray:
     if kind == "fullscale":
         return rng.uniform(-1.0, 1.0, n)
     raise ValueError(kind)
+
+
+# ---- long-form transcription: upstream whisper/transcribe.py transcribe() ---------------------------
+# PARITY UNPINNED like the rest of this file (openai-whisper is not in the image): restated from the published source of
+# openai-whisper v20230314 ... v20231117 — `log_mel_spectrogram(audio, padding=N_SAMPLES)`, `decode_with_fallback`, the
+# no-speech skip, the consecutive-timestamp segment cutter, `seek` arithmetic, the prompt reset above temperature 0.5 —
+# without word_timestamps / clip_timestamps / hallucination_silence_threshold. The pieces that ARE pinned independently:
+# the log-mel of a long signal against torch.stft here, the token table / compression ratio against tiktoken and Python's
+# zlib (tests/test_host.py), the timestamp rules against transformers (tests/test_oracle_whisper.py).
+#
+# Sampling at temperature > 0: upstream draws `Categorical(logits=logits / temperature).sample()` from torch's global
+# generator, which no second implementation can reproduce. Both this restatement and the CUDA path define the draw as
+# the Gumbel-max form of the same distribution over a counter-based generator (include/whisper_b200.h, decoder.cu
+# sample_rows_kernel), so that they see the same noise.
+_M64 = (1 << 64) - 1
+
+
+def splitmix64(x):
+    """Vectorised over numpy uint64 arrays (wraps modulo 2**64) or a Python int."""
+    if isinstance(x, np.ndarray):
+        with np.errstate(over="ignore"):
+            x = x + np.uint64(0x9E3779B97F4A7C15)
+            x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            return x ^ (x >> np.uint64(31))
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
+
+
+def call_seed(seed: int, seek: int, temperature_index: int) -> int:
+    return splitmix64((splitmix64((seed ^ seek) & _M64) + temperature_index) & _M64)
+
+
+def gumbel_noise(seed: int, sample: int, position: int, n_vocab: int) -> torch.Tensor:
+    key = splitmix64((seed ^ splitmix64(((sample << 32) | position) & _M64)) & _M64)
+    with np.errstate(over="ignore"):
+        r = splitmix64(np.uint64(key) + np.arange(n_vocab, dtype=np.uint64))
+    u = ((r >> np.uint64(41)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 8388608.0)   # 23 bits: strictly inside (0, 1) in fp32
+    return torch.from_numpy(-np.log(-np.log(u))).float()
+
+
+def log_mel_stream(audio: np.ndarray, mel_filters: np.ndarray, padding: int = 480000) -> torch.Tensor:
+    """upstream whisper/audio.py log_mel_spectrogram(audio, padding=N_SAMPLES): [80, (n + padding) // 160] float32."""
+    a = F.pad(torch.from_numpy(np.asarray(audio, dtype=np.float32)), (0, padding))
+    stft = torch.stft(a, 400, 160, window=torch.hann_window(400), return_complex=True)
+    magnitudes = stft[..., :-1].abs() ** 2
+    mel_spec = torch.from_numpy(np.asarray(mel_filters, dtype=np.float32).reshape(80, 201)) @ magnitudes   # m80.npy holds 80 x 201
+    log_spec = torch.clamp(mel_spec, min=1e-10).log10()
+    log_spec = torch.maximum(log_spec, log_spec.max() - 8.0)
+    return (log_spec + 4.0) / 4.0
+
+
+def text_compression_ratio(raw: bytes) -> float:
+    text = raw.decode("utf-8", errors="replace").strip().encode("utf-8")
+    import zlib
+    return len(text) / len(zlib.compress(text))
+
+
+@dataclass
+class WindowResult:
+    tokens: List[int]
+    avg_logprob: float
+    no_speech_prob: float
+    temperature: float
+    compression_ratio: float
+
+
+@torch.no_grad()
+def decode_window(model: "WhisperRef", xa: torch.Tensor, opts: "DecodeOptions", prompt: Sequence[int], temperature: float, seed: int,
+                  best_of: int = 0, sot_index: int = 0, table: Optional[List[bytes]] = None) -> WindowResult:
+    """upstream DecodingTask.run for one window: [sot_prev] + prompt[-(n_ctx // 2 - 1):] + sot sequence, no_speech_probs at the
+    sot position, GreedyDecoder at `temperature` with best_of samples, MaximumLikelihoodRanker, DecodingResult fields."""
+    v, dims = model.vocab, model.dims
+    n_ctx = dims.n_text_ctx
+    init: List[int] = []
+    if len(prompt):
+        init = [v.sot_prev] + list(prompt)[-(n_ctx // 2 - 1):]
+    sot_at = len(init) + sot_index
+    init = init + list(opts.initial_tokens)
+    sample_begin = len(init)
+    sample_len = min(opts.sample_len, n_ctx - sample_begin)          # the CUDA path's cap (upstream: one more)
+    G = best_of if (temperature > 0 and best_of > 1) else 1
+    tokens = torch.tensor([init] * G, dtype=torch.long)
+    xg = xa[:1].repeat_interleave(G, dim=0)
+    cross = model.cross_kv(xg)
+    cache: List[Optional[tuple]] = [None] * dims.n_text_layer
+    sum_logprobs = torch.zeros(G)
+    no_speech_prob = 0.0
+    for i in range(sample_len):
+        feed = tokens if i == 0 else tokens[:, -1:]
+        all_logits = model.decoder_logits(feed, xg, cross, cache)
+        if i == 0:
+            no_speech_prob = float(all_logits[0, sot_at].float().softmax(dim=-1)[v.no_speech])
+        logits = all_logits[:, -1].clone()
+        if tokens.shape[1] == sample_begin and len(opts.suppress_begin):
+            logits[:, list(opts.suppress_begin)] = float("-inf")
+        if len(opts.suppress):
+            logits[:, list(opts.suppress)] = float("-inf")
+        if opts.timestamps:
+            logits = apply_timestamp_rules(logits, tokens, sample_begin, v, opts.max_initial_timestamp_index)
+        if temperature == 0:
+            nxt = logits.argmax(dim=-1)
+        else:
+            position = tokens.shape[1]
+            inv_t = np.float32(1.0) / np.float32(temperature)
+            nxt = torch.stack([(logits[j] * float(inv_t) + gumbel_noise(seed, j, position, dims.n_vocab)).argmax() for j in range(G)])
+        logprobs = F.log_softmax(logits.float(), dim=-1)
+        cur = logprobs[torch.arange(G), nxt]
+        sum_logprobs += cur * (tokens[:, -1] != v.eot)
+        nxt[tokens[:, -1] == v.eot] = v.eot
+        tokens = torch.cat([tokens, nxt[:, None]], dim=-1)
+        if (tokens[:, -1] == v.eot).all():
+            break
+    best, best_score, best_tokens = -1, 0.0, []
+    for j in range(G):
+        t = tokens[j, sample_begin:].tolist()
+        t = t[:t.index(v.eot)] if v.eot in t else t
+        score = float(sum_logprobs[j]) / max(len(t), 1)
+        if best < 0 or score > best_score:
+            best, best_score, best_tokens = j, score, t
+    cr = 0.0
+    if table is not None:
+        drop = v.timestamp_begin if opts.timestamps else v.eot
+        cr = text_compression_ratio(b"".join(table[t] for t in best_tokens if t < drop and t < len(table)))
+    return WindowResult(best_tokens, float(sum_logprobs[best]) / (len(best_tokens) + 1), no_speech_prob, float(temperature), cr)
+
+
+@torch.no_grad()
+def transcribe_seek(model: "WhisperRef", audio: np.ndarray, mel_filters: np.ndarray, opts: "DecodeOptions", *,
+                    temperatures: Sequence[float] = (0.0, 0.2, 0.4, 0.6, 0.8, 1.0), compression_ratio_threshold: Optional[float] = 2.4,
+                    logprob_threshold: Optional[float] = -1.0, no_speech_threshold: Optional[float] = 0.6,
+                    condition_on_previous_text: bool = True, initial_prompt: Sequence[int] = (), table: Optional[List[bytes]] = None,
+                    seed: int = 0, best_of: int = 0, sot_index: int = 0):
+    """upstream transcribe(): returns (all_tokens without the initial prompt, segments as dicts, log of (seek, temperatures tried))."""
+    v = model.vocab
+    N_FRAMES, HOP, SR = 3000, 160, 16000
+    mel = log_mel_stream(audio, mel_filters)
+    content_frames = mel.shape[-1] - N_FRAMES
+    input_stride = N_FRAMES // model.dims.n_audio_ctx
+    time_precision = input_stride * HOP / SR
+    ts_begin = v.timestamp_begin if opts.timestamps else 1 << 30
+    use_cr = compression_ratio_threshold is not None and table is not None
+    all_tokens: List[int] = list(initial_prompt)
+    n_prompt0 = len(all_tokens)
+    prompt_reset_since = 0
+    segments, trace = [], []
+    seek = 0
+    while seek < content_frames:
+        time_offset = float(seek * HOP / SR)
+        mel_segment = mel[:, seek:seek + N_FRAMES]
+        segment_size = min(N_FRAMES, content_frames - seek)
+        segment_duration = segment_size * HOP / SR
+        if mel_segment.shape[-1] < N_FRAMES:
+            mel_segment = F.pad(mel_segment, (0, N_FRAMES - mel_segment.shape[-1]))
+        xa = model.encode(mel_segment[None])
+        prompt = all_tokens[prompt_reset_since:]
+        tried = []
+        for ti, t in enumerate(temperatures):
+            res = decode_window(model, xa, opts, prompt, t, call_seed(seed, seek, ti), best_of, sot_index, table)
+            tried.append(t)
+            needs_fallback = False
+            if use_cr and res.compression_ratio > compression_ratio_threshold:
+                needs_fallback = True
+            if logprob_threshold is not None and res.avg_logprob < logprob_threshold:
+                needs_fallback = True
+            if no_speech_threshold is not None and res.no_speech_prob > no_speech_threshold:
+                needs_fallback = False
+            if not needs_fallback:
+                break
+        trace.append((seek, tried, res))
+        tokens = res.tokens
+        if no_speech_threshold is not None:
+            should_skip = res.no_speech_prob > no_speech_threshold
+            if logprob_threshold is not None and res.avg_logprob > logprob_threshold:
+                should_skip = False
+            if should_skip:
+                seek += segment_size
+                continue
+        current = []
+
+        def new_segment(start, end, toks):
+            current.append({"seek": seek, "start": start, "end": end, "tokens": list(toks), "temperature": res.temperature,
+                            "avg_logprob": res.avg_logprob, "compression_ratio": res.compression_ratio, "no_speech_prob": res.no_speech_prob})
+
+        is_ts = [t >= ts_begin for t in tokens]
+        single_timestamp_ending = is_ts[-2:] == [False, True]
+        consecutive = [i + 1 for i in range(len(tokens) - 1) if is_ts[i] and is_ts[i + 1]]
+        if consecutive:
+            slices = list(consecutive)
+            if single_timestamp_ending:
+                slices.append(len(tokens))
+            last_slice = 0
+            for current_slice in slices:
+                sliced = tokens[last_slice:current_slice]
+                new_segment(time_offset + (sliced[0] - ts_begin) * time_precision, time_offset + (sliced[-1] - ts_begin) * time_precision, sliced)
+                last_slice = current_slice
+            if single_timestamp_ending:
+                seek += segment_size
+            else:
+                seek += (tokens[last_slice - 1] - ts_begin) * input_stride
+        else:
+            duration = segment_duration
+            stamps = [t for t in tokens if t >= ts_begin]
+            if stamps and stamps[-1] != ts_begin:
+                duration = (stamps[-1] - ts_begin) * time_precision
+            new_segment(time_offset, time_offset + duration, tokens)
+            seek += segment_size
+        for s in current:
+            text_tokens = [t for t in s["tokens"] if t < v.eot]
+            if table is not None:
+                has_text = b"".join(table[t] for t in text_tokens if t < len(table)).decode("utf-8", errors="replace").strip() != ""
+            else:
+                has_text = len(text_tokens) > 0
+            # the CUDA path reports float32 seconds: compare start and end as it does
+            if np.float32(s["start"]) == np.float32(s["end"]) or not has_text:
+                s["tokens"] = []
+        segments.extend(current)
+        all_tokens.extend(t for s in current for t in s["tokens"])
+        if not condition_on_previous_text or res.temperature > 0.5:
+            prompt_reset_since = len(all_tokens)
+    return all_tokens[n_prompt0:], segments, trace
