@@ -84,11 +84,12 @@ def test_product_never_imports_the_oracle():
 
 
 def test_struct_layouts_match_the_header(wbm, tmp_path):
-    """The ctypes mirrors of wb_dims / wb_decode_opts have exactly the layout a C compiler gives the header's structs
+    """The ctypes mirrors of wb_dims / wb_decode_opts / wb_long_opts / wb_segment have exactly the layout a C compiler gives the header's structs
     (what a Swift / cgo / JNI binding generated from include/whisper_b200.h would see): sizes and every field offset."""
     from importlib import import_module
     mod = import_module("openai-whisper-coreml_b200.whisper")
-    fields = {"wb_dims": [n for n, _ in mod._Dims._fields_], "wb_decode_opts": [n for n, _ in mod._DecodeOpts._fields_]}
+    mirrors = (("wb_dims", mod._Dims), ("wb_decode_opts", mod._DecodeOpts), ("wb_long_opts", mod._LongOpts), ("wb_segment", mod._Segment))
+    fields = {st: [n for n, _ in cls._fields_] for st, cls in mirrors}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "whisper_b200.h"', 'int main(void) {']
     for st, names in fields.items():
         lines.append(f'  printf("{st} %zu\\n", sizeof({st}));')
@@ -100,7 +101,7 @@ def test_struct_layouts_match_the_header(wbm, tmp_path):
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
-    for st, cls in (("wb_dims", mod._Dims), ("wb_decode_opts", mod._DecodeOpts)):
+    for st, cls in mirrors:
         assert int(got[st]) == ctypes.sizeof(cls), st
         for n in fields[st]:
             assert int(got[f"{st}.{n}"]) == getattr(cls, n).offset, (st, n)

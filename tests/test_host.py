@@ -111,3 +111,131 @@ def test_gather_tokens_world_size_2_gloo(n_total):
     want_l = [c % 5 + 1 for c in range(n_total)]
     for _, t, l in got:
         assert t == want_t and l == want_l
+
+
+# ---- token table, text rules of the long-form loop (host code of the C ABI: no GPU needed) ----------------------------------
+def _synthetic_ranks():
+    """256 byte tokens + BPE merges learned from a small multilingual corpus (no vocabulary file exists offline)."""
+    import collections
+    corpus = ("the quick brown fox jumps over the lazy dog. The theme of the thesis: thé naïve café — 東京 tokyo! 12345 12 123\n\n"
+              "  indented   text's it's we'll they've I'm he'd 3.14 <tag> end\t\ttabs ")
+    ranks = {bytes([b]): b for b in range(256)}
+    seqs = [[bytes([b]) for b in w.encode()] for w in corpus.split(" ")]
+    for _ in range(80):
+        cnt = collections.Counter()
+        for s in seqs:
+            for a, b in zip(s, s[1:]):
+                cnt[a + b] += 1
+        cnt = {k: c for k, c in cnt.items() if k not in ranks}
+        if not cnt:
+            break
+        best = max(cnt, key=lambda k: (cnt[k], k))
+        ranks[best] = len(ranks)
+        for s in seqs:
+            i = 0
+            while i < len(s) - 1:
+                if s[i] + s[i + 1] == best:
+                    s[i:i + 2] = [best]
+                else:
+                    i += 1
+    return corpus, ranks
+
+
+def test_tokenizer_against_tiktoken(wbm, tmp_path):
+    """Encode (Python merge loop) and decode (C ABI) against tiktoken, the library upstream whisper's tokenizer is built on,
+    constructed offline from the same ranks; the .tiktoken file reader of the C ABI; vocab.json with GPT-2's byte alphabet."""
+    import base64
+    import ctypes
+    import json
+    tiktoken = pytest.importorskip("tiktoken")
+    corpus, ranks = _synthetic_ranks()
+    pat = r"""'s|'t|'re|'ve|'m|'ll|'d| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+"""
+    enc = tiktoken.Encoding("synthetic", pat_str=pat, mergeable_ranks=ranks, special_tokens={})
+    t = wbm.Tokenizer(ranks)
+    assert len(t) == len(ranks)
+    for text in [corpus, " hello the theme", "東京the", "", "   ", "it's 12 o'clock", corpus[::-1]]:
+        a, b = enc.encode_ordinary(text), t.encode(text)
+        assert a == b, text
+        assert t.decode(b) == text == enc.decode(a)
+    ids = t.encode(corpus)
+    assert t.decode(ids, drop_from=256) == enc.decode([i for i in ids if i < 256])        # the timestamp / special-token filter
+    assert t.decode(ids[:3] + [10 ** 6, -1] + ids[3:]) == corpus                           # ids outside the table decode to nothing
+    f = tmp_path / "synthetic.tiktoken"
+    f.write_bytes(b"".join(base64.b64encode(tok) + b" " + str(r).encode() + b"\n" for tok, r in ranks.items()))
+    t2 = wbm.Tokenizer.from_tiktoken(str(f))
+    assert t2.table == t.table
+    lib = wbm.load_library()
+    h = ctypes.c_void_p(lib.wb_tokenizer_load_tiktoken(str(f).encode()))
+    assert h and lib.wb_tokenizer_size(h) == len(ranks)
+    a = np.asarray(ids, dtype=np.int32)
+    n = ctypes.c_size_t(0)
+    out = np.zeros(4096, dtype=np.uint8)
+    assert lib.wb_tokenizer_decode(h, a.ctypes.data_as(ctypes.c_void_p), a.size, 1 << 30, out.ctypes.data_as(ctypes.c_void_p), out.size,
+                                   ctypes.byref(n)) == 0
+    assert out[:n.value].tobytes() == corpus.encode()
+    lib.wb_tokenizer_destroy(h)
+    assert not lib.wb_tokenizer_load_tiktoken(str(tmp_path / "missing").encode()) and b"cannot open" in lib.wb_last_error()
+    bad = tmp_path / "bad.tiktoken"
+    bad.write_bytes(b"not base64 !!\n")
+    assert not lib.wb_tokenizer_load_tiktoken(str(bad).encode())
+    b2u = wbm.bytes_to_unicode()
+    from transformers.convert_slow_tokenizer import bytes_to_unicode as hf_b2u
+    assert b2u == hf_b2u()                                                                 # an independent copy of the byte alphabet
+    vj = tmp_path / "vocab.json"
+    vocab = {"".join(b2u[b] for b in tok): r for tok, r in ranks.items()}
+    vocab["<|endoftext|>"] = len(ranks)
+    vj.write_text(json.dumps(vocab, ensure_ascii=False), encoding="utf-8")
+    t3 = wbm.Tokenizer.from_vocab_json(str(vj))
+    assert t3.table[:len(ranks)] == t.table and t3.decode(ids) == corpus
+
+
+def test_compression_ratio_and_text_rules_against_python(wbm):
+    """upstream compression_ratio(tokenizer.decode(tokens).strip()): the C ABI's UTF-8 decoding with replacement, Unicode
+    strip and zlib deflate against CPython's, on random byte strings rich in invalid sequences and white space."""
+    import random
+    import zlib
+    t = wbm.Tokenizer({bytes([b]): b for b in range(256)})
+    rng = random.Random(0)
+    special = b" \t\n\x0b\x0c\r\x1c\x1f\x85\xc2\xa0\xc2\x85\xe1\x9a\x80\xe2\x80\x83\xe2\x80\xa8\xe2\x81\x9f\xe3\x80\x80abc\xf0\x9f\x98\x80\xed\xa0\x80\xc0\xf5\xe0\x80\xf4\x90"
+    for i in range(3000):
+        raw = bytes(rng.choice([rng.randrange(256), rng.choice(special)]) for _ in range(rng.randrange(0, 48)))
+        text = raw.decode("utf-8", errors="replace").strip().encode("utf-8")
+        want = len(text) / len(zlib.compress(text))
+        assert abs(t.compression_ratio(list(raw)) - want) < 1e-6, raw
+    rep = list(b"again and again and " * 40)
+    text = bytes(rep).decode().strip().encode()
+    assert abs(t.compression_ratio(rep) - len(text) / len(zlib.compress(text))) < 1e-5 and t.compression_ratio(rep) > 2.4
+    assert t.compression_ratio([]) == 0.0
+
+
+def test_oracle_sampling_generator(ref):
+    """The counter-based generator both sides draw from: splitmix64 known answers (Vigna's reference sequence from state 0),
+    uniform range strictly inside (0, 1) in fp32, Gumbel statistics."""
+    x, outs = 0, []
+    for _ in range(3):                                           # the reference generator advances its state by the golden gamma
+        outs.append(ref.splitmix64(x))
+        x = (x + 0x9E3779B97F4A7C15) & ((1 << 64) - 1)
+    assert outs == [0xE220A8397B1DCDAF, 0x6E789E6AA1B965F4, 0x06C45D188009454F]
+    arr = ref.splitmix64(np.array([0, 0x9E3779B97F4A7C15], dtype=np.uint64))
+    assert [int(a) for a in arr] == outs[:2]
+    g = ref.gumbel_noise(7, 1, 3, 51864)
+    assert torch.isfinite(g).all() and abs(float(g.mean()) - 0.5772) < 0.02 and abs(float(g.var()) - np.pi ** 2 / 6) < 0.05
+    assert not torch.equal(g, ref.gumbel_noise(7, 2, 3, 51864)) and not torch.equal(g, ref.gumbel_noise(7, 1, 4, 51864))
+    assert ref.call_seed(5, 300, 2) != ref.call_seed(5, 300, 1) != ref.call_seed(5, 301, 1)
+
+
+def test_call_seed_matches_the_c_abi(wbm, ref):
+    lib = wbm.load_library()
+    for seed, seek, ti in [(0, 0, 0), (3, 1804, 2), (2 ** 63 + 11, 179999, 5)]:
+        assert lib.wb_call_seed(seed, seek, ti) == ref.call_seed(seed, seek, ti)
+
+
+def test_oracle_stream_logmel_first_window_against_chunk_oracle(ref, oracle_logmel, golden_dir):
+    """The long-form front end restated with torch.stft agrees with the chunk oracle (lib.rs restatement, f64) wherever the
+    two definitions coincide: a 30 s clip whose last 2 s are silent — the stream's zero padding and the chunk's reflection
+    then see the same samples, and both normalise with the same maximum."""
+    a = ref.synth_audio(3, "noise")
+    a[-32000:] = 0.0
+    got = ref.log_mel_stream(a.astype(np.float32), np.load(os.path.join(golden_dir, "m80.npy")))[:, :3000].numpy()
+    want = oracle_logmel(a.astype(np.float32).astype(np.float64))
+    assert np.abs(got - want).max() < 2e-4
