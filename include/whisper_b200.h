@@ -161,6 +161,16 @@ int wb_transcribe(wb_handle* h, const float* audio, int32_t B, const wb_decode_o
 int wb_transcribe_dev(wb_handle* h, const float* audio_dev, int32_t B, const wb_decode_opts* opts, int32_t* tokens_out,
                       int32_t* lens, float* sum_logprob);
 
+/* ---- checkpoint files ------------------------------------------------------------------------
+ * The reference bakes real weights into its .mlmodels at export time (whisper_to_cml.py:7 `whisper.load_model("small")`); here a
+ * handle is filled from a safetensors file: F32 / F16 / BF16 tensors under upstream openai-whisper names or transformers names
+ * (`model.decoder.layers.0.self_attn.q_proj.weight`; proj_out.weight and k_proj.bias have no upstream counterpart and are
+ * ignored). wb_safetensors_read_dims derives the ten model dimensions from the tensor shapes (host only, no GPU needed), so
+ * that wb_create can be called from the file alone. wb_load_safetensors sets every weight and commits; a missing tensor is an
+ * error, except the encoder's sinusoidal positions, which are regenerated. */
+int wb_safetensors_read_dims(const char* path, wb_dims* out);
+int wb_load_safetensors(wb_handle* h, const char* path, int32_t* n_loaded);
+
 /* ---- long-form transcription ---------------------------------------------------------------
  * The reference transcribes exactly one fixed 30 s window (Whisper/Whisper/ContentView.swift:57-62). For longer recordings
  * "transcribe" means upstream openai-whisper `transcribe()` (whisper/transcribe.py), restated here: log-mel of the whole

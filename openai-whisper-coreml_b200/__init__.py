@@ -9,7 +9,7 @@ All compute happens in libwhisper_b200.so (hand-written sm_100a CUDA). There is 
 anywhere, but every compute call raises if the library is missing or no CUDA device is present.
 """
 from .whisper import (DIMS, LANGUAGES, DecodeOptions, ModelDims, Tokenizer, Whisper, WhisperB200Error, bytes_to_unicode,
-                      generateSpectrogram, hf_to_upstream_name, library_path, load_library, pad_or_trim, split_windows)
+                      generateSpectrogram, hf_to_upstream_name, library_path, load_library, pad_or_trim, read_checkpoint_dims, split_windows)
 
 __all__ = ["DIMS", "LANGUAGES", "DecodeOptions", "ModelDims", "Tokenizer", "Whisper", "WhisperB200Error", "bytes_to_unicode", "generateSpectrogram",
-           "hf_to_upstream_name", "library_path", "load_library", "pad_or_trim", "split_windows"]
+           "hf_to_upstream_name", "library_path", "load_library", "pad_or_trim", "read_checkpoint_dims", "split_windows"]

@@ -1068,6 +1068,11 @@ struct HeadAttnArgs {
   int d, n_rows_fixed, kv_share, n_stages;
   int l2_prefetch_tiles;   // cross attention: stage tiles beyond the ring requested into L2 while q is still being computed
   int pdl_late;            // release the dependent kernel after the main loop instead of at entry
+  // Interleaved sub-batch pair: this launch is the n-th KV-cache kernel of its sub-batch's decode (n = cur_len * n_layer +
+  // layer); its producer does not start streaming before the peer sub-batch has finished peer_lead + n of its own (counted in
+  // the peer's DecodeState::x_done, one per CTA), so that the two bandwidth-bound streams alternate instead of coinciding.
+  const DecodeState* peer;   // null: no ordering
+  int peer_ctas, peer_lead, layer, n_layer;
 };
 
 // 8 weight rows x d of a [.][d] fp16 matrix against one fp32 vector in shared memory: lane l owns the 16-byte chunks
@@ -1149,6 +1154,11 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
     if (lane == 0) {
       const int slab = b / a.kv_share;
       const uint64_t kvpol = fixed ? stream_policy() : ptx::l2_policy(0);   // cross K/V: read once per step
+      if (a.peer) {
+        DecodeState* me = const_cast<DecodeState*>(a.state);
+        const int n = ld_state(&me->cur_len) * a.n_layer + a.layer;
+        poll_at_least(&a.peer->x_done, a.peer_ctas * (n + a.peer_lead), &me->spin_timeout);
+      }
       if (fixed) {   // the producer of a cross-attention CTA runs ahead of q: pull the tiles after the ring into L2 meanwhile
         const int pf_end = n_stages + a.l2_prefetch_tiles < n_tiles ? n_stages + a.l2_prefetch_tiles : n_tiles;
         for (int t = n_stages; t < pf_end; ++t) {
@@ -1307,6 +1317,7 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
   }
   __syncthreads();   // all stages consumed; reuse the ring for the cross-warp merge: [8][68] floats
   if (a.pdl_late == 1) ptx::grid_dep_launch();
+  if (a.peer && tid == 0) red_release_gpu_add(&const_cast<DecodeState*>(a.state)->x_done, 1);   // this CTA's share of the stream is in
   float* red = reinterpret_cast<float*>(smem);
   if (warp < 8) {
     float L = l_run;
@@ -1634,6 +1645,7 @@ static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int
   rc = gemm_get_tmap(p.tmaps, p.v, p.d, p.n_ctx, nslab, p.d, (long long)p.n_ctx * p.d, kHaStageRows, &tmV);
   if (rc) return rc;
   HeadAttnArgs a{p.q, p.x, p.ln_g, p.ln_b, p.wq, p.bq, p.out16, p.state, p.d, p.n_rows_fixed, p.kv_share, 3, 0, 0};   // L2 prefetch measured slightly negative in-step: off
+  a.peer = p.n_rows_fixed > 0 ? p.peer_state : nullptr, a.peer_ctas = p.peer_ctas, a.peer_lead = p.peer_lead, a.layer = p.layer, a.n_layer = p.n_layer;
   static int pdl_xa = -1;
   if (pdl_xa < 0) {
     const char* e = getenv("WB_PDL_XA");

@@ -150,6 +150,9 @@ struct wb_handle {
   cudaEvent_t sub_ev[kMaxSub], fork_ev;
   cudaGraphExec_t g_step[kMaxSub], g_sample[kMaxSub];
   cudaGraphExec_t g_sample_n[kMaxSub];   // several sampling steps in one graph (fewer graph launches, dependent launch across steps)
+  cudaGraphExec_t g_pair[3];             // interleaved pair of sub-batches: prompt step, one sampling step, sample_n sampling steps
+  int64_t nodes_pair[3];
+  cudaEvent_t pair_ev[2];
   int sample_n;                          // steps per g_sample_n graph
   int64_t nodes_step, nodes_sample;
   std::string graph_key;
@@ -387,6 +390,13 @@ struct StepOpts {
   int timestamps;     // upstream ApplyTimestampRules among the logit filters (sampling steps only)
   int ts_begin, ts_last_allowed;
   int use_chosen;     // the finish kernel takes the tokens sample_rows_kernel drew (temperature > 0)
+  // interleaved sub-batch pair (decode_steps_pair): layers [l_begin, l_end) of the step, the logits / finish tail only with
+  // `tail`; the KV-cache kernel waits for xwait (the other sub-batch's previous KV-cache kernel) and records xrec behind itself
+  int partial, l_begin, l_end, tail;
+  cudaEvent_t xwait, xrec;
+  // the same ordering by device counters instead of events (keeps the programmatic launch edges of each sub-batch's own graph):
+  // peer_sub >= 0 names the other sub-batch, peer_Mb its sequences, peer_lead = 0 for the sub-batch that goes first, 1 for the other
+  int peer_on, peer_sub, peer_Mb, peer_lead;
 };
 
 static bool use_handoff_flags() {
@@ -432,7 +442,9 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
   __half* dmlp16 = h->dmlp16 + b0 * 4 * d;
   const size_t self_off = b0 * (size_t)D.n_text_ctx * d;
   const size_t cross_off = (b0 / o.beams) * (size_t)D.n_audio_ctx * d;
-  if (layer_block_supported(H, d)) {
+  const int l_begin = o.partial ? o.l_begin : 0, l_end = o.partial ? o.l_end : D.n_text_layer;
+  const bool tail = o.partial ? o.tail != 0 : true;
+  if (!o.partial && layer_block_supported(H, d)) {
     // d = 384 / 512: one cluster kernel per layer boundary (post part of layer l-1 + self-attention block of layer l + the
     // cross-attention query of layer l), and between two of them the KV-cache kernel as a pure stream: 2 launches per layer
     for (int l = 0; l <= D.n_text_layer; ++l) {
@@ -460,7 +472,7 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
       WB_TRY(launch_attn_decode(c, st, &h->launches));
     }
   } else
-  for (int l = 0; l < D.n_text_layer; ++l) {
+  for (int l = l_begin; l < l_end; ++l) {
     const LayerW& L = h->dec[l];
     AttnDecodeDesc a{};
     a.Mb = Mb, a.d = d, a.n_head = H, a.q = q32, a.k = h->selfK[l] + self_off, a.v = h->selfV[l] + self_off;
@@ -492,7 +504,10 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
     c.kv_share = o.beams;
     c.q = nullptr, c.x = xdec, c.ln_g = L.lnc_g, c.ln_b = L.lnc_b, c.wq = L.wq_c, c.bq = L.bq_c;
     c.pdl_late_ok = post_block_supported(H, d) ? 1 : 0;
+    if (o.xwait) WB_CUDA_OK(cudaStreamWaitEvent(st, o.xwait, 0));
+    if (o.peer_on) c.peer_state = h->state + o.peer_sub, c.peer_ctas = H * o.peer_Mb, c.peer_lead = o.peer_lead, c.layer = l, c.n_layer = D.n_text_layer;
     WB_TRY(launch_attn_decode(c, st, &h->launches));
+    if (o.xrec) WB_CUDA_OK(cudaEventRecord(o.xrec, st));
     if (post_block_supported(H, d)) {
       // d = 384 / 512: output projection + residual + LayerNorm + MLP + residual in one cluster kernel
       PostBlockDesc pb{};
@@ -514,6 +529,7 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
     m2.in_mode = SKINNY_IN_F16, m2.in = dmlp16, m2.out_mode = SKINNY_OUT_RESID, m2.out = xdec;
     WB_TRY(launch_skinny_gemm(m2, st, &h->launches));
   }
+  if (!tail) return 0;
   if (o.store_logits || o.sample) {
     // final LN + tied-embedding logits; filters and per-CTA (max, argmax, sum-exp) fused into the epilogue
     SkinnyDesc lg{};
@@ -535,7 +551,7 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
 
 // cur_len = -1, then embed the token at position 0 (which advances cur_len to 0)
 static int reset_decode_state(wb_handle* h, const StepOpts& o) {
-  static const DecodeState k_init_untraced{-1, 0, 0, 0, nullptr, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, 0, {0, 0, 0}};
+  static const DecodeState k_init_untraced{-1, 0, 0, 0, nullptr, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, 0, 0, {0, 0}};
   DecodeState init = k_init_untraced;
   if (h->trace) init.trace = h->trace + (size_t)o.sub * 16384 * 8;   // a quarter of the trace buffer per sub-batch
   static thread_local DecodeState staged[wb_handle::kMaxSub];
@@ -550,6 +566,10 @@ static void destroy_graphs(wb_handle* h) {
     if (h->g_sample[i]) cudaGraphExecDestroy(h->g_sample[i]);
     if (h->g_sample_n[i]) cudaGraphExecDestroy(h->g_sample_n[i]);
     h->g_step[i] = h->g_sample[i] = h->g_sample_n[i] = nullptr;
+  }
+  for (int i = 0; i < 3; ++i) {
+    if (h->g_pair[i]) cudaGraphExecDestroy(h->g_pair[i]);
+    h->g_pair[i] = nullptr;
   }
   h->graph_key.clear();
 }
@@ -566,6 +586,53 @@ static int capture(wb_handle* h, const StepOpts& o, cudaGraphExec_t* out, int64_
   h->launches = before;
   if (rc) return rc;
   WB_CUDA_OK(e);
+  WB_CUDA_OK(cudaGraphInstantiate(out, g, 0));
+  WB_CUDA_OK(cudaGraphDestroy(g));
+  return 0;
+}
+
+// Two sub-batches as ONE interleaved schedule (the three-kernel path): the bandwidth-bound KV-cache kernels of the two halves
+// are ordered against each other (A.l, B.l, A.l+1, ...: each streams alone, at full HBM rate), and between two of them a
+// half's latency-bound block kernels run under the other half's stream. Left to themselves, two sub-batch streams fall into
+// lockstep (both in the same kind of kernel at the same time: tools/trace_sub.py) and gain nothing.
+static int decode_steps_pair(wb_handle* h, const StepOpts& oa, const StepOpts& ob, int n_steps) {
+  const int L = h->dims.n_text_layer;
+  bool first = true;
+  for (int k = 0; k < n_steps; ++k) {
+    for (int l = 0; l < L; ++l) {
+      StepOpts a = oa, b = ob;
+      a.partial = b.partial = 1, a.l_begin = b.l_begin = l, a.l_end = b.l_end = l + 1, a.tail = b.tail = 0;
+      a.xwait = first ? nullptr : h->pair_ev[1], a.xrec = h->pair_ev[0];
+      b.xwait = h->pair_ev[0], b.xrec = h->pair_ev[1];
+      WB_TRY(decode_step(h, a));
+      WB_TRY(decode_step(h, b));
+      first = false;
+    }
+    StepOpts a = oa, b = ob;
+    a.partial = b.partial = 1, a.l_begin = b.l_begin = a.l_end = b.l_end = L, a.tail = b.tail = 1;
+    WB_TRY(decode_step(h, a));
+    WB_TRY(decode_step(h, b));
+  }
+  return 0;
+}
+
+static int capture_pair(wb_handle* h, const StepOpts& oa, const StepOpts& ob, cudaGraphExec_t* out, int64_t* nodes, int n_steps) {
+  cudaGraph_t g;
+  const int64_t before = h->launches;
+  cudaStream_t sa = step_stream(h, oa), sb = step_stream(h, ob);
+  WB_CUDA_OK(cudaStreamBeginCapture(sa, cudaStreamCaptureModeThreadLocal));
+  cudaError_t e = cudaEventRecord(h->fork_ev, sa);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(sb, h->fork_ev, 0);
+  int rc = e == cudaSuccess ? decode_steps_pair(h, oa, ob, n_steps) : -1;
+  if (cudaEventRecord(h->sub_ev[1], sb) != cudaSuccess || cudaStreamWaitEvent(sa, h->sub_ev[1], 0) != cudaSuccess) rc = rc ? rc : -1;
+  const cudaError_t ee = cudaStreamEndCapture(sa, &g);
+  *nodes = h->launches - before;
+  h->launches = before;
+  if (rc) {
+    if (e != cudaSuccess) set_error("pair capture: %s", cudaGetErrorString(e));
+    return rc < 0 ? WB_ERR_CUDA : rc;
+  }
+  WB_CUDA_OK(ee);
   WB_CUDA_OK(cudaGraphInstantiate(out, g, 0));
   WB_CUDA_OK(cudaGraphDestroy(g));
   return 0;
@@ -607,6 +674,8 @@ static void free_handle(wb_handle* h) {
   for (int i = 0; i < wb_handle::kMaxSub; ++i)
     if (h->sub_ev[i]) cudaEventDestroy(h->sub_ev[i]);
   if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+  for (int i = 0; i < 2; ++i)
+    if (h->pair_ev[i]) cudaEventDestroy(h->pair_ev[i]);
   if (h->h_done) cudaFreeHost(h->h_done);
   if (h->arena.base) cudaFree(h->arena.base);
   if (h->ws.base) cudaFree(h->ws.base);
@@ -662,6 +731,7 @@ static int create_impl(wb_handle* h, void* stream) {
   for (int i = 1; i < wb_handle::kMaxSub; ++i) WB_CUDA_OK(cudaStreamCreateWithFlags(&h->sub_stream[i], cudaStreamNonBlocking));
   for (int i = 0; i < wb_handle::kMaxSub; ++i) WB_CUDA_OK(cudaEventCreateWithFlags(&h->sub_ev[i], cudaEventDisableTiming));
   WB_CUDA_OK(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+  for (int i = 0; i < 2; ++i) WB_CUDA_OK(cudaEventCreateWithFlags(&h->pair_ev[i], cudaEventDisableTiming));
   // everything above (the zero fill the bqkv key-bias slice, the melT pad rows and x1 row 0 rely on, the tables) is complete
   // on the device before the handle is handed out, whatever stream later work uses
   WB_CUDA_OK(cudaDeviceSynchronize());
@@ -1140,10 +1210,18 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
   int multi = interval;
   if (const char* e = getenv("WB_GRAPH_STEPS")) multi = atoi(e);
   multi = multi < 1 ? 1 : (multi > 32 ? 32 : multi);
-  char key[128];
-  snprintf(key, sizeof(key), "B%d i%d e%d s%d m%d t%d.%d.%d", B, n_init, opts->eot, nsb, multi, ts_on ? 1 : 0,
-           ts_on ? opts->timestamp_begin : 0, ts_on ? opts->max_initial_timestamp_index : 0);
   const bool use_graph = getenv("WB_NO_GRAPH") == nullptr;
+  // two sub-batches as one interleaved schedule (decode_steps_pair): graph replay only, the three-kernel decoder path
+  bool pair = false;
+  if (const char* e = getenv("WB_PAIR")) pair = e[0] == '1';
+  bool pair_flags = false;   // WB_PAIR=2: the same alternation through device counters, each sub-batch in its own graph and stream
+  if (const char* e = getenv("WB_PAIR")) pair_flags = e[0] == '2';
+  pair_flags = pair_flags && nsb == 2 && use_graph && !layer_block_supported(D.n_text_head, D.n_text_state) && opts->no_speech_prob == nullptr &&
+               post_block_supported(D.n_text_head, D.n_text_state);
+  pair = pair && nsb == 2 && use_graph && !layer_block_supported(D.n_text_head, D.n_text_state) && opts->no_speech_prob == nullptr;
+  char key[128];
+  snprintf(key, sizeof(key), "B%d i%d e%d s%d m%d t%d.%d.%d p%d", B, n_init, opts->eot, nsb, multi, ts_on ? 1 : 0,
+           ts_on ? opts->timestamp_begin : 0, ts_on ? opts->max_initial_timestamp_index : 0, pair ? 1 : (pair_flags ? 2 : 0));
   if (use_graph && h->graph_key != key) {
     destroy_graphs(h);
     h->sample_n = multi;
@@ -1153,12 +1231,24 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
       WB_TRY(decode_step(h, plain[i]));
       WB_TRY(decode_step(h, samp[i]));
       WB_CUDA_OK(cudaStreamSynchronize(step_stream(h, plain[i])));
-      WB_TRY(capture(h, plain[i], &h->g_step[i], &h->nodes_step));
-      WB_TRY(capture(h, samp[i], &h->g_sample[i], &h->nodes_sample));
+      if (pair) continue;
+      StepOpts gp = plain[i], gs = samp[i];
+      if (pair_flags) {   // the captured kernels wait for their peer; the eager passes above ran one sub-batch at a time, without
+        gp.peer_on = gs.peer_on = 1, gp.peer_sub = gs.peer_sub = 1 - i, gp.peer_Mb = gs.peer_Mb = plain[1 - i].Mb;
+        gp.peer_lead = gs.peer_lead = i;
+      }
+      WB_TRY(capture(h, gp, &h->g_step[i], &h->nodes_step));
+      WB_TRY(capture(h, gs, &h->g_sample[i], &h->nodes_sample));
       if (h->sample_n > 1) {
         int64_t nodes_n = 0;
-        WB_TRY(capture(h, samp[i], &h->g_sample_n[i], &nodes_n, h->sample_n));
+        WB_TRY(capture(h, gs, &h->g_sample_n[i], &nodes_n, h->sample_n));
       }
+    }
+    if (pair) {
+      WB_TRY(capture_pair(h, plain[0], plain[1], &h->g_pair[0], &h->nodes_pair[0], 1));
+      WB_TRY(capture_pair(h, samp[0], samp[1], &h->g_pair[1], &h->nodes_pair[1], 1));
+      h->g_pair[2] = nullptr, h->nodes_pair[2] = 0;
+      if (h->sample_n > 1) WB_TRY(capture_pair(h, samp[0], samp[1], &h->g_pair[2], &h->nodes_pair[2], h->sample_n));
     }
     h->graph_key = key;
     // the eager passes wrote tokens and log-probs: restore
@@ -1173,8 +1263,17 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
   WB_CUDA_OK(cudaEventRecord(h->fork_ev, st));
   for (int i = 1; i < nsb; ++i) WB_CUDA_OK(cudaStreamWaitEvent(h->sub_stream[i], h->fork_ev, 0));
   for (int i = 0; i < nsb; ++i) WB_TRY(reset_decode_state(h, plain[i]));
+  if (pair) {   // the pair graphs run from the main stream: the second sub-batch's reset joins it first
+    WB_CUDA_OK(cudaEventRecord(h->sub_ev[1], h->sub_stream[1]));
+    WB_CUDA_OK(cudaStreamWaitEvent(st, h->sub_ev[1], 0));
+  }
   const bool probe = opts->no_speech_prob != nullptr;
   for (int k = 0; k + 1 < n_init; ++k) {
+    if (pair) {
+      WB_CUDA_OK(cudaGraphLaunch(h->g_pair[0], st));
+      h->launches += h->nodes_pair[0];
+      continue;
+    }
     for (int i = 0; i < nsb; ++i) {
       if (probe && k == opts->sot_index) {
         WB_TRY(no_speech_probe_step(h, plain[i], opts->no_speech, k, true));
@@ -1200,7 +1299,12 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
       restagger = false;
     }
     for (int i = 0; i < nsb; ++i) {
-      if (use_graph) {
+      if (pair) {
+        if (i == 0) {
+          WB_CUDA_OK(cudaGraphLaunch(n > 1 ? h->g_pair[2] : h->g_pair[1], st));
+          h->launches += n > 1 ? h->nodes_pair[2] : h->nodes_pair[1];
+        }
+      } else if (use_graph) {
         WB_CUDA_OK(cudaGraphLaunch(n > 1 ? h->g_sample_n[i] : h->g_sample[i], step_stream(h, samp[i])));
         h->launches += h->nodes_sample * n;
       } else {
@@ -1212,7 +1316,7 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
     if (s % interval == 0 && s < opts->sample_len) {
       for (int i = 0; i < nsb; ++i)
         WB_CUDA_OK(cudaMemcpyAsync(h->h_done + plain[i].b0, h->done + plain[i].b0, sizeof(int32_t) * plain[i].Mb, cudaMemcpyDeviceToHost,
-                                   step_stream(h, plain[i])));
+                                   pair ? st : step_stream(h, plain[i])));
       for (int i = 0; i < nsb; ++i) WB_CUDA_OK(cudaStreamSynchronize(step_stream(h, plain[i])));
       bool all = true;
       for (int b = 0; b < B; ++b) all = all && h->h_done[b];
@@ -1721,6 +1825,7 @@ void generate_spectrogram(double* audio, double* output) {
   }
 }
 
+#include "checkpoint.inc"
 #include "longform.inc"
 
 }  // extern "C"

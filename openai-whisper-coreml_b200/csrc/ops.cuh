@@ -84,7 +84,8 @@ struct DecodeState {      // lives in device memory; read by every kernel of a s
   int q_ready[8];
   int a_done[8];
   int spin_timeout;       // set if a poll gave up (never expected; keeps a bug from hanging the device)
-  int pad2[3];
+  int x_done;             // interleaved sub-batch pair: CTAs of this sub-batch's KV-cache kernels that finished streaming
+  int pad2[2];
 };
 
 // Input transform of a skinny GEMM (how the [Mb][K] fp16 activation tile in shared memory is produced)
@@ -148,6 +149,8 @@ struct AttnDecodeDesc {
   int stream_ok;          // cross attention between two layer-block kernels: may run as the persistent one-CTA-per-SM stream
   int layer, n_layer;     // stream_ok with flags: which decoder layer this launch is (hand-off epochs), 0-based
   int use_flags;          // hand-offs by DecodeState counters instead of whole-kernel dependencies
+  const DecodeState* peer_state;   // interleaved sub-batch pair (HeadAttnArgs::peer): the other sub-batch's state, or null
+  int peer_ctas, peer_lead;
   GemmContext* tmaps;     // tensor-map cache
 };
 int launch_attn_decode(const AttnDecodeDesc& d, cudaStream_t st, int64_t* launches);

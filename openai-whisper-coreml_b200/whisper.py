@@ -199,6 +199,8 @@ _SYMBOLS = {
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "wb_transcribe_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(_DecodeOpts),
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "wb_safetensors_read_dims": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_Dims)]),
+    "wb_load_safetensors": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int32)]),
     "wb_tokenizer_create": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]),
     "wb_tokenizer_load_tiktoken": (ctypes.c_void_p, [ctypes.c_char_p]),
     "wb_tokenizer_destroy": (None, [ctypes.c_void_p]),
@@ -281,6 +283,13 @@ def generateSpectrogram(audio: Sequence[float]) -> np.ndarray:
     lib = load_library()
     _check(lib.wb_generate_spectrogram_f64(_ptr(buf), 1, _ptr(result)), "generate_spectrogram")
     return result
+
+
+def read_checkpoint_dims(path: str) -> ModelDims:
+    """Model dimensions of a safetensors checkpoint, from its tensor shapes (wb_safetensors_read_dims; host only)."""
+    d = _Dims()
+    _check(load_library().wb_safetensors_read_dims(path.encode(), ctypes.byref(d)), "wb_safetensors_read_dims")
+    return ModelDims(*[getattr(d, f[0]) for f in _Dims._fields_])
 
 
 def bytes_to_unicode() -> Dict[int, str]:
@@ -422,6 +431,26 @@ class Whisper:
             self.load_state_dict(weights)
         elif seed is not None:
             _check(self._lib.wb_init_random_weights(self._h, seed), "wb_init_random_weights")
+
+    @classmethod
+    def from_checkpoint(cls, path: str, **kw) -> "Whisper":
+        """A model from a checkpoint file (whisper_to_cml.py:7 loads one by name from the network). `.safetensors` (upstream or
+        transformers tensor names; F32 / F16 / BF16) is read natively by the C ABI; an upstream `.pt` ({"dims", "model_state_dict"})
+        is unpickled with torch and handed over as a state dict."""
+        if path.endswith(".safetensors"):
+            w = cls(read_checkpoint_dims(path), seed=None, **kw)
+            n = ctypes.c_int32(0)
+            _check(w._lib.wb_load_safetensors(w._h, path.encode(), ctypes.byref(n)), "wb_load_safetensors")
+            w.n_loaded = n.value
+            return w
+        import torch
+        ck = torch.load(path, map_location="cpu", weights_only=True)
+        sd = ck["model_state_dict"] if "model_state_dict" in ck else ck
+        d = ck.get("dims") if isinstance(ck, dict) else None
+        dims = ModelDims(**{k: int(v) for k, v in d.items()}) if d else None
+        if dims is None:
+            raise WhisperB200Error(f"{path}: no 'dims' entry; save as safetensors (dimensions are derived from the shapes)")
+        return cls(dims, weights=sd, **kw)
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:

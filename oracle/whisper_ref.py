@@ -588,6 +588,7 @@ class WindowResult:
     no_speech_prob: float
     temperature: float
     compression_ratio: float
+    min_margin: float = float("inf")   # smallest top-1 / top-2 gap of the (perturbed) logits over every draw of this decode
 
 
 @torch.no_grad()
@@ -611,6 +612,7 @@ def decode_window(model: "WhisperRef", xa: torch.Tensor, opts: "DecodeOptions", 
     cache: List[Optional[tuple]] = [None] * dims.n_text_layer
     sum_logprobs = torch.zeros(G)
     no_speech_prob = 0.0
+    min_margin = float("inf")
     for i in range(sample_len):
         feed = tokens if i == 0 else tokens[:, -1:]
         all_logits = model.decoder_logits(feed, xg, cross, cache)
@@ -624,11 +626,16 @@ def decode_window(model: "WhisperRef", xa: torch.Tensor, opts: "DecodeOptions", 
         if opts.timestamps:
             logits = apply_timestamp_rules(logits, tokens, sample_begin, v, opts.max_initial_timestamp_index)
         if temperature == 0:
-            nxt = logits.argmax(dim=-1)
+            scored = logits
         else:
             position = tokens.shape[1]
             inv_t = np.float32(1.0) / np.float32(temperature)
-            nxt = torch.stack([(logits[j] * float(inv_t) + gumbel_noise(seed, j, position, dims.n_vocab)).argmax() for j in range(G)])
+            scored = torch.stack([logits[j] * float(inv_t) + gumbel_noise(seed, j, position, dims.n_vocab) for j in range(G)])
+        nxt = scored.argmax(dim=-1)
+        top2 = scored.topk(2, dim=-1).values
+        live = tokens[:, -1] != v.eot
+        if bool(live.any()):
+            min_margin = min(min_margin, float((top2[:, 0] - top2[:, 1])[live].min()))
         logprobs = F.log_softmax(logits.float(), dim=-1)
         cur = logprobs[torch.arange(G), nxt]
         sum_logprobs += cur * (tokens[:, -1] != v.eot)
@@ -647,7 +654,7 @@ def decode_window(model: "WhisperRef", xa: torch.Tensor, opts: "DecodeOptions", 
     if table is not None:
         drop = v.timestamp_begin if opts.timestamps else v.eot
         cr = text_compression_ratio(b"".join(table[t] for t in best_tokens if t < drop and t < len(table)))
-    return WindowResult(best_tokens, float(sum_logprobs[best]) / (len(best_tokens) + 1), no_speech_prob, float(temperature), cr)
+    return WindowResult(best_tokens, float(sum_logprobs[best]) / (len(best_tokens) + 1), no_speech_prob, float(temperature), cr, min_margin)
 
 
 @torch.no_grad()
@@ -680,9 +687,11 @@ def transcribe_seek(model: "WhisperRef", audio: np.ndarray, mel_filters: np.ndar
         xa = model.encode(mel_segment[None])
         prompt = all_tokens[prompt_reset_since:]
         tried = []
+        worst = float("inf")
         for ti, t in enumerate(temperatures):
             res = decode_window(model, xa, opts, prompt, t, call_seed(seed, seek, ti), best_of, sot_index, table)
             tried.append(t)
+            worst = min(worst, res.min_margin)
             needs_fallback = False
             if use_cr and res.compression_ratio > compression_ratio_threshold:
                 needs_fallback = True
@@ -692,6 +701,7 @@ def transcribe_seek(model: "WhisperRef", audio: np.ndarray, mel_filters: np.ndar
                 needs_fallback = False
             if not needs_fallback:
                 break
+        res.min_margin = worst            # over every decode of this window, the rejected ones included
         trace.append((seek, tried, res))
         tokens = res.tokens
         if no_speech_threshold is not None:

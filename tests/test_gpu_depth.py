@@ -205,7 +205,8 @@ def test_language_id_tie_break_is_first_max(wbm, ref):
     w.close()
 
 
-@pytest.mark.parametrize("env", [{"WB_LAYER_BLOCK": "1"}, {"WB_LAYER_BLOCK": "1", "WB_HANDOFF_FLAGS": "0"}, {"WB_SUBBATCHES": "2"}])
+@pytest.mark.parametrize("env", [{"WB_LAYER_BLOCK": "1"}, {"WB_LAYER_BLOCK": "1", "WB_HANDOFF_FLAGS": "0"}, {"WB_SUBBATCHES": "2"},
+                                 {"WB_SUBBATCHES": "2", "WB_PAIR": "1"}, {"WB_SUBBATCHES": "2", "WB_PAIR": "2"}])
 def test_alternate_decode_paths_keep_parity(env):
     """The decode paths that are not the default (the two-launch-per-layer cluster kernel + persistent attention stream, with
     and without the per-group hand-off counters; two sub-batches on two streams) stay behind environment switches that are
@@ -217,3 +218,54 @@ def test_alternate_decode_paths_keep_parity(env):
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", *sel.split()], cwd=root, env={**os.environ, **env},
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
+
+
+def test_checkpoint_files_round_trip(wbm, ref, tmp_path):
+    """a handle filled from a safetensors file (upstream names F32; transformers names F16, without the tied
+    proj_out / with the sinusoidal encoder positions regenerated when absent; BF16) holds exactly the tensors of the state
+    dict; an upstream-style .pt ({"dims", "model_state_dict"}) loads through from_checkpoint; a file of another model size is
+    rejected. Logits of the file-loaded model equal those of the dict-loaded one bit for bit."""
+    from safetensors.torch import save_file
+    dims = ref.ModelDims(80, 1500, 128, 2, 2, 51865, 448, 128, 2, 3)
+    w_ref = ref.random_weights(dims, seed=5)
+    up = str(tmp_path / "upstream.safetensors")
+    save_file({k: v.contiguous() for k, v in w_ref.items()}, up)
+    hf = ref.to_hf(dims, w_ref)
+    sd = {k: v.detach().clone().contiguous().half() for k, v in hf.state_dict().items()
+          if k not in ("proj_out.weight", "model.encoder.embed_positions.weight")}
+    hfp = str(tmp_path / "hf_f16.safetensors")
+    save_file(sd, hfp, metadata={"format": "pt"})
+    bfp = str(tmp_path / "upstream_bf16.safetensors")
+    save_file({k: v.contiguous().bfloat16() for k, v in w_ref.items()}, bfp)
+    ptp = str(tmp_path / "upstream.pt")
+    torch.save({"dims": {f: getattr(dims, f) for f in dims.__dataclass_fields__}, "model_state_dict": w_ref}, ptp)
+
+    base = wbm.Whisper(_pd(wbm, dims), weights=w_ref, max_batch=1)
+    xa = (torch.randn(1, 1500, 128, generator=torch.Generator().manual_seed(2)) * 0.7).half().float().numpy()
+    toks = np.arange(7, dtype=np.int32)[None] * 1000 + 3
+    base.set_audio_features(xa)
+    want_logits = base.decoder_logits(toks)
+    want_sd = base.state_dict()
+    for path, n_expected in ((up, len(w_ref)), (hfp, len(w_ref) - 1), (ptp, None)):
+        w = wbm.Whisper.from_checkpoint(path, max_batch=1)
+        assert tuple(getattr(w.dims, f) for f in w.dims.__dataclass_fields__) == tuple(getattr(dims, f) for f in dims.__dataclass_fields__)
+        if n_expected is not None:
+            assert w.n_loaded == n_expected
+        got_sd = w.state_dict()
+        for k in want_sd:
+            if k == "encoder.positional_embedding" and path == hfp:
+                assert np.abs(got_sd[k] - want_sd[k]).max() < 1e-6           # regenerated sinusoids
+            else:
+                assert np.array_equal(got_sd[k], want_sd[k]), (path, k)
+        w.set_audio_features(xa)
+        assert np.array_equal(w.decoder_logits(toks), want_logits)
+        w.close()
+    wb16 = wbm.Whisper.from_checkpoint(bfp, max_batch=1)
+    k = "decoder.blocks.1.mlp.0.weight"
+    assert np.array_equal(wb16.get_weight(k), w_ref[k].bfloat16().half().float().numpy().reshape(-1))      # bf16 -> the arena's fp16
+    wb16.close()
+    other = wbm.Whisper("tiny", seed=None, max_batch=1)
+    import ctypes
+    assert wbm.load_library().wb_load_safetensors(other.handle, up.encode(), None) == -1
+    assert b"wrong model size" in wbm.load_library().wb_last_error()
+    other.close(), base.close()

@@ -82,9 +82,31 @@ def test_temperature_sampling_and_no_speech_prob_match_oracle(wbm, ref, name, be
     w.close()
 
 
-def _compare(res, toks_ref, segs_ref):
-    assert res["tokens"].tolist() == toks_ref
-    assert len(res["segments"]) == len(segs_ref)
+TOL_TIE = 2e-2   # as tests/parity_util.py: a top-1 / top-2 gap of the oracle's (perturbed) logits below this is a tie for the fp16 path
+
+
+def _compare(res, toks_ref, segs_ref, trace):
+    """Segments and tokens identical to the oracle's. Every decision of the loop is an arg-max over (perturbed) logits the CUDA
+    path computes with fp16 operands, so a draw whose top-2 gap in the oracle is below TOL_TIE may fall the other way and the
+    recordings' paths part from that window on: then everything before that window must be identical, and the oracle's own
+    smallest gap inside that window (over every decode of it, rejected ones included) must indeed be a tie."""
+    n_same = 0
+    for g, r in zip(res["segments"], segs_ref):
+        if g["seek"] != r["seek"] or g["tokens"] != r["tokens"] or g["temperature"] != pytest.approx(r["temperature"]):
+            break
+        n_same += 1
+    if n_same < len(segs_ref) or len(res["segments"]) != len(segs_ref):
+        cands = [x["seek"] for x in (res["segments"][n_same:n_same + 1] + segs_ref[n_same:n_same + 1])]
+        w = min(cands)
+        margins = {s: r.min_margin for s, _, r in trace}
+        assert w in margins, f"paths part at a window the oracle never visited (seek {w})"
+        assert margins[w] <= TOL_TIE, f"window at seek {w} differs although the oracle's smallest gap there is {margins[w]:.4f}"
+        assert all(g["seek"] < w for g in res["segments"][:n_same])
+        print(f"\n[long-form] tie at seek {w} (oracle gap {margins[w]:.4f}): {n_same} of {len(segs_ref)} segments compared")
+        segs_ref = segs_ref[:n_same]
+        res = {"segments": res["segments"][:n_same], "tokens": None}
+    else:
+        assert res["tokens"].tolist() == toks_ref
     for g, r in zip(res["segments"], segs_ref):
         assert g["seek"] == r["seek"] and g["tokens"] == r["tokens"], (g, r)
         assert abs(g["start"] - r["start"]) < 1e-3 and abs(g["end"] - r["end"]) < 1e-3
@@ -111,7 +133,7 @@ def test_transcribe_seek_matches_oracle(wbm, ref, golden_dir):
     res = w.transcribe_seek(audio, o, tokenizer=_table_tokenizer(wbm, table), **kw)
     print("\n[long-form tiny.en 110 s] windows (seek, temperatures tried, tokens): " +
           str([(s, t, len(r.tokens)) for s, t, r in trace]))
-    _compare(res, toks_ref, segs_ref)
+    _compare(res, toks_ref, segs_ref, trace)
     tried = [t for _, t, _ in trace]
     assert any(len(t) > 1 for t in tried) and any(len(t) == 1 for t in tried)              # fallback taken and not taken
     assert len({s["seek"] for s in segs_ref}) < len(segs_ref)                              # several segments in one window
@@ -121,17 +143,18 @@ def test_transcribe_seek_matches_oracle(wbm, ref, golden_dir):
     kw1 = dict(temperatures=(0.0,), logprob_threshold=-3.7, compression_ratio_threshold=2.0, no_speech_threshold=0.85)
     toks1, segs1, trace1 = ref.transcribe_seek(oracle, audio, _mel_filters(golden_dir), o_ref, table=table, seed=3, **kw1)
     res1 = w.transcribe_seek(audio, o, tokenizer=_table_tokenizer(wbm, table), **kw1)
-    _compare(res1, toks1, segs1)
+    _compare(res1, toks1, segs1, trace1)
     assert len(segs1) and len(trace1) > len({s["seek"] for s in segs1})                    # a window was skipped as silence
     # without a tokenizer (no compression-ratio rule), without conditioning on the previous text, with an initial prompt
-    kw2 = dict(temperatures=(0.0, 1.0), logprob_threshold=-4.5, compression_ratio_threshold=None, no_speech_threshold=None,
+    kw2 = dict(temperatures=(0.0, 1.0), logprob_threshold=-3.0, compression_ratio_threshold=None, no_speech_threshold=None,
                condition_on_previous_text=False)
     prompt = [2000, 2001, 2002]
-    toks2, segs2, trace2 = ref.transcribe_seek(oracle, audio[: 16000 * 50], _mel_filters(golden_dir), o_ref, table=None, seed=9, best_of=2,
+    toks2, segs2, trace2 = ref.transcribe_seek(oracle, audio[: 16000 * 50], _mel_filters(golden_dir), o_ref, table=None, seed=10, best_of=2,
                                                initial_prompt=prompt, **kw2)
-    o.seed = 9
+    o.seed = 10
     res2 = w.transcribe_seek(audio[: 16000 * 50], o, initial_prompt=prompt, **kw2)
-    _compare(res2, toks2, segs2)
+    _compare(res2, toks2, segs2, trace2)
+    assert all(len(t) == 2 for _, t, _ in trace2)                                          # every window fell back to temperature 1
     w.close()
 
 
@@ -157,11 +180,11 @@ def test_transcribe_seek_multilingual_with_language_detection(wbm, ref, golden_d
     lang = int(oracle.detect_language(oracle.encode(mel[None, :, :3000]))[0])
     o_ref = ref.DecodeOptions.default_for(dims, sample_len=32, language=lang, without_timestamps=False)
     kw = dict(temperatures=(0.0, 0.8), logprob_threshold=-4.5, compression_ratio_threshold=None, no_speech_threshold=0.85)
-    toks_ref, segs_ref, _ = ref.transcribe_seek(oracle, audio, _mel_filters(golden_dir), o_ref, seed=4, **kw)
+    toks_ref, segs_ref, trace = ref.transcribe_seek(oracle, audio, _mel_filters(golden_dir), o_ref, seed=4, **kw)
     w = wbm.Whisper("tiny", weights=weights, max_batch=1)
     o = wbm.DecodeOptions.default_for(wbm.DIMS["tiny"], sample_len=32, language=0, without_timestamps=False)
     o.seed = 4
     res = w.transcribe_seek(audio, o, detect_language=True, **kw)
     assert res["language"] == lang
-    _compare(res, toks_ref, segs_ref)
+    _compare(res, toks_ref, segs_ref, trace)
     w.close()

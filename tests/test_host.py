@@ -239,3 +239,40 @@ def test_oracle_stream_logmel_first_window_against_chunk_oracle(ref, oracle_logm
     got = ref.log_mel_stream(a.astype(np.float32), np.load(os.path.join(golden_dir, "m80.npy")))[:, :3000].numpy()
     want = oracle_logmel(a.astype(np.float32).astype(np.float64))
     assert np.abs(got - want).max() < 2e-4
+
+
+# ---- checkpoint files (host part: the safetensors header reader and the shape -> dimensions rule) ---------------------------
+def _write_checkpoints(ref, tmp_path, dims, seed=1):
+    from safetensors.torch import save_file
+    w = ref.random_weights(dims, seed=seed)
+    up = tmp_path / "upstream.safetensors"
+    save_file({k: v.contiguous() for k, v in w.items()}, str(up))
+    hf = ref.to_hf(dims, w)
+    sd = {k: v.detach().clone().contiguous().half() for k, v in hf.state_dict().items() if k != "proj_out.weight"}
+    hfp = tmp_path / "hf_f16.safetensors"
+    save_file(sd, str(hfp), metadata={"format": "pt", "note": "nested \"quotes\" and a brace } in metadata"})
+    return w, str(up), str(hfp)
+
+
+def test_safetensors_dims_from_shapes(wbm, ref, tmp_path):
+    """A file written by the `safetensors` package (an independent writer) under upstream names in F32 and under transformers
+    names in F16: the ten model dimensions come out of the tensor shapes; malformed files are errors with a message."""
+    import ctypes
+    dims = ref.ModelDims(80, 1500, 128, 2, 2, 51865, 448, 128, 2, 3)
+    _, up, hfp = _write_checkpoints(ref, tmp_path, dims)
+    for path in (up, hfp):
+        got = wbm.read_checkpoint_dims(path)
+        assert tuple(getattr(got, f) for f in got.__dataclass_fields__) == tuple(getattr(dims, f) for f in dims.__dataclass_fields__)
+    lib = wbm.load_library()
+    raw = open(up, "rb").read()
+    cases = {"short": raw[:5], "hdr_len": (10 ** 12).to_bytes(8, "little") + raw[8:200], "not_json": (16).to_bytes(8, "little") + b"[1, 2, 3]       ",
+             "truncated": raw[:len(raw) // 2], "empty": (2).to_bytes(8, "little") + b"{}"}
+    from importlib import import_module
+    D = import_module("openai-whisper-coreml_b200.whisper")._Dims
+    for tag, blob in cases.items():
+        p = tmp_path / f"{tag}.safetensors"
+        p.write_bytes(blob)
+        assert lib.wb_safetensors_read_dims(str(p).encode(), ctypes.byref(D())) == -1, tag
+        assert b"safetensors" in lib.wb_last_error()
+    with pytest.raises(wbm.WhisperB200Error, match="cannot open"):
+        wbm.read_checkpoint_dims(str(tmp_path / "missing.safetensors"))
