@@ -45,27 +45,6 @@ int decoder_set_l2_mode(int mode) {
 // Weights and the cross-attention K/V are constant during a decode and use the non-coherent path.
 __device__ __forceinline__ int ld_state(const int* p) { return __ldcg(p); }
 
-// Hand-off counters in DecodeState (q_ready / a_done): producers fence their data stores, synchronise, and one thread adds
-// with release semantics; a consumer thread polls with acquire semantics, then the rest of its CTA / warp is released by a
-// barrier and reads the data through L2. The poll is bounded so that a protocol bug cannot hang the device.
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
-  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void poll_at_least(const int* counter, int target, int* timeout_flag) {
-  unsigned int spins = 0;
-  while (ld_acquire_gpu(counter) < target) {
-    if (++spins > (1u << 24)) {   // tens of milliseconds: thousands of times longer than any legitimate wait
-      atomicExch(timeout_flag, 1);
-      break;
-    }
-  }
-}
-
 // Development tracing: block (0,0) thread 0 of every decode kernel stamps %globaltimer at entry and exit (WB_TRACE=1).
 __device__ __forceinline__ unsigned long long globaltimer() {
   unsigned long long t;
@@ -1068,11 +1047,6 @@ struct HeadAttnArgs {
   int d, n_rows_fixed, kv_share, n_stages;
   int l2_prefetch_tiles;   // cross attention: stage tiles beyond the ring requested into L2 while q is still being computed
   int pdl_late;            // release the dependent kernel after the main loop instead of at entry
-  // Interleaved sub-batch pair: this launch is the n-th KV-cache kernel of its sub-batch's decode (n = cur_len * n_layer +
-  // layer); its producer does not start streaming before the peer sub-batch has finished peer_lead + n of its own (counted in
-  // the peer's DecodeState::x_done, one per CTA), so that the two bandwidth-bound streams alternate instead of coinciding.
-  const DecodeState* peer;   // null: no ordering
-  int peer_ctas, peer_lead, layer, n_layer;
 };
 
 // 8 weight rows x d of a [.][d] fp16 matrix against one fp32 vector in shared memory: lane l owns the 16-byte chunks
@@ -1154,11 +1128,6 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
     if (lane == 0) {
       const int slab = b / a.kv_share;
       const uint64_t kvpol = fixed ? stream_policy() : ptx::l2_policy(0);   // cross K/V: read once per step
-      if (a.peer) {
-        DecodeState* me = const_cast<DecodeState*>(a.state);
-        const int n = ld_state(&me->cur_len) * a.n_layer + a.layer;
-        poll_at_least(&a.peer->x_done, a.peer_ctas * (n + a.peer_lead), &me->spin_timeout);
-      }
       if (fixed) {   // the producer of a cross-attention CTA runs ahead of q: pull the tiles after the ring into L2 meanwhile
         const int pf_end = n_stages + a.l2_prefetch_tiles < n_tiles ? n_stages + a.l2_prefetch_tiles : n_tiles;
         for (int t = n_stages; t < pf_end; ++t) {
@@ -1317,7 +1286,6 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
   }
   __syncthreads();   // all stages consumed; reuse the ring for the cross-warp merge: [8][68] floats
   if (a.pdl_late == 1) ptx::grid_dep_launch();
-  if (a.peer && tid == 0) red_release_gpu_add(&const_cast<DecodeState*>(a.state)->x_done, 1);   // this CTA's share of the stream is in
   float* red = reinterpret_cast<float*>(smem);
   if (warp < 8) {
     float L = l_run;
@@ -1351,292 +1319,6 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
   trace.end();
 }
 
-// ---- KV-cache attention as a persistent stream: one CTA per SM looping over (sequence, head) items ------------------------------------
-// The cross-attention kernel of the layer-block path (queries already projected, in global memory). Same arithmetic per item as
-// attn_decode_head_kernel, but ONE resident CTA per SM (9 warps, ~28K registers, the ring + 3 KB of shared memory): the cluster
-// kernels before and after it fit on the same SMs next to it, so they become resident — constants loaded, first weights in flight —
-// while this kernel streams, and this kernel's ring fills while they compute. The producer runs ahead across item boundaries.
-// Online-softmax state of one warp over the rows it owns (16 of every 128-row tile)
-struct AttnAcc {
-  float o[4][4];
-  float m_run, l_run;
-};
-// One warp, NT (1 or 2) K/V stage tiles at once: S = K q^T (q split into fp16 hi + lo, separate accumulator chains), ONE
-// running-max update for the NT x 16 rows, P V accumulated into the 4 output blocks. Two tiles per call halve the number of
-// dependent max -> exp2 -> rescale chains per byte streamed and give the tensor pipe 4 independent chains instead of 1.
-// sk[i]: shared-memory address of K tile i (V follows at + kHaTileBytes); row0[i]: global row of this warp's first row in tile i.
-// Requires row0[0] < n_rows (at least one live row), rows >= n_rows are masked (the TMA unit zero-filled them).
-template <int NT>
-__device__ __forceinline__ void attn_tiles(AttnAcc& A, const uint32_t (&qh)[4][2], const uint32_t (&ql)[4][2], const uint32_t (&sk)[NT],
-                                           const int (&row0)[NT], int n_rows, int warp, int lane) {
-  const int grp = lane >> 2, tq = lane & 3, mi = lane >> 3, r8 = lane & 7;
-  float ch[NT][4], cl[NT][4];
-#pragma unroll
-  for (int i = 0; i < NT; ++i) {
-    ch[i][0] = ch[i][1] = ch[i][2] = ch[i][3] = 0.f;
-    cl[i][0] = cl[i][1] = cl[i][2] = cl[i][3] = 0.f;
-  }
-  const int Rk = warp * 16 + (mi & 1) * 8 + r8;       // tile row this lane addresses for ldmatrix (K)
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-    for (int i = 0; i < NT; ++i) {
-      uint32_t af[4];
-      ptx::ldmatrix_x4(af, sk[i] + Rk * 128 + (((kk * 2 + (mi >> 1)) ^ (Rk & 7)) << 4));
-      ptx::mma_16816(ch[i], af, qh[kk]);
-      ptx::mma_16816(cl[i], af, ql[kk]);
-    }
-  }
-  float s_lo[NT], s_hi[NT], tmax = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < NT; ++i) {
-    s_lo[i] = (row0[i] + grp < n_rows) ? ch[i][0] + cl[i][0] : -INFINITY;
-    s_hi[i] = (row0[i] + grp + 8 < n_rows) ? ch[i][2] + cl[i][2] : -INFINITY;
-    tmax = fmaxf(tmax, fmaxf(s_lo[i], s_hi[i]));
-  }
-  tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 4));
-  tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 8));
-  tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 16));
-  if (tmax > A.m_run) {                                // warp-uniform (identical in every lane)
-    const float corr = exp2f(A.m_run - tmax);
-    A.m_run = tmax;
-    A.l_run *= corr;
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt) A.o[mt][0] *= corr, A.o[mt][1] *= corr, A.o[mt][2] *= corr, A.o[mt][3] *= corr;
-  }
-  const int Rv = warp * 16 + (mi >> 1) * 8 + r8;      // (V, transposed load)
-#pragma unroll
-  for (int i = 0; i < NT; ++i) {
-    const float p_lo = exp2f(s_lo[i] - A.m_run), p_hi = exp2f(s_hi[i] - A.m_run);
-    A.l_run += p_lo + p_hi;
-    const float e0 = __shfl_sync(0xffffffffu, p_lo, (2 * tq) * 4), e1 = __shfl_sync(0xffffffffu, p_lo, (2 * tq + 1) * 4);
-    const float e2 = __shfl_sync(0xffffffffu, p_hi, (2 * tq) * 4), e3 = __shfl_sync(0xffffffffu, p_hi, (2 * tq + 1) * 4);
-    const __half2 ph0 = __floats2half2_rn(e0, e1), ph1 = __floats2half2_rn(e2, e3);
-    const float2 f0 = __half22float2(ph0), f1 = __half22float2(ph1);
-    const __half2 pl0 = __floats2half2_rn(e0 - f0.x, e1 - f0.y), pl1 = __floats2half2_rn(e2 - f1.x, e3 - f1.y);
-    const uint32_t pbh[2] = {*reinterpret_cast<const uint32_t*>(&ph0), *reinterpret_cast<const uint32_t*>(&ph1)};
-    const uint32_t pbl[2] = {*reinterpret_cast<const uint32_t*>(&pl0), *reinterpret_cast<const uint32_t*>(&pl1)};
-    const uint32_t sv = sk[i] + kHaTileBytes;
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
-      uint32_t af[4];
-      ptx::ldmatrix_x4_trans(af, sv + Rv * 128 + (((mt * 2 + (mi & 1)) ^ (Rv & 7)) << 4));
-      ptx::mma_16816(A.o[mt], af, pbh);
-      ptx::mma_16816(A.o[mt], af, pbl);
-    }
-  }
-}
-// q (64 fp32 values of one head) -> B fragments replicated over the 8 n columns, fp16 hi + lo parts, pre-scaled into the log2 domain
-__device__ __forceinline__ void attn_q_frags(uint32_t (&qh)[4][2], uint32_t (&ql)[4][2], const float* q64, bool from_global, int tq) {
-  const float sl = 0.125f * kLog2e;   // (d_head^-0.25)^2 = 1/8 exactly
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    const float* qp = q64 + kk * 16 + 2 * tq;
-    float2 q0, q1;
-    if (from_global)
-      q0 = __ldcg(reinterpret_cast<const float2*>(qp)), q1 = __ldcg(reinterpret_cast<const float2*>(qp + 8));
-    else
-      q0 = *reinterpret_cast<const float2*>(qp), q1 = *reinterpret_cast<const float2*>(qp + 8);
-    const float v[4] = {q0.x * sl, q0.y * sl, q1.x * sl, q1.y * sl};
-    __half hi[4], lo[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      hi[e] = __float2half_rn(v[e]);
-      lo[e] = __float2half_rn(v[e] - __half2float(hi[e]));
-    }
-    __half2 h0 = __halves2half2(hi[0], hi[1]), h1 = __halves2half2(hi[2], hi[3]);
-    __half2 l0 = __halves2half2(lo[0], lo[1]), l1 = __halves2half2(lo[2], lo[3]);
-    qh[kk][0] = *reinterpret_cast<uint32_t*>(&h0), qh[kk][1] = *reinterpret_cast<uint32_t*>(&h1);
-    ql[kk][0] = *reinterpret_cast<uint32_t*>(&l0), ql[kk][1] = *reinterpret_cast<uint32_t*>(&l1);
-  }
-}
-
-struct StreamAttnArgs {
-  const float* q;          // [Mb][d] queries (fp32)
-  __half* out16;           // [Mb][d]
-  const DecodeState* state;
-  int d, n_head, n_items, n_rows, kv_share, n_stages;
-  int pdl_early;           // release the dependent kernel at entry (it only becomes resident; it waits for this kernel's completion itself)
-  int use_flags;           // 1: per-group hand-off counters in DecodeState (q_ready / a_done) instead of griddepcontrol.wait
-  int layer, n_layer, Mb;
-};
-
-__global__ void __maxnreg__(96) attn_stream_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                                                                    StreamAttnArgs a) {
-  extern __shared__ unsigned char smem_dyn[];
-  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8];
-  __shared__ float s_red[2][8 * 68];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int grp = lane >> 2, tq = lane & 3, mi = lane >> 3, r8 = lane & 7;
-  TraceScope trace(a.state, 202);
-  const int n_stages = a.n_stages;
-  if (tid == 0) {
-    ptx::prefetch_tensormap(&tmK);
-    ptx::prefetch_tensormap(&tmV);
-    for (int s = 0; s < n_stages; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 8);
-    }
-    ptx::fence_mbar_init();
-  }
-  __syncthreads();
-  if (a.pdl_early) ptx::grid_dep_launch();
-  const int n_rows = a.n_rows;
-  const int n_tiles = (n_rows + kHaStageRows - 1) / kHaStageRows;
-
-  if (warp == 8) {
-    if (lane == 0) {
-      const uint64_t kvpol = stream_policy();
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-        const int h = item % a.n_head, slab = (item / a.n_head) / a.kv_share;
-        for (int t = 0; t < n_tiles; ++t, ++it) {
-          const int s = it % n_stages;
-          const uint32_t ph = (it / n_stages) & 1u;
-          ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
-          ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * kHaTileBytes);
-          unsigned char* dk = smem + (size_t)s * 2 * kHaTileBytes;
-          ptx::tma_load_3d(dk, &tmK, &full_bar[s], h * 64, t * kHaStageRows, slab, kvpol);
-          ptx::tma_load_3d(dk + kHaTileBytes, &tmV, &full_bar[s], h * 64, t * kHaStageRows, slab, kvpol);
-        }
-      }
-    }
-  } else {
-    DecodeState* st = const_cast<DecodeState*>(a.state);
-    int q_target = 0;
-    if (a.use_flags) {
-      // the launch is only ordered after the START of the layer-block kernel (which itself started after the previous step's
-      // finish kernel completed, so cur_len is this step's); a group's queries are ready when all C = 2 * n_head CTAs of
-      // its cluster have counted in
-      q_target = 2 * a.n_head * (ld_state(&st->cur_len) * a.n_layer + a.layer + 1);
-    } else {
-      ptx::grid_dep_sync();             // the queries come from the previous kernel
-    }
-    uint32_t it = 0, n_done = 0;
-    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++n_done) {
-      const int h = item % a.n_head, b = item / a.n_head;
-      if (a.use_flags) {
-        if (lane == 0) poll_at_least(&st->q_ready[b >> 3], q_target, &st->spin_timeout);
-        __syncwarp();
-      }
-      uint32_t qh[4][2], ql[4][2];
-      attn_q_frags(qh, ql, a.q + (size_t)b * a.d + h * 64, true, tq);
-      AttnAcc acc;
-      acc.m_run = -INFINITY, acc.l_run = 0.f;
-#pragma unroll
-      for (int mt = 0; mt < 4; ++mt) acc.o[mt][0] = acc.o[mt][1] = acc.o[mt][2] = acc.o[mt][3] = 0.f;
-      int t = 0;
-      for (; t + 2 <= n_tiles; t += 2, it += 2) {            // two stage tiles per pass
-        const int s0 = it % n_stages, s1 = (it + 1) % n_stages;
-        ptx::mbar_wait(&full_bar[s0], (it / n_stages) & 1u);
-        ptx::mbar_wait(&full_bar[s1], ((it + 1) / n_stages) & 1u);
-        const int row0[2] = {t * kHaStageRows + warp * 16, (t + 1) * kHaStageRows + warp * 16};
-        if (row0[0] < n_rows) {                              // warp-uniform
-          const uint32_t sk[2] = {ptx::smem_u32(smem + (size_t)s0 * 2 * kHaTileBytes), ptx::smem_u32(smem + (size_t)s1 * 2 * kHaTileBytes)};
-          attn_tiles<2>(acc, qh, ql, sk, row0, n_rows, warp, lane);
-        }
-        __syncwarp();
-        if (lane == 0) {
-          ptx::mbar_arrive(&empty_bar[s0]);
-          ptx::mbar_arrive(&empty_bar[s1]);
-        }
-      }
-      for (; t < n_tiles; ++t, ++it) {                       // odd tile count: the last one alone
-        const int s0 = it % n_stages;
-        ptx::mbar_wait(&full_bar[s0], (it / n_stages) & 1u);
-        const int row0[1] = {t * kHaStageRows + warp * 16};
-        if (row0[0] < n_rows) {
-          const uint32_t sk[1] = {ptx::smem_u32(smem + (size_t)s0 * 2 * kHaTileBytes)};
-          attn_tiles<1>(acc, qh, ql, sk, row0, n_rows, warp, lane);
-        }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&empty_bar[s0]);
-      }
-      const float m_run = acc.m_run, l_run = acc.l_run;
-      float (&o)[4][4] = acc.o;
-      // cross-warp merge of the item (double-buffered scratch: one named barrier per item; the producer warp is not involved)
-      float* red = s_red[n_done & 1u];
-      float L = l_run;
-      L += __shfl_xor_sync(0xffffffffu, L, 4);
-      L += __shfl_xor_sync(0xffffffffu, L, 8);
-      L += __shfl_xor_sync(0xffffffffu, L, 16);
-      if (tq == 0) {
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
-          red[warp * 68 + mt * 16 + grp] = o[mt][0];
-          red[warp * 68 + mt * 16 + grp + 8] = o[mt][2];
-        }
-        if (grp == 0) red[warp * 68 + 64] = m_run, red[warp * 68 + 65] = L;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (tid < 64) {
-        float M = -INFINITY;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) M = fmaxf(M, red[w * 68 + 64]);
-        float Ls = 0.f, A = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-          const float mw = red[w * 68 + 64];
-          const float wgt = (mw == -INFINITY) ? 0.f : exp2f(mw - M);
-          Ls += wgt * red[w * 68 + 65];
-          A += wgt * red[w * 68 + tid];
-        }
-        a.out16[(size_t)b * a.d + h * 64 + tid] = __float2half_rn(A / Ls);
-        if (a.use_flags) {
-          __threadfence();
-          asm volatile("bar.sync 2, 64;" ::: "memory");     // the 64 writers of this item
-          if (tid == 0) red_release_gpu_add(&st->a_done[b >> 3], 1);
-        }
-      }
-    }
-  }
-  trace.end();
-}
-
-static int launch_attn_stream(const AttnDecodeDesc& p, cudaStream_t st, int64_t* launches) {
-  CUtensorMap tmK, tmV;
-  const long long nslab = (p.Mb + p.kv_share - 1) / p.kv_share;
-  int rc = gemm_get_tmap(p.tmaps, p.k, p.d, p.n_ctx, nslab, p.d, (long long)p.n_ctx * p.d, kHaStageRows, &tmK);
-  if (rc) return rc;
-  rc = gemm_get_tmap(p.tmaps, p.v, p.d, p.n_ctx, nslab, p.d, (long long)p.n_ctx * p.d, kHaStageRows, &tmV);
-  if (rc) return rc;
-  static int n_sm_dev[kMaxDevices] = {};
-  int& n_sm = n_sm_dev[current_device_slot()];
-  if (!n_sm) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (n_sm <= 0) n_sm = 148;
-  }
-  static int stages = -1, early = -1;
-  if (stages < 0) {
-    const char* e = getenv("WB_XS_STAGES");
-    stages = e ? atoi(e) : 4;
-    stages = stages < 2 ? 2 : (stages > 6 ? 6 : stages);
-    e = getenv("WB_XS_EARLY");
-    early = e ? atoi(e) : 1;
-  }
-  StreamAttnArgs a{p.q, p.out16, p.state, p.d, p.n_head, p.n_head * p.Mb, p.n_rows_fixed, p.kv_share, stages, early, p.use_flags, p.layer, p.n_layer, p.Mb};
-  const size_t smem = (size_t)stages * 2 * kHaTileBytes + 1024;
-  static size_t smem_set_dev[kMaxDevices] = {};
-  size_t& smem_set = smem_set_dev[current_device_slot()];
-  if (smem > smem_set) {
-    WB_CUDA_OK(cudaFuncSetAttribute(attn_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(a.n_items < n_sm ? a.n_items : n_sm), cfg.blockDim = dim3(kHaThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at, cfg.numAttrs = use_pdl() ? 1 : 0;
-  const cudaError_t le = cudaLaunchKernelEx(&cfg, attn_stream_kernel, tmK, tmV, a);
-  if (launches) *launches += 1;
-  WB_CUDA_OK(le);
-  return 0;
-}
-
 static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int64_t* launches) {
   CUtensorMap tmK, tmV;
   const long long nslab = (p.Mb + p.kv_share - 1) / p.kv_share;
@@ -1645,7 +1327,6 @@ static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int
   rc = gemm_get_tmap(p.tmaps, p.v, p.d, p.n_ctx, nslab, p.d, (long long)p.n_ctx * p.d, kHaStageRows, &tmV);
   if (rc) return rc;
   HeadAttnArgs a{p.q, p.x, p.ln_g, p.ln_b, p.wq, p.bq, p.out16, p.state, p.d, p.n_rows_fixed, p.kv_share, 3, 0, 0};   // L2 prefetch measured slightly negative in-step: off
-  a.peer = p.n_rows_fixed > 0 ? p.peer_state : nullptr, a.peer_ctas = p.peer_ctas, a.peer_lead = p.peer_lead, a.layer = p.layer, a.n_layer = p.n_layer;
   static int pdl_xa = -1;
   if (pdl_xa < 0) {
     const char* e = getenv("WB_PDL_XA");
@@ -1700,12 +1381,6 @@ int launch_attn_decode(const AttnDecodeDesc& p, cudaStream_t st, int64_t* launch
     set_error("attn_decode: unsupported d=%d heads=%d", p.d, p.n_head);
     return -1;
   }
-  static int use_stream = -1;
-  if (use_stream < 0) {
-    const char* e = getenv("WB_ATTN_STREAM");
-    use_stream = (e && e[0] == '0') ? 0 : 1;
-  }
-  if (use_stream && p.stream_ok && p.q && !p.wq && p.n_rows_fixed > 0) return launch_attn_stream(p, st, launches);
   return launch_attn_decode_head(p, st, launches);
 }
 
@@ -2568,684 +2243,6 @@ int launch_post_block(const PostBlockDesc& p, cudaStream_t st, int64_t* launches
     le = launch_post_block_t<512, 16>(a, n_groups, st);
   else
     le = launch_post_block_t<512, 8>(a, n_groups, st);
-  if (launches) *launches += 1;
-  WB_CUDA_OK(le);
-  return 0;
-}
-
-// ---- fused layer-boundary kernel: post part of layer l-1 + self-attention block of layer l + cross-attention query of layer l -------
-// One launch per layer boundary instead of two (post block, self block), and the LayerNorm + query projection prologue of the
-// cross attention moves here, so that the KV-cache kernel between two of these is a pure stream. Grid (C, groups of 8 sequences),
-// one cluster of C = 2 * n_head CTAs per group (16 for d = 512, 12 for d = 384: non-portable sizes). CTA r plays two roles:
-//   column role   it owns OC = d / C = 32 columns of the residual stream for all 8 sequences of the group
-//                 (output projections, MLP2 reduction, query projection) and HS = 4d / C hidden units of the MLP;
-//   head role     head h = r % n_head, sequences half * 4 .. + 3 of the group (half = r / n_head): QKV rows of its head,
-//                 cache append, attention over the cached rows.
-// The residual stream of the group lives in the shared memory of every CTA (xp, fp32 [8][d]); after each step that
-// produces new columns the owners push their slices into all C copies (DSMEM all-gather) and the cluster synchronises:
-//   0. x' = x + a16 Wo_c^T + bo_c (own columns)                                  -> all-gather, barrier 1       } has_post
-//   1. LayerNorm(x'; mlp_ln)   2. hidden slice gelu(W1 . + b1)   3. partial W2 over the slice  -> barrier 2   }
-//   4. own columns: x = x' + b2 + sum of the C partials (rank order, remote reads) -> all-gather, barrier 3     }
-//   5. LayerNorm(x; attn_ln), QKV of head h for the 8 sequences, k / v of the own half appended to the cache    } has_self
-//   6. attention of the own 4 sequences over the cached rows + the new one   -> all-gather of the outputs, barrier 4
-//   7. x'' = x + attn Wo^T + bo (own columns), also written to global memory  -> all-gather, barrier 5
-//   8. q = LayerNorm(x''; cross_attn_ln) Wq_c^T + bq_c (own columns)           -> global memory (read by the KV-cache kernel)
-// The first kernel of a step has no post part (x comes from the embedding in global memory), the last one has only the post
-// part (x goes back to global memory for the logits kernel). Reductions are in fixed order: deterministic.
-constexpr int kLbThreads = 384;
-constexpr int kLbWarps = kLbThreads / 32;
-
-struct LayerBlockArgs {
-  float* x;                 // [Mb][d] residual stream (global)
-  const __half* a16;        // [Mb][d] cross-attention outputs of the previous layer
-  const __half* wo_c;
-  const float* bo_c;
-  const float* ln2_g;
-  const float* ln2_b;
-  const __half* w1;
-  const float* b1;
-  const __half* w2;
-  const float* b2;
-  const float* ln1_g;
-  const float* ln1_b;
-  const __half* wqkv;
-  const float* bqkv;
-  const __half* wo;
-  const float* bo;
-  __half* kcache;
-  __half* vcache;
-  const float* lnc_g;
-  const float* lnc_b;
-  const __half* wq_c;
-  const float* bq_c;
-  float* q_out;             // [Mb][d] cross-attention queries (global)
-  int Mb, n_ctx, has_post, has_self;
-  int pdl_point;            // where the dependent kernel may start: 0 at entry, 1 after the post part, 2 after QKV, 3 after attention
-  int use_flags, layer, n_layer;
-  int stagger_ns;           // first kernel of a step: group g starts g * stagger_ns late, so that the groups' attention streams do not coincide
-  DecodeState* state;
-};
-
-template <int D, int C>
-struct LbCfg {
-  static constexpr int H = D / 64, OC = D / C, HS = 4 * D / C, NBLK = D / 32;
-  static constexpr int XS = D * 2 + 64, HSS = HS * 2 + 64, PS = D + 4;                 // row strides: bytes, bytes, floats
-  static constexpr int S0 = OC / 16, KP = kLbWarps / S0, NB0 = (NBLK + KP - 1) / KP;   // OC-row GEMMs: strips, K parts, blocks per part
-  static constexpr int SB = HS / 16;                                                   // MLP1 strips (one per warp, warps 0..SB-1)
-  static constexpr int SCW = D / 16 / 8, NBC = HS / 32, NPAIR = SCW * NBC;             // MLP2: strips per warp (warps 0..7), blocks per strip
-  static constexpr int RED = (KP * 8 * OC > 8 * HS) ? KP * 8 * OC : 8 * HS;
-  static constexpr size_t smem_used = (size_t)3 * 8 * XS + (size_t)8 * HSS +
-                                      ((size_t)8 * D + 8 * PS + RED + 6 * D + HS + 3 * 8 * 64 + 4 * 3 * 66) * 4;
-  // requested as is (~88 KB): together with one resident CTA of the persistent attention stream (4 x 32 KB ring) it fits an SM,
-  // and its 384 x 96 registers next to the stream's 288 x 96 fill the register file, so two CTAs of this kernel never share an SM
-  static constexpr size_t smem = smem_used;
-  static_assert(C == 2 * H && OC == 32 && S0 * KP == kLbWarps && SB == 8 && HS % 32 == 0 && (D / 16) % 8 == 0 && 8 * OC <= kLbThreads, "shape");
-};
-
-// one warp: up to NB weight blocks [kb0, kb1) of a 16-row strip, requested at once / multiplied with the activation tile
-template <int NB>
-__device__ __forceinline__ void lb_load(uint4 (&wa)[NB], uint4 (&wb)[NB], const __half* wrow0, const __half* wrow1, int kb0, int kb1, uint64_t wpol) {
-#pragma unroll
-  for (int u = 0; u < NB; ++u) {
-    const int blk = kb0 + u < kb1 ? kb0 + u : kb0;
-    wa[u] = ptx::ldg_nc_16(wrow0 + blk * 32, wpol);
-    wb[u] = ptx::ldg_nc_16(wrow1 + blk * 32, wpol);
-  }
-}
-template <int NB>
-__device__ __forceinline__ void lb_mma(float (&acc)[4], const uint4 (&wa)[NB], const uint4 (&wb)[NB], const unsigned char* bl, int kb0, int kb1) {
-#pragma unroll
-  for (int u = 0; u < NB; ++u) {
-    if (kb0 + u < kb1) {
-      const uint32_t a0[4] = {wa[u].x, wb[u].x, wa[u].y, wb[u].y}, a1[4] = {wa[u].z, wb[u].z, wa[u].w, wb[u].w};
-      const uint4 xb = *reinterpret_cast<const uint4*>(bl + (kb0 + u) * 64);
-      const uint32_t bf0[2] = {xb.x, xb.y}, bf1[2] = {xb.z, xb.w};
-      ptx::mma_16816(acc, a0, bf0);
-      ptx::mma_16816(acc, a1, bf1);
-    }
-  }
-}
-// warp w < 8: LayerNorm of row w of xp (fp32, two passes over registers) -> fp16 row w of xs; rows of absent sequences become zero
-template <int D>
-__device__ __forceinline__ void lb_layernorm(const float* xp, unsigned char* xs, int XS, const float* s_g, const float* s_b, int warp, int lane, bool live) {
-  if (warp >= 8) return;
-  const float* xr = xp + warp * D;
-  __half* dst = reinterpret_cast<__half*>(xs + warp * XS);
-  constexpr int N4 = D / 4;
-  float4 v[4];
-  float sum = 0.f, sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = lane + 32 * i;
-    v[i] = c < N4 ? *reinterpret_cast<const float4*>(xr + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
-  }
-  sum = warp_sum(sum), sq = warp_sum(sq);
-  const float mean = sum / (float)D;
-  const float rstd = live ? rsqrtf(fmaxf(sq / (float)D - mean * mean, 0.f) + 1e-5f) : 0.f;
-  const float ab = live ? 1.f : 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = lane + 32 * i;
-    if (c < N4) {
-      const float4 g = *reinterpret_cast<const float4*>(s_g + c * 4), bb = *reinterpret_cast<const float4*>(s_b + c * 4);
-      const __half2 h0 = __floats2half2_rn((v[i].x - mean) * rstd * g.x + ab * bb.x, (v[i].y - mean) * rstd * g.y + ab * bb.y);
-      const __half2 h1 = __floats2half2_rn((v[i].z - mean) * rstd * g.z + ab * bb.z, (v[i].w - mean) * rstd * g.w + ab * bb.w);
-      uint2 u;
-      u.x = *reinterpret_cast<const uint32_t*>(&h0), u.y = *reinterpret_cast<const uint32_t*>(&h1);
-      *reinterpret_cast<uint2*>(dst + c * 4) = u;
-    }
-  }
-}
-
-template <int D, int C>
-__global__ void __maxnreg__(96) layer_block_kernel(LayerBlockArgs a) {
-  using Cfg = LbCfg<D, C>;
-  constexpr int H = Cfg::H, OC = Cfg::OC, HS = Cfg::HS, NBLK = Cfg::NBLK, XS = Cfg::XS, HSS = Cfg::HSS, PS = Cfg::PS;
-  constexpr int S0 = Cfg::S0, KP = Cfg::KP, NB0 = Cfg::NB0;
-  extern __shared__ __align__(16) unsigned char lb_smem[];
-  TraceScope trace(a.state, 230);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int grp = lane >> 2, tq = lane & 3;
-  const int r = blockIdx.x, b0 = blockIdx.y * 8;                 // cluster rank (gridDim.x == C), first sequence of the group
-  const int h = r % H, half = r / H;                             // head role
-  unsigned char* as16 = lb_smem;                                 // [8][XS] fp16 cross-attention outputs (post part)
-  unsigned char* xs = as16 + 8 * XS;                             // [8][XS] fp16 LayerNorm output
-  unsigned char* sa = xs + 8 * XS;                               // [8][XS] fp16 self-attention outputs of all heads (written by the cluster)
-  unsigned char* hs = sa + 8 * XS;                               // [8][HSS] fp16 hidden slice
-  float* xp = reinterpret_cast<float*>(hs + 8 * HSS);            // [8][D] residual stream of the group
-  float* s_part = xp + 8 * D;                                    // [8][PS] MLP2 partial (read by the cluster)
-  float* s_red = s_part + 8 * PS;                                // K-split partials
-  float* s_ln = s_red + Cfg::RED;                                // [6][D]: mlp_ln g, b; attn_ln g, b; cross_attn_ln g, b
-  float* s_b1 = s_ln + 6 * D;                                    // [HS]
-  float* s_qkv = s_b1 + HS;                                      // [3][8][64] q, k, v of head h
-  float* s_att = s_qkv + 3 * 8 * 64;                             // [4][3][66] attention partials
-
-  // ---- before the wait: weights of the first phase, constants, L2 hints ------------------------------------------------------------------
-  const uint64_t wpol = weight_policy();
-  const int strip0 = warp % S0, kp0 = warp / S0;                 // OC-row GEMMs (phases 0, 7, 8): strip, K part
-  const int kb0 = kp0 * NBLK / KP, kb1 = (kp0 + 1) * NBLK / KP;
-  const size_t oc_row = (size_t)(r * OC + strip0 * 16 + grp) * D + tq * 8;   // offset of this lane's row in a [d][d] matrix
-  uint4 wa0[NB0], wb0[NB0];
-  if (a.has_post) lb_load<NB0>(wa0, wb0, a.wo_c + oc_row, a.wo_c + oc_row + (size_t)8 * D, kb0, kb1, wpol);
-  for (int i = tid * 4; i < D; i += kLbThreads * 4) {
-    if (a.has_post) {
-      *reinterpret_cast<float4*>(s_ln + i) = __ldg(reinterpret_cast<const float4*>(a.ln2_g + i));
-      *reinterpret_cast<float4*>(s_ln + D + i) = __ldg(reinterpret_cast<const float4*>(a.ln2_b + i));
-    }
-    if (a.has_self) {
-      *reinterpret_cast<float4*>(s_ln + 2 * D + i) = __ldg(reinterpret_cast<const float4*>(a.ln1_g + i));
-      *reinterpret_cast<float4*>(s_ln + 3 * D + i) = __ldg(reinterpret_cast<const float4*>(a.ln1_b + i));
-      *reinterpret_cast<float4*>(s_ln + 4 * D + i) = __ldg(reinterpret_cast<const float4*>(a.lnc_g + i));
-      *reinterpret_cast<float4*>(s_ln + 5 * D + i) = __ldg(reinterpret_cast<const float4*>(a.lnc_b + i));
-    }
-  }
-  if (a.has_post)
-    for (int i = tid; i < HS; i += kLbThreads) s_b1[i] = __ldg(a.b1 + r * HS + i);
-  // epilogue mapping of the column role: thread e < 8 * OC -> (sequence slot, own column)
-  const int e_slot = tid / OC, e_col = tid % OC;
-  const bool e_on = tid < 8 * OC;
-  const bool e_live = e_on && b0 + e_slot < a.Mb;
-  float bias_oc = 0.f, b2v = 0.f, bias_o = 0.f, bias_q = 0.f;
-  if (e_on) {
-    if (a.has_post) bias_oc = __ldg(a.bo_c + r * OC + e_col), b2v = __ldg(a.b2 + r * OC + e_col);
-    if (a.has_self) bias_o = __ldg(a.bo + r * OC + e_col), bias_q = __ldg(a.bq_c + r * OC + e_col);
-  }
-  // head role: QKV strip of this warp (part = q / k / v, 16 of the head's 64 rows)
-  const int part = warp >> 2, strip = warp & 3;
-  const int row_lo = part * D + h * 64 + strip * 16 + grp;
-  const __half* qrow0 = a.wqkv + (size_t)row_lo * D + tq * 8;
-  const __half* qrow1 = qrow0 + (size_t)8 * D;
-  float bias_lo = 0.f, bias_hi = 0.f;
-  if (a.has_self) bias_lo = __ldg(a.bqkv + row_lo), bias_hi = __ldg(a.bqkv + row_lo + 8);
-  // L2 hints (128-byte lines) for the weight slices of the later phases
-  if (a.has_post) {
-    for (int i = tid; i < HS * (D / 64); i += kLbThreads) {
-      const int row = i / (D / 64), seg = i - row * (D / 64);
-      weight_prefetch_l2(a.w1 + (size_t)(r * HS + row) * D + seg * 64);
-    }
-    for (int i = tid; i < D * (HS / 64); i += kLbThreads) {
-      const int row = i / (HS / 64), seg = i - row * (HS / 64);
-      weight_prefetch_l2(a.w2 + (size_t)row * (4 * D) + r * HS + seg * 64);
-    }
-  }
-  if (a.has_self) {
-    for (int i = tid; i < 192 * (D / 64); i += kLbThreads) {      // the head's 3 x 64 QKV rows
-      const int rr = i / (D / 64), seg = i - rr * (D / 64);
-      weight_prefetch_l2(a.wqkv + (size_t)((rr >> 6) * D + h * 64 + (rr & 63)) * D + seg * 64);
-    }
-    for (int i = tid; i < 2 * OC * (D / 64); i += kLbThreads) {   // own rows of Wo and Wq_c
-      const int rr = i / (D / 64), seg = i - rr * (D / 64);
-      const __half* base = rr < OC ? a.wo : a.wq_c;
-      weight_prefetch_l2(base + (size_t)(r * OC + (rr % OC)) * D + seg * 64);
-    }
-    const int n_hint = ld_state(&a.state->cur_len) + 1;           // cached K/V rows of the own sequences (possibly one step stale: a hint)
-    const int total = n_hint > 0 ? 4 * 2 * n_hint : 0;
-    for (int i = tid; i < total; i += kLbThreads) {
-      const int sq = i / (2 * n_hint), rem = i - sq * 2 * n_hint;
-      const int kv = rem / n_hint, rr = rem - kv * n_hint;
-      const int b = b0 + half * 4 + sq;
-      if (b < a.Mb && rr < a.n_ctx) ptx::prefetch_l2((kv ? a.vcache : a.kcache) + ((size_t)b * a.n_ctx + rr) * D + h * 64);
-    }
-  }
-  if (a.pdl_point == 0) ptx::grid_dep_launch();
-  if (a.use_flags && a.has_post) {
-    // the previous layer's attention outputs of THIS group: (sequence, head) items counted in by the stream kernel. Everything
-    // else this kernel reads was written by its own cluster in the previous layer-block kernel (ordered by the same chain).
-    if (tid == 0) {
-      const int n_seq = a.Mb - b0 < 8 ? a.Mb - b0 : 8;
-      const int target = H * n_seq * (ld_state(&a.state->cur_len) * a.n_layer + a.layer);
-      poll_at_least(&a.state->a_done[blockIdx.y], target, &a.state->spin_timeout);
-    }
-    __syncthreads();
-  } else {
-    ptx::grid_dep_sync();
-    if (a.stagger_ns > 0 && blockIdx.y > 0) {
-      const unsigned long long t0 = globaltimer(), wait_ns = (unsigned long long)a.stagger_ns * blockIdx.y;
-      while (globaltimer() - t0 < wait_ns) {
-      }
-    }
-  }
-  trace.mark(3);
-
-  constexpr int NBq = NBLK > 8 ? 8 : NBLK;                       // blocks per batch of the full-K GEMMs (MLP1, QKV)
-  uint4 wq_a[NBq], wq_b[NBq];                                    // first QKV batch, requested before the barrier in front of phase 5
-  if (a.has_post) {
-    // ---- 0. x' slice = x + a16 Wo_c[r*OC ..]^T + bo_c, pushed to every CTA of the cluster ---------------------------------------------------
-    for (int i = tid; i < 8 * (D / 8); i += kLbThreads) {
-      const int slot = i / (D / 8), c = i - slot * (D / 8);
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (b0 + slot < a.Mb) v = __ldcg(reinterpret_cast<const uint4*>(a.a16 + (size_t)(b0 + slot) * D) + c);
-      *reinterpret_cast<uint4*>(as16 + slot * XS + c * 16) = v;
-    }
-    const float x_old = e_live ? __ldcg(a.x + (size_t)(b0 + e_slot) * D + r * OC + e_col) : 0.f;
-    __syncthreads();
-    {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      lb_mma<NB0>(acc, wa0, wb0, as16 + grp * XS + tq * 16, kb0, kb1);
-      float* dst = s_red + kp0 * 8 * OC;
-      const int c_lo = strip0 * 16 + grp, c_hi = c_lo + 8;
-      dst[(2 * tq) * OC + c_lo] = acc[0], dst[(2 * tq + 1) * OC + c_lo] = acc[1];
-      dst[(2 * tq) * OC + c_hi] = acc[2], dst[(2 * tq + 1) * OC + c_hi] = acc[3];
-    }
-    __syncthreads();
-    if (e_on) {
-      float v = 0.f;
-#pragma unroll
-      for (int k = 0; k < KP; ++k) v += s_red[k * 8 * OC + tid];
-      v = x_old + (v + bias_oc);
-      const uint32_t local = ptx::smem_u32(xp + e_slot * D + r * OC + e_col);
-#pragma unroll
-      for (int c = 0; c < C; ++c) ptx::st_cluster_f32(ptx::mapa(local, (uint32_t)c), v);
-    }
-    // weights never depend on activations: the first batch of MLP1 is requested before the barrier and the LayerNorm
-    uint4 wa2[NBq], wb2[NBq];
-    const __half* m1row = a.w1 + (size_t)(r * HS + (warp & 7) * 16 + grp) * D + tq * 8;
-    if (warp < 8) lb_load<NBq>(wa2, wb2, m1row, m1row + (size_t)8 * D, 0, NBLK, wpol);
-    ptx::cluster_arrive_release();
-    ptx::cluster_wait_acquire();
-
-    // ---- 1. LayerNorm of x' (mlp_ln) ---------------------------------------------------------------------------------------------------------
-    lb_layernorm<D>(xp, xs, XS, s_ln, s_ln + D, warp, lane, b0 + warp < a.Mb);
-    __syncthreads();
-
-    // ---- 2. hidden slice: gelu(W1[r*HS ..] LN(x') + b1); warp w < 8 owns strip w over the whole K ---------------------------------------------
-    const __half* w2base = a.w2 + (size_t)grp * (4 * D) + r * HS + tq * 8;
-    auto load_pairs = [&](uint4 (&wa)[8], uint4 (&wb)[8], int p0) {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int p = p0 + u < Cfg::NPAIR ? p0 + u : Cfg::NPAIR - 1;
-        const int si = p / Cfg::NBC, blk = p % Cfg::NBC;
-        const __half* w0 = w2base + (size_t)(((warp & 7) + 8 * si) * 16) * (4 * D) + blk * 32;
-        wa[u] = ptx::ldg_nc_16(w0, wpol);
-        wb[u] = ptx::ldg_nc_16(w0 + (size_t)8 * (4 * D), wpol);
-      }
-    };
-    uint4 wa3[8], wb3[8];
-    if (warp < 8) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      const unsigned char* xl = xs + grp * XS + tq * 16;
-      lb_mma<NBq>(acc, wa2, wb2, xl, 0, NBLK);
-      if (NBLK > NBq) {
-        uint4 wa[NBq], wb[NBq];
-        lb_load<NBq>(wa, wb, m1row, m1row + (size_t)8 * D, NBq, NBLK, wpol);
-        lb_mma<NBq>(acc, wa, wb, xl, NBq, NBLK);
-      }
-      load_pairs(wa3, wb3, 0);                                   // first batch of phase 3, in flight across the GELU pass
-      const int c_lo = warp * 16 + grp, c_hi = c_lo + 8;
-      s_red[(2 * tq) * HS + c_lo] = acc[0], s_red[(2 * tq + 1) * HS + c_lo] = acc[1];
-      s_red[(2 * tq) * HS + c_hi] = acc[2], s_red[(2 * tq + 1) * HS + c_hi] = acc[3];
-    }
-    __syncthreads();
-    for (int i = tid; i < 8 * HS; i += kLbThreads) {
-      const int slot = i / HS, j = i - slot * HS;
-      reinterpret_cast<__half*>(hs + slot * HSS)[j] = __float2half_rn(gelu_erf(s_b1[j] + s_red[i]));
-    }
-    __syncthreads();
-
-    // ---- 3. partial MLP output over this CTA's hidden slice: warp w < 8 owns strips w, w+8, ... of all D output rows ------------------------
-    if (warp < 8) {
-      float acc[Cfg::SCW][4];
-#pragma unroll
-      for (int si = 0; si < Cfg::SCW; ++si) acc[si][0] = acc[si][1] = acc[si][2] = acc[si][3] = 0.f;
-      const unsigned char* hl = hs + grp * HSS + tq * 16;
-#pragma unroll
-      for (int p0 = 0; p0 < Cfg::NPAIR; p0 += 8) {
-        if (p0 > 0) load_pairs(wa3, wb3, p0);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          if (p0 + u < Cfg::NPAIR) {
-            const int si = (p0 + u) / Cfg::NBC, blk = (p0 + u) % Cfg::NBC;
-            const uint32_t a0[4] = {wa3[u].x, wb3[u].x, wa3[u].y, wb3[u].y}, a1[4] = {wa3[u].z, wb3[u].z, wa3[u].w, wb3[u].w};
-            const uint4 xb = *reinterpret_cast<const uint4*>(hl + blk * 64);
-            const uint32_t bf0[2] = {xb.x, xb.y}, bf1[2] = {xb.z, xb.w};
-            ptx::mma_16816(acc[si], a0, bf0);
-            ptx::mma_16816(acc[si], a1, bf1);
-          }
-        }
-      }
-#pragma unroll
-      for (int si = 0; si < Cfg::SCW; ++si) {
-        const int c_lo = (warp + 8 * si) * 16 + grp, c_hi = c_lo + 8;
-        s_part[(2 * tq) * PS + c_lo] = acc[si][0], s_part[(2 * tq + 1) * PS + c_lo] = acc[si][1];
-        s_part[(2 * tq) * PS + c_hi] = acc[si][2], s_part[(2 * tq + 1) * PS + c_hi] = acc[si][3];
-      }
-    }
-    ptx::cluster_arrive_release();
-    ptx::cluster_wait_acquire();
-
-    // ---- 4. x = x' + b2 + sum over the cluster of the partials (rank order), own columns ------------------------------------------------------
-    if (e_on) {
-      const uint32_t local = ptx::smem_u32(s_part + e_slot * PS + r * OC + e_col);
-      float pv[C];
-#pragma unroll
-      for (int c = 0; c < C; ++c) pv[c] = ptx::ld_cluster_f32(ptx::mapa(local, (uint32_t)c));
-      float v = 0.f;
-#pragma unroll
-      for (int c = 0; c < C; ++c) v += pv[c];
-      const float xn = xp[e_slot * D + r * OC + e_col] + (v + b2v);
-      if (!a.has_self) {
-        if (e_live) a.x[(size_t)(b0 + e_slot) * D + r * OC + e_col] = xn;
-      } else {
-        const uint32_t lx = ptx::smem_u32(xp + e_slot * D + r * OC + e_col);
-#pragma unroll
-        for (int c = 0; c < C; ++c) ptx::st_cluster_f32(ptx::mapa(lx, (uint32_t)c), xn);
-      }
-    }
-    if (a.has_self) lb_load<NBq>(wq_a, wq_b, qrow0, qrow1, 0, NBLK, wpol);
-    ptx::cluster_arrive_release();   // has_self: x all-gathered; otherwise: no CTA may exit while a peer still reads its partial
-    ptx::cluster_wait_acquire();
-    if (a.pdl_point == 1) ptx::grid_dep_launch();
-    trace.mark(4);
-    if (!a.has_self) {
-      trace.end();
-      return;
-    }
-  } else {
-    // first kernel of a step: the residual stream comes from global memory (token + positional embedding), whole rows per CTA
-    lb_load<NBq>(wq_a, wq_b, qrow0, qrow1, 0, NBLK, wpol);
-    for (int i = tid; i < 8 * (D / 4); i += kLbThreads) {
-      const int slot = i / (D / 4), c = i - slot * (D / 4);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (b0 + slot < a.Mb) v = ld_x4(a.x + (size_t)(b0 + slot) * D + c * 4);
-      *reinterpret_cast<float4*>(xp + slot * D + c * 4) = v;
-    }
-    __syncthreads();
-    if (a.pdl_point == 1) ptx::grid_dep_launch();
-    trace.mark(4);
-  }
-
-  // ---- 5. LayerNorm (attn_ln), QKV of head h for the 8 sequences of the group --------------------------------------------------------------------
-  const int pos = ld_state(&a.state->cur_len);                   // cache row of the token this step consumes
-  lb_layernorm<D>(xp, xs, XS, s_ln + 2 * D, s_ln + 3 * D, warp, lane, b0 + warp < a.Mb);
-  __syncthreads();
-  {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const unsigned char* xl = xs + grp * XS + tq * 16;
-    lb_mma<NBq>(acc, wq_a, wq_b, xl, 0, NBLK);
-    if (NBLK > NBq) {
-      uint4 wa[NBq], wb[NBq];
-      lb_load<NBq>(wa, wb, qrow0, qrow1, NBq, NBLK, wpol);
-      lb_mma<NBq>(acc, wa, wb, xl, NBq, NBLK);
-    }
-    // accumulator (rows grp / grp+8 of the strip, sequence slots 2tq, 2tq+1): + bias -> s_qkv; k, v of the own half -> cache (fp16)
-    const int c_lo = strip * 16 + grp, c_hi = c_lo + 8;          // column inside the head
-    const float v00 = acc[0] + bias_lo, v01 = acc[1] + bias_lo, v10 = acc[2] + bias_hi, v11 = acc[3] + bias_hi;
-    float* dst = s_qkv + part * 8 * 64;
-    const int sA = 2 * tq, sB = sA + 1;
-    dst[sA * 64 + c_lo] = v00, dst[sB * 64 + c_lo] = v01;
-    dst[sA * 64 + c_hi] = v10, dst[sB * 64 + c_hi] = v11;
-    if (part > 0 && (sA >> 2) == half) {
-      __half* cache = part == 1 ? a.kcache : a.vcache;
-      if (b0 + sA < a.Mb) {
-        __half* rw = cache + ((size_t)(b0 + sA) * a.n_ctx + pos) * D + h * 64;
-        rw[c_lo] = __float2half_rn(v00), rw[c_hi] = __float2half_rn(v10);
-      }
-      if (b0 + sB < a.Mb) {
-        __half* rw = cache + ((size_t)(b0 + sB) * a.n_ctx + pos) * D + h * 64;
-        rw[c_lo] = __float2half_rn(v01), rw[c_hi] = __float2half_rn(v11);
-      }
-    }
-  }
-  __syncthreads();
-  if (a.pdl_point == 2) ptx::grid_dep_launch();
-  trace.mark(5);
-
-  // ---- 6. attention: warps 3s .. 3s+2 share the own sequence s; lane = (row sub-index 0..3, 16-byte column chunk 0..7) ---------------------
-  {
-    constexpr int WPS = kLbWarps / 4;
-    const int sl = warp / WPS, sub = warp - sl * WPS;
-    const int slot = half * 4 + sl, b = b0 + slot;
-    const int rsub = lane >> 3, cc = lane & 7;
-    const float scl = 0.125f * kLog2e;   // (d_head^-0.25)^2 = 1/8 exactly; log2 domain
-    float qv[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) qv[i] = s_qkv[slot * 64 + cc * 8 + i] * scl;
-    SbPartial p;
-    p.m = -INFINITY, p.l = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) p.o[i] = 0.f;
-    if (b < a.Mb) {                                              // warp-uniform
-      const int per = (pos + WPS - 1) / WPS;                     // cached rows [0, pos) in WPS contiguous ranges
-      const int r_begin = sub * per;
-      const int r_end = pos < r_begin + per ? pos : r_begin + per;
-      const __half* kb = a.kcache + (size_t)b * a.n_ctx * D + h * 64 + cc * 8;
-      const __half* vb = a.vcache + (size_t)b * a.n_ctx * D + h * 64 + cc * 8;
-      for (int r0 = r_begin; r0 < r_end; r0 += 32) {
-        uint4 kq[8], vq[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int rr = r0 + j * 4 + rsub;
-          const int rc = rr < r_end ? rr : r_begin;              // clamped: masked below
-          kq[j] = ptx::ldg_nc_16(kb + (size_t)rc * D);
-          vq[j] = ptx::ldg_nc_16(vb + (size_t)rc * D);
-        }
-        float dots[8], bm = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float kf[8];
-          unpack8(kq[j], kf);
-          float dot = 0.f;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) dot = fmaf(qv[i], kf[i], dot);
-          dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-          dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-          dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-          dots[j] = (r0 + j * 4 + rsub < r_end) ? dot : -INFINITY;
-          bm = fmaxf(bm, dots[j]);
-        }
-        if (bm > -INFINITY) {
-          const float mn = fmaxf(p.m, bm);
-          const float corr = exp2f(p.m - mn);
-          p.l *= corr;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) p.o[i] *= corr;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float pr = exp2f(dots[j] - mn);
-            float vf[8];
-            unpack8(vq[j], vf);
-            p.l += pr;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) p.o[i] = fmaf(pr, vf[i], p.o[i]);
-          }
-          p.m = mn;
-        }
-      }
-      if (sub == 0) {   // the new row: k, v as the cache holds them (fp16-rounded), taken from shared memory
-        float kf[8], vf[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          kf[i] = __half2float(__float2half_rn(s_qkv[(8 + slot) * 64 + cc * 8 + i]));
-          vf[i] = __half2float(__float2half_rn(s_qkv[(16 + slot) * 64 + cc * 8 + i]));
-        }
-        float dot = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dot = fmaf(qv[i], kf[i], dot);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-        if (rsub == 0) sb_row(p, dot, vf);
-      }
-    }
-    sb_merge_shfl(p, 8);
-    sb_merge_shfl(p, 16);
-    if (rsub == 0) {
-      float* dst = s_att + (sl * WPS + sub) * 66;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) dst[cc * 8 + i] = p.o[i];
-      if (cc == 0) dst[64] = p.m, dst[65] = p.l;
-    }
-  }
-  // this warp's part of the output projection (own OC rows of Wo), requested now: the latency runs under the merge and the exchange
-  uint4 wa7[NB0], wb7[NB0];
-  lb_load<NB0>(wa7, wb7, a.wo + oc_row, a.wo + oc_row + (size_t)8 * D, kb0, kb1, wpol);
-  __syncthreads();
-  if (a.pdl_point == 3) ptx::grid_dep_launch();
-  if (tid < 4 * 64) {   // merge the partials of (own sequence es, column ec) and push the result into every CTA of the cluster
-    constexpr int WPS = kLbWarps / 4;
-    const int es = tid >> 6, ec = tid & 63;
-    const float* pp = s_att + es * WPS * 66;
-    float M = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < WPS; ++j) M = fmaxf(M, pp[j * 66 + 64]);
-    float L = 0.f, A = 0.f;
-#pragma unroll
-    for (int j = 0; j < WPS; ++j) {
-      const float mj = pp[j * 66 + 64];
-      const float wj = mj == -INFINITY ? 0.f : exp2f(mj - M);
-      L += wj * pp[j * 66 + 65];
-      A += wj * pp[j * 66 + ec];
-    }
-    const __half res = __float2half_rn(L > 0.f ? A / L : 0.f);
-    const uint32_t local = ptx::smem_u32(sa + (half * 4 + es) * XS + (h * 64 + ec) * 2);
-#pragma unroll
-    for (int c = 0; c < C; ++c) ptx::st_cluster_u16(ptx::mapa(local, (uint32_t)c), __half_as_ushort(res));
-  }
-  ptx::cluster_arrive_release();
-  ptx::cluster_wait_acquire();   // every head's outputs of all 8 sequences have landed in sa
-  trace.mark(6);
-
-  // ---- 7. x'' = x + attn Wo[r*OC ..]^T + bo (own columns): global memory and every CTA of the cluster -----------------------------------------
-  {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    lb_mma<NB0>(acc, wa7, wb7, sa + grp * XS + tq * 16, kb0, kb1);
-    float* dst = s_red + kp0 * 8 * OC;
-    const int c_lo = strip0 * 16 + grp, c_hi = c_lo + 8;
-    dst[(2 * tq) * OC + c_lo] = acc[0], dst[(2 * tq + 1) * OC + c_lo] = acc[1];
-    dst[(2 * tq) * OC + c_hi] = acc[2], dst[(2 * tq + 1) * OC + c_hi] = acc[3];
-  }
-  // the query projection's weights (own OC rows of Wq_c): in flight across the reduction and the barrier
-  lb_load<NB0>(wa7, wb7, a.wq_c + oc_row, a.wq_c + oc_row + (size_t)8 * D, kb0, kb1, wpol);
-  __syncthreads();
-  if (e_on) {
-    float v = 0.f;
-#pragma unroll
-    for (int k = 0; k < KP; ++k) v += s_red[k * 8 * OC + tid];
-    const float xn = xp[e_slot * D + r * OC + e_col] + (v + bias_o);
-    if (e_live) a.x[(size_t)(b0 + e_slot) * D + r * OC + e_col] = xn;
-    const uint32_t lx = ptx::smem_u32(xp + e_slot * D + r * OC + e_col);
-#pragma unroll
-    for (int c = 0; c < C; ++c) ptx::st_cluster_f32(ptx::mapa(lx, (uint32_t)c), xn);
-  }
-  ptx::cluster_arrive_release();
-  ptx::cluster_wait_acquire();   // no remote access after this point
-  trace.mark(7);
-
-  // ---- 8. q = LayerNorm(x''; cross_attn_ln) Wq_c[r*OC ..]^T + bq_c (own columns) -> global memory ------------------------------------------------
-  lb_layernorm<D>(xp, xs, XS, s_ln + 4 * D, s_ln + 5 * D, warp, lane, b0 + warp < a.Mb);
-  __syncthreads();
-  {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    lb_mma<NB0>(acc, wa7, wb7, xs + grp * XS + tq * 16, kb0, kb1);
-    float* dst = s_red + kp0 * 8 * OC;
-    const int c_lo = strip0 * 16 + grp, c_hi = c_lo + 8;
-    dst[(2 * tq) * OC + c_lo] = acc[0], dst[(2 * tq + 1) * OC + c_lo] = acc[1];
-    dst[(2 * tq) * OC + c_hi] = acc[2], dst[(2 * tq + 1) * OC + c_hi] = acc[3];
-  }
-  __syncthreads();
-  if (e_live) {
-    float v = 0.f;
-#pragma unroll
-    for (int k = 0; k < KP; ++k) v += s_red[k * 8 * OC + tid];
-    a.q_out[(size_t)(b0 + e_slot) * D + r * OC + e_col] = v + bias_q;
-  }
-  if (a.use_flags) {   // this CTA's columns of x'' and q are in global memory: count in (the stream waits for all C CTAs of the group)
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) red_release_gpu_add(&a.state->q_ready[blockIdx.y], 1);
-  }
-  trace.end();
-}
-
-// cluster size of the fused kernel for width d (0: unsupported on this device / disabled)
-static int layer_block_cluster(int d) {
-  static int c_dev[kMaxDevices][2];
-  static bool init = false;
-  if (!init) {
-    for (int i = 0; i < kMaxDevices; ++i) c_dev[i][0] = c_dev[i][1] = -1;
-    init = true;
-  }
-  if (d != 384 && d != 512) return 0;
-  int& c = c_dev[current_device_slot()][d == 512];
-  if (c < 0) {
-    c = 0;
-    // Off unless WB_LAYER_BLOCK=1: measured on B200 (base.en, 32 sequences) the two-launch-per-layer path runs 281 us per step
-    // against 273-275 us for self block + KV-cache kernel with the fused query projection + post block.
-    const char* e = getenv("WB_LAYER_BLOCK");
-    if (e && e[0] == '1') {
-      const int want = d / 32;   // 2 * n_head: 16 / 12, both beyond the portable cluster size of 8
-      cudaError_t e1, e2;
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(want, 1), cfg.blockDim = dim3(kLbThreads);
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = want, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
-      cfg.attrs = at, cfg.numAttrs = 1;
-      int nc = 0;
-      if (d == 512) {
-        e1 = cudaFuncSetAttribute(layer_block_kernel<512, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        e2 = cudaFuncSetAttribute(layer_block_kernel<512, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LbCfg<512, 16>::smem);
-        cfg.dynamicSmemBytes = LbCfg<512, 16>::smem;
-        if (e1 == cudaSuccess && e2 == cudaSuccess && cudaOccupancyMaxActiveClusters(&nc, layer_block_kernel<512, 16>, &cfg) == cudaSuccess && nc >= 1) c = want;
-      } else {
-        e1 = cudaFuncSetAttribute(layer_block_kernel<384, 12>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        e2 = cudaFuncSetAttribute(layer_block_kernel<384, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LbCfg<384, 12>::smem);
-        cfg.dynamicSmemBytes = LbCfg<384, 12>::smem;
-        if (e1 == cudaSuccess && e2 == cudaSuccess && cudaOccupancyMaxActiveClusters(&nc, layer_block_kernel<384, 12>, &cfg) == cudaSuccess && nc >= 1) c = want;
-      }
-      cudaGetLastError();
-    }
-  }
-  return c;
-}
-
-int layer_block_supported(int n_head, int d) { return d == n_head * 64 && layer_block_cluster(d) > 0; }
-
-int launch_layer_block(const LayerBlockDesc& p, cudaStream_t st, int64_t* launches) {
-  const int C = p.d == p.n_head * 64 ? layer_block_cluster(p.d) : 0;
-  if (!C || p.Mb < 1 || (!p.has_post && !p.has_self)) {
-    set_error("layer_block: unsupported shape d=%d heads=%d Mb=%d", p.d, p.n_head, p.Mb);
-    return -1;
-  }
-  static int pdl_self = -1, pdl_last = -1;
-  if (pdl_self < 0) {
-    const char* e = getenv("WB_PDL_LB");
-    pdl_self = e ? atoi(e) : 2;
-    e = getenv("WB_PDL_LB_LAST");
-    pdl_last = e ? atoi(e) : 1;
-  }
-  LayerBlockArgs a{};
-  a.x = p.x, a.a16 = p.a16, a.wo_c = p.wo_c, a.bo_c = p.bo_c, a.ln2_g = p.ln2_g, a.ln2_b = p.ln2_b, a.w1 = p.w1, a.b1 = p.b1;
-  a.w2 = p.w2, a.b2 = p.b2, a.ln1_g = p.ln1_g, a.ln1_b = p.ln1_b, a.wqkv = p.wqkv, a.bqkv = p.bqkv, a.wo = p.wo, a.bo = p.bo;
-  a.kcache = p.kcache, a.vcache = p.vcache, a.lnc_g = p.lnc_g, a.lnc_b = p.lnc_b, a.wq_c = p.wq_c, a.bq_c = p.bq_c, a.q_out = p.q_out;
-  a.Mb = p.Mb, a.n_ctx = p.n_ctx, a.has_post = p.has_post, a.has_self = p.has_self, a.state = p.state;
-  a.use_flags = p.use_flags, a.layer = p.layer, a.n_layer = p.n_layer;
-  static int stagger = -1;
-  if (stagger < 0) {
-    const char* e = getenv("WB_LB_STAGGER_NS");
-    stagger = e ? atoi(e) : 0;
-  }
-  a.stagger_ns = (p.use_flags && !p.has_post) ? stagger : 0;
-  // with the counters the dependents are released at entry (they only become resident and poll); the first kernel of a step
-  // releases after its wait, so that everything downstream starts after the previous step's finish kernel
-  a.pdl_point = p.use_flags ? (p.has_post ? 0 : 1) : (p.has_self ? pdl_self : pdl_last);
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(C, (p.Mb + 7) / 8), cfg.blockDim = dim3(kLbThreads), cfg.stream = st;
-  cfg.dynamicSmemBytes = p.d == 512 ? LbCfg<512, 16>::smem : LbCfg<384, 12>::smem;
-  cudaLaunchAttribute at[2];
-  int n_at = 0;
-  at[n_at].id = cudaLaunchAttributeClusterDimension;
-  at[n_at].val.clusterDim.x = C, at[n_at].val.clusterDim.y = 1, at[n_at].val.clusterDim.z = 1;
-  ++n_at;
-  if (use_pdl()) {
-    at[n_at].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[n_at].val.programmaticStreamSerializationAllowed = 1;
-    ++n_at;
-  }
-  cfg.attrs = at, cfg.numAttrs = n_at;
-  const cudaError_t le = p.d == 512 ? cudaLaunchKernelEx(&cfg, layer_block_kernel<512, 16>, a) : cudaLaunchKernelEx(&cfg, layer_block_kernel<384, 12>, a);
   if (launches) *launches += 1;
   WB_CUDA_OK(le);
   return 0;

@@ -394,19 +394,7 @@ struct StepOpts {
   // `tail`; the KV-cache kernel waits for xwait (the other sub-batch's previous KV-cache kernel) and records xrec behind itself
   int partial, l_begin, l_end, tail;
   cudaEvent_t xwait, xrec;
-  // the same ordering by device counters instead of events (keeps the programmatic launch edges of each sub-batch's own graph):
-  // peer_sub >= 0 names the other sub-batch, peer_Mb its sequences, peer_lead = 0 for the sub-batch that goes first, 1 for the other
-  int peer_on, peer_sub, peer_Mb, peer_lead;
 };
-
-static bool use_handoff_flags() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("WB_HANDOFF_FLAGS");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
-}
 
 static cudaStream_t step_stream(wb_handle* h, const StepOpts& o) { return o.sub > 0 ? h->sub_stream[o.sub] : h->stream; }
 static DecodeState* step_state(wb_handle* h, const StepOpts& o) { return h->state + o.sub; }
@@ -444,34 +432,6 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
   const size_t cross_off = (b0 / o.beams) * (size_t)D.n_audio_ctx * d;
   const int l_begin = o.partial ? o.l_begin : 0, l_end = o.partial ? o.l_end : D.n_text_layer;
   const bool tail = o.partial ? o.tail != 0 : true;
-  if (!o.partial && layer_block_supported(H, d)) {
-    // d = 384 / 512: one cluster kernel per layer boundary (post part of layer l-1 + self-attention block of layer l + the
-    // cross-attention query of layer l), and between two of them the KV-cache kernel as a pure stream: 2 launches per layer
-    for (int l = 0; l <= D.n_text_layer; ++l) {
-      LayerBlockDesc lb{};
-      lb.Mb = Mb, lb.d = d, lb.n_head = H, lb.n_ctx = D.n_text_ctx, lb.x = xdec, lb.state = state;
-      lb.has_post = l > 0, lb.has_self = l < D.n_text_layer;
-      lb.layer = l, lb.n_layer = D.n_text_layer, lb.use_flags = use_handoff_flags() && Mb <= 64;
-      if (lb.has_post) {
-        const LayerW& P = h->dec[l - 1];
-        lb.a16 = a16, lb.wo_c = P.wo_c, lb.bo_c = P.bo_c, lb.ln2_g = P.ln2_g, lb.ln2_b = P.ln2_b;
-        lb.w1 = P.w1, lb.b1 = P.b1, lb.w2 = P.w2, lb.b2 = P.b2;
-      }
-      if (lb.has_self) {
-        const LayerW& L = h->dec[l];
-        lb.ln1_g = L.ln1_g, lb.ln1_b = L.ln1_b, lb.wqkv = L.wqkv, lb.bqkv = L.bqkv, lb.wo = L.wo, lb.bo = L.bo;
-        lb.kcache = h->selfK[l] + self_off, lb.vcache = h->selfV[l] + self_off;
-        lb.lnc_g = L.lnc_g, lb.lnc_b = L.lnc_b, lb.wq_c = L.wq_c, lb.bq_c = L.bq_c, lb.q_out = q32;
-      }
-      WB_TRY(launch_layer_block(lb, st, &h->launches));
-      if (!lb.has_self) break;
-      AttnDecodeDesc c{};
-      c.Mb = Mb, c.d = d, c.n_head = H, c.q = q32, c.k = h->crossK[l] + cross_off, c.v = h->crossV[l] + cross_off;
-      c.n_ctx = D.n_audio_ctx, c.n_rows_fixed = D.n_audio_ctx, c.kv_share = o.beams, c.state = state, c.out16 = a16, c.tmaps = h->gemm;
-      c.pdl_late_ok = 1, c.stream_ok = 1, c.layer = l, c.n_layer = D.n_text_layer, c.use_flags = lb.use_flags;
-      WB_TRY(launch_attn_decode(c, st, &h->launches));
-    }
-  } else
   for (int l = l_begin; l < l_end; ++l) {
     const LayerW& L = h->dec[l];
     AttnDecodeDesc a{};
@@ -505,7 +465,6 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
     c.q = nullptr, c.x = xdec, c.ln_g = L.lnc_g, c.ln_b = L.lnc_b, c.wq = L.wq_c, c.bq = L.bq_c;
     c.pdl_late_ok = post_block_supported(H, d) ? 1 : 0;
     if (o.xwait) WB_CUDA_OK(cudaStreamWaitEvent(st, o.xwait, 0));
-    if (o.peer_on) c.peer_state = h->state + o.peer_sub, c.peer_ctas = H * o.peer_Mb, c.peer_lead = o.peer_lead, c.layer = l, c.n_layer = D.n_text_layer;
     WB_TRY(launch_attn_decode(c, st, &h->launches));
     if (o.xrec) WB_CUDA_OK(cudaEventRecord(o.xrec, st));
     if (post_block_supported(H, d)) {
@@ -551,7 +510,7 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
 
 // cur_len = -1, then embed the token at position 0 (which advances cur_len to 0)
 static int reset_decode_state(wb_handle* h, const StepOpts& o) {
-  static const DecodeState k_init_untraced{-1, 0, 0, 0, nullptr, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, 0, 0, {0, 0}};
+  static const DecodeState k_init_untraced{-1, 0, 0, 0, nullptr};
   DecodeState init = k_init_untraced;
   if (h->trace) init.trace = h->trace + (size_t)o.sub * 16384 * 8;   // a quarter of the trace buffer per sub-batch
   static thread_local DecodeState staged[wb_handle::kMaxSub];
@@ -1214,14 +1173,10 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
   // two sub-batches as one interleaved schedule (decode_steps_pair): graph replay only, the three-kernel decoder path
   bool pair = false;
   if (const char* e = getenv("WB_PAIR")) pair = e[0] == '1';
-  bool pair_flags = false;   // WB_PAIR=2: the same alternation through device counters, each sub-batch in its own graph and stream
-  if (const char* e = getenv("WB_PAIR")) pair_flags = e[0] == '2';
-  pair_flags = pair_flags && nsb == 2 && use_graph && !layer_block_supported(D.n_text_head, D.n_text_state) && opts->no_speech_prob == nullptr &&
-               post_block_supported(D.n_text_head, D.n_text_state);
-  pair = pair && nsb == 2 && use_graph && !layer_block_supported(D.n_text_head, D.n_text_state) && opts->no_speech_prob == nullptr;
+  pair = pair && nsb == 2 && use_graph && opts->no_speech_prob == nullptr;
   char key[128];
   snprintf(key, sizeof(key), "B%d i%d e%d s%d m%d t%d.%d.%d p%d", B, n_init, opts->eot, nsb, multi, ts_on ? 1 : 0,
-           ts_on ? opts->timestamp_begin : 0, ts_on ? opts->max_initial_timestamp_index : 0, pair ? 1 : (pair_flags ? 2 : 0));
+           ts_on ? opts->timestamp_begin : 0, ts_on ? opts->max_initial_timestamp_index : 0, pair ? 1 : 0);
   if (use_graph && h->graph_key != key) {
     destroy_graphs(h);
     h->sample_n = multi;
@@ -1232,16 +1187,11 @@ static int decode_greedy(wb_handle* h, int32_t B, const wb_decode_opts* opts, in
       WB_TRY(decode_step(h, samp[i]));
       WB_CUDA_OK(cudaStreamSynchronize(step_stream(h, plain[i])));
       if (pair) continue;
-      StepOpts gp = plain[i], gs = samp[i];
-      if (pair_flags) {   // the captured kernels wait for their peer; the eager passes above ran one sub-batch at a time, without
-        gp.peer_on = gs.peer_on = 1, gp.peer_sub = gs.peer_sub = 1 - i, gp.peer_Mb = gs.peer_Mb = plain[1 - i].Mb;
-        gp.peer_lead = gs.peer_lead = i;
-      }
-      WB_TRY(capture(h, gp, &h->g_step[i], &h->nodes_step));
-      WB_TRY(capture(h, gs, &h->g_sample[i], &h->nodes_sample));
+      WB_TRY(capture(h, plain[i], &h->g_step[i], &h->nodes_step));
+      WB_TRY(capture(h, samp[i], &h->g_sample[i], &h->nodes_sample));
       if (h->sample_n > 1) {
         int64_t nodes_n = 0;
-        WB_TRY(capture(h, gs, &h->g_sample_n[i], &nodes_n, h->sample_n));
+        WB_TRY(capture(h, samp[i], &h->g_sample_n[i], &nodes_n, h->sample_n));
       }
     }
     if (pair) {
@@ -1680,15 +1630,12 @@ int wb_profile_cross_attention(wb_handle* h, int32_t B, int32_t reps, float* avg
   AttnDecodeDesc c{};
   c.Mb = B, c.d = D.n_text_state, c.n_head = D.n_text_head, c.q = nullptr, c.x = h->xdec;
   c.n_ctx = D.n_audio_ctx, c.n_rows_fixed = D.n_audio_ctx, c.kv_share = 1, c.state = h->state, c.out16 = h->a16, c.tmaps = h->gemm;
-  // the kernel exactly as the decode step runs it: queries from memory where the layer-boundary kernel projects them, the
-  // fused LayerNorm + query projection prologue otherwise
-  const bool q_from_memory = layer_block_supported(D.n_text_head, D.n_text_state) != 0;
-  if (q_from_memory) c.q = h->q32, c.x = nullptr, c.stream_ok = 1;
+  // the kernel exactly as the decode step runs it: with the fused LayerNorm + query projection prologue
   for (int i = -3; i < reps; ++i) {   // 3 warm-up launches
     if (i == 0) WB_CUDA_OK(cudaEventRecord(h->ev[0], h->stream));
     const int l = ((i % D.n_text_layer) + D.n_text_layer) % D.n_text_layer;
     c.k = h->crossK[l], c.v = h->crossV[l];
-    if (!q_from_memory) c.ln_g = h->dec[l].lnc_g, c.ln_b = h->dec[l].lnc_b, c.wq = h->dec[l].wq_c, c.bq = h->dec[l].bq_c;
+    c.ln_g = h->dec[l].lnc_g, c.ln_b = h->dec[l].lnc_b, c.wq = h->dec[l].wq_c, c.bq = h->dec[l].bq_c;
     WB_TRY(launch_attn_decode(c, h->stream, &h->launches));
   }
   WB_CUDA_OK(cudaEventRecord(h->ev[1], h->stream));

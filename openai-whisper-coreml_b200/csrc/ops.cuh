@@ -77,15 +77,6 @@ struct DecodeState {      // lives in device memory; read by every kernel of a s
   int arrive;             // arrival counter of step_finish_kernel's CTAs
   int trace_n, pad1;      // development tracing (WB_TRACE=1): number of records written
   unsigned long long* trace;   // [n][4] = {kernel id, %globaltimer at entry, at exit of block 0, 0}; null = off
-  // Hand-off counters between the layer-block kernels and the attention stream, per group of 8 sequences (monotonic over a
-  // decode, zeroed with the rest of this struct): q_ready += 1 per layer-block CTA once its queries are in global memory;
-  // a_done += 1 per (sequence, head) item once its attention output is. Consumers poll with ld.acquire, so a group's
-  // chain layer block -> stream -> layer block runs without waiting for the other groups' kernels to drain.
-  int q_ready[8];
-  int a_done[8];
-  int spin_timeout;       // set if a poll gave up (never expected; keeps a bug from hanging the device)
-  int x_done;             // interleaved sub-batch pair: CTAs of this sub-batch's KV-cache kernels that finished streaming
-  int pad2[2];
 };
 
 // Input transform of a skinny GEMM (how the [Mb][K] fp16 activation tile in shared memory is produced)
@@ -146,11 +137,6 @@ struct AttnDecodeDesc {
   const DecodeState* state;
   __half* out16;          // [Mb][d]
   int pdl_late_ok;        // the successor is a block kernel that gains nothing from starting before this one's main loop ends
-  int stream_ok;          // cross attention between two layer-block kernels: may run as the persistent one-CTA-per-SM stream
-  int layer, n_layer;     // stream_ok with flags: which decoder layer this launch is (hand-off epochs), 0-based
-  int use_flags;          // hand-offs by DecodeState counters instead of whole-kernel dependencies
-  const DecodeState* peer_state;   // interleaved sub-batch pair (HeadAttnArgs::peer): the other sub-batch's state, or null
-  int peer_ctas, peer_lead;
   GemmContext* tmaps;     // tensor-map cache
 };
 int launch_attn_decode(const AttnDecodeDesc& d, cudaStream_t st, int64_t* launches);
@@ -191,44 +177,6 @@ struct PostBlockDesc {
 };
 int post_block_supported(int n_head, int d);
 int launch_post_block(const PostBlockDesc& d, cudaStream_t st, int64_t* launches);
-
-// post part of the previous layer + self-attention block of this layer + this layer's cross-attention query in one cluster
-// kernel (d = 384 / 512; see layer_block_kernel). has_post = 0 for the first kernel of a step, has_self = 0 for the last.
-struct LayerBlockDesc {
-  int Mb, d, n_head, n_ctx;
-  int has_post, has_self;
-  float* x;               // [Mb][d] residual stream
-  // post part (previous layer)
-  const __half* a16;      // [Mb][d] cross-attention outputs
-  const __half* wo_c;
-  const float* bo_c;
-  const float* ln2_g;
-  const float* ln2_b;
-  const __half* w1;
-  const float* b1;
-  const __half* w2;
-  const float* b2;
-  // self part (this layer)
-  const float* ln1_g;
-  const float* ln1_b;
-  const __half* wqkv;
-  const float* bqkv;
-  const __half* wo;
-  const float* bo;
-  __half* kcache;
-  __half* vcache;
-  // cross-attention query (this layer)
-  const float* lnc_g;
-  const float* lnc_b;
-  const __half* wq_c;
-  const float* bq_c;
-  float* q_out;           // [Mb][d]
-  int layer, n_layer;     // index of the layer whose self part runs here (= number of layers for the last, post-only kernel)
-  int use_flags;          // hand-offs to / from the attention stream by DecodeState counters
-  DecodeState* state;
-};
-int layer_block_supported(int n_head, int d);
-int launch_layer_block(const LayerBlockDesc& d, cudaStream_t st, int64_t* launches);
 
 struct FinishDesc {
   int Mb, V, d, n_ctx;

@@ -205,12 +205,11 @@ def test_language_id_tie_break_is_first_max(wbm, ref):
     w.close()
 
 
-@pytest.mark.parametrize("env", [{"WB_LAYER_BLOCK": "1"}, {"WB_LAYER_BLOCK": "1", "WB_HANDOFF_FLAGS": "0"}, {"WB_SUBBATCHES": "2"},
-                                 {"WB_SUBBATCHES": "2", "WB_PAIR": "1"}, {"WB_SUBBATCHES": "2", "WB_PAIR": "2"}])
+@pytest.mark.parametrize("env", [{"WB_SUBBATCHES": "2"}, {"WB_SUBBATCHES": "2", "WB_PAIR": "1"}, {"WB_SELF_BLOCK": "0", "WB_POST_BLOCK": "0"}])
 def test_alternate_decode_paths_keep_parity(env):
-    """The decode paths that are not the default (the two-launch-per-layer cluster kernel + persistent attention stream, with
-    and without the per-group hand-off counters; two sub-batches on two streams) stay behind environment switches that are
-    read once per process: the oracle parity tests of the block-kernel widths run again in a child process with them set."""
+    """The decode schedules that are not the default (two sub-batches on two streams, the same as one interleaved two-stream
+    graph, the kernel-per-linear path without the cluster block kernels) stay behind environment switches that are read once
+    per process: the oracle parity tests of the block-kernel widths run again in a child process with them set."""
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sel = "tests/test_gpu_parity.py::test_base_width_block_kernels tests/test_gpu_parity.py::test_thirty_six_sequences_tiny " \
@@ -254,11 +253,11 @@ def test_checkpoint_files_round_trip(wbm, ref, tmp_path):
         got_sd = w.state_dict()
         for k in want_sd:
             if k == "encoder.positional_embedding" and path == hfp:
-                assert np.abs(got_sd[k] - want_sd[k]).max() < 1e-6           # regenerated sinusoids
+                assert np.abs(got_sd[k] - want_sd[k]).max() < 5e-4           # regenerated sinusoids vs the fp16-rounded table of the dict
             else:
                 assert np.array_equal(got_sd[k], want_sd[k]), (path, k)
         w.set_audio_features(xa)
-        assert np.array_equal(w.decoder_logits(toks), want_logits)
+        assert np.array_equal(w.decoder_logits(toks), want_logits)           # the decoder does not read the encoder's positions
         w.close()
     wb16 = wbm.Whisper.from_checkpoint(bfp, max_batch=1)
     k = "decoder.blocks.1.mlp.0.weight"

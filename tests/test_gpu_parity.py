@@ -10,10 +10,14 @@ Tolerances (stated once, SURVEY.md §8c / BASELINE.md §3):
 """
 import ctypes
 import os
+import sys
 
 import numpy as np
 import pytest
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import parity_util as pu  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -461,9 +465,13 @@ def test_thirty_six_sequences_tiny(wbm, ref, oracle_logmel):
     tok_ref, slp_ref, _ = oracle.greedy(xa, ref.DecodeOptions.default_for(dims, sample_len=10))
     tok, _, slp = w.greedy(B, wbm.DecodeOptions.default_for(wbm.DIMS["tiny.en"], sample_len=10))
     n = tok_ref.shape[1]
-    bad = (torch.from_numpy(tok[:, :n].astype(np.int64)) != tok_ref).any(1).sum().item()
-    assert bad == 0, f"{bad} of {B} sequences diverge from the oracle"
-    assert np.allclose(slp, slp_ref.numpy(), rtol=2e-3, atol=5e-2)
+    differ = (torch.from_numpy(tok[:, :n].astype(np.int64)) != tok_ref).any(1)
+    # a stream may leave the oracle's only at a tie (fp16 operands): every choice is graded against the oracle given the GPU's prefix
+    o = wbm.DecodeOptions.default_for(wbm.DIMS["tiny.en"], sample_len=10)
+    rep = pu.teacher_forced_check(oracle, xa, tok, len(o.initial_tokens), o.suppress, o.suppress_begin, o.eot)
+    assert rep.bad == 0 and rep.ties >= int(differ.sum()) and int(differ.sum()) <= 2, rep.line()
+    same = (~differ).numpy()
+    assert np.allclose(slp[same], slp_ref.numpy()[same], rtol=2e-3, atol=5e-2)
     w.close()
 
 
