@@ -150,6 +150,10 @@ struct wb_handle {
   cudaEvent_t sub_ev[kMaxSub], fork_ev;
   cudaGraphExec_t g_step[kMaxSub], g_sample[kMaxSub];
   cudaGraphExec_t g_sample_n[kMaxSub];   // several sampling steps in one graph (fewer graph launches, dependent launch across steps)
+  cudaGraphExec_t g_beam[2];             // beam search: the scored step (+ top-k), one graph per K/V buffer orientation
+  const __half* beam_kv[2];
+  int64_t nodes_beam;
+  std::string beam_key;
   cudaGraphExec_t g_pair[3];             // interleaved pair of sub-batches: prompt step, one sampling step, sample_n sampling steps
   int64_t nodes_pair[3];
   cudaEvent_t pair_ev[2];
@@ -530,6 +534,11 @@ static void destroy_graphs(wb_handle* h) {
     if (h->g_pair[i]) cudaGraphExecDestroy(h->g_pair[i]);
     h->g_pair[i] = nullptr;
   }
+  for (int i = 0; i < 2; ++i) {
+    if (h->g_beam[i]) cudaGraphExecDestroy(h->g_beam[i]);
+    h->g_beam[i] = nullptr, h->beam_kv[i] = nullptr;
+  }
+  h->beam_key.clear();
   h->graph_key.clear();
 }
 
@@ -1437,9 +1446,48 @@ static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int3
   std::vector<float> top_lp((size_t)Mb * 8);
   std::vector<int32_t> top_idx((size_t)Mb * 8), src(Mb), next_col(Mb);
   int steps = 0;
+  // The scored step (decoder step with stored filtered logits + top-k) replays from a CUDA graph: on the wide models it is 7
+  // kernels per layer, and launched one by one the host, not the GPU, paces the step. The re-indexing swaps the two K/V buffer
+  // sets, so there is one graph per orientation (keyed by the buffer the first layer reads), captured when first needed.
+  char bkey[96];
+  snprintf(bkey, sizeof(bkey), "B%d b%d i%d e%d", B, beam, n_init, eot);
+  const bool beam_graph = getenv("WB_NO_GRAPH") == nullptr;
+  if (h->beam_key != bkey) {
+    for (int i = 0; i < 2; ++i) {
+      if (h->g_beam[i]) cudaGraphExecDestroy(h->g_beam[i]);
+      h->g_beam[i] = nullptr, h->beam_kv[i] = nullptr;
+    }
+    h->beam_key = bkey;
+  }
   for (int s = 0; s < opts->sample_len; ++s) {
-    WB_TRY(decode_step(h, scored));
-    WB_TRY(launch_topk_logprobs(h->logits, Mb, D.n_vocab, K, h->top_lp, h->top_idx, st, &h->launches));
+    int slot = -1;
+    if (beam_graph && s > 0) {   // the first scored step runs eagerly (function attributes are set outside of capture)
+      for (int i = 0; i < 2; ++i)
+        if (h->beam_kv[i] == h->selfK[0]) slot = i;
+      if (slot < 0) {
+        slot = h->beam_kv[0] ? 1 : 0;
+        if (h->g_beam[slot]) cudaGraphExecDestroy(h->g_beam[slot]);
+        h->g_beam[slot] = nullptr;
+        cudaGraph_t g;
+        const int64_t before = h->launches;
+        WB_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        int rc = decode_step(h, scored);
+        if (rc == 0) rc = launch_topk_logprobs(h->logits, Mb, D.n_vocab, K, h->top_lp, h->top_idx, st, &h->launches);
+        const cudaError_t ce = cudaStreamEndCapture(st, &g);
+        h->nodes_beam = h->launches - before;
+        h->launches = before;
+        if (rc) return rc;
+        WB_CUDA_OK(ce);
+        WB_CUDA_OK(cudaGraphInstantiate(&h->g_beam[slot], g, 0));
+        WB_CUDA_OK(cudaGraphDestroy(g));
+        h->beam_kv[slot] = h->selfK[0];
+      }
+      WB_CUDA_OK(cudaGraphLaunch(h->g_beam[slot], st));
+      h->launches += h->nodes_beam;
+    } else {
+      WB_TRY(decode_step(h, scored));
+      WB_TRY(launch_topk_logprobs(h->logits, Mb, D.n_vocab, K, h->top_lp, h->top_idx, st, &h->launches));
+    }
     WB_CUDA_OK(cudaMemcpyAsync(top_lp.data(), h->top_lp, top_lp.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
     WB_CUDA_OK(cudaMemcpyAsync(top_idx.data(), h->top_idx, top_idx.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     WB_CUDA_OK(cudaStreamSynchronize(st));

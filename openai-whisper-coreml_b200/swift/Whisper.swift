@@ -49,4 +49,48 @@ struct Whisper {
         try wbCheck(wb_detect_language(handle, 1, 50258, 50259, &langIdx))
         print(Self.LANGUAGES[Int(langIdx)])
     }
+
+    // reference: `whisper.load_model("small")` at export time (whisper_to_cml.py:7) — here the checkpoint is read at run time
+    init(checkpoint path: String, maxBatch: Int32 = 1, device: Int32 = 0) throws {
+        var d = wb_dims()
+        try wbCheck(wb_safetensors_read_dims(path, &d))
+        var h: OpaquePointer?
+        try wbCheck(wb_create(&d, maxBatch, 1, device, nil, &h))
+        handle = h!
+        dims = d
+        var loaded: Int32 = 0
+        try wbCheck(wb_load_safetensors(handle, path, &loaded))
+    }
+
+    // A recording of any length (the reference stops at one 30 s window, ContentView.swift:57-62): upstream transcribe()
+    func transcribe(pcm: [Float], tokenizer: OpaquePointer?, language: Int32? = nil) throws -> (tokens: [Int32], segments: [wb_segment]) {
+        // multilingual token layout (Whisper.swift:35,37 pin sot = 50258, languages from 50259)
+        var sotSequence: [Int32] = [50258, 50259 + (language ?? 0), 50359]
+        var suppress: [Int32] = [50258, 50358, 50359, 50360, 50361, 50362], suppressBegin: [Int32] = [220, 50257]
+        var lo = wb_long_opts()
+        var nSeg: Int32 = 0, nTok: Int32 = 0, lang: Int32 = -1
+        var segs = [wb_segment](repeating: wb_segment(), count: 64 * (pcm.count / 480000 + 2))
+        var toks = [Int32](repeating: 0, count: 256 * (pcm.count / 480000 + 2))
+        try sotSequence.withUnsafeMutableBufferPointer { sot in
+            try suppress.withUnsafeMutableBufferPointer { sup in
+                try suppressBegin.withUnsafeMutableBufferPointer { supb in
+                    lo.decode.initial_tokens = UnsafePointer(sot.baseAddress); lo.decode.n_initial = 3; lo.decode.sot_index = 0
+                    lo.decode.eot = 50257; lo.decode.no_speech = 50362
+                    lo.decode.suppress = UnsafePointer(sup.baseAddress); lo.decode.n_suppress = Int32(sup.count)
+                    lo.decode.suppress_begin = UnsafePointer(supb.baseAddress); lo.decode.n_suppress_begin = 2
+                    lo.decode.timestamps = 1; lo.decode.timestamp_begin = 50364; lo.decode.no_timestamps = 50363
+                    lo.decode.max_initial_timestamp_index = 50
+                    lo.compression_ratio_threshold = 2.4; lo.logprob_threshold = -1.0; lo.no_speech_threshold = 0.6
+                    lo.condition_on_previous_text = 1; lo.sot_prev = 50361; lo.tokenizer = tokenizer
+                    lo.detect_language = language == nil ? 1 : 0; lo.lang0 = 50259
+                    try withUnsafeMutablePointer(to: &lang) { lp in
+                        lo.detected_language = lp
+                        try wbCheck(wb_transcribe_long(handle, pcm, Int64(pcm.count), &lo, &segs, Int32(segs.count), &nSeg, &toks,
+                                                       Int32(toks.count), &nTok))
+                    }
+                }
+            }
+        }
+        return (Array(toks[0..<Int(nTok)]), Array(segs[0..<Int(nSeg)]))
+    }
 }
