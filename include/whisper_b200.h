@@ -135,6 +135,8 @@ int wb_encode_mel(wb_handle* h, const float* mel, int32_t B, float* xa_out);
 int wb_encode_dev(wb_handle* h, const float* audio_dev, int32_t B);
 /* Load externally computed audio features (decoder.prediction's `xa` argument, Whisper.swift:36): xa [B][1500][d]. */
 int wb_set_audio_features(wb_handle* h, const float* xa, int32_t B);
+/* The resident features of the last wb_encode* / wb_transcribe* call (`audioFeatures`, Whisper.swift:30): xa_out [B][1500][d]. */
+int wb_get_audio_features(wb_handle* h, float* xa_out, int32_t B);
 
 /* ---- decoder ------------------------------------------------------------------------------------------------------
  * wb_decoder_logits replaces `decoderModel.prediction(x_1: tokens, xa: audioFeatures).var_2217`

@@ -15,6 +15,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <stdio.h>
 #include <zlib.h>
 
@@ -160,6 +161,11 @@ struct wb_handle {
   int sample_n;                          // steps per g_sample_n graph
   int64_t nodes_step, nodes_sample;
   std::string graph_key;
+
+  // host audio arrives in slabs on its own stream, so that all but the first slab's copy runs under the encoder (wb_transcribe)
+  static constexpr int kMaxSlabs = 4;
+  cudaStream_t copy_stream;
+  cudaEvent_t copy_ev[kMaxSlabs], copy_fence;
 
   // host staging + timing
   int32_t* h_done;
@@ -337,49 +343,62 @@ static int plain_gemm(wb_handle* h, const __half* a, int M, const __half* w, int
   return launch_gemm(h->gemm, g, h->stream, &h->launches);
 }
 
-// melT (already filled) -> xa16 / xa32 and the cross-attention K/V of every decoder layer
-static int encoder_forward(wb_handle* h, int B) {
+// melT (already filled) -> xa16 / xa32 and the cross-attention K/V of every decoder layer, for chunks [b0, b0 + n) of the
+// batch. Every buffer is chunk-major, so a slab is the same computation on offset pointers (results do not depend on the
+// slab split: every output element is one K-ordered reduction).
+static int encoder_forward(wb_handle* h, int b0, int n) {
   const wb_dims& D = h->dims;
-  const int d = D.n_audio_state, T = D.n_audio_ctx, M = B * T;
+  const int d = D.n_audio_state, T = D.n_audio_ctx, M = n * T;
+  const size_t r0 = (size_t)b0 * T;   // first row of the slab in the [B*T][.] matrices
   cudaStream_t st = h->stream;
+  __half* melT = h->melT + (size_t)b0 * (WB_N_FRAMES + 2) * WB_N_MELS;
+  __half* x1 = h->x1 + (size_t)b0 * (2 * T + 1) * d;
+  float* xenc = h->xenc + r0 * d;
+  __half *h16 = h->h16 + r0 * d, *qkv16 = h->qkv16 + r0 * 3 * d, *att16 = h->att16 + r0 * d, *mlp16 = h->mlp16 + r0 * 4 * d;
   {   // conv1 + GELU: im2col row t = 240 contiguous halves at melT[b][t][0]
     GemmDesc g{};
-    g.a = h->melT, g.a_row_stride = WB_N_MELS, g.a_batch_stride = (long long)(WB_N_FRAMES + 2) * WB_N_MELS;
-    g.rows = WB_N_FRAMES, g.n_batch = B, g.w = h->conv1_w, g.N = d, g.K = 3 * WB_N_MELS, g.bias = h->conv1_b, g.gelu = 1;
-    g.c16 = h->x1, g.ldc = d, g.c_batch_rows = 2 * T + 1, g.c_row_off = 1;
+    g.a = melT, g.a_row_stride = WB_N_MELS, g.a_batch_stride = (long long)(WB_N_FRAMES + 2) * WB_N_MELS;
+    g.rows = WB_N_FRAMES, g.n_batch = n, g.w = h->conv1_w, g.N = d, g.K = 3 * WB_N_MELS, g.bias = h->conv1_b, g.gelu = 1;
+    g.c16 = x1, g.ldc = d, g.c_batch_rows = 2 * T + 1, g.c_row_off = 1;
     WB_TRY(launch_gemm(h->gemm, g, st, &h->launches));
   }
   {   // conv2 (stride 2) + GELU + sinusoidal positions: row t = 3d contiguous halves at x1[b][2t][0]
     GemmDesc g{};
-    g.a = h->x1, g.a_row_stride = 2 * d, g.a_batch_stride = (long long)(2 * T + 1) * d;
-    g.rows = T, g.n_batch = B, g.w = h->conv2_w, g.N = d, g.K = 3 * d, g.bias = h->conv2_b, g.gelu = 1;
-    g.res_mode = 2, g.res = h->enc_pos, g.c32 = h->xenc, g.ldc = d, g.c_batch_rows = T, g.c_row_off = 0;
+    g.a = x1, g.a_row_stride = 2 * d, g.a_batch_stride = (long long)(2 * T + 1) * d;
+    g.rows = T, g.n_batch = n, g.w = h->conv2_w, g.N = d, g.K = 3 * d, g.bias = h->conv2_b, g.gelu = 1;
+    g.res_mode = 2, g.res = h->enc_pos, g.c32 = xenc, g.ldc = d, g.c_batch_rows = T, g.c_row_off = 0;
     WB_TRY(launch_gemm(h->gemm, g, st, &h->launches));
   }
   for (int l = 0; l < D.n_audio_layer; ++l) {
     const LayerW& L = h->enc[l];
-    WB_TRY(launch_layernorm(h->xenc, L.ln1_g, L.ln1_b, M, d, h->h16, nullptr, st, &h->launches));
-    WB_TRY(plain_gemm(h, h->h16, M, L.wqkv, 3 * d, d, L.bqkv, 0, nullptr, h->qkv16, nullptr));
-    WB_TRY(launch_encoder_attention(h->gemm, h->qkv16, B, T, D.n_audio_head, h->att16, st, &h->launches));
-    WB_TRY(plain_gemm(h, h->att16, M, L.wo, d, d, L.bo, 0, h->xenc, nullptr, h->xenc));
-    WB_TRY(launch_layernorm(h->xenc, L.ln2_g, L.ln2_b, M, d, h->h16, nullptr, st, &h->launches));
-    WB_TRY(plain_gemm(h, h->h16, M, L.w1, 4 * d, d, L.b1, 1, nullptr, h->mlp16, nullptr));
-    WB_TRY(plain_gemm(h, h->mlp16, M, L.w2, d, 4 * d, L.b2, 0, h->xenc, nullptr, h->xenc));
+    WB_TRY(launch_layernorm(xenc, L.ln1_g, L.ln1_b, M, d, h16, nullptr, st, &h->launches));
+    WB_TRY(plain_gemm(h, h16, M, L.wqkv, 3 * d, d, L.bqkv, 0, nullptr, qkv16, nullptr));
+    WB_TRY(launch_encoder_attention(h->gemm, qkv16, n, T, D.n_audio_head, att16, st, &h->launches));
+    WB_TRY(plain_gemm(h, att16, M, L.wo, d, d, L.bo, 0, xenc, nullptr, xenc));
+    WB_TRY(launch_layernorm(xenc, L.ln2_g, L.ln2_b, M, d, h16, nullptr, st, &h->launches));
+    WB_TRY(plain_gemm(h, h16, M, L.w1, 4 * d, d, L.b1, 1, nullptr, mlp16, nullptr));
+    WB_TRY(plain_gemm(h, mlp16, M, L.w2, d, 4 * d, L.b2, 0, xenc, nullptr, xenc));
   }
-  WB_TRY(launch_layernorm(h->xenc, h->lnpost_g, h->lnpost_b, M, d, h->xa16, h->xa32, st, &h->launches));
+  WB_TRY(launch_layernorm(xenc, h->lnpost_g, h->lnpost_b, M, d, h->xa16 + r0 * d, h->xa32 + r0 * d, st, &h->launches));
   return 0;
 }
+static int encoder_forward(wb_handle* h, int B) { return encoder_forward(h, 0, B); }
 
-static int cross_kv(wb_handle* h, int B) {
+static int cross_kv(wb_handle* h, int b0, int n) {
   const wb_dims& D = h->dims;
-  const int d = D.n_text_state, M = B * D.n_audio_ctx;
+  const int d = D.n_text_state, M = n * D.n_audio_ctx;
+  const size_t off = (size_t)b0 * D.n_audio_ctx * d;
   for (int l = 0; l < D.n_text_layer; ++l) {
     const LayerW& L = h->dec[l];
-    WB_TRY(plain_gemm(h, h->xa16, M, L.wk_c, d, d, nullptr, 0, nullptr, h->crossK[l], nullptr));
-    WB_TRY(plain_gemm(h, h->xa16, M, L.wv_c, d, d, L.bv_c, 0, nullptr, h->crossV[l], nullptr));
+    WB_TRY(plain_gemm(h, h->xa16 + off, M, L.wk_c, d, d, nullptr, 0, nullptr, h->crossK[l] + off, nullptr));
+    WB_TRY(plain_gemm(h, h->xa16 + off, M, L.wv_c, d, d, L.bv_c, 0, nullptr, h->crossV[l] + off, nullptr));
   }
-  h->enc_batch = B;
+  if (b0 == 0 || h->enc_batch == b0) h->enc_batch = b0 + n;   // slabs arrive in order
   return 0;
+}
+static int cross_kv(wb_handle* h, int B) {
+  h->enc_batch = 0;
+  return cross_kv(h, 0, B);
 }
 
 // ---- decoder ---------------------------------------------------------------------------------------------------------------
@@ -644,6 +663,10 @@ static void free_handle(wb_handle* h) {
   if (h->fork_ev) cudaEventDestroy(h->fork_ev);
   for (int i = 0; i < 2; ++i)
     if (h->pair_ev[i]) cudaEventDestroy(h->pair_ev[i]);
+  for (int i = 0; i < wb_handle::kMaxSlabs; ++i)
+    if (h->copy_ev[i]) cudaEventDestroy(h->copy_ev[i]);
+  if (h->copy_fence) cudaEventDestroy(h->copy_fence);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->h_done) cudaFreeHost(h->h_done);
   if (h->arena.base) cudaFree(h->arena.base);
   if (h->ws.base) cudaFree(h->ws.base);
@@ -700,6 +723,9 @@ static int create_impl(wb_handle* h, void* stream) {
   for (int i = 0; i < wb_handle::kMaxSub; ++i) WB_CUDA_OK(cudaEventCreateWithFlags(&h->sub_ev[i], cudaEventDisableTiming));
   WB_CUDA_OK(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) WB_CUDA_OK(cudaEventCreateWithFlags(&h->pair_ev[i], cudaEventDisableTiming));
+  WB_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < wb_handle::kMaxSlabs; ++i) WB_CUDA_OK(cudaEventCreateWithFlags(&h->copy_ev[i], cudaEventDisableTiming));
+  WB_CUDA_OK(cudaEventCreateWithFlags(&h->copy_fence, cudaEventDisableTiming));
   // everything above (the zero fill the bqkv key-bias slice, the melT pad rows and x1 row 0 rely on, the tables) is complete
   // on the device before the handle is handed out, whatever stream later work uses
   WB_CUDA_OK(cudaDeviceSynchronize());
@@ -993,6 +1019,13 @@ static int need_features(wb_handle* h, int B) {
     return WB_ERR_STATE;
   }
   return 0;
+}
+
+int wb_get_audio_features(wb_handle* h, float* xa_out, int32_t B) {
+  WB_TRY(check_batch(h, B));
+  WB_TRY(need_features(h, B));
+  if (!xa_out) return WB_ERR_ARG;
+  return fetch_xa(h, B, xa_out);
 }
 
 int wb_decoder_logits(wb_handle* h, const int32_t* tokens, int32_t B, int32_t t, float* logits) {
@@ -1409,6 +1442,12 @@ static int decode_sampled(wb_handle* h, int32_t B, const wb_decode_opts* opts, i
 // decoder step for n_audio*beam sequences (cross K/V shared by the beams of a chunk) and extracts the top beam+1
 // log-probabilities per row; the candidate bookkeeping of a step is a few hundred scalar operations and runs on the host;
 // the self-attention cache is re-indexed by source beam on the device.
+static double now_ms() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int32_t* tokens_out, int32_t* lens, float* sum_logprob) {
   const wb_dims& D = h->dims;
   const int beam = opts->beam_size, Mb = B * beam, K = beam + 1;
@@ -1449,6 +1488,8 @@ static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int3
   // The scored step (decoder step with stored filtered logits + top-k) replays from a CUDA graph: on the wide models it is 7
   // kernels per layer, and launched one by one the host, not the GPU, paces the step. The re-indexing swaps the two K/V buffer
   // sets, so there is one graph per orientation (keyed by the buffer the first layer reads), captured when first needed.
+  const bool prof = getenv("WB_BEAM_PROF") != nullptr;   // development: where a beam step's wall time goes
+  double t_wait = 0.0, t_host = 0.0, t_reorder = 0.0;
   char bkey[96];
   snprintf(bkey, sizeof(bkey), "B%d b%d i%d e%d", B, beam, n_init, eot);
   const bool beam_graph = getenv("WB_NO_GRAPH") == nullptr;
@@ -1490,7 +1531,10 @@ static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int3
     }
     WB_CUDA_OK(cudaMemcpyAsync(top_lp.data(), h->top_lp, top_lp.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
     WB_CUDA_OK(cudaMemcpyAsync(top_idx.data(), h->top_idx, top_idx.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    const double t_a = prof ? now_ms() : 0.0;
     WB_CUDA_OK(cudaStreamSynchronize(st));
+    const double t_b = prof ? now_ms() : 0.0;
+    t_wait += t_b - t_a;
     ++steps;
     std::vector<Seq> next_seqs;
     std::vector<float> next_slp;
@@ -1542,6 +1586,7 @@ static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int3
       }
     }
     seqs.swap(next_seqs), slp.swap(next_slp);
+    if (prof) t_host += now_ms() - t_b;
     bool completed = true;
     for (int a = 0; a < B; ++a) completed = completed && finished[a].size() >= max_candidates;
     if (completed || s + 1 == opts->sample_len) break;
@@ -1561,8 +1606,13 @@ static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int3
       h->selfK.swap(h->selfK_alt), h->selfV.swap(h->selfV_alt);
     }
     WB_TRY(step_finish(h, plain, 0));
+    const double t_c = prof ? now_ms() : 0.0;
     WB_CUDA_OK(cudaStreamSynchronize(st));   // next_col / src are reused next iteration
+    if (prof) t_reorder += now_ms() - t_c;
   }
+  if (prof)
+    fprintf(stderr, "[wb] beam search, %d steps: waiting for the scored step %.1f ms, host bookkeeping %.1f ms, waiting for re-index + embed %.1f ms\n",
+            steps, t_wait, t_host, t_reorder);
   WB_CUDA_OK(cudaEventRecord(h->ev[3], st));
   h->timings[3] = (float)(steps + n_init - 1);
   // finalize: unfinished beams (eot appended) fill up to `beam` candidates; rank by sum_logprob / length
@@ -1637,12 +1687,60 @@ int wb_transcribe_dev(wb_handle* h, const float* audio_dev, int32_t B, const wb_
   return WB_OK;
 }
 
+// Slab sizes for a host batch of B chunks: the encoder takes ~3.4x as long per chunk as the PCIe copy, so after a first slab
+// (whose copy is the only exposed one) every later copy runs under the previous slab's compute. Measured at base.en, 32 chunks
+// (gpurun_out/exp1_slabs.log): pinned host memory 68.5 -> 68.1 ms per step with {8, 24} (smaller first slabs lose more in
+// the encoder's tile quantisation than their copy saves), pageable 73.5 -> 71.6 ms ({4, 12, 16}: 70.3 ms).
+// WB_H2D_SLABS="a,b,c" (chunks per slab, the last one takes the rest) overrides; "0" = one copy.
+static int slab_plan(int B, int (&slab)[wb_handle::kMaxSlabs]) {
+  int n = 0, used = 0;
+  if (const char* e = getenv("WB_H2D_SLABS")) {
+    while (*e && n < wb_handle::kMaxSlabs - 1) {
+      const int v = atoi(e);
+      if (v <= 0 || used + v >= B) break;
+      slab[n++] = v, used += v;
+      while (*e && *e != ',') ++e;
+      if (*e == ',') ++e;
+    }
+  } else if (B >= 8) {
+    slab[n++] = B / 4, used += B / 4;
+  }
+  slab[n++] = B - used;
+  return n;
+}
+
 int wb_transcribe(wb_handle* h, const float* audio, int32_t B, const wb_decode_opts* opts, int32_t* tokens_out, int32_t* lens,
                   float* sum_logprob) {
   WB_TRY(check_batch(h, B));
+  WB_TRY(need_weights(h));
   if (!audio) return WB_ERR_ARG;
-  WB_CUDA_OK(cudaMemcpyAsync(h->audio_dev, audio, (size_t)B * WB_N_SAMPLES * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  return wb_transcribe_dev(h, h->audio_dev, B, opts, tokens_out, lens, sum_logprob);
+  int slab[wb_handle::kMaxSlabs];
+  const int n_slab = slab_plan(B, slab);
+  // the copies may not overtake work already queued on the handle's stream that still reads audio_dev
+  WB_CUDA_OK(cudaEventRecord(h->copy_fence, h->stream));
+  WB_CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->copy_fence, 0));
+  WB_CUDA_OK(cudaEventRecord(h->ev[0], h->stream));
+  h->enc_batch = 0;
+  for (int s = 0, b0 = 0; s < n_slab; b0 += slab[s], ++s) {
+    const size_t off = (size_t)b0 * WB_N_SAMPLES;
+    WB_CUDA_OK(cudaMemcpyAsync(h->audio_dev + off, audio + off, (size_t)slab[s] * WB_N_SAMPLES * sizeof(float), cudaMemcpyHostToDevice,
+                               h->copy_stream));
+    WB_CUDA_OK(cudaEventRecord(h->copy_ev[s], h->copy_stream));
+    WB_CUDA_OK(cudaStreamWaitEvent(h->stream, h->copy_ev[s], 0));
+    WB_TRY(launch_logmel<float>(h->audio_dev + off, WB_N_SAMPLES, 0, slab[s], h->tab32, h->logspec + (size_t)b0 * WB_N_MELS * WB_N_FRAMES,
+                                reinterpret_cast<unsigned int*>(h->gmax) + b0 /* OrderedMax<float>::U */, nullptr,
+                                h->melT + (size_t)b0 * (WB_N_FRAMES + 2) * WB_N_MELS, h->stream, &h->launches));
+    if (s == 0) WB_CUDA_OK(cudaEventRecord(h->ev[1], h->stream));   // timings[0]: the first slab's copy + log-mel
+    WB_TRY(encoder_forward(h, b0, slab[s]));
+    WB_TRY(cross_kv(h, b0, slab[s]));
+  }
+  WB_CUDA_OK(cudaEventRecord(h->ev[2], h->stream));
+  WB_TRY(wb_decode(h, B, opts, tokens_out, lens, sum_logprob));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->timings[0] = ms;
+  if (cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]) == cudaSuccess) h->timings[1] = ms;
+  if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) h->timings[2] = ms;
+  return WB_OK;
 }
 
 int64_t wb_launch_count(const wb_handle* h) { return h ? h->launches : -1; }

@@ -268,3 +268,38 @@ def test_checkpoint_files_round_trip(wbm, ref, tmp_path):
     assert wbm.load_library().wb_load_safetensors(other.handle, up.encode(), None) == -1
     assert b"wrong model size" in wbm.load_library().wb_last_error()
     other.close(), base.close()
+
+
+def test_host_batch_in_slabs_is_bit_identical(wbm):
+    """wb_transcribe copies a host batch in slabs and encodes slab i while slab i+1 is on the bus (WB_H2D_SLABS): tokens, log-
+    probabilities and the audio features are identical, bit for bit, to the single-copy schedule, whatever the split."""
+    B = 11
+    w = wbm.Whisper("tiny.en", seed=21, max_batch=B)
+    o = wbm.DecodeOptions.default_for(wbm.DIMS["tiny.en"], sample_len=24)
+    o.suppress = list(o.suppress) + [o.eot]
+    audio = (np.random.default_rng(5).standard_normal((B, 480000)) * 0.1).astype(np.float32)
+    lib = wbm.load_library()
+    import ctypes
+    n = B * 1500 * 384
+
+    def run(plan):
+        if plan is None:
+            os.environ.pop("WB_H2D_SLABS", None)
+        else:
+            os.environ["WB_H2D_SLABS"] = plan
+        tok, lens, slp = w.transcribe(audio, o)
+        xa = np.empty(n, dtype=np.float32)   # the features the decode just used
+        assert lib.wb_get_audio_features(w.handle, xa.ctypes.data_as(ctypes.c_void_p), B) == 0, lib.wb_last_error()
+        return tok, slp, xa
+
+    try:
+        base = run("0")
+        for plan in (None, "1,1,1", "3,5", "10", "4"):
+            got = run(plan)
+            for a, b in zip(base, got):
+                assert np.array_equal(a, b), plan
+    finally:
+        os.environ.pop("WB_H2D_SLABS", None)
+    ref_dev = w.encode(audio)               # wb_encode: one copy, one slab
+    assert np.array_equal(ref_dev.reshape(-1), base[2])
+    w.close()
