@@ -44,6 +44,10 @@ CONFIGS = {
     "small_beam5_b8": dict(model="small", batch=8, beam=5, sample_len=224, what="configs[3]: Whisper-small multilingual, 5-beam, batch 8, 1 GPU"),
     "large_v2_60w": dict(model="large-v2", batch=30, beam=0, sample_len=224, windows=60,
                          what="configs[4]: Whisper-large-v2, 30 min = 60 x 30 s windows sharded over the ranks, greedy"),
+    # not a BASELINE configuration: the headline model at the handle's largest batch (the latency-bound block kernels of a
+    # decode step cost the same for 64 sequences as for 32)
+    "base_b64": dict(model="base.en", batch=64, beam=0, sample_len=224,
+                     what="beyond BASELINE: Whisper-base.en, 64 chunks per GPU (the handle's limit), greedy, 1 GPU"),
 }
 
 

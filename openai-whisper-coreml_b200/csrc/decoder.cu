@@ -34,8 +34,18 @@ __device__ __forceinline__ void weight_prefetch_l2(const void* p) {
   else
     ptx::prefetch_l2(p);
 }
+// The embedding matrix (53 MB at base.en) is streamed once per step by the logits kernel and does not survive the 590 MB
+// cross K/V stream of the next step whatever its policy (in-step ncu: 52.7 MB of DRAM reads per launch either way), but
+// loaded evict_last it pushes the weights of decoder layers 0-1 out of L2 (2-4 MB of DRAM reads in their block kernels).
+// WB_EMB_KEEP8 = eighths of its row groups loaded evict_last, the rest evict_first like the K/V stream; default 0
+// (measured 61.74 -> 61.59 ms per 225-step decode).
+__constant__ int c_emb_keep8 = 0;
 int decoder_set_l2_mode(int mode) {
   WB_CUDA_OK(cudaMemcpyToSymbol(c_l2_mode, &mode, sizeof(int)));
+  int keep = 0;
+  if (const char* e = getenv("WB_EMB_KEEP8")) keep = atoi(e);
+  keep = keep < 0 ? 0 : (keep > 8 ? 8 : keep);
+  WB_CUDA_OK(cudaMemcpyToSymbol(c_emb_keep8, &keep, sizeof(int)));
   return 0;
 }
 
@@ -656,9 +666,11 @@ __global__ void __launch_bounds__(kLtThreads, 1) logits_tc_kernel(const __grid_c
   if (warp == 0) {
     // ---- TMA producer: the embedding matrix does not depend on the previous kernel, so the ring fills during its tail -----------------
     if (lane == 0) {
-      const uint64_t wpol = weight_policy();
+      const uint64_t pol_keep = weight_policy(), pol_stream = stream_policy();
+      const int keep_groups = (a.n_groups * c_emb_keep8) >> 3;
       uint32_t it = 0;
       for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x) {
+        const uint64_t wpol = g < keep_groups ? pol_keep : pol_stream;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % n_stages;
           const uint32_t ph = (it / n_stages) & 1u;
@@ -879,7 +891,7 @@ __global__ void __launch_bounds__(kLtThreads, 1) logits_tc_kernel(const __grid_c
 }
 
 static int launch_logits_tc(const SkinnyDesc& d, cudaStream_t st, int64_t* launches) {
-  const int NB = d.Mb <= 16 ? 16 : (d.Mb <= 32 ? 32 : 48);
+  const int NB = d.Mb <= 16 ? 16 : (d.Mb <= 32 ? 32 : (d.Mb <= 48 ? 48 : 64));
   const int nkb = d.K / 64, n_groups = skinny_logits_ctas(d.N);
   CUtensorMap tmW;
   const int rc = gemm_get_tmap(d.tmaps, d.w, d.K, d.N, 1, d.K, (long long)d.N * d.K, 128, &tmW);
@@ -919,7 +931,7 @@ static int launch_logits_tc(const SkinnyDesc& d, cudaStream_t st, int64_t* launc
                     : cudaLaunchKernelEx(&cfg, logits_tc_kernel<N_, false>, tmW, a);                                   \
   } break;
   switch (NB) {
-    WB_LT_CASE(16) WB_LT_CASE(32) WB_LT_CASE(48)
+    WB_LT_CASE(16) WB_LT_CASE(32) WB_LT_CASE(48) WB_LT_CASE(64)
   }
 #undef WB_LT_CASE
   if (launches) *launches += 1;
@@ -937,7 +949,8 @@ static bool use_logits_tc() {
 }
 
 int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches) {
-  if (d.Mb < 1 || d.Mb > 40 || d.K % 128 != 0 || d.N < 16) {
+  const bool to_tc = d.out_mode == SKINNY_OUT_LOGITS && d.in_mode == SKINNY_IN_LN && d.K <= kSkKC && use_logits_tc() && d.tmaps && d.K % 64 == 0;
+  if (d.Mb < 1 || d.Mb > (to_tc ? kMaxSequences : kMaxSequencesWide) || d.K % 128 != 0 || d.N < 16) {
     set_error("skinny_gemm: unsupported shape Mb=%d N=%d K=%d", d.Mb, d.N, d.K);
     return -1;
   }
@@ -950,9 +963,9 @@ int launch_skinny_gemm(const SkinnyDesc& d, cudaStream_t st, int64_t* launches) 
       set_error("logits GEMM: LayerNorm input with K <= %d required", kSkKC);
       return -1;
     }
-    if (use_logits_tc() && d.tmaps && d.K % 64 == 0 && d.Mb <= 48) return launch_logits_tc(d, st, launches);
+    if (use_logits_tc() && d.tmaps && d.K % 64 == 0 && d.Mb <= 64) return launch_logits_tc(d, st, launches);
     if (d.ts_state) {
-      set_error("logits GEMM: the timestamp rules are implemented by the tcgen05 kernel only (Mb <= 48, K %% 64 == 0)");
+      set_error("logits GEMM: the timestamp rules are implemented by the tcgen05 kernel only (Mb <= 64, K %% 64 == 0)");
       return -1;
     }
     const int n_groups = skinny_logits_ctas(d.N);

@@ -741,6 +741,11 @@ int wb_create(const wb_dims* dims, int32_t max_batch, int32_t max_beams, int32_t
     set_error("wb_create: unsupported model dimensions");
     return WB_ERR_ARG;
   }
+  const bool blocks = self_block_supported(dims->n_text_head, dims->n_text_state) && post_block_supported(dims->n_text_head, dims->n_text_state);
+  if (!blocks && max_batch * max_beams > kMaxSequencesWide) {
+    set_error("wb_create: max_batch * max_beams must be in [1, %d] for this model width (%d up to d = 512)", kMaxSequencesWide, kMaxSequences);
+    return WB_ERR_ARG;
+  }
   WB_TRY(select_device(device));
   wb_handle* h = new wb_handle();   // value-initialised: every pointer null, every counter zero
   h->dims = *dims, h->max_batch = max_batch, h->max_beams = max_beams, h->device = device;
@@ -1138,8 +1143,8 @@ static int validate_decode_opts(const wb_handle* h, int32_t B, const wb_decode_o
       return WB_ERR_ARG;
     }
     if (opts->timestamp_begin <= opts->eot || opts->timestamp_begin >= D.n_vocab || opts->no_timestamps < 0 ||
-        opts->no_timestamps >= D.n_vocab || B > 48) {
-      set_error("wb_decode: timestamp rules need eot < timestamp_begin < n_vocab, a valid no_timestamps token and <= 48 sequences");
+        opts->no_timestamps >= D.n_vocab || B > 64) {
+      set_error("wb_decode: timestamp rules need eot < timestamp_begin < n_vocab, a valid no_timestamps token and <= 64 sequences");
       return WB_ERR_ARG;
     }
   }
@@ -1351,8 +1356,8 @@ static int decode_sampled(wb_handle* h, int32_t B, const wb_decode_opts* opts, i
   const int G = opts->best_of > 1 ? opts->best_of : 1, Mb = B * G, V = D.n_vocab;
   const int n_init = opts->n_initial, total = n_init + opts->sample_len, eot = opts->eot;
   const bool ts_on = opts->timestamps != 0;
-  if (G > h->max_beams || Mb > h->Mb_max || (ts_on && Mb > 48)) {
-    set_error("wb_decode: best_of %d exceeds the handle's max_beams %d, or batch * best_of %d exceeds %d (48 with timestamp rules)", G,
+  if (G > h->max_beams || Mb > h->Mb_max || (ts_on && Mb > 64)) {
+    set_error("wb_decode: best_of %d exceeds the handle's max_beams %d, or batch * best_of %d exceeds %d (64 with timestamp rules)", G,
               h->max_beams, Mb, h->Mb_max);
     return WB_ERR_ARG;
   }

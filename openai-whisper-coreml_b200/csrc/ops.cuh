@@ -5,7 +5,8 @@
 
 namespace wb {
 
-constexpr int kMaxSequences = 40;   // decoder rows per handle (chunks x beams): 5 MMA column tiles of 8 in the skinny GEMMs
+constexpr int kMaxSequences = 64;       // decoder rows per handle (chunks x beams) where the layer runs as the block kernels (tiny / base)
+constexpr int kMaxSequencesWide = 40;   // ... on the skinny-GEMM path of the wider models: 5 MMA column tiles of 8
 
 // ---- log-mel (logmel.cu) ---------------------------------------------------------------------------------------------
 template <typename T>

@@ -76,6 +76,24 @@ def test_legacy_symbol_buffer_protocol_and_pad_mutation(wbm):
     assert np.isfinite(out).all() and out.max() <= 2.0
 
 
+def test_logmel_nan_samples_take_the_floor_like_the_reference(tiny, wbm, ref, oracle_logmel):
+    """lib.rs:76 `x.max(1e-10)` is Rust's f64::max: a NaN operand is ignored, so every frame whose window holds a NaN sample
+    becomes log10(1e-10) = -10 in all 80 bands before the maximum is taken (lib.rs:82-88 never sees a NaN and does not panic).
+    The kernels' `sum > 1e-10 ? sum : 1e-10` keeps that, in f64 (legacy symbol) and in f32."""
+    a = ref.synth_audio(5, "noise")
+    a[100000] = np.nan
+    a[300007] = np.nan
+    want = oracle_logmel(a)
+    assert np.isfinite(want).all()
+    hit = [f for f in range(3000) if any(f * 160 - 200 <= s < f * 160 + 200 for s in (100000, 300007))]
+    assert len(hit) == 6 and all(np.ptp(want[:, f]) == 0 for f in hit)          # three frames per NaN sample, all bands at the floor
+    got64 = wbm.generateSpectrogram(a).reshape(80, 3000)
+    assert np.isfinite(got64).all() and np.abs(got64 - want).max() <= TOL_MEL64
+    w, _ = tiny
+    got32 = w.logmel(a.astype(np.float32))[0]
+    assert np.isfinite(got32).all() and np.abs(got32 - want).max() <= TOL_MEL32
+
+
 def test_logmel_batch_slot_independence(tiny, ref):
     w, _ = tiny
     a = np.stack([ref.synth_audio(30 + i, "noise") for i in range(4)]).astype(np.float32)
@@ -397,6 +415,33 @@ def test_beam_search_on_block_kernels(wbm, ref, oracle_logmel):
     w.close()
 
 
+def test_beam_search_at_small_width(wbm, ref):
+    """BASELINE config 4's shape (whisper_to_cml.py:7 exports `small`: d = 768, 12 heads, multilingual vocabulary) with 2
+    layers: 8 chunks x 5 beams = 40 sequences on the decoder path of the wide models (seven kernels per layer), the cross K/V
+    shared by the beams of a chunk, the graph-replayed scored step. Weights / features: a seed whose oracle result is stable
+    under logit noise of 2e-2 (tools/pick_beam_seed.py), since whole token lists are compared."""
+    dims = ref.ModelDims(80, 1500, 768, 12, 2, 51865, 448, 768, 12, 2)
+    seed, B, beam = 7, 8, 5
+    weights = ref.random_weights(dims, seed=seed)
+    oracle = ref.WhisperRef(dims, weights)
+    pd = wbm.ModelDims(*[getattr(dims, f) for f in dims.__dataclass_fields__])
+    w = wbm.Whisper(pd, weights=weights, max_batch=B, max_beams=beam)
+    xa = (torch.randn(B, 1500, 768, generator=torch.Generator().manual_seed(100 + seed)) * 0.7).half().float()
+    w.set_audio_features(xa.numpy())
+    opts_ref = ref.DecodeOptions.default_for(dims, sample_len=9)
+    want_tokens, want_scores = oracle.beam_search(xa, opts_ref, beam_size=beam)
+    o = wbm.DecodeOptions.default_for(pd, sample_len=9)
+    o.beam_size = beam
+    tok, lens, slp = w.decode_tokens(B, o)
+    for b in range(B):
+        n = len(want_tokens[b])
+        assert tok[b, :n].tolist() == want_tokens[b], (b, tok[b].tolist(), want_tokens[b])
+        assert abs(float(slp[b]) - want_scores[b]) <= 0.05
+    tok2, _, slp2 = w.decode_tokens(B, o)                       # second call replays the captured graphs
+    assert np.array_equal(tok, tok2) and np.array_equal(slp, slp2)
+    w.close()
+
+
 @pytest.mark.parametrize("name,B,text_scale", [("tiny.en", 3, 1.0), ("tiny.en", 3, 1.8), ("tiny", 2, 1.8)])
 def test_greedy_with_timestamp_rules_matches_oracle(wbm, ref, oracle_logmel, name, B, text_scale):
     """Upstream's default decoding (without_timestamps=False): ApplyTimestampRules among the logit filters — first token a
@@ -473,6 +518,33 @@ def test_thirty_six_sequences_tiny(wbm, ref, oracle_logmel):
     same = (~differ).numpy()
     assert np.allclose(slp[same], slp_ref.numpy()[same], rtol=2e-3, atol=5e-2)
     w.close()
+
+
+def test_sixty_four_sequences_base_width(wbm, ref):
+    """The handle's upper limit where a layer runs as the block kernels: 64 sequences = 16 self-block clusters, 8 post-block
+    clusters, the logits kernel with 64 MMA columns (two full TMEM loads per row). Wider models stay at 40 (skinny-GEMM path)."""
+    dims = ref.ModelDims(80, 1500, 512, 8, 2, 51864, 448, 512, 8, 2)
+    weights = ref.random_weights(dims, seed=8)
+    oracle = ref.WhisperRef(dims, weights)
+    wd = wbm.ModelDims(*[getattr(dims, f) for f in dims.__dataclass_fields__])
+    B = 64
+    w = wbm.Whisper(wd, weights=weights, max_batch=B)
+    xa = (torch.randn(B, 1500, 512, generator=torch.Generator().manual_seed(19)) * 0.7).half().float()
+    w.set_audio_features(xa.numpy())
+    toks = torch.randint(0, 50000, (B, 3), generator=torch.Generator().manual_seed(5))
+    want = oracle.decoder_logits(toks, xa)
+    got = torch.from_numpy(w.decoder_logits(toks.numpy()))
+    assert (got - want).abs().max().item() <= TOL_ABS and _rel(got, want) <= TOL_REL
+    o = wbm.DecodeOptions.default_for(wd, sample_len=12)
+    tok, _, slp = w.greedy(B, o)
+    rep = pu.teacher_forced_check(oracle, xa, tok, len(o.initial_tokens), o.suppress, o.suppress_begin, o.eot)
+    print("\n[d=512 x 2 layers, 64 sequences x 12] " + rep.line())
+    assert rep.decisions == B * 12 and rep.bad == 0 and rep.ties <= 3, rep.line()
+    w.close()
+    with pytest.raises(wbm.WhisperB200Error, match="max_batch"):
+        wbm.Whisper("small", max_batch=41)
+    with pytest.raises(wbm.WhisperB200Error, match="max_batch"):
+        wbm.Whisper("tiny.en", max_batch=65)
 
 
 def test_error_paths(tiny, wbm):

@@ -99,3 +99,19 @@ def test_kernel_emulation_matches_oracle(emu, oracle_logmel, ref, kind):
     o64 = np.zeros(240000)
     emu.emu_logmel_f64(a.ctypes.data_as(ctypes.c_void_p), o64.ctypes.data_as(ctypes.c_void_p))
     assert np.abs(o64 - oracle_logmel(a).reshape(-1)).max() <= 1e-12
+
+
+def test_nan_samples_are_floored_not_propagated(oracle_logmel, ref):
+    """Rust's f64::max (lib.rs:76) drops a NaN operand: frames that hold a NaN sample come out at the floor, nothing panics."""
+    a = ref.synth_audio(5, "noise")
+    clean = oracle_logmel(a.copy())
+    a[100000] = np.nan
+    out = oracle_logmel(a)
+    assert np.isfinite(out).all()
+    frames = [f for f in range(3000) if f * 160 - 200 <= 100000 < f * 160 + 200]
+    assert len(frames) == 3
+    floor = clean.max() - 2.0                 # ((M - 8) + 4) / 4 with the normalised maximum (M + 4) / 4
+    assert np.allclose(out[:, frames], floor, atol=1e-12)
+    keep = np.ones(3000, dtype=bool)
+    keep[frames] = False
+    assert np.array_equal(out[:, keep], clean[:, keep])
