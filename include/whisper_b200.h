@@ -52,7 +52,7 @@ typedef struct wb_decode_opts {
   int32_t n_suppress_begin;
   int32_t beam_size;             /* 0 or 1 = greedy; 2..7 = beam search, patience 1 (needs max_beams >= beam_size)  */
   int32_t eot_check_interval;    /* how often (in steps) the host polls "all sequences ended"; 0 = default (8)      */
-  /* upstream ApplyTimestampRules (DecodingOptions.without_timestamps = False, upstream's own default): greedy only.   */
+  /* upstream ApplyTimestampRules (DecodingOptions.without_timestamps = False, upstream's own default)                */
   int32_t timestamps;            /* 0 = off (the prompt then ends with <|notimestamps|>)                            */
   int32_t timestamp_begin;       /* first timestamp token <|0.00|>: 50363 (.en) / 50364 (multilingual)              */
   int32_t no_timestamps;         /* <|notimestamps|>: 50362 / 50363; never sampled when the rules are on            */
@@ -201,7 +201,7 @@ int wb_text_compression_ratio(const uint8_t* raw, size_t n, float* ratio, size_t
 typedef struct wb_long_opts {
   wb_decode_opts decode;           /* per-window options: initial_tokens = the sot sequence WITHOUT prompt, sot_index into it,
                                       no_speech, timestamps (upstream default: on), suppress lists, sample_len (0 = n_text_ctx/2),
-                                      beam_size (temperature 0 only, without timestamps), best_of (temperature > 0), seed;
+                                      beam_size (temperature 0 only; no no_speech_prob then), best_of (temperature > 0), seed;
                                       temperature and no_speech_prob are set by the loop                                     */
   const float* temperatures;       /* fallback schedule; null = {0, 0.2, 0.4, 0.6, 0.8, 1.0}                                 */
   int32_t n_temperatures;

@@ -2607,19 +2607,57 @@ int launch_set_cur_len(DecodeState* state, int v, cudaStream_t st, int64_t* laun
 // Top-k of one logits row (k <= 8) and its log-sum-exp: every thread keeps a sorted top-k of its strided elements and an
 // online (max, sum-exp); the candidates are merged through shared memory by one warp. Output log-probabilities = logit - LSE
 // (upstream: F.log_softmax(logits).topk(beam_size + 1)).
-__global__ void __launch_bounds__(256) topk_logprobs_kernel(const float* __restrict__ logits, int V, int k, float* __restrict__ top_lp,
-                                                            int32_t* __restrict__ top_idx) {
+__global__ void __launch_bounds__(256) topk_logprobs_kernel(const float* __restrict__ logits, int V, int k, int ts_begin,
+                                                            float* __restrict__ top_lp, int32_t* __restrict__ top_idx) {
   __shared__ float c_val[256 * 8];
   __shared__ int c_idx[256 * 8];
   __shared__ float s_m[8], s_s[8];
+  __shared__ float s_mt[8];
+  __shared__ int s_lo;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* row = logits + (size_t)b * V;
+  int lo = 0;
+  if (ts_begin < V) {
+    // upstream ApplyTimestampRules, last rule: logsumexp(timestamps) > max(text)  <=>  M_ts + log S_ts > M_text  =>  text rows masked
+    float mt = -INFINITY, ms = -INFINITY, ss = 0.f;
+    for (int i = tid; i < ts_begin; i += 256) mt = fmaxf(mt, row[i]);
+    for (int i = ts_begin + tid; i < V; i += 256) {
+      const float x = row[i];
+      if (x > ms) {
+        ss = ss * expf(ms - x) + 1.0f;
+        ms = x;
+      } else if (x > -INFINITY) {
+        ss += expf(x - ms);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+      const float om = __shfl_xor_sync(0xffffffffu, ms, o), os = __shfl_xor_sync(0xffffffffu, ss, o);
+      const float nm = fmaxf(ms, om);
+      ss = (ms > -INFINITY ? ss * expf(ms - nm) : 0.f) + (om > -INFINITY ? os * expf(om - nm) : 0.f);
+      ms = nm;
+    }
+    if (lane == 0) s_mt[warp] = mt, s_m[warp] = ms, s_s[warp] = ss;
+    __syncthreads();
+    if (tid == 0) {
+      float MT = -INFINITY, M = -INFINITY;
+      for (int w = 0; w < 8; ++w) MT = fmaxf(MT, s_mt[w]), M = fmaxf(M, s_m[w]);
+      float S = 0.f;
+      for (int w = 0; w < 8; ++w) S += s_m[w] > -INFINITY ? s_s[w] * expf(s_m[w] - M) : 0.f;
+      const float lse_ts = M > -INFINITY ? M + logf(S) : -INFINITY;
+      s_lo = lse_ts > MT ? ts_begin : 0;
+    }
+    __syncthreads();
+    lo = s_lo;
+    __syncthreads();   // s_m / s_s are reused below
+  }
   float tv[8];
   int ti[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) tv[j] = -INFINITY, ti[j] = 0x7fffffff;
   float m = -INFINITY, ssum = 0.f;
-  for (int i = tid; i < V; i += 256) {
+  for (int i = lo + tid; i < V; i += 256) {
     const float x = row[i];
     if (x > m) {
       ssum = ssum * expf(m - x) + 1.0f;
@@ -2680,13 +2718,13 @@ __global__ void __launch_bounds__(256) topk_logprobs_kernel(const float* __restr
   }
 }
 
-int launch_topk_logprobs(const float* logits, int Mb, int V, int k, float* top_logprob, int32_t* top_index, cudaStream_t st,
+int launch_topk_logprobs(const float* logits, int Mb, int V, int k, int ts_begin, float* top_logprob, int32_t* top_index, cudaStream_t st,
                          int64_t* launches) {
   if (k < 1 || k > 8) {
     set_error("topk: k=%d out of range [1,8]", k);
     return -1;
   }
-  topk_logprobs_kernel<<<Mb, 256, 0, st>>>(logits, V, k, top_logprob, top_index);
+  topk_logprobs_kernel<<<Mb, 256, 0, st>>>(logits, V, k, ts_begin, top_logprob, top_index);
   if (launches) *launches += 1;
   WB_CUDA_OK(cudaGetLastError());
   return 0;

@@ -1138,10 +1138,6 @@ static int validate_decode_opts(const wb_handle* h, int32_t B, const wb_decode_o
     return WB_ERR_ARG;
   }
   if (opts->timestamps) {
-    if (opts->beam_size > 1) {
-      set_error("wb_decode: the timestamp rules are implemented for greedy decoding only");
-      return WB_ERR_ARG;
-    }
     if (opts->timestamp_begin <= opts->eot || opts->timestamp_begin >= D.n_vocab || opts->no_timestamps < 0 ||
         opts->no_timestamps >= D.n_vocab || B > 64) {
       set_error("wb_decode: timestamp rules need eot < timestamp_begin < n_vocab, a valid no_timestamps token and <= 64 sequences");
@@ -1470,6 +1466,9 @@ static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int3
     if (opts->suppress_begin[i] >= 0 && opts->suppress_begin[i] < D.n_vocab) mask[opts->suppress_begin[i]] = 2;
   for (int i = 0; i < opts->n_suppress; ++i)
     if (opts->suppress[i] >= 0 && opts->suppress[i] < D.n_vocab) mask[opts->suppress[i]] = 1;
+  const bool ts_on = opts->timestamps != 0;
+  const int ts_begin = ts_on ? opts->timestamp_begin : 0x7fffffff;
+  if (ts_on) mask[opts->no_timestamps] = 1;   // ApplyTimestampRules: <|notimestamps|> is never sampled
   WB_CUDA_OK(cudaMemcpyAsync(h->tokens, rows.data(), rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   WB_CUDA_OK(cudaMemcpyAsync(h->mask, mask.data(), mask.size(), cudaMemcpyHostToDevice, st));
   WB_CUDA_OK(cudaStreamSynchronize(st));
@@ -1478,6 +1477,12 @@ static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int3
   plain.Mb = Mb, plain.beams = beam, plain.n_initial = n_init, plain.eot = eot;
   scored = plain;
   scored.sample = 1, scored.store_logits = 1, scored.no_finish = 1;   // filtered logits stored, host decides the next tokens
+  // Timestamp rules: the per-sequence rule state the finish kernel keeps in greedy decoding is a function of the sequence, and
+  // the sequences live on the host here: it is recomputed per step and uploaded in front of the scored step; the logits kernel
+  // applies the per-row rules, the top-k kernel the probability-mass rule.
+  scored.timestamps = ts_on ? 1 : 0, scored.ts_begin = opts->timestamp_begin;
+  scored.ts_last_allowed = opts->max_initial_timestamp_index >= 0 ? opts->timestamp_begin + opts->max_initial_timestamp_index : 0x7fffffff;
+  std::vector<int4> ts_host(Mb);
   WB_CUDA_OK(cudaEventRecord(h->ev[2], st));
   WB_TRY(reset_decode_state(h, plain));
   for (int i = 0; i + 1 < n_init; ++i) WB_TRY(decode_step(h, plain));
@@ -1496,7 +1501,8 @@ static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int3
   const bool prof = getenv("WB_BEAM_PROF") != nullptr;   // development: where a beam step's wall time goes
   double t_wait = 0.0, t_host = 0.0, t_reorder = 0.0;
   char bkey[96];
-  snprintf(bkey, sizeof(bkey), "B%d b%d i%d e%d", B, beam, n_init, eot);
+  snprintf(bkey, sizeof(bkey), "B%d b%d i%d e%d t%d.%d.%d", B, beam, n_init, eot, ts_on ? 1 : 0, ts_on ? opts->timestamp_begin : 0,
+           ts_on ? opts->max_initial_timestamp_index : 0);
   const bool beam_graph = getenv("WB_NO_GRAPH") == nullptr;
   if (h->beam_key != bkey) {
     for (int i = 0; i < 2; ++i) {
@@ -1506,6 +1512,23 @@ static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int3
     h->beam_key = bkey;
   }
   for (int s = 0; s < opts->sample_len; ++s) {
+    if (ts_on) {
+      for (int b = 0; b < Mb; ++b) {   // FinishDesc::ts_state from the sampled part of the sequence (empty at s = 0)
+        const Seq& q = seqs[b];
+        const int len = (int)q.size() - n_init;
+        int z = 0;
+        for (int i = n_init; i < (int)q.size(); ++i)
+          if (q[i] >= ts_begin) z = q[i];
+        const bool last_ts = len >= 1 && q.back() >= ts_begin;
+        const bool penult_ts = len < 2 || q[q.size() - 2] >= ts_begin;
+        int4 v;
+        v.x = (last_ts && penult_ts ? 1 : 0) | (last_ts && !penult_ts ? 2 : 0);
+        v.y = z ? ((last_ts && !penult_ts) ? z : z + 1) : 0;
+        v.z = z, v.w = 0;
+        ts_host[b] = v;
+      }
+      WB_CUDA_OK(cudaMemcpyAsync(h->ts_state, ts_host.data(), (size_t)Mb * sizeof(int4), cudaMemcpyHostToDevice, st));
+    }
     int slot = -1;
     if (beam_graph && s > 0) {   // the first scored step runs eagerly (function attributes are set outside of capture)
       for (int i = 0; i < 2; ++i)
@@ -1518,7 +1541,7 @@ static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int3
         const int64_t before = h->launches;
         WB_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         int rc = decode_step(h, scored);
-        if (rc == 0) rc = launch_topk_logprobs(h->logits, Mb, D.n_vocab, K, h->top_lp, h->top_idx, st, &h->launches);
+        if (rc == 0) rc = launch_topk_logprobs(h->logits, Mb, D.n_vocab, K, ts_begin, h->top_lp, h->top_idx, st, &h->launches);
         const cudaError_t ce = cudaStreamEndCapture(st, &g);
         h->nodes_beam = h->launches - before;
         h->launches = before;
@@ -1532,7 +1555,7 @@ static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int3
       h->launches += h->nodes_beam;
     } else {
       WB_TRY(decode_step(h, scored));
-      WB_TRY(launch_topk_logprobs(h->logits, Mb, D.n_vocab, K, h->top_lp, h->top_idx, st, &h->launches));
+      WB_TRY(launch_topk_logprobs(h->logits, Mb, D.n_vocab, K, ts_begin, h->top_lp, h->top_idx, st, &h->launches));
     }
     WB_CUDA_OK(cudaMemcpyAsync(top_lp.data(), h->top_lp, top_lp.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
     WB_CUDA_OK(cudaMemcpyAsync(top_idx.data(), h->top_idx, top_idx.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));

@@ -215,7 +215,9 @@ int launch_delay(unsigned long long ns, cudaStream_t st, int64_t* launches);
 
 // beam search support: per-row top-k (k <= 8) of the filtered logits with their log-softmax values, and the re-indexing
 // of the self-attention K/V cache by source beam (upstream rearrange_kv_cache)
-int launch_topk_logprobs(const float* logits, int Mb, int V, int k, float* top_logprob /*[Mb][8]*/, int32_t* top_index /*[Mb][8]*/,
+// ts_begin < V: the last rule of upstream ApplyTimestampRules first - rows below ts_begin (text) are dropped when the
+// probability mass over the rows from ts_begin on (timestamps) exceeds every text row
+int launch_topk_logprobs(const float* logits, int Mb, int V, int k, int ts_begin, float* top_logprob /*[Mb][8]*/, int32_t* top_index /*[Mb][8]*/,
                          cudaStream_t st, int64_t* launches);
 int launch_reorder_kv(const __half* const* src_k, const __half* const* src_v, __half* const* dst_k, __half* const* dst_v, int n_layer,
                       int Mb, int n_ctx, int d, const int32_t* source, const DecodeState* state, cudaStream_t st, int64_t* launches);

@@ -333,6 +333,8 @@ class WhisperRef:
                 logits[:, list(opts.suppress_begin)] = float("-inf")
             if len(opts.suppress):
                 logits[:, list(opts.suppress)] = float("-inf")
+            if opts.timestamps:                     # upstream logit_filters order: SuppressBlank, SuppressTokens, ApplyTimestampRules
+                logits = apply_timestamp_rules(logits, tokens, sample_begin, v, opts.max_initial_timestamp_index)
             logprobs = F.log_softmax(logits.float(), dim=-1)
             next_tokens, source_indices, newly = [], [], []
             for a in range(n_audio):

@@ -186,8 +186,8 @@ def test_decode_option_validation_is_shared_by_both_paths(wbm, ref):
         c, keep = w._opts(o)
         c.eot = 60000
         assert lib.wb_decode(w.handle, 1, ctypes.byref(c), tokens.ctypes.data_as(ctypes.c_void_p), None, None) == -1
-    o.beam_size, o.timestamps, o.timestamp_begin, o.no_timestamps = 3, True, 50363, 50362
-    with pytest.raises(wbm.WhisperB200Error, match="greedy decoding only"):
+    o.beam_size, o.timestamps, o.timestamp_begin, o.no_timestamps = 3, True, o.eot, 50362   # timestamps must start above eot
+    with pytest.raises(wbm.WhisperB200Error, match="timestamp rules need"):
         w.decode_tokens(1, o)
     w.close()
 

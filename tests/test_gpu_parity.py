@@ -478,6 +478,43 @@ def test_greedy_with_timestamp_rules_matches_oracle(wbm, ref, oracle_logmel, nam
     w.close(), w2.close()
 
 
+def test_beam_search_with_timestamp_rules(wbm, ref):
+    """ApplyTimestampRules under beam search (upstream's default options with beam_size set): the per-sequence rule state is
+    rebuilt from the host-side sequences every step, the logits kernel applies the per-row rules to all chunks x beams rows,
+    the top-k kernel the probability-mass rule before the log-softmax. Seed / text scale from tools/pick_beam_ts_seed.py
+    (both token classes sampled, result stable under logit noise of 2e-2)."""
+    dims = ref.DIMS["tiny"]
+    v = ref.Vocab.for_dims(dims)
+    seed, B, beam = 2, 2, 3
+    weights = ref.random_weights(dims, seed=seed)
+    weights["decoder.token_embedding.weight"][:v.eot] *= 1.8
+    oracle = ref.WhisperRef(dims, weights)
+    w = wbm.Whisper("tiny", weights=weights, max_batch=B, max_beams=beam)
+    xa = (torch.randn(B, 1500, dims.n_audio_state, generator=torch.Generator().manual_seed(200 + seed)) * 0.7).half().float()
+    w.set_audio_features(xa.numpy())
+    opts_ref = ref.DecodeOptions.default_for(dims, sample_len=12, without_timestamps=False)
+    want_tokens, want_scores = oracle.beam_search(xa, opts_ref, beam_size=beam)
+    o = wbm.DecodeOptions.default_for(wbm.DIMS["tiny"], sample_len=12, without_timestamps=False)
+    o.beam_size = beam
+    tok, lens, slp = w.decode_tokens(B, o)
+    n_init = len(o.initial_tokens)
+    for b in range(B):
+        n = len(want_tokens[b])
+        assert tok[b, :n].tolist() == want_tokens[b], (b, tok[b].tolist(), want_tokens[b])
+        assert abs(float(slp[b]) - want_scores[b]) <= 0.05
+        body = want_tokens[b][n_init:]
+        assert body[0] >= v.timestamp_begin and any(t < v.eot for t in body)        # the rules acted, text was sampled too
+    # the rules off again on the same handle: identical to a fresh handle (no rule state left behind, graphs re-keyed)
+    o2 = wbm.DecodeOptions.default_for(wbm.DIMS["tiny"], sample_len=6)
+    o2.beam_size = beam
+    t1, _, s1 = w.decode_tokens(B, o2)
+    w2 = wbm.Whisper("tiny", weights=weights, max_batch=B, max_beams=beam)
+    w2.set_audio_features(xa.numpy())
+    t2, _, s2 = w2.decode_tokens(B, o2)
+    assert np.array_equal(t1, t2) and np.array_equal(s1, s2)
+    w.close(), w2.close()
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_handles_on_two_devices_in_one_process(wbm, ref):
     """One process, one handle per GPU (the launch-attribute caches of the kernels are per device): same tokens on both."""
