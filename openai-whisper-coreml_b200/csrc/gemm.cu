@@ -9,7 +9,9 @@
 //   warp 1    TMEM allocator + MMA issuer: 4 x tcgen05.mma (M=128, N=BN, K=16) per stage, tcgen05.commit frees the stage;
 //             two accumulator buffers in TMEM, so tile i+1 is multiplied while tile i is drained
 //   warps 2-9 epilogue: tcgen05.ld the fp32 accumulator (one TMEM lane = one output row per thread), bias / GELU /
-//             residual in registers, fp16 and/or fp32 stores
+//             residual in registers; the results leave through a swizzled shared-memory staging tile per warp and
+//             cp.async.bulk.tensor stores ([32 rows][128 bytes] boxes; rows past the end of a batch are clipped by the TMA
+//             unit), instead of 16-byte stores that touch 32 different lines per instruction
 #include <cuda.h>
 
 #include <map>
@@ -33,6 +35,7 @@ struct GemmEpi {
   int N, K, rows, gelu, res_mode, ldc, c_row_off;
   long long c_batch_rows;
   int tiles_m, tiles_n, n_tiles;   // per batch: tiles_m x tiles_n; n_tiles = n_batch * tiles_m * tiles_n
+  int tma_store;                   // outputs through shared memory + tensor stores (tmC16 / tmC32)
 };
 
 template <int BN>
@@ -41,7 +44,8 @@ struct GemmSmem {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOff = kStages * kStageBytes;
+  static constexpr int kStageOutOff = kStages * kStageBytes;   // [8 epilogue warps][32 rows][128 B], 1024-byte aligned, SWIZZLE_128B
+  static constexpr int kBarOff = kStageOutOff + 8 * 4096;
   static constexpr int kTotal = kBarOff + 256 + 1024;   // barriers + slack for the 1024-byte alignment
 };
 
@@ -89,7 +93,9 @@ __device__ __forceinline__ float2 gelu_erf_fast2(float2 x) {
 // (2 x BN columns), so the epilogue of tile i (8 warps: TMEM lane quadrant x column half) overlaps the MMAs of tile i+1.
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                  const __grid_constant__ CUtensorMap tmB, GemmEpi ep) {
+                                                                  const __grid_constant__ CUtensorMap tmB,
+                                                                  const __grid_constant__ CUtensorMap tmC16,
+                                                                  const __grid_constant__ CUtensorMap tmC32, GemmEpi ep) {
   using S = GemmSmem<BN>;
   constexpr int kStages = S::kStages;
   extern __shared__ unsigned char smem_dyn[];
@@ -106,6 +112,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
+    if (ep.tma_store && ep.c16) ptx::prefetch_tensormap(&tmC16);
+    if (ep.tma_store && ep.c32) ptx::prefetch_tensormap(&tmC32);
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], 1);
@@ -169,11 +177,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     // epilogue: warp w may touch TMEM lanes [32*(w%4), +32); warps 2-5 take the first column half, 6-9 the second
     const int q = warp & 3, half = (warp - 2) >> 2;
     constexpr int kChunks = BN / 64;   // 32-column chunks per warp
+    // staging tile of this warp: row = lane, 128 bytes per row, 16-byte chunk j of a row at position j ^ (row & 7) (SWIZZLE_128B)
+    unsigned char* stage = smem + S::kStageOutOff + (warp - 2) * 4096;
+    unsigned char* srow = stage + lane * 128;
+    const int sw = lane & 7;
+    bool store_pending = false;        // a tensor store of this warp may still be reading `stage`
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < ep.n_tiles; tile += gridDim.x, ++lt) {
       const int nt = tile % ep.tiles_n, mt = (tile / ep.tiles_n) % ep.tiles_m, b = tile / (ep.tiles_n * ep.tiles_m);
       const uint32_t buf = lt & 1u, tph = (lt >> 1) & 1u;
-      const int t = mt * kBM + q * 32 + lane;
+      const int t0 = mt * kBM + q * 32;
+      const int t = t0 + lane;
       const bool row_ok = t < ep.rows;
       const long long crow = (long long)b * ep.c_batch_rows + ep.c_row_off + t;
       ptx::mbar_wait(&tfull[buf], tph);
@@ -190,32 +204,76 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           if (lane == 0) ptx::mbar_arrive(&tempty[buf]);
         }
         const int nb = nt * BN + col;
-        if (row_ok) {
-          float f[32];
+        float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (ep.bias) {
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (ep.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.bias + nb + j));
-              f[j] += bb.x, f[j + 1] += bb.y, f[j + 2] += bb.z, f[j + 3] += bb.w;
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.bias + nb + j));
+            f[j] += bb.x, f[j + 1] += bb.y, f[j + 2] += bb.z, f[j + 3] += bb.w;
+          }
+        }
+        if (ep.gelu) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float2 g = gelu_erf_fast2(make_float2(f[j], f[j + 1]));
+            f[j] = g.x, f[j + 1] = g.y;
+          }
+        }
+        if (ep.res_mode && row_ok) {
+          const float* rp = ep.res + (ep.res_mode == 1 ? crow * ep.ldc : (long long)t * ep.N) + nb;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 rr = *reinterpret_cast<const float4*>(rp + j);
+            f[j] += rr.x, f[j + 1] += rr.y, f[j + 2] += rr.z, f[j + 3] += rr.w;
+          }
+        }
+        if (ep.tma_store) {
+          // (exactly one of c32 / c16 is set on this path) rows past the end of the batch hold finite garbage - the A rows
+          // there were zero-filled - and the tensor store clips them
+          if (ep.c32) {   // 32 fp32 columns = one 128-byte row of the staging tile
+            if (store_pending) {
+              if (lane == 0) ptx::bulk_wait_read0();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(srow + ((j ^ sw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_3d(&tmC32, stage, nb, t0, b);
+              ptx::bulk_commit();
+            }
+            store_pending = true;
+          }
+          if (ep.c16) {   // 32 fp16 columns = half a row: chunks 0-3 (even c) or 4-7 (odd c); stored once the row is complete
+            if ((c & 1) == 0 && store_pending) {
+              if (lane == 0) ptx::bulk_wait_read0();
+              __syncwarp();
+              store_pending = false;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __half2 h0 = __floats2half2_rn(f[8 * j], f[8 * j + 1]), h1 = __floats2half2_rn(f[8 * j + 2], f[8 * j + 3]);
+              const __half2 h2 = __floats2half2_rn(f[8 * j + 4], f[8 * j + 5]), h3 = __floats2half2_rn(f[8 * j + 6], f[8 * j + 7]);
+              uint4 u;
+              u.x = *reinterpret_cast<const uint32_t*>(&h0), u.y = *reinterpret_cast<const uint32_t*>(&h1);
+              u.z = *reinterpret_cast<const uint32_t*>(&h2), u.w = *reinterpret_cast<const uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(srow + ((((c & 1) * 4 + j) ^ sw) << 4)) = u;
+            }
+            if (c & 1) {
+              ptx::fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                ptx::tma_store_3d(&tmC16, stage, nb - 32, t0, b);
+                ptx::bulk_commit();
+              }
+              store_pending = true;
             }
           }
-          if (ep.gelu) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const float2 g = gelu_erf_fast2(make_float2(f[j], f[j + 1]));
-              f[j] = g.x, f[j + 1] = g.y;
-            }
-          }
-          if (ep.res_mode) {
-            const float* rp = ep.res + (ep.res_mode == 1 ? crow * ep.ldc : (long long)t * ep.N) + nb;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 rr = *reinterpret_cast<const float4*>(rp + j);
-              f[j] += rr.x, f[j + 1] += rr.y, f[j + 2] += rr.z, f[j + 3] += rr.w;
-            }
-          }
+        } else if (row_ok) {
           if (ep.c32) {
             float* cp = ep.c32 + crow * ep.ldc + nb;
 #pragma unroll
@@ -236,6 +294,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         }
       }
     }
+    if (store_pending && lane == 0) ptx::bulk_wait0();   // the last tiles are in global memory before the CTA retires
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -297,6 +356,38 @@ static int get_tmap(GemmContext* ctx, const void* ptr, long long K, long long ro
   return 0;
 }
 
+// fp16 / fp32 output (n, rows, batch) with element strides (1, ldc, batch_rows * ldc); box (128 bytes, 32 rows, 1); 128B swizzle
+static int get_store_tmap(GemmContext* ctx, const void* ptr, bool f32, long long N, long long rows, long long nb, long long ldc,
+                          long long batch_rows, CUtensorMap* out) {
+  auto key = std::make_tuple(ptr, N, rows, nb, ldc, batch_rows, f32 ? -32 : -16);
+  auto it = ctx->cache.find(key);
+  if (it != ctx->cache.end()) {
+    *out = it->second;
+    return 0;
+  }
+  if (!ctx->encode) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return -2;
+  }
+  const cuuint64_t esz = f32 ? 4 : 2;
+  const long long brows = (nb > 1 && batch_rows > 0) ? batch_rows : rows;   // a single batch: any valid stride
+  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)rows, (cuuint64_t)nb};
+  cuuint64_t strides[2] = {(cuuint64_t)ldc * esz, (cuuint64_t)brows * (cuuint64_t)ldc * esz};
+  cuuint32_t box[3] = {(cuuint32_t)(128 / esz), 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  const CUresult r = ctx->encode(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims,
+                                 strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(C) failed: %d (N=%lld rows=%lld nb=%lld ldc=%lld)", (int)r, N, rows, nb, ldc);
+    return -2;
+  }
+  ctx->cache[key] = m;
+  *out = m;
+  return 0;
+}
+
 int gemm_get_tmap(GemmContext* ctx, const void* ptr, long long K, long long rows, long long nb, long long row_stride,
                   long long batch_stride, int box_rows, void* out128) {
   return get_tmap(ctx, ptr, K, rows, nb, row_stride, batch_stride, box_rows, reinterpret_cast<CUtensorMap*>(out128));
@@ -330,13 +421,28 @@ static int launch_tc(GemmContext* ctx, const GemmDesc& d, const GemmEpi& ep, cud
     }
     ctx->cache[key] = tmB;
   }
+  // output maps for the tensor-store epilogue: (columns, rows of a batch, batches); fp16 boxes [32][64], fp32 boxes [32][32]
+  // (128 bytes per row either way); one output only, whole 64-column pairs per warp (BN / 64 even)
+  static int tma_store_env = -1;
+  if (tma_store_env < 0) {
+    const char* e = getenv("WB_GEMM_TMA_STORE");   // development: 0 = per-thread 16-byte stores
+    tma_store_env = (e && e[0] == '0') ? 0 : 1;
+  }
+  CUtensorMap tmC16{}, tmC32{};
+  GemmEpi e2 = ep;
+  e2.tma_store = (tma_store_env && ((d.c16 != nullptr) != (d.c32 != nullptr)) && (BN / 64) % 2 == 0) ? 1 : 0;
+  if (e2.tma_store) {
+    const bool f32 = d.c32 != nullptr;
+    rc = get_store_tmap(ctx, f32 ? (const void*)(d.c32 + (long long)d.c_row_off * d.ldc) : (const void*)(d.c16 + (long long)d.c_row_off * d.ldc),
+                        f32, d.N, d.rows, d.n_batch, d.ldc, d.c_batch_rows, f32 ? &tmC32 : &tmC16);
+    if (rc) return rc;
+  }
   auto kern = gemm_tc_kernel<BN>;
   static bool attr_set_dev[kMaxDevices] = {}; bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
     WB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
     attr_set = true;
   }
-  GemmEpi e2 = ep;
   e2.tiles_n = d.N / BN, e2.tiles_m = (d.rows + kBM - 1) / kBM, e2.n_tiles = e2.tiles_n * e2.tiles_m * d.n_batch;
   static int n_sm = 0;
   if (!n_sm) {
@@ -346,7 +452,7 @@ static int launch_tc(GemmContext* ctx, const GemmDesc& d, const GemmEpi& ep, cud
     if (n_sm <= 0) n_sm = 148;
   }
   const int grid = e2.n_tiles < n_sm ? e2.n_tiles : n_sm;   // persistent: one CTA per SM
-  kern<<<grid, kGemmThreads, GemmSmem<BN>::kTotal, st>>>(tmA, tmB, e2);
+  kern<<<grid, kGemmThreads, GemmSmem<BN>::kTotal, st>>>(tmA, tmB, tmC16, tmC32, e2);
   WB_CUDA_OK(cudaGetLastError());
   return 0;
 }
