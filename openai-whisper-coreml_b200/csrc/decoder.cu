@@ -1464,6 +1464,9 @@ __global__ void __maxnreg__(96) self_block_kernel(SelfBlockArgs a) {
   constexpr int WPS = kSbWarps / kSbG;
   extern __shared__ __align__(16) unsigned char sb_smem[];
   TraceScope trace(a.state, 210);
+  // Distributed shared memory may only be written once the owning CTA is known to run: every CTA arrives here, and waits for
+  // its peers right before the first remote store (phase 3 -> 4, microseconds later: the wait never blocks).
+  ptx::cluster_arrive_release();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = lane >> 2, tq = lane & 3;
   const int h = blockIdx.x, b0 = blockIdx.y * kSbG;
@@ -1745,6 +1748,7 @@ __global__ void __maxnreg__(96) self_block_kernel(SelfBlockArgs a) {
   __syncthreads();
   if (a.pdl_point == 3) ptx::grid_dep_launch();
   trace.mark(6);
+  ptx::cluster_wait_acquire();   // all CTAs of the cluster have started (arrival at kernel entry)
   if (tid < kSbG * 64) {   // merge the partials of (slot es, column ec) and push the result into every CTA of the cluster
     const float* pp = s_part + es * WPS * 66;
     float M = -INFINITY;
@@ -1922,6 +1926,7 @@ __global__ void __maxnreg__(128) post_block_kernel(PostBlockArgs a) {
   constexpr int OC = Cfg::OC, HS = Cfg::HS, XS = Cfg::XS, HSS = Cfg::HSS, PS = Cfg::PS;
   extern __shared__ __align__(16) unsigned char pb_smem[];
   TraceScope trace(a.state, 220);
+  ptx::cluster_arrive_release();   // remote shared memory is written only after every CTA of the cluster is known to run (phase 0)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = lane >> 2, tq = lane & 3;
   const int r = blockIdx.x, b0 = blockIdx.y * 8;                // cluster rank, first sequence of the group
@@ -2000,6 +2005,7 @@ __global__ void __maxnreg__(128) post_block_kernel(PostBlockArgs a) {
     dst[(2 * tq) * OC + c_hi] = acc[2], dst[(2 * tq + 1) * OC + c_hi] = acc[3];
   }
   __syncthreads();
+  ptx::cluster_wait_acquire();     // pairs with the arrival at kernel entry
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     const int i = tid + j * kPbThreads;
