@@ -276,6 +276,23 @@ def main():
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": k_bytes, "us_per_launch": k_ms * 1e3}
 
+    def logmel_leg(wh, audio_ptr, B, reps=30):
+        """The log-mel front end alone: device f32 PCM in, [B][80][3000] f32 out, CUDA events on the handle's stream.
+        Algorithmic bytes per chunk: 480000 * 4 in + 80 * 3000 * 4 out = 2.88 MB."""
+        out = torch.empty((B, 80, 3000), dtype=torch.float32, device=dev)
+        lib = wbm.load_library()
+        for _ in range(3):
+            assert lib.wb_logmel_dev(wh.handle, audio_ptr, B, out.data_ptr()) == 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            lib.wb_logmel_dev(wh.handle, audio_ptr, B, out.data_ptr())
+        e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        nbytes = B * (480000 * 4 + 80 * 3000 * 4)
+        return {"chunks": B, "us": ms * 1e3, "GB/s": nbytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peak}
+
     with torch.cuda.stream(stream):
         # ------------------------------------------------------------------------------------------------ headline: base.en B=32
         w, bcast_bytes = make_handle(MODEL, BATCH)
@@ -330,6 +347,14 @@ def main():
         tokens, lens, slp = step_dev()
         # dominant kernel: KV-cache attention over the resident cross K/V, timed alone with CUDA events on the same stream
         roof = roofline_of(w, BATCH)
+        logmel_legs = [logmel_leg(w, audio_dev.data_ptr(), BATCH)]
+        if world == 1 and args.configs != "headline":
+            w64, _ = make_handle("tiny.en", 64)                   # the widest batch a handle takes (SURVEY asks for 256)
+            a64 = synth_chunks(7000, 64).to(dev, non_blocking=True)
+            stream.synchronize()
+            logmel_legs.append(logmel_leg(w64, a64.data_ptr(), 64))
+            w64.close()
+            del a64
 
         extras = {}
         want = [] if args.configs == "headline" else (list(CONFIGS) if args.configs == "all" else args.configs.split(","))
@@ -445,7 +470,10 @@ def main():
                              "note": "same call with an ordinary (non-pinned) host buffer"},
             "gpu_launches": int(launches),
             "phase_ms": {"logmel": phase[0], "encoder_and_cross_kv": phase[1], "decode": phase[2], "decode_steps": phase[3]},
-            "roofline": roof, "weights_broadcast_bytes": bcast_bytes, "ranks_verified": ranks_verified, "extra_configs": extras}
+            "roofline": roof,
+            "logmel": {"kernel": "logmel_kernel + logmel_normalize_kernel (f32, device in / out)", "bound": "instruction issue, not HBM (DESIGN.md section 4)",
+                       "algorithmic_bytes_per_chunk": 2880000, "runs": logmel_legs},
+            "weights_broadcast_bytes": bcast_bytes, "ranks_verified": ranks_verified, "extra_configs": extras}
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         chunks = args.cpu_chunks or 4

@@ -1113,10 +1113,15 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
   __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8];
   __shared__ __align__(16) float s_x[NJW * 256];   // normalised residual row (fused query projection)
   __shared__ float s_q[64], s_red[16];
+  __shared__ float s_xred[8 * 66];                 // row split: (outputs[64], max, sum) per cluster rank, written by the peers
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = lane >> 2, tq = lane & 3, mi = lane >> 3, r8 = lane & 7;
   const int h = blockIdx.x, b = blockIdx.y;
+  // Few sequences (a single window of a long-form stream, configs[1]): the rows of a (sequence, head) are split over the
+  // gridDim.z CTAs of a cluster, whose partial (max, sum, outputs) meet in the rank-0 CTA over distributed shared memory
+  const int n_split = (int)gridDim.z, z = (int)blockIdx.z;
+  if (n_split > 1) ptx::cluster_arrive_release();   // paired with the wait in front of the remote stores below
   const bool fixed = a.n_rows_fixed > 0;
   TraceScope trace(a.state, fixed ? 201 : 200);
   const int n_stages = a.n_stages;
@@ -1133,7 +1138,10 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
   if (!a.pdl_late) ptx::grid_dep_launch();
   if (!fixed) ptx::grid_dep_sync();   // self attention: the row count and the newest K/V row come from the previous kernel
   const int n_rows = fixed ? a.n_rows_fixed : ld_state(&a.state->cur_len) + 1;
-  const int n_tiles = (n_rows + kHaStageRows - 1) / kHaStageRows;
+  const int n_tiles_all = (n_rows + kHaStageRows - 1) / kHaStageRows;
+  const int tiles_per = (n_tiles_all + n_split - 1) / n_split;
+  const int t_first = z * tiles_per;                                                   // this CTA's tiles: [t_first, t_first + n_tiles)
+  const int n_tiles = n_tiles_all - t_first < tiles_per ? (n_tiles_all - t_first > 0 ? n_tiles_all - t_first : 0) : tiles_per;
 
   float o[4][4], m_run = -INFINITY, l_run = 0.f;
 
@@ -1144,8 +1152,8 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
       if (fixed) {   // the producer of a cross-attention CTA runs ahead of q: pull the tiles after the ring into L2 meanwhile
         const int pf_end = n_stages + a.l2_prefetch_tiles < n_tiles ? n_stages + a.l2_prefetch_tiles : n_tiles;
         for (int t = n_stages; t < pf_end; ++t) {
-          ptx::tma_prefetch_l2_3d(&tmK, h * 64, t * kHaStageRows, slab);
-          ptx::tma_prefetch_l2_3d(&tmV, h * 64, t * kHaStageRows, slab);
+          ptx::tma_prefetch_l2_3d(&tmK, h * 64, (t_first + t) * kHaStageRows, slab);
+          ptx::tma_prefetch_l2_3d(&tmV, h * 64, (t_first + t) * kHaStageRows, slab);
         }
       }
       for (int t = 0; t < n_tiles; ++t) {
@@ -1157,8 +1165,8 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
         ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
         ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * kHaTileBytes);
         unsigned char* dk = smem + (size_t)s * 2 * kHaTileBytes;
-        ptx::tma_load_3d(dk, &tmK, &full_bar[s], h * 64, t * kHaStageRows, slab, kvpol);
-        ptx::tma_load_3d(dk + kHaTileBytes, &tmV, &full_bar[s], h * 64, t * kHaStageRows, slab, kvpol);
+        ptx::tma_load_3d(dk, &tmK, &full_bar[s], h * 64, (t_first + t) * kHaStageRows, slab, kvpol);
+        ptx::tma_load_3d(dk + kHaTileBytes, &tmV, &full_bar[s], h * 64, (t_first + t) * kHaStageRows, slab, kvpol);
       }
     }
   } else {
@@ -1245,7 +1253,7 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
       const int s = t % n_stages;
       const uint32_t ph = (uint32_t)(t / n_stages) & 1u;
       ptx::mbar_wait(&full_bar[s], ph);
-      const int row0 = t * kHaStageRows + warp * 16;       // first of this warp's 16 rows
+      const int row0 = (t_first + t) * kHaStageRows + warp * 16;   // first of this warp's 16 rows
       if (row0 < n_rows) {                                 // warp-uniform
         const uint32_t sk = ptx::smem_u32(smem + (size_t)s * 2 * kHaTileBytes);
         const uint32_t sv = sk + kHaTileBytes;
@@ -1315,11 +1323,10 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
     }
   }
   __syncthreads();
+  float M = -INFINITY, L = 0.f, A = 0.f;
   if (tid < 64) {
-    float M = -INFINITY;
 #pragma unroll
     for (int w = 0; w < 8; ++w) M = fmaxf(M, red[w * 68 + 64]);
-    float L = 0.f, A = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
       const float mw = red[w * 68 + 64];
@@ -1327,7 +1334,38 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
       L += wgt * red[w * 68 + 65];
       A += wgt * red[w * 68 + tid];
     }
-    a.out16[(size_t)b * a.d + h * 64 + tid] = __float2half_rn(A / L);
+  }
+  if (n_split == 1) {
+    if (tid < 64) a.out16[(size_t)b * a.d + h * 64 + tid] = __float2half_rn(A / L);
+    trace.end();
+    return;
+  }
+  // cluster merge: every CTA puts (A[64], M, L) of its row range into slot z of the rank-0 CTA's table (its own shared
+  // array: the ring of rank 0 may still be receiving tiles); rank 0 folds the slots in rank order. A CTA without rows
+  // contributes M = -inf, L = 0.
+  float* xred = s_xred;                                         // [n_split][66]
+  ptx::cluster_wait_acquire();                                  // every CTA of the cluster runs (arrival at entry)
+  if (tid < 64) {
+    const uint32_t dst = ptx::mapa(ptx::smem_u32(xred + z * 66), 0u);
+    ptx::st_cluster_f32(dst + 4u * (uint32_t)tid, A);
+    if (tid == 0) {
+      ptx::st_cluster_f32(dst + 4u * 64u, M);
+      ptx::st_cluster_f32(dst + 4u * 65u, L);
+    }
+  }
+  ptx::cluster_arrive_release();
+  ptx::cluster_wait_acquire();
+  if (z == 0 && tid < 64) {
+    float Mx = -INFINITY;
+    for (int c = 0; c < n_split; ++c) Mx = fmaxf(Mx, xred[c * 66 + 64]);
+    float Lx = 0.f, Ax = 0.f;
+    for (int c = 0; c < n_split; ++c) {
+      const float mc = xred[c * 66 + 64];
+      const float wgt = (mc == -INFINITY) ? 0.f : exp2f(mc - Mx);
+      Lx += wgt * xred[c * 66 + 65];
+      Ax += wgt * xred[c * 66 + tid];
+    }
+    a.out16[(size_t)b * a.d + h * 64 + tid] = __float2half_rn(Ax / Lx);
   }
   trace.end();
 }
@@ -1361,12 +1399,43 @@ static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int
   }
   if (pf_env >= 1000) a.l2_prefetch_tiles = pf_env - 1000;
   const size_t smem = (size_t)a.n_stages * 2 * kHaTileBytes + 1024;
+  // row split for small grids (cross attention only: the row count is known on the host): the largest cluster size <= 8 that
+  // divides the tiles evenly-ish and keeps the grid within one CTA per SM
+  int n_split = 1;
+  static int split_env = -1;
+  if (split_env < 0) {
+    const char* e = getenv("WB_HA_SPLIT");   // development: 0 = never split, n = force
+    split_env = e ? atoi(e) : -2;
+  }
+  if (p.n_rows_fixed > 0 && split_env != 0) {
+    const int tiles = (p.n_rows_fixed + kHaStageRows - 1) / kHaStageRows;
+    if (split_env > 0) {
+      n_split = split_env < 8 ? split_env : 8;
+    } else {
+      for (int c = 8; c >= 2; --c)
+        if (ctas * c <= 148 && tiles >= 2 * c - 1 && (tiles + c - 1) / c * (c - 1) < tiles) {   // every CTA of the cluster gets rows
+          n_split = c;
+          break;
+        }
+    }
+    if (n_split > tiles) n_split = tiles;
+    if (n_split < 1) n_split = 1;
+  }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(p.n_head, p.Mb), cfg.blockDim = dim3(kHaThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at, cfg.numAttrs = use_pdl() ? 1 : 0;
+  cfg.gridDim = dim3(p.n_head, p.Mb, n_split), cfg.blockDim = dim3(kHaThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int n_at = 0;
+  if (use_pdl()) {
+    at[n_at].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n_at].val.programmaticStreamSerializationAllowed = 1;
+    ++n_at;
+  }
+  if (n_split > 1) {
+    at[n_at].id = cudaLaunchAttributeClusterDimension;
+    at[n_at].val.clusterDim.x = 1, at[n_at].val.clusterDim.y = 1, at[n_at].val.clusterDim.z = (unsigned)n_split;
+    ++n_at;
+  }
+  cfg.attrs = at, cfg.numAttrs = n_at;
   cudaError_t le = cudaSuccess;
 #define WB_HA_CASE(J)                                                                                                     \
   case J: {                                                                                                               \
@@ -1377,7 +1446,10 @@ static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int
     }                                                                                                                     \
     le = cudaLaunchKernelEx(&cfg, attn_decode_head_kernel<J>, tmK, tmV, a);                                               \
   } break;
-  switch ((p.d + 255) / 256) {
+  // the template parameter sizes the register arrays of the fused query projection only: without it (self attention, or cross
+  // attention behind a separate projection) the smallest instantiation runs - 96 registers, two CTAs per SM - whatever the
+  // width (the wide instantiations hold 160 registers of weight rows and run one CTA per SM)
+  switch (p.wq ? (p.d + 255) / 256 : 1) {
     WB_HA_CASE(1) WB_HA_CASE(2) WB_HA_CASE(3) WB_HA_CASE(4) WB_HA_CASE(5)
     default:
       set_error("attn_decode: unsupported width %d", p.d);
@@ -1881,14 +1953,20 @@ struct PostBlockArgs {
   const DecodeState* state;
 };
 
+constexpr int pb_batch(int n) {   // largest divisor of n that is <= 8: blocks requested at once (16 registers each)
+  return n % 8 == 0 ? 8 : (n % 7 == 0 ? 7 : (n % 6 == 0 ? 6 : (n % 5 == 0 ? 5 : (n % 4 == 0 ? 4 : (n % 3 == 0 ? 3 : (n % 2 == 0 ? 2 : 1))))));
+}
 template <int D, int C>
 struct PbCfg {
   static constexpr int OC = D / C, HS = 4 * D / C, NBLK = D / 32;
   static constexpr int S0 = OC / 16, KS0 = 8 / S0, NB0 = NBLK / KS0;                 // phase 0: strips, K split, blocks per unit
+  static constexpr int NB0b = pb_batch(NB0);                                          //   ... requested NB0b at a time
   static constexpr int SB = HS / 16, KSB = (SB % 8 == 0) ? 1 : 2, NBU = NBLK / KSB;  // phase 2
   static constexpr int UPW = SB * KSB / 8;                                           //   units per warp
   static constexpr int SCW = D / 16 / 8, NBC = HS / 32;                              // phase 3: strips per warp, blocks per strip
   static constexpr int XS = D * 2 + 64, HSS = HS * 2 + 64, PS = D + 4;               // row strides: bytes, bytes, floats
+  static constexpr int NJ = (OC * 8 + 255) / 256;                                    // (slot, column) outputs per thread
+  static constexpr int LNV = (D / 4 + 31) / 32;                                      // float4 per lane and row in the LayerNorm
   static constexpr int RED = (KS0 * 8 * OC > KSB * 8 * HS) ? KS0 * 8 * OC : KSB * 8 * HS;
   static constexpr size_t smem_used = (size_t)2 * 8 * XS + (size_t)8 * HSS + ((size_t)8 * D + 8 * PS + RED + 2 * D + HS) * 4;
   // Requested size: more than half of an SM's shared memory, so that two CTAs of this kernel never share an SM. Released
@@ -1896,7 +1974,7 @@ struct PbCfg {
   // ones and every weight-streaming phase took twice as long (per-SM L2 bandwidth).
   static constexpr size_t smem = smem_used > (size_t)118 * 1024 ? smem_used : (size_t)118 * 1024;
   static_assert(OC % 16 == 0 && HS % 32 == 0 && NBLK % KS0 == 0 && NBLK % KSB == 0 && (SB * KSB) % 8 == 0 && (D / 16) % 8 == 0, "shape");
-  static_assert(NB0 <= 8 && OC * 8 <= 2 * kPbThreads, "shape");
+  static_assert(smem <= (size_t)227 * 1024, "shared memory");
 };
 
 // one warp: acc += W[16 rows][blocks blk0 .. blk0+NB) x B tile (8 slots); NB <= 8 blocks requested at once
@@ -1921,7 +1999,7 @@ __device__ __forceinline__ void pb_mma(float (&acc)[4], const uint4 (&wa)[NB], c
 }
 
 template <int D, int C>
-__global__ void __maxnreg__(128) post_block_kernel(PostBlockArgs a) {
+__global__ void __maxnreg__(D > 1024 ? 224 : 128) post_block_kernel(PostBlockArgs a) {
   using Cfg = PbCfg<D, C>;
   constexpr int OC = Cfg::OC, HS = Cfg::HS, XS = Cfg::XS, HSS = Cfg::HSS, PS = Cfg::PS;
   extern __shared__ __align__(16) unsigned char pb_smem[];
@@ -1944,11 +2022,9 @@ __global__ void __maxnreg__(128) post_block_kernel(PostBlockArgs a) {
   const int strip0 = warp % Cfg::S0, kp0 = warp / Cfg::S0;
   const bool act0 = warp < Cfg::S0 * Cfg::KS0;
   const uint64_t wpol = weight_policy();
-  uint4 wa0[Cfg::NB0], wb0[Cfg::NB0];
-  {
-    const __half* w0 = a.wo + (size_t)(r * OC + strip0 * 16 + grp) * D + tq * 8;
-    pb_load<Cfg::NB0>(wa0, wb0, w0, w0 + (size_t)8 * D, act0 ? kp0 * Cfg::NB0 : 0, wpol);
-  }
+  uint4 wa0[Cfg::NB0b], wb0[Cfg::NB0b];
+  const __half* w0row = a.wo + (size_t)(r * OC + strip0 * 16 + grp) * D + tq * 8;
+  pb_load<Cfg::NB0b>(wa0, wb0, w0row, w0row + (size_t)8 * D, act0 ? kp0 * Cfg::NB0 : 0, wpol);
   for (int i = tid * 4; i < D; i += kPbThreads * 4) {
     *reinterpret_cast<float4*>(s_g + i) = __ldg(reinterpret_cast<const float4*>(a.ln_g + i));
     *reinterpret_cast<float4*>(s_b + i) = __ldg(reinterpret_cast<const float4*>(a.ln_b + i));
@@ -1968,9 +2044,10 @@ __global__ void __maxnreg__(128) post_block_kernel(PostBlockArgs a) {
     }
   };
   if (!a.hints_after_wait) weight_hints();
-  float bias_o[2], b2v[2];
+  constexpr int NJ = Cfg::NJ;
+  float bias_o[NJ], b2v[NJ];
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
+  for (int j = 0; j < NJ; ++j) {
     const int i = tid + j * kPbThreads;
     const int col = i % OC;
     bias_o[j] = i < OC * 8 ? __ldg(a.bo + r * OC + col) : 0.f;
@@ -1988,9 +2065,9 @@ __global__ void __maxnreg__(128) post_block_kernel(PostBlockArgs a) {
     if (b0 + slot < a.Mb) v = __ldcg(reinterpret_cast<const uint4*>(a.a16 + (size_t)(b0 + slot) * D) + c);
     *reinterpret_cast<uint4*>(as16 + slot * XS + c * 16) = v;
   }
-  float x_old[2];
+  float x_old[NJ];
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
+  for (int j = 0; j < NJ; ++j) {
     const int i = tid + j * kPbThreads;
     const int slot = i / OC, col = i - slot * OC;
     x_old[j] = (i < OC * 8 && b0 + slot < a.Mb) ? __ldcg(a.x + (size_t)(b0 + slot) * D + r * OC + col) : 0.f;
@@ -1998,7 +2075,12 @@ __global__ void __maxnreg__(128) post_block_kernel(PostBlockArgs a) {
   __syncthreads();
   if (act0) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    pb_mma<Cfg::NB0>(acc, wa0, wb0, as16 + grp * XS + tq * 16, kp0 * Cfg::NB0);
+    pb_mma<Cfg::NB0b>(acc, wa0, wb0, as16 + grp * XS + tq * 16, kp0 * Cfg::NB0);
+#pragma unroll
+    for (int bb = Cfg::NB0b; bb < Cfg::NB0; bb += Cfg::NB0b) {   // wider models: the rest of the unit's blocks
+      pb_load<Cfg::NB0b>(wa0, wb0, w0row, w0row + (size_t)8 * D, kp0 * Cfg::NB0 + bb, wpol);
+      pb_mma<Cfg::NB0b>(acc, wa0, wb0, as16 + grp * XS + tq * 16, kp0 * Cfg::NB0 + bb);
+    }
     float* dst = s_red + kp0 * 8 * OC;
     const int c_lo = strip0 * 16 + grp, c_hi = c_lo + 8;
     dst[(2 * tq) * OC + c_lo] = acc[0], dst[(2 * tq + 1) * OC + c_lo] = acc[1];
@@ -2007,7 +2089,7 @@ __global__ void __maxnreg__(128) post_block_kernel(PostBlockArgs a) {
   __syncthreads();
   ptx::cluster_wait_acquire();     // pairs with the arrival at kernel entry
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
+  for (int j = 0; j < NJ; ++j) {
     const int i = tid + j * kPbThreads;
     if (i < OC * 8) {
       const int slot = i / OC, col = i - slot * OC;
@@ -2021,7 +2103,7 @@ __global__ void __maxnreg__(128) post_block_kernel(PostBlockArgs a) {
     }
   }
   // weights never depend on activations: the first batch of phase 2 is requested before the barrier and the LayerNorm
-  constexpr int NBb = Cfg::NBU > 8 ? 8 : Cfg::NBU;               // blocks per batch
+  constexpr int NBb = pb_batch(Cfg::NBU);                        // blocks per batch
   uint4 wa2[NBb], wb2[NBb];
   {
     const int strip = warp % Cfg::SB, kp = warp / Cfg::SB;
@@ -2039,10 +2121,10 @@ __global__ void __maxnreg__(128) post_block_kernel(PostBlockArgs a) {
     const float* xr = xp + warp * D;
     __half* dst = reinterpret_cast<__half*>(xs + warp * XS);
     constexpr int N4 = D / 4;
-    float4 v[4];
+    float4 v[Cfg::LNV];
     float sum = 0.f, sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < Cfg::LNV; ++i) {
       const int c = lane + 32 * i;
       v[i] = c < N4 ? *reinterpret_cast<const float4*>(xr + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
@@ -2053,7 +2135,7 @@ __global__ void __maxnreg__(128) post_block_kernel(PostBlockArgs a) {
     const float rstd = live ? rsqrtf(fmaxf(sq / (float)D - mean * mean, 0.f) + 1e-5f) : 0.f;
     const float ab = live ? 1.f : 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < Cfg::LNV; ++i) {
       const int c = lane + 32 * i;
       if (c < N4) {
         const float4 g = *reinterpret_cast<const float4*>(s_g + c * 4), bb = *reinterpret_cast<const float4*>(s_b + c * 4);
@@ -2152,7 +2234,7 @@ __global__ void __maxnreg__(128) post_block_kernel(PostBlockArgs a) {
 
   // ---- 4. x = x' + b2 + sum over the cluster of the partials (rank order), own OC columns -----------------------------------------------
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
+  for (int j = 0; j < NJ; ++j) {
     const int i = tid + j * kPbThreads;
     if (i < OC * 8) {
       const int slot = i / OC, col = i - slot * OC;
@@ -2171,36 +2253,51 @@ __global__ void __maxnreg__(128) post_block_kernel(PostBlockArgs a) {
   trace.end();
 }
 
-// cluster size the post block uses for width d (0: unsupported)
+// cluster size the post block uses for width d (0: unsupported). Sizes above 8 are non-portable: asked for once per device.
+template <int D, int C>
+static bool post_block_cluster_fits() {
+  if (cudaFuncSetAttribute(post_block_kernel<D, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PbCfg<D, C>::smem) != cudaSuccess) return false;
+  if (C > 8 && cudaFuncSetAttribute(post_block_kernel<D, C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return false;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(C, 1), cfg.blockDim = dim3(kPbThreads), cfg.dynamicSmemBytes = PbCfg<D, C>::smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = C, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+  cfg.attrs = at, cfg.numAttrs = 1;
+  int nc = 0;
+  return cudaOccupancyMaxActiveClusters(&nc, post_block_kernel<D, C>, &cfg) == cudaSuccess && nc >= 1;
+}
 static int post_block_cluster(int d) {
-  static int c512_dev[kMaxDevices];
-  static bool c512_init = false;
-  if (!c512_init) {
-    for (int i = 0; i < kMaxDevices; ++i) c512_dev[i] = -1;
-    c512_init = true;
+  static int cached[kMaxDevices][5];
+  static bool init = false;
+  if (!init) {
+    for (int i = 0; i < kMaxDevices; ++i)
+      for (int j = 0; j < 5; ++j) cached[i][j] = -1;
+    init = true;
   }
-  int& c512 = c512_dev[current_device_slot()];
-  if (d == 384) return 8;
-  if (d != 512) return 0;
-  if (c512 < 0) {   // 16 CTAs per cluster is a non-portable size: ask whether this device schedules it
-    c512 = 8;
+  const int slot = d == 384 ? 0 : d == 512 ? 1 : d == 768 ? 2 : d == 1024 ? 3 : d == 1280 ? 4 : -1;
+  if (slot < 0) return 0;
+  int& c = cached[current_device_slot()][slot];
+  if (c < 0) {
+    // d = 768 / 1024: measured at 40 sequences 1284 -> 1098 and 3629 -> 3502 us per step against the skinny-GEMM chain;
+    // d = 1280 (ten CTAs per cluster, 1.3 MB of W1 per CTA): 6175 -> 6435, so off unless WB_POST_BLOCK_WIDE=2. 0 = all off.
+    static int wide = -1;
+    if (wide < 0) {
+      const char* e = getenv("WB_POST_BLOCK_WIDE");
+      wide = e ? atoi(e) : 1;
+    }
     const char* e = getenv("WB_POST_CLUSTER");
     const int want = e ? atoi(e) : 16;
-    if (want == 16 &&
-        cudaFuncSetAttribute(post_block_kernel<512, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-        cudaFuncSetAttribute(post_block_kernel<512, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PbCfg<512, 16>::smem) == cudaSuccess) {
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(16, 1), cfg.blockDim = dim3(kPbThreads), cfg.dynamicSmemBytes = PbCfg<512, 16>::smem;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = 16, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
-      cfg.attrs = at, cfg.numAttrs = 1;
-      int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, post_block_kernel<512, 16>, &cfg) == cudaSuccess && nc >= 1) c512 = 16;
+    switch (d) {
+      case 384: c = 8; break;
+      case 512: c = (want == 16 && post_block_cluster_fits<512, 16>()) ? 16 : 8; break;
+      case 768: c = (wide && post_block_cluster_fits<768, 12>()) ? 12 : 0; break;
+      case 1024: c = (wide && post_block_cluster_fits<1024, 16>()) ? 16 : 0; break;
+      default: c = (wide >= 2 && post_block_cluster_fits<1280, 10>()) ? 10 : 0; break;
     }
     cudaGetLastError();
   }
-  return c512;
+  return c;
 }
 
 int post_block_supported(int n_head, int d) {
@@ -2209,7 +2306,7 @@ int post_block_supported(int n_head, int d) {
     const char* e = getenv("WB_POST_BLOCK");
     env = (e && e[0] == '0') ? 0 : 1;
   }
-  return env && d == n_head * 64 && (d == 384 || d == 512);
+  return env && d == n_head * 64 && post_block_cluster(d) > 0;
 }
 
 template <int D, int C>
@@ -2258,6 +2355,12 @@ int launch_post_block(const PostBlockDesc& p, cudaStream_t st, int64_t* launches
   cudaError_t le;
   if (p.d == 384)
     le = launch_post_block_t<384, 8>(a, n_groups, st);
+  else if (p.d == 768)
+    le = launch_post_block_t<768, 12>(a, n_groups, st);
+  else if (p.d == 1024)
+    le = launch_post_block_t<1024, 16>(a, n_groups, st);
+  else if (p.d == 1280)
+    le = launch_post_block_t<1280, 10>(a, n_groups, st);
   else if (C == 16)
     le = launch_post_block_t<512, 16>(a, n_groups, st);
   else

@@ -487,6 +487,24 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
     c.kv_share = o.beams;
     c.q = nullptr, c.x = xdec, c.ln_g = L.lnc_g, c.ln_b = L.lnc_b, c.wq = L.wq_c, c.bq = L.bq_c;
     c.pdl_late_ok = post_block_supported(H, d) ? 1 : 0;
+    {
+      // d >= 1024: the fused projection keeps 160 registers of weight rows per thread (one CTA per SM) and re-reads 128 / 164 KB
+      // of Wq per (sequence, head); a separate LayerNorm + projection kernel in front of a two-CTAs-per-SM attention kernel
+      // instead (WB_XA_FUSE_Q = 0 / 1 forces either)
+      static int fuse_env = -2;
+      if (fuse_env == -2) {
+        const char* e = getenv("WB_XA_FUSE_Q");
+        fuse_env = e ? atoi(e) : -1;
+      }
+      const bool fuse = fuse_env >= 0 ? fuse_env != 0 : d < 1024;
+      if (!fuse) {
+        SkinnyDesc sq{};
+        sq.Mb = Mb, sq.state = state, sq.N = d, sq.K = d, sq.w = L.wq_c, sq.bias = L.bq_c, sq.in_mode = SKINNY_IN_LN, sq.in = xdec;
+        sq.ln_g = L.lnc_g, sq.ln_b = L.lnc_b, sq.out_mode = SKINNY_OUT_F32, sq.out = q32;
+        WB_TRY(launch_skinny_gemm(sq, st, &h->launches));
+        c.q = q32, c.x = nullptr, c.wq = nullptr, c.bq = nullptr, c.ln_g = nullptr, c.ln_b = nullptr;
+      }
+    }
     if (o.xwait) WB_CUDA_OK(cudaStreamWaitEvent(st, o.xwait, 0));
     WB_TRY(launch_attn_decode(c, st, &h->launches));
     if (o.xrec) WB_CUDA_OK(cudaEventRecord(o.xrec, st));
@@ -741,8 +759,7 @@ int wb_create(const wb_dims* dims, int32_t max_batch, int32_t max_beams, int32_t
     set_error("wb_create: unsupported model dimensions");
     return WB_ERR_ARG;
   }
-  const bool blocks = self_block_supported(dims->n_text_head, dims->n_text_state) && post_block_supported(dims->n_text_head, dims->n_text_state);
-  if (!blocks && max_batch * max_beams > kMaxSequencesWide) {
+  if (!self_block_supported(dims->n_text_head, dims->n_text_state) && max_batch * max_beams > kMaxSequencesWide) {
     set_error("wb_create: max_batch * max_beams must be in [1, %d] for this model width (%d up to d = 512)", kMaxSequencesWide, kMaxSequences);
     return WB_ERR_ARG;
   }

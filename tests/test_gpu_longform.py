@@ -81,7 +81,10 @@ def test_temperature_sampling_and_no_speech_prob_match_oracle(wbm, ref, name, be
     res0 = ref.decode_window(oracle, xa, o_ref, prompt, 0.0, 0, 0, 0, None)
     got0 = tok0[0, n0:lens0[0]].tolist()
     got0 = got0[:got0.index(o.eot)] if o.eot in got0 else got0
-    assert got0 == res0.tokens and abs(nsp0[0] - res0.no_speech_prob) <= 2e-3 + 2e-2 * res0.no_speech_prob
+    if got0 != res0.tokens:   # as above: only where the oracle's own top-2 gap is a tie for the fp16 path
+        assert res0.min_margin <= TOL_TIE, f"{got0} vs {res0.tokens} (oracle's smallest gap {res0.min_margin:.4f})"
+        print(f"\n[arg-max] tie (oracle gap {res0.min_margin:.4f})")
+    assert abs(nsp0[0] - res0.no_speech_prob) <= 2e-3 + 2e-2 * res0.no_speech_prob
     w.close()
 
 
