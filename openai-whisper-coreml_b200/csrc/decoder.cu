@@ -1060,6 +1060,7 @@ struct HeadAttnArgs {
   int d, n_rows_fixed, kv_share, n_stages;
   int l2_prefetch_tiles;   // cross attention: stage tiles beyond the ring requested into L2 while q is still being computed
   int pdl_late;            // release the dependent kernel after the main loop instead of at entry
+  int Mb;                  // sequences (attn_decode_multi_kernel: the last slab may hold fewer than kv_share)
 };
 
 // 8 weight rows x d of a [.][d] fp16 matrix against one fp32 vector in shared memory: lane l owns the 16-byte chunks
@@ -1370,6 +1371,238 @@ __global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_head
   trace.end();
 }
 
+// ---- KV-cache attention for sequences that share one K/V slab (the beams of a chunk, the best_of draws of a window) -------------------
+// One CTA per (slab, head) instead of one per (sequence, head): the up to 8 queries are the 8 columns of every mma.sync that the
+// single-query kernel fills with copies of one query, so the slab is streamed once (5 beams: a fifth of the L2 -> SM traffic and
+// of the CTAs: configs[3]'s 480 CTAs were two waves on 296 slots). Per column online softmax: a lane owns columns 2 tq, 2 tq + 1 of
+// rows grp, grp + 8; P goes back in as the B operand of O^T += V^T P through one shuffle pair per element.
+template <int NJW>
+__global__ void __launch_bounds__(kHaThreads, NJW <= 3 ? 2 : 1) attn_decode_multi_kernel(const __grid_constant__ CUtensorMap tmK,
+                                                                       const __grid_constant__ CUtensorMap tmV, HeadAttnArgs a) {
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8];
+  __shared__ __align__(16) float s_q[8 * 64];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 2, tq = lane & 3, mi = lane >> 3, r8 = lane & 7;
+  const int h = blockIdx.x, slab = blockIdx.y;
+  // behind the ring: LayerNorm gamma / beta and the normalised rows of the slab's sequences (fused projection only)
+  float* s_g = reinterpret_cast<float*>(smem + (size_t)a.n_stages * 2 * kHaTileBytes);
+  float* s_b = s_g + NJW * 256;
+  float* s_xm = s_b + NJW * 256;                             // [8][NJW * 256]
+  const int b0 = slab * a.kv_share;
+  const int nq = a.Mb - b0 < a.kv_share ? a.Mb - b0 : a.kv_share;
+  TraceScope trace(a.state, 201);
+  const int n_stages = a.n_stages;
+  if (tid == 0) {
+    ptx::prefetch_tensormap(&tmK);
+    ptx::prefetch_tensormap(&tmV);
+    for (int s = 0; s < n_stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 8);
+    }
+    ptx::fence_mbar_init();
+  }
+  for (int i = tid; i < 8 * 64; i += kHaThreads) s_q[i] = 0.f;   // unused columns: zero queries
+  __syncthreads();
+  if (!a.pdl_late) ptx::grid_dep_launch();
+  const int n_rows = a.n_rows_fixed;
+  const int n_tiles = (n_rows + kHaStageRows - 1) / kHaStageRows;
+
+  float o[4][4], m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      const uint64_t kvpol = stream_policy();
+      for (int t = 0; t < n_tiles; ++t) {
+        if (a.pdl_late > 1 && t == (n_tiles > a.pdl_late ? n_tiles - a.pdl_late : 0)) ptx::grid_dep_launch();
+        const int s = t % n_stages;
+        const uint32_t ph = (uint32_t)(t / n_stages) & 1u;
+        ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * kHaTileBytes);
+        unsigned char* dk = smem + (size_t)s * 2 * kHaTileBytes;
+        ptx::tma_load_3d(dk, &tmK, &full_bar[s], h * 64, t * kHaStageRows, slab, kvpol);
+        ptx::tma_load_3d(dk + kHaTileBytes, &tmV, &full_bar[s], h * 64, t * kHaStageRows, slab, kvpol);
+      }
+    }
+  } else {
+    const float sl = 0.125f * kLog2e;   // (d_head^-0.25)^2 = 1/8 exactly
+    if (a.wq) {
+      // fused LayerNorm + query projection: warp s normalises the row of sequence s into shared memory (fp32), then every warp
+      // multiplies its 8 weight rows - held in registers - with all nq rows
+      const int d = a.d;
+      const __half* wbase = a.wq + (size_t)(h * 64 + warp * 8) * d;
+      uint4 w0[4][NJW];
+      const uint64_t wpol = weight_policy();
+      head_rows_load<NJW>(w0, wbase, d, lane, wpol);
+      for (int i = tid * 4; i < d; i += 256 * 4) {
+        *reinterpret_cast<float4*>(s_g + i) = __ldg(reinterpret_cast<const float4*>(a.ln_g + i));
+        *reinterpret_cast<float4*>(s_b + i) = __ldg(reinterpret_cast<const float4*>(a.ln_b + i));
+      }
+      const float bias = lane < 8 ? __ldg(a.bq + h * 64 + warp * 8 + lane) : 0.f;
+      ptx::grid_dep_sync();
+      asm volatile("bar.sync 1, 256;" ::: "memory");        // gamma / beta staged
+      if (warp < nq) {
+        constexpr int kV4 = NJW * 2;                        // float4 per lane: NJW * 256 columns / (32 lanes * 4)
+        float4 xv[kV4];
+        float sum = 0.f, sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < kV4; ++i) {
+          const int c = (lane + 32 * i) * 4;
+          xv[i] = c < d ? __ldcg(reinterpret_cast<const float4*>(a.x + (size_t)(b0 + warp) * d + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          sum += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+          sq += (xv[i].x * xv[i].x + xv[i].y * xv[i].y) + (xv[i].z * xv[i].z + xv[i].w * xv[i].w);
+        }
+        sum = warp_sum(sum), sq = warp_sum(sq);
+        const float mean = sum / (float)d;
+        const float rstd = rsqrtf(fmaxf(sq / (float)d - mean * mean, 0.f) + 1e-5f);
+        float* dst = s_xm + (size_t)warp * (NJW * 256);
+#pragma unroll
+        for (int i = 0; i < kV4; ++i) {
+          const int c = (lane + 32 * i) * 4;
+          float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c < d) {
+            const float4 g = *reinterpret_cast<const float4*>(s_g + c), bb = *reinterpret_cast<const float4*>(s_b + c);
+            r = make_float4((xv[i].x - mean) * rstd * g.x + bb.x, (xv[i].y - mean) * rstd * g.y + bb.y,
+                            (xv[i].z - mean) * rstd * g.z + bb.z, (xv[i].w - mean) * rstd * g.w + bb.w);
+          }
+          *reinterpret_cast<float4*>(dst + c) = r;
+        }
+      }
+      uint4 w1[4][NJW];                                     // second half of the rows: requested under the barrier
+      head_rows_load<NJW>(w1, wbase + (size_t)4 * d, d, lane, wpol);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int s = 0; s < nq; ++s) {
+        const float mine = head_rows_dot<NJW>(w0, w1, s_xm + (size_t)s * (NJW * 256), lane);
+        if (lane < 8) s_q[s * 64 + warp * 8 + lane] = mine + bias;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    } else {
+      ptx::grid_dep_sync();                                 // q comes from the previous kernel
+      for (int i = tid; i < nq * 64; i += 256) s_q[i] = __ldcg(a.q + (size_t)(b0 + (i >> 6)) * a.d + h * 64 + (i & 63));
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    // q as B fragments: column n = grp is query grp; hi + lo fp16 parts, pre-scaled into the log2 domain
+    uint32_t qh[4][2], ql[4][2];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float2 q0 = *reinterpret_cast<const float2*>(s_q + grp * 64 + kk * 16 + 2 * tq);
+      const float2 q1 = *reinterpret_cast<const float2*>(s_q + grp * 64 + kk * 16 + 2 * tq + 8);
+      const float v[4] = {q0.x * sl, q0.y * sl, q1.x * sl, q1.y * sl};
+      __half hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        hi[e] = __float2half_rn(v[e]);
+        lo[e] = __float2half_rn(v[e] - __half2float(hi[e]));
+      }
+      __half2 h0 = __halves2half2(hi[0], hi[1]), h1 = __halves2half2(hi[2], hi[3]);
+      __half2 lw0 = __halves2half2(lo[0], lo[1]), lw1 = __halves2half2(lo[2], lo[3]);
+      qh[kk][0] = *reinterpret_cast<uint32_t*>(&h0), qh[kk][1] = *reinterpret_cast<uint32_t*>(&h1);
+      ql[kk][0] = *reinterpret_cast<uint32_t*>(&lw0), ql[kk][1] = *reinterpret_cast<uint32_t*>(&lw1);
+    }
+    const int src0 = (2 * tq) * 4 + (grp >> 1), src1 = src0 + 4;   // lanes that hold rows 2 tq / 2 tq + 1 (and + 8) of column grp
+    const bool odd = grp & 1;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int s = t % n_stages;
+      const uint32_t ph = (uint32_t)(t / n_stages) & 1u;
+      ptx::mbar_wait(&full_bar[s], ph);
+      const int row0 = t * kHaStageRows + warp * 16;
+      if (row0 < n_rows) {                                 // warp-uniform
+        const uint32_t sk = ptx::smem_u32(smem + (size_t)s * 2 * kHaTileBytes);
+        const uint32_t sv = sk + kHaTileBytes;
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        {
+          const int R = warp * 16 + (mi & 1) * 8 + r8;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            uint32_t af[4];
+            ptx::ldmatrix_x4(af, sk + R * 128 + (((kk * 2 + (mi >> 1)) ^ (R & 7)) << 4));
+            ptx::mma_16816(c, af, qh[kk]);
+            ptx::mma_16816(c, af, ql[kk]);
+          }
+        }
+        const bool ok_lo = row0 + grp < n_rows, ok_hi = row0 + grp + 8 < n_rows;
+        const float s00 = ok_lo ? c[0] : -INFINITY, s01 = ok_lo ? c[1] : -INFINITY;
+        const float s10 = ok_hi ? c[2] : -INFINITY, s11 = ok_hi ? c[3] : -INFINITY;
+        float t0 = fmaxf(s00, s10), t1 = fmaxf(s01, s11);
+#pragma unroll
+        for (int off = 4; off <= 16; off <<= 1) {
+          t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, off));
+          t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, off));
+        }
+        const float n0 = fmaxf(m0, t0), n1 = fmaxf(m1, t1);         // finite: row0 itself exists
+        const float corr0 = exp2f(m0 - n0), corr1 = exp2f(m1 - n1);  // m = -inf: 0
+        m0 = n0, m1 = n1;
+        l0 *= corr0, l1 *= corr1;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) o[mt][0] *= corr0, o[mt][2] *= corr0, o[mt][1] *= corr1, o[mt][3] *= corr1;
+        const float p00 = exp2f(s00 - m0), p01 = exp2f(s01 - m1), p10 = exp2f(s10 - m0), p11 = exp2f(s11 - m1);
+        l0 += p00 + p10, l1 += p01 + p11;
+        // B fragment of P (k = row, n = column grp): rows 2 tq, 2 tq + 1, 2 tq + 8, 2 tq + 9
+        const float a00 = __shfl_sync(0xffffffffu, p00, src0), a01 = __shfl_sync(0xffffffffu, p01, src0);
+        const float b00 = __shfl_sync(0xffffffffu, p00, src1), b01 = __shfl_sync(0xffffffffu, p01, src1);
+        const float a10 = __shfl_sync(0xffffffffu, p10, src0), a11 = __shfl_sync(0xffffffffu, p11, src0);
+        const float b10 = __shfl_sync(0xffffffffu, p10, src1), b11 = __shfl_sync(0xffffffffu, p11, src1);
+        const float e0 = odd ? a01 : a00, e1 = odd ? b01 : b00, e2 = odd ? a11 : a10, e3 = odd ? b11 : b10;
+        const __half2 ph0 = __floats2half2_rn(e0, e1), ph1 = __floats2half2_rn(e2, e3);
+        const float2 f0 = __half22float2(ph0), f1 = __half22float2(ph1);
+        const __half2 pl0 = __floats2half2_rn(e0 - f0.x, e1 - f0.y), pl1 = __floats2half2_rn(e2 - f1.x, e3 - f1.y);
+        const uint32_t pbh[2] = {*reinterpret_cast<const uint32_t*>(&ph0), *reinterpret_cast<const uint32_t*>(&ph1)};
+        const uint32_t pbl[2] = {*reinterpret_cast<const uint32_t*>(&pl0), *reinterpret_cast<const uint32_t*>(&pl1)};
+        {
+          const int R = warp * 16 + (mi >> 1) * 8 + r8;
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) {
+            uint32_t af[4];
+            ptx::ldmatrix_x4_trans(af, sv + R * 128 + (((mt * 2 + (mi & 1)) ^ (R & 7)) << 4));
+            ptx::mma_16816(o[mt], af, pbh);
+            ptx::mma_16816(o[mt], af, pbl);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&empty_bar[s]);
+    }
+  }
+  __syncthreads();   // all stages consumed; the ring becomes the cross-warp merge table [8 warps][8 columns][68]
+  if (a.pdl_late == 1) ptx::grid_dep_launch();
+  float* red = reinterpret_cast<float*>(smem);
+  if (warp < 8) {
+#pragma unroll
+    for (int off = 4; off <= 16; off <<= 1) {
+      l0 += __shfl_xor_sync(0xffffffffu, l0, off);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, off);
+    }
+    float* r0 = red + (size_t)(warp * 8 + 2 * tq) * 68;
+    float* r1 = r0 + 68;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      r0[mt * 16 + grp] = o[mt][0], r0[mt * 16 + grp + 8] = o[mt][2];
+      r1[mt * 16 + grp] = o[mt][1], r1[mt * 16 + grp + 8] = o[mt][3];
+    }
+    if (grp == 0) r0[64] = m0, r0[65] = l0, r1[64] = m1, r1[65] = l1;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < nq * 64; idx += kHaThreads) {
+    const int col = idx >> 6, dim = idx & 63;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) M = fmaxf(M, red[(w * 8 + col) * 68 + 64]);
+    float L = 0.f, A = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float mw = red[(w * 8 + col) * 68 + 64];
+      const float wgt = (mw == -INFINITY) ? 0.f : exp2f(mw - M);
+      L += wgt * red[(w * 8 + col) * 68 + 65];
+      A += wgt * red[(w * 8 + col) * 68 + dim];
+    }
+    a.out16[(size_t)(b0 + col) * a.d + h * 64 + dim] = __float2half_rn(A / L);
+  }
+  trace.end();
+}
+
 static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int64_t* launches) {
   CUtensorMap tmK, tmV;
   const long long nslab = (p.Mb + p.kv_share - 1) / p.kv_share;
@@ -1377,7 +1610,7 @@ static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int
   if (rc) return rc;
   rc = gemm_get_tmap(p.tmaps, p.v, p.d, p.n_ctx, nslab, p.d, (long long)p.n_ctx * p.d, kHaStageRows, &tmV);
   if (rc) return rc;
-  HeadAttnArgs a{p.q, p.x, p.ln_g, p.ln_b, p.wq, p.bq, p.out16, p.state, p.d, p.n_rows_fixed, p.kv_share, 3, 0, 0};   // L2 prefetch measured slightly negative in-step: off
+  HeadAttnArgs a{p.q, p.x, p.ln_g, p.ln_b, p.wq, p.bq, p.out16, p.state, p.d, p.n_rows_fixed, p.kv_share, 3, 0, 0, p.Mb};   // L2 prefetch measured slightly negative in-step: off
   static int pdl_xa = -1;
   if (pdl_xa < 0) {
     const char* e = getenv("WB_PDL_XA");
@@ -1437,6 +1670,45 @@ static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int
   }
   cfg.attrs = at, cfg.numAttrs = n_at;
   cudaError_t le = cudaSuccess;
+  // sequences that share a slab (beam search, best_of): one CTA per (slab, head) with the sequences as MMA columns
+  static int multi_env = -1;
+  if (multi_env < 0) {
+    const char* e = getenv("WB_HA_MULTI");   // development: 0 = one CTA per (sequence, head) also for shared slabs
+    multi_env = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (multi_env && p.kv_share > 1 && p.kv_share <= 8 && p.n_rows_fixed > 0) {
+    // (a row split over a cluster, as in the single-query kernel, measured slower here: 282 -> 394 ms per decode of configs[3])
+    cudaLaunchConfig_t cm = cfg;
+    cm.gridDim = dim3(p.n_head, (unsigned)nslab, 1);
+    cudaLaunchAttribute am[1];
+    am[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    am[0].val.programmaticStreamSerializationAllowed = 1;
+    cm.attrs = am, cm.numAttrs = use_pdl() ? 1 : 0;
+    HeadAttnArgs am_args = a;
+    am_args.n_stages = stages_env > 0 ? stages_env : 3;
+    const int njw = p.wq ? (p.d + 255) / 256 : 1;
+    const size_t smem_m = (size_t)am_args.n_stages * 2 * kHaTileBytes + 1024 + (p.wq ? (size_t)10 * njw * 256 * 4 : 0);
+    cm.dynamicSmemBytes = smem_m;
+#define WB_HM_CASE(J)                                                                                                      \
+  case J: {                                                                                                                \
+    static size_t smem_set_dev[kMaxDevices] = {}; size_t& smem_set = smem_set_dev[current_device_slot()];                  \
+    if (smem_m > smem_set) {                                                                                               \
+      WB_CUDA_OK(cudaFuncSetAttribute(attn_decode_multi_kernel<J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m)); \
+      smem_set = smem_m;                                                                                                   \
+    }                                                                                                                      \
+    le = cudaLaunchKernelEx(&cm, attn_decode_multi_kernel<J>, tmK, tmV, am_args);                                          \
+  } break;
+    switch (njw) {
+      WB_HM_CASE(1) WB_HM_CASE(2) WB_HM_CASE(3) WB_HM_CASE(4) WB_HM_CASE(5)
+      default:
+        set_error("attn_decode: unsupported width %d", p.d);
+        return -1;
+    }
+#undef WB_HM_CASE
+    if (launches) *launches += 1;
+    WB_CUDA_OK(le);
+    return 0;
+  }
 #define WB_HA_CASE(J)                                                                                                     \
   case J: {                                                                                                               \
     static size_t smem_set_dev[kMaxDevices] = {}; size_t& smem_set = smem_set_dev[current_device_slot()];                                                                                           \

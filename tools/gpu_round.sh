@@ -14,7 +14,7 @@ tail -2 gpurun_out/profile_step.log
 echo "== ncu full: attn_decode ==" 
 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:attn_decode_head -s 2 -c 2 -f -o gpurun_out/prof_attn_decode python tools/profile_step.py base.en 32 2 > gpurun_out/prof1.log 2>&1; tail -2 gpurun_out/prof1.log
 echo "== ncu full: gemm_tc ==" 
-timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:gemm_tc -s 2 -c 3 -f -o gpurun_out/prof_gemm_tc python tools/profile_step.py base.en 32 1 > gpurun_out/prof2.log 2>&1; tail -2 gpurun_out/prof2.log
+timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:gemm_tc -s 2 -c 4 -f -o gpurun_out/prof_gemm_tc python tools/profile_step.py base.en 32 1 > gpurun_out/prof2.log 2>&1; tail -2 gpurun_out/prof2.log
 echo "== ncu full: decoder block kernels, logits, finish ==" 
 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"self_block|post_block|logits_tc|step_finish" -s 4 -c 8 -f -o gpurun_out/prof_blocks python tools/profile_step.py base.en 32 2 > gpurun_out/prof3.log 2>&1; tail -2 gpurun_out/prof3.log
 echo "== ncu full: encoder attention, layernorm, log-mel ==" 

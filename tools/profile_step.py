@@ -9,6 +9,8 @@ import sys
 import numpy as np
 import torch
 
+os.environ.setdefault("WB_H2D_SLABS", "0")   # one copy, one encoder pass over the whole batch: kernel shapes as DESIGN.md quotes them
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 wbm = importlib.import_module("openai-whisper-coreml_b200")
