@@ -1673,10 +1673,12 @@ static int launch_attn_decode_head(const AttnDecodeDesc& p, cudaStream_t st, int
   // sequences that share a slab (beam search, best_of): one CTA per (slab, head) with the sequences as MMA columns
   static int multi_env = -1;
   if (multi_env < 0) {
-    const char* e = getenv("WB_HA_MULTI");   // development: 0 = one CTA per (sequence, head) also for shared slabs
-    multi_env = (e && e[0] == '0') ? 0 : 1;
+    const char* e = getenv("WB_HA_MULTI");   // development: 0 = one CTA per (sequence, head) also for shared slabs, 2 = shared slabs always
+    multi_env = e ? atoi(e) : 1;
   }
-  if (multi_env && p.kv_share > 1 && p.kv_share <= 8 && p.n_rows_fixed > 0) {
+  // ... when that still leaves enough CTAs to pull the stream: a single window with best_of draws (6-20 heads x 1 slab) stays on the
+  // one-CTA-per-(sequence, head) kernel, whose grid the row split above widens
+  if (multi_env && p.kv_share > 1 && p.kv_share <= 8 && p.n_rows_fixed > 0 && (multi_env >= 2 || p.n_head * (int)nslab >= 64)) {
     // (a row split over a cluster, as in the single-query kernel, measured slower here: 282 -> 394 ms per decode of configs[3])
     cudaLaunchConfig_t cm = cfg;
     cm.gridDim = dim3(p.n_head, (unsigned)nslab, 1);

@@ -219,6 +219,22 @@ def test_alternate_decode_paths_keep_parity(env):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
 
 
+@pytest.mark.parametrize("env", [{"WB_HA_MULTI": "2"}, {"WB_HA_MULTI": "0", "WB_HA_SPLIT": "0"}, {"WB_POST_BLOCK_WIDE": "0", "WB_XA_FUSE_Q": "1"}])
+def test_alternate_attention_paths_keep_parity(env):
+    """The KV-cache kernel has three shapes — one CTA per (sequence, head), its rows split over a cluster for small grids, one
+    CTA per (slab, head) for sequences that share a slab — chosen by grid size; here the beam-search, sampling (best_of) and
+    wide-model tests run again with the shared-slab kernel forced for every grid, with neither variant, and with the wide
+    models' skinny-GEMM chain / fused query projection."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sel = "tests/test_gpu_parity.py::test_beam_search_matches_oracle tests/test_gpu_parity.py::test_beam_search_on_block_kernels " \
+          "tests/test_gpu_parity.py::test_beam_search_at_small_width tests/test_gpu_parity.py::test_wider_models_two_layers " \
+          "tests/test_gpu_longform.py::test_temperature_sampling_and_no_speech_prob_match_oracle"
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", *sel.split()], cwd=root, env={**os.environ, **env},
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
+
+
 def test_checkpoint_files_round_trip(wbm, ref, tmp_path):
     """a handle filled from a safetensors file (upstream names F32; transformers names F16, without the tied
     proj_out / with the sinusoidal encoder positions regenerated when absent; BF16) holds exactly the tensors of the state
