@@ -156,7 +156,9 @@ int wb_detect_language(wb_handle* h, int32_t B, int32_t sot, int32_t lang0, int3
  * (initial tokens included, first eot included), sum_logprob [B]. Beam search returns, per chunk, the candidate with the
  * best sum_logprob / length (upstream MaximumLikelihoodRanker without length penalty). */
 int wb_decode(wb_handle* h, int32_t B, const wb_decode_opts* opts, int32_t* tokens_out, int32_t* lens, float* sum_logprob);
-/* audio -> tokens in one call (= wb_encode + wb_decode). Host pointers. */
+/* audio -> tokens in one call (= wb_encode + wb_decode). Host pointers. The batch is copied in slabs on a copy stream of the
+ * handle (the first quarter, then the rest while the first slab is encoded; env WB_H2D_SLABS), so pinned host memory hides
+ * most of the transfer; results do not depend on the split. */
 int wb_transcribe(wb_handle* h, const float* audio, int32_t B, const wb_decode_opts* opts, int32_t* tokens_out,
                   int32_t* lens, float* sum_logprob);
 /* Same with the audio already on the device (throughput path; device pointer, results to host). */
@@ -240,7 +242,8 @@ uint64_t wb_call_seed(uint64_t seed, int64_t seek, int32_t temperature_index);
 /* Number of kernels this library launched on the handle since creation (graph replays count their nodes). */
 int64_t wb_launch_count(const wb_handle* h);
 /* Device time (ms) of the last call's phases, measured with CUDA events on the handle's stream:
- * out[0]=logmel, out[1]=encoder (incl. cross K/V), out[2]=decode loop, out[3]=number of decode steps run. */
+ * out[0]=logmel, out[1]=encoder (incl. cross K/V), out[2]=decode loop, out[3]=number of decode steps run. After wb_transcribe
+ * (host audio, slabs) out[0] is the first slab's copy + log-mel and out[1] everything up to the last slab's cross K/V. */
 int wb_last_timings(const wb_handle* h, float out[4]);
 int wb_sync(wb_handle* h);
 /* Times the decoder's KV-cache attention kernel alone on the resident cross-attention K/V of B chunks: `reps` launches
