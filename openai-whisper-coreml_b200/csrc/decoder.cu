@@ -586,6 +586,16 @@ static bool use_pdl() {
 
 // launch with the programmatic-dependent-launch attribute: the kernel may start while its predecessor drains; every
 // kernel launched this way calls griddepcontrol.wait before touching anything the predecessor wrote
+template <typename Kern, typename... Args>
+static cudaError_t launch_pdl_n(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at, cfg.numAttrs = use_pdl() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
 template <typename Kern, typename Arg>
 static cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const Arg& arg) {
   cudaLaunchConfig_t cfg{};
@@ -2810,6 +2820,63 @@ __global__ void __launch_bounds__(256) step_finish_kernel(FinishDesc p) {
 
 int launch_step_finish(const FinishDesc& d, cudaStream_t st, int64_t* launches) {
   const cudaError_t le = launch_pdl(step_finish_kernel, dim3(d.Mb), dim3(256), 0, st, d);
+  if (launches) *launches += 1;
+  WB_CUDA_OK(le);
+  return 0;
+}
+
+// ---- LayerNorm of the decoder rows, one warp per row (wider models) -----------------------------------------------------------------
+// fp32 statistics in one pass (sum, sum of squares), as the fused input stage of the skinny GEMM computes them; gamma / beta are
+// requested before the wait. d <= 1280: at most 10 float4 per lane.
+__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      int Mb, int d, __half* __restrict__ out16, const DecodeState* state) {
+  TraceScope trace(state, 150);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  const int n4 = d >> 2;
+  float4 g[10], bt[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const int c = lane + 32 * i;
+    g[i] = c < n4 ? __ldg(reinterpret_cast<const float4*>(gamma) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    bt[i] = c < n4 ? __ldg(reinterpret_cast<const float4*>(beta) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  ptx::grid_dep_launch();
+  ptx::grid_dep_sync();
+  if (row < Mb) {
+    float4 v[10];
+    float sum = 0.f, sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < n4 ? ld_x4(x + (size_t)row * d + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    sum = warp_sum(sum), sq = warp_sum(sq);
+    const float mean = sum / (float)d;
+    const float rstd = rsqrtf(fmaxf(sq / (float)d - mean * mean, 0.f) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const int c = lane + 32 * i;
+      if (c < n4) {
+        const __half2 h0 = __floats2half2_rn((v[i].x - mean) * rstd * g[i].x + bt[i].x, (v[i].y - mean) * rstd * g[i].y + bt[i].y);
+        const __half2 h1 = __floats2half2_rn((v[i].z - mean) * rstd * g[i].z + bt[i].z, (v[i].w - mean) * rstd * g[i].w + bt[i].w);
+        uint2 u;
+        u.x = *reinterpret_cast<const uint32_t*>(&h0), u.y = *reinterpret_cast<const uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(out16 + (size_t)row * d + c * 4) = u;
+      }
+    }
+  }
+  trace.end();
+}
+int launch_ln_rows(const float* x, const float* gamma, const float* beta, int Mb, int d, __half* out16, const DecodeState* state,
+                   cudaStream_t st, int64_t* launches) {
+  if (Mb < 1 || d % 4 != 0 || d > 1280) {
+    set_error("ln_rows: unsupported shape Mb=%d d=%d", Mb, d);
+    return -1;
+  }
+  const cudaError_t le = launch_pdl_n(ln_rows_kernel, dim3((Mb + 7) / 8), dim3(256), 0, st, x, gamma, beta, Mb, d, out16, state);
   if (launches) *launches += 1;
   WB_CUDA_OK(le);
   return 0;

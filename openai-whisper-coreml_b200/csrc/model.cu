@@ -137,7 +137,7 @@ struct wb_handle {
   // long-form (wb_transcribe_long): the whole recording and its unnormalised log-mel, allocated on demand
   float *long_audio, *long_logspec;
   size_t long_audio_cap, long_windows_cap;
-  __half *dmlp16, *a16;
+  __half *dmlp16, *a16, *dln16;   // dln16: LayerNorm rows of the current use (wider models)
   int32_t* done;
   unsigned char* mask;
   int n_logit_ctas;
@@ -302,6 +302,7 @@ static void layout_workspace(wb_handle* h) {
   h->xdec = A.take<float>(Mb * dt);
   h->q32 = A.take<float>(Mb * dt);
   h->dmlp16 = A.take<__half>(Mb * 4 * dt);
+  h->dln16 = A.take<__half>(Mb * dt);
   h->logits = A.take<float>(Mb * (size_t)D.n_vocab);
   h->sum_logprob = A.take<float>(Mb);
   h->done = A.take<int32_t>(Mb);
@@ -451,6 +452,15 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
   float* q32 = h->q32 + b0 * d;
   __half* a16 = h->a16 + b0 * d;
   __half* dmlp16 = h->dmlp16 + b0 * 4 * d;
+  __half* dln16 = h->dln16 + b0 * d;
+  // wider models (the skinny-GEMM chain): LayerNorm as its own one-warp-per-row kernel in front of the GEMMs that consume it
+  // (WB_LN_ROWS=0: fused into every CTA of the GEMM, as for the block-kernel path's fallbacks)
+  static int ln_rows_env = -1;
+  if (ln_rows_env < 0) {
+    const char* e = getenv("WB_LN_ROWS");
+    ln_rows_env = e ? atoi(e) : 1;
+  }
+  const bool ln_rows = ln_rows_env != 0 && d >= 768;
   const size_t self_off = b0 * (size_t)D.n_text_ctx * d;
   const size_t cross_off = (b0 / o.beams) * (size_t)D.n_audio_ctx * d;
   const int l_begin = o.partial ? o.l_begin : 0, l_end = o.partial ? o.l_end : D.n_text_layer;
@@ -477,6 +487,10 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
       s.N = 3 * d, s.K = d, s.w = L.wqkv, s.bias = L.bqkv, s.in_mode = SKINNY_IN_LN, s.in = xdec, s.ln_g = L.ln1_g,
       s.ln_b = L.ln1_b, s.out_mode = SKINNY_OUT_QKV, s.q32 = q32, s.kcache = h->selfK[l] + self_off, s.vcache = h->selfV[l] + self_off,
       s.n_ctx = D.n_text_ctx;
+      if (ln_rows) {   // the rows are normalised once, not by each of the GEMM's 144 .. 240 CTAs
+        WB_TRY(launch_ln_rows(xdec, L.ln1_g, L.ln1_b, Mb, d, dln16, state, st, &h->launches));
+        s.in_mode = SKINNY_IN_F16, s.in = dln16, s.ln_g = s.ln_b = nullptr;
+      }
       WB_TRY(launch_skinny_gemm(s, st, &h->launches));
       WB_TRY(launch_attn_decode(a, st, &h->launches));
       WB_TRY(launch_skinny_gemm(so, st, &h->launches));
@@ -501,6 +515,10 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
         SkinnyDesc sq{};
         sq.Mb = Mb, sq.state = state, sq.N = d, sq.K = d, sq.w = L.wq_c, sq.bias = L.bq_c, sq.in_mode = SKINNY_IN_LN, sq.in = xdec;
         sq.ln_g = L.lnc_g, sq.ln_b = L.lnc_b, sq.out_mode = SKINNY_OUT_F32, sq.out = q32;
+        if (ln_rows) {
+          WB_TRY(launch_ln_rows(xdec, L.lnc_g, L.lnc_b, Mb, d, dln16, state, st, &h->launches));
+          sq.in_mode = SKINNY_IN_F16, sq.in = dln16, sq.ln_g = sq.ln_b = nullptr;
+        }
         WB_TRY(launch_skinny_gemm(sq, st, &h->launches));
         c.q = q32, c.x = nullptr, c.wq = nullptr, c.bq = nullptr, c.ln_g = nullptr, c.ln_b = nullptr;
       }
@@ -523,6 +541,10 @@ static int decode_step(wb_handle* h, const StepOpts& o) {
     SkinnyDesc m1{};
     m1.Mb = Mb, m1.state = state, m1.N = 4 * d, m1.K = d, m1.w = L.w1, m1.bias = L.b1, m1.gelu = 1;
     m1.in_mode = SKINNY_IN_LN, m1.in = xdec, m1.ln_g = L.ln2_g, m1.ln_b = L.ln2_b, m1.out_mode = SKINNY_OUT_F16, m1.out = dmlp16;
+    if (ln_rows) {
+      WB_TRY(launch_ln_rows(xdec, L.ln2_g, L.ln2_b, Mb, d, dln16, state, st, &h->launches));
+      m1.in_mode = SKINNY_IN_F16, m1.in = dln16, m1.ln_g = m1.ln_b = nullptr;
+    }
     WB_TRY(launch_skinny_gemm(m1, st, &h->launches));
     SkinnyDesc m2{};
     m2.Mb = Mb, m2.state = state, m2.N = d, m2.K = 4 * d, m2.w = L.w2, m2.bias = L.b2;

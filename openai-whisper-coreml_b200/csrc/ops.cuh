@@ -212,6 +212,10 @@ int launch_row_token_prob(const float* logits, int Mb, int V, int token, float* 
 // L2 residency hints of the decode kernels on the current device: 1 = weights evict_last, cross K/V stream evict_first
 int decoder_set_l2_mode(int mode);
 int launch_delay(unsigned long long ns, cudaStream_t st, int64_t* launches);
+// LayerNorm of the Mb rows of the residual stream into fp16 [Mb][d], once per use instead of once per CTA of the following
+// skinny GEMM (wider models: a row of d = 768 .. 1280 floats is two or three dependent load batches per thread there)
+int launch_ln_rows(const float* x, const float* gamma, const float* beta, int Mb, int d, __half* out16, const DecodeState* state,
+                   cudaStream_t st, int64_t* launches);
 
 // beam search support: per-row top-k (k <= 8) of the filtered logits with their log-softmax values, and the re-indexing
 // of the self-attention K/V cache by source beam (upstream rearrange_kv_cache)

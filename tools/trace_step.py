@@ -21,7 +21,7 @@ buf = np.zeros((65536, 8), dtype=np.uint64)
 n = lib.wb_debug_trace(w.handle, buf.ctypes.data_as(ctypes.c_void_p), 65536)
 rec = buf[:n]
 names = {210: "self_block", 220: "post_block", 230: "layer_block", 200: "self_attn", 201: "cross_attn", 202: "cross_stream", 300: "finish", 301: "finish+sample", 131: "QKV(LN)", 120: "out/mlp2(f16,resid)", 111: "Q(LN,f32)",
-         101: "mlp1(LN,f16)", 141: "logits(LN)", 142: "logits_tc"}
+         101: "mlp1(LN,f16)", 141: "logits(LN)", 142: "logits_tc", 150: "LN rows", 130: "QKV(f16)", 110: "Q(f16,f32)", 100: "mlp1(f16,f16)"}
 # last full step: records between the last two finish kernels
 fin = [i for i in range(n) if rec[i, 0] in (300, 301)]
 s, e = fin[-2] + 1, fin[-1] + 1
