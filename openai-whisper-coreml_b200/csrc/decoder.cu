@@ -3107,21 +3107,33 @@ __global__ void __launch_bounds__(256) topk_logprobs_kernel(const float* __restr
 #pragma unroll
   for (int j = 0; j < 8; ++j) tv[j] = -INFINITY, ti[j] = 0x7fffffff;
   float m = -INFINITY, ssum = 0.f;
-  for (int i = lo + tid; i < V; i += 256) {
-    const float x = row[i];
-    if (x > m) {
-      ssum = ssum * expf(m - x) + 1.0f;
-      m = x;
-    } else if (x > -INFINITY) {
-      ssum += expf(x - m);
-    }
-    if (x > tv[7]) {   // insert into the sorted list (descending; earlier index wins ties)
-      tv[7] = x, ti[7] = i;
+  // eight independent loads per thread and batch: with one load per iteration the loop ran at one L2 / DRAM latency per element
+  // (203 dependent round trips per thread: 132 us per launch at 40 rows, 12 % of a beam-search step)
+  for (int i0 = lo + tid; i0 < V; i0 += 256 * 8) {
+    float xs[8];
 #pragma unroll
-      for (int j = 7; j > 0; --j) {
-        if (tv[j] > tv[j - 1]) {
-          const float fv = tv[j]; tv[j] = tv[j - 1]; tv[j - 1] = fv;
-          const int iv = ti[j]; ti[j] = ti[j - 1]; ti[j - 1] = iv;
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * 256;
+      xs[u] = i < V ? __ldcg(row + i) : -INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float x = xs[u];
+      const int i = i0 + u * 256;
+      if (x > m) {
+        ssum = ssum * expf(m - x) + 1.0f;
+        m = x;
+      } else if (x > -INFINITY) {
+        ssum += expf(x - m);
+      }
+      if (x > tv[7]) {   // insert into the sorted list (descending; earlier index wins ties)
+        tv[7] = x, ti[7] = i;
+#pragma unroll
+        for (int j = 7; j > 0; --j) {
+          if (tv[j] > tv[j - 1]) {
+            const float fv = tv[j]; tv[j] = tv[j - 1]; tv[j - 1] = fv;
+            const int iv = ti[j]; ti[j] = ti[j - 1]; ti[j - 1] = iv;
+          }
         }
       }
     }

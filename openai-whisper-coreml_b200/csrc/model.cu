@@ -169,6 +169,11 @@ struct wb_handle {
 
   // host staging + timing
   int32_t* h_done;
+  // beam search staging in pinned host memory: top-k values / indices, and - double-buffered by step parity, so that no second
+  // synchronisation per step is needed - the source-beam map, the newest token column and the timestamp-rule states
+  float* hb_top_lp;
+  int32_t *hb_top_idx, *hb_src, *hb_col;
+  int4* hb_ts;
   cudaEvent_t ev[4];
   float timings[4];
 };
@@ -708,6 +713,7 @@ static void free_handle(wb_handle* h) {
   if (h->copy_fence) cudaEventDestroy(h->copy_fence);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->h_done) cudaFreeHost(h->h_done);
+  if (h->hb_top_lp) cudaFreeHost(h->hb_top_lp);
   if (h->arena.base) cudaFree(h->arena.base);
   if (h->ws.base) cudaFree(h->ws.base);
   if (h->long_audio) cudaFree(h->long_audio);
@@ -758,6 +764,16 @@ static int create_impl(wb_handle* h, void* stream) {
     WB_TRY(decoder_set_l2_mode(e ? atoi(e) : 1));
   }
   WB_CUDA_OK(cudaMallocHost(&h->h_done, sizeof(int32_t) * h->Mb_max));
+  if (h->max_beams > 1) {   // one pinned block: [Mb*8] f32 | [Mb*8] i32 | 2 x [Mb] i32 | 2 x [Mb] i32 | 2 x [Mb] int4
+    const size_t Mb = (size_t)h->Mb_max;
+    unsigned char* blk = nullptr;
+    WB_CUDA_OK(cudaMallocHost(&blk, Mb * 8 * 4 + Mb * 8 * 4 + 2 * Mb * 4 + 2 * Mb * 4 + 2 * Mb * 16));
+    h->hb_top_lp = reinterpret_cast<float*>(blk);
+    h->hb_top_idx = reinterpret_cast<int32_t*>(blk + Mb * 32);
+    h->hb_src = h->hb_top_idx + Mb * 8;
+    h->hb_col = h->hb_src + 2 * Mb;
+    h->hb_ts = reinterpret_cast<int4*>(h->hb_col + 2 * Mb);
+  }
   for (int i = 0; i < 4; ++i) WB_CUDA_OK(cudaEventCreate(&h->ev[i]));
   for (int i = 1; i < wb_handle::kMaxSub; ++i) WB_CUDA_OK(cudaStreamCreateWithFlags(&h->sub_stream[i], cudaStreamNonBlocking));
   for (int i = 0; i < wb_handle::kMaxSub; ++i) WB_CUDA_OK(cudaEventCreateWithFlags(&h->sub_ev[i], cudaEventDisableTiming));
@@ -1521,7 +1537,7 @@ static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int3
   // applies the per-row rules, the top-k kernel the probability-mass rule.
   scored.timestamps = ts_on ? 1 : 0, scored.ts_begin = opts->timestamp_begin;
   scored.ts_last_allowed = opts->max_initial_timestamp_index >= 0 ? opts->timestamp_begin + opts->max_initial_timestamp_index : 0x7fffffff;
-  std::vector<int4> ts_host(Mb);
+  int4* const ts_host2 = h->hb_ts;   // [2][Mb], by step parity
   WB_CUDA_OK(cudaEventRecord(h->ev[2], st));
   WB_TRY(reset_decode_state(h, plain));
   for (int i = 0; i + 1 < n_init; ++i) WB_TRY(decode_step(h, plain));
@@ -1531,8 +1547,8 @@ static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int3
   std::vector<float> slp(Mb, 0.f);
   std::vector<std::vector<std::pair<Seq, float>>> finished(B);   // insertion-ordered, unique keys (Python dict semantics)
   const size_t max_candidates = (size_t)beam;                    // round(beam_size * patience), patience = 1
-  std::vector<float> top_lp((size_t)Mb * 8);
-  std::vector<int32_t> top_idx((size_t)Mb * 8), src(Mb), next_col(Mb);
+  float* const top_lp = h->hb_top_lp;
+  int32_t* const top_idx = h->hb_top_idx;
   int steps = 0;
   // The scored step (decoder step with stored filtered logits + top-k) replays from a CUDA graph: on the wide models it is 7
   // kernels per layer, and launched one by one the host, not the GPU, paces the step. The re-indexing swaps the two K/V buffer
@@ -1552,6 +1568,7 @@ static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int3
   }
   for (int s = 0; s < opts->sample_len; ++s) {
     if (ts_on) {
+      int4* const ts_host = ts_host2 + (size_t)(s & 1) * Mb;
       for (int b = 0; b < Mb; ++b) {   // FinishDesc::ts_state from the sampled part of the sequence (empty at s = 0)
         const Seq& q = seqs[b];
         const int len = (int)q.size() - n_init;
@@ -1566,7 +1583,7 @@ static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int3
         v.z = z, v.w = 0;
         ts_host[b] = v;
       }
-      WB_CUDA_OK(cudaMemcpyAsync(h->ts_state, ts_host.data(), (size_t)Mb * sizeof(int4), cudaMemcpyHostToDevice, st));
+      WB_CUDA_OK(cudaMemcpyAsync(h->ts_state, ts_host, (size_t)Mb * sizeof(int4), cudaMemcpyHostToDevice, st));
     }
     int slot = -1;
     if (beam_graph && s > 0) {   // the first scored step runs eagerly (function attributes are set outside of capture)
@@ -1596,8 +1613,8 @@ static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int3
       WB_TRY(decode_step(h, scored));
       WB_TRY(launch_topk_logprobs(h->logits, Mb, D.n_vocab, K, ts_begin, h->top_lp, h->top_idx, st, &h->launches));
     }
-    WB_CUDA_OK(cudaMemcpyAsync(top_lp.data(), h->top_lp, top_lp.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
-    WB_CUDA_OK(cudaMemcpyAsync(top_idx.data(), h->top_idx, top_idx.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    WB_CUDA_OK(cudaMemcpyAsync(top_lp, h->top_lp, (size_t)Mb * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    WB_CUDA_OK(cudaMemcpyAsync(top_idx, h->top_idx, (size_t)Mb * 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     const double t_a = prof ? now_ms() : 0.0;
     WB_CUDA_OK(cudaStreamSynchronize(st));
     const double t_b = prof ? now_ms() : 0.0;
@@ -1659,23 +1676,25 @@ static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int3
     if (completed || s + 1 == opts->sample_len) break;
     // device side of the update: newest token column, cache re-indexing, then embed + advance
     bool identity = true;
+    int32_t* const src = h->hb_src + (size_t)(s & 1) * Mb;        // read by the copies below while the next step's are written
+    int32_t* const next_col = h->hb_col + (size_t)(s & 1) * Mb;
     for (int b = 0; b < Mb; ++b) {
       src[b] = next_src[b], next_col[b] = seqs[b].back();
       identity = identity && src[b] == b;
     }
     const int col = n_init + s;
-    WB_CUDA_OK(cudaMemcpy2DAsync(h->tokens + col, h->tokens_ld * sizeof(int32_t), next_col.data(), sizeof(int32_t), sizeof(int32_t), Mb,
+    WB_CUDA_OK(cudaMemcpy2DAsync(h->tokens + col, h->tokens_ld * sizeof(int32_t), next_col, sizeof(int32_t), sizeof(int32_t), Mb,
                                  cudaMemcpyHostToDevice, st));
     if (!identity) {
-      WB_CUDA_OK(cudaMemcpyAsync(h->beam_src, src.data(), Mb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      WB_CUDA_OK(cudaMemcpyAsync(h->beam_src, src, Mb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
       WB_TRY(launch_reorder_kv(h->selfK.data(), h->selfV.data(), h->selfK_alt.data(), h->selfV_alt.data(), D.n_text_layer, Mb,
                                D.n_text_ctx, D.n_text_state, h->beam_src, h->state, st, &h->launches));
       h->selfK.swap(h->selfK_alt), h->selfV.swap(h->selfV_alt);
     }
     WB_TRY(step_finish(h, plain, 0));
-    const double t_c = prof ? now_ms() : 0.0;
-    WB_CUDA_OK(cudaStreamSynchronize(st));   // next_col / src are reused next iteration
-    if (prof) t_reorder += now_ms() - t_c;
+    // no synchronisation here: the staging buffers alternate by step parity, and the copies of step s have run before the
+    // synchronisation that follows the scored step of s + 1
+    (void)t_reorder;
   }
   if (prof)
     fprintf(stderr, "[wb] beam search, %d steps: waiting for the scored step %.1f ms, host bookkeeping %.1f ms, waiting for re-index + embed %.1f ms\n",

@@ -18,8 +18,10 @@ wbm = importlib.import_module("openai-whisper-coreml_b200")
 model = sys.argv[1] if len(sys.argv) > 1 else "base.en"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 4
-w = wbm.Whisper(model, seed=0, max_batch=B)
+beam = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+w = wbm.Whisper(model, seed=0, max_batch=B, max_beams=max(beam, 1))
 o = wbm.DecodeOptions.default_for(wbm.DIMS[model], sample_len=steps)
+o.beam_size = beam
 o.suppress = list(o.suppress) + [o.eot]
 audio = (np.random.default_rng(0).standard_normal((B, 480000)) * 0.1).astype(np.float32)
 w.transcribe(audio, o)
