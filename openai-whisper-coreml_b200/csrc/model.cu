@@ -1778,7 +1778,7 @@ int wb_transcribe_dev(wb_handle* h, const float* audio_dev, int32_t B, const wb_
 // (gpurun_out/exp1_slabs.log): pinned host memory 68.5 -> 68.1 ms per step with {8, 24} (smaller first slabs lose more in
 // the encoder's tile quantisation than their copy saves), pageable 73.5 -> 71.6 ms ({4, 12, 16}: 70.3 ms).
 // WB_H2D_SLABS="a,b,c" (chunks per slab, the last one takes the rest) overrides; "0" = one copy.
-static int slab_plan(int B, int (&slab)[wb_handle::kMaxSlabs]) {
+static int slab_plan(int B, bool pageable, int (&slab)[wb_handle::kMaxSlabs]) {
   int n = 0, used = 0;
   if (const char* e = getenv("WB_H2D_SLABS")) {
     while (*e && n < wb_handle::kMaxSlabs - 1) {
@@ -1788,6 +1788,9 @@ static int slab_plan(int B, int (&slab)[wb_handle::kMaxSlabs]) {
       while (*e && *e != ',') ++e;
       if (*e == ',') ++e;
     }
+  } else if (pageable && B >= 16) {   // a pageable copy blocks the host and is slower: a smaller first slab starts the GPU earlier
+    slab[n++] = B / 8, used += B / 8;
+    slab[n++] = (3 * B) / 8, used += (3 * B) / 8;
   } else if (B >= 8) {
     slab[n++] = B / 4, used += B / 4;
   }
@@ -1801,7 +1804,10 @@ int wb_transcribe(wb_handle* h, const float* audio, int32_t B, const wb_decode_o
   WB_TRY(need_weights(h));
   if (!audio) return WB_ERR_ARG;
   int slab[wb_handle::kMaxSlabs];
-  const int n_slab = slab_plan(B, slab);
+  cudaPointerAttributes pa{};
+  const bool pageable = cudaPointerGetAttributes(&pa, audio) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered;
+  cudaGetLastError();   // an ordinary malloc'ed pointer may report an error on older drivers: not ours to keep
+  const int n_slab = slab_plan(B, pageable, slab);
   // the copies may not overtake work already queued on the handle's stream that still reads audio_dev
   WB_CUDA_OK(cudaEventRecord(h->copy_fence, h->stream));
   WB_CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->copy_fence, 0));
