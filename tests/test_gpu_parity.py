@@ -415,18 +415,20 @@ def test_beam_search_on_block_kernels(wbm, ref, oracle_logmel):
     w.close()
 
 
-def test_beam_search_at_small_width(wbm, ref):
+@pytest.mark.parametrize("d,seed", [(768, 7), (1024, 32)])
+def test_beam_search_at_small_width(wbm, ref, d, seed):
     """BASELINE config 4's shape (whisper_to_cml.py:7 exports `small`: d = 768, 12 heads, multilingual vocabulary) with 2
-    layers: 8 chunks x 5 beams = 40 sequences on the decoder path of the wide models (seven kernels per layer), the cross K/V
-    shared by the beams of a chunk, the graph-replayed scored step. Weights / features: a seed whose oracle result is stable
-    under logit noise of 2e-2 (tools/pick_beam_seed.py), since whole token lists are compared."""
-    dims = ref.ModelDims(80, 1500, 768, 12, 2, 51865, 448, 768, 12, 2)
-    seed, B, beam = 7, 8, 5
+    layers: 8 chunks x 5 beams = 40 sequences on the decoder path of the wide models (LayerNorm rows kernel, skinny GEMMs, post
+    block), the cross K/V shared by the beams of a chunk (one CTA per (chunk, head)), the graph-replayed scored step; and
+    medium's width (d = 1024, 16 heads), where the query projection is a kernel of its own. Weights / features: seeds whose
+    oracle result is stable under logit noise of 2e-2 (tools/pick_beam_seed.py), since whole token lists are compared."""
+    dims = ref.ModelDims(80, 1500, d, d // 64, 2, 51865, 448, d, d // 64, 2)
+    B, beam = 8, 5
     weights = ref.random_weights(dims, seed=seed)
     oracle = ref.WhisperRef(dims, weights)
     pd = wbm.ModelDims(*[getattr(dims, f) for f in dims.__dataclass_fields__])
     w = wbm.Whisper(pd, weights=weights, max_batch=B, max_beams=beam)
-    xa = (torch.randn(B, 1500, 768, generator=torch.Generator().manual_seed(100 + seed)) * 0.7).half().float()
+    xa = (torch.randn(B, 1500, d, generator=torch.Generator().manual_seed(100 + seed)) * 0.7).half().float()
     w.set_audio_features(xa.numpy())
     opts_ref = ref.DecodeOptions.default_for(dims, sample_len=9)
     want_tokens, want_scores = oracle.beam_search(xa, opts_ref, beam_size=beam)

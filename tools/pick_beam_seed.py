@@ -12,11 +12,12 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import whisper_ref as ref  # noqa: E402
 
 B, BEAM, STEPS, NOISE = 8, 5, 9, 2e-2
-dims = ref.ModelDims(80, 1500, 768, 12, 2, 51865, 448, 768, 12, 2)
+D = int(sys.argv[2]) if len(sys.argv) > 2 else 768          # model width (heads = D / 64)
+dims = ref.ModelDims(80, 1500, D, D // 64, 2, 51865, 448, D, D // 64, 2)
 for seed in range(int(sys.argv[1]) if len(sys.argv) > 1 else 0, 40):
     weights = ref.random_weights(dims, seed=seed)
     oracle = ref.WhisperRef(dims, weights)
-    xa = (torch.randn(B, 1500, 768, generator=torch.Generator().manual_seed(100 + seed)) * 0.7).half().float()
+    xa = (torch.randn(B, 1500, D, generator=torch.Generator().manual_seed(100 + seed)) * 0.7).half().float()
     opts = ref.DecodeOptions.default_for(dims, sample_len=STEPS)
     base, scores = oracle.beam_search(xa, opts, beam_size=BEAM)
     plain = oracle.decoder_logits
