@@ -319,3 +319,40 @@ def test_host_batch_in_slabs_is_bit_identical(wbm):
     ref_dev = w.encode(audio)               # wb_encode: one copy, one slab
     assert np.array_equal(ref_dev.reshape(-1), base[2])
     w.close()
+
+
+def test_small_at_full_depth_matches_oracle(wbm, ref, oracle_logmel):
+    """The model the reference ships (`whisper.load_model("small")`, whisper_to_cml.py:7: d = 768, 12 heads, 12 + 12 layers,
+    multilingual vocabulary) at full depth: `Whisper.encode` features, `Whisper.decode`'s language ID, teacher-forced logits
+    and a greedy stream against the oracle on identical seeded weights. (The width-dependent code paths are covered with two
+    layers elsewhere; this is the depth the reference runs: 24 residual blocks of fp16-operand arithmetic.)"""
+    dims = ref.DIMS["small"]
+    weights = ref.random_weights(dims, seed=13)
+    oracle = ref.WhisperRef(dims, weights)
+    B = 2
+    w = wbm.Whisper("small", weights=weights, max_batch=B)
+    audio = np.stack([ref.synth_audio(1300 + i, "noise") for i in range(B)])
+    xa_ref = oracle.encode(torch.from_numpy(np.stack([oracle_logmel(a) for a in audio])).float())
+    xa = torch.from_numpy(w.encode(audio.astype(np.float32)))
+    print(f"\n[small, 12 + 12 layers] encoder features: max|d| {(xa - xa_ref).abs().max().item():.3e}, rel-L2 {_rel(xa, xa_ref):.3e}")
+    assert (xa - xa_ref).abs().max().item() <= TOL_ABS and _rel(xa, xa_ref) <= TOL_REL
+    # Whisper.decode (Whisper.swift:33-40): one decoder call on [sot], arg-max over the 99 language logits
+    lang_ref = oracle.detect_language(xa_ref)
+    lang = w.detect_language(B)
+    v = oracle.vocab
+    sot_logits = oracle.decoder_logits(torch.full((B, 1), v.sot, dtype=torch.long), xa_ref)[:, 0, v.lang0:v.lang0 + 99]
+    for b in range(B):   # identical, or a tie of the oracle's own language logits (fp16 operands)
+        gap = float(sot_logits[b, int(lang_ref[b])] - sot_logits[b, int(lang[b])])
+        assert int(lang[b]) == int(lang_ref[b]) or 0.0 <= gap <= pu.TOL_TIE, (b, int(lang[b]), int(lang_ref[b]), gap)
+    toks = torch.randint(0, 50000, (B, 6), generator=torch.Generator().manual_seed(77))
+    want = oracle.decoder_logits(toks, xa_ref)
+    got = torch.from_numpy(w.decoder_logits(toks.numpy()))
+    print(f"[small, 12 + 12 layers] teacher-forced logits: max|d| {(got - want).abs().max().item():.3e}, rel-L2 {_rel(got, want):.3e}")
+    assert (got - want).abs().max().item() <= TOL_ABS and _rel(got, want) <= TOL_REL
+    o = wbm.DecodeOptions.default_for(wbm.DIMS["small"], sample_len=16)
+    o.suppress = list(o.suppress) + [o.eot]
+    tok, _, slp = w.greedy(B, o)
+    rep = pu.teacher_forced_check(oracle, xa_ref, tok, len(o.initial_tokens), o.suppress, o.suppress_begin, o.eot)
+    print("[small, 12 + 12 layers, 2 x 16 tokens] " + rep.line())
+    assert rep.decisions == B * 16 and rep.bad == 0 and rep.ties <= 2, rep.bad_at[:8]
+    w.close()
