@@ -2584,7 +2584,13 @@ static int post_block_cluster(int d) {
     switch (d) {
       case 384: c = 8; break;
       case 512: c = (want == 16 && post_block_cluster_fits<512, 16>()) ? 16 : 8; break;
-      case 768: c = (wide && post_block_cluster_fits<768, 12>()) ? 12 : 0; break;
+      case 768: {
+        // 16 CTAs of 48 output columns / 192 hidden units each (80 CTAs at 40 sequences) against 12 of 64 / 256 (60 CTAs): the
+        // phases are bound by what one SM pulls from L2: 1030 -> 1009 us per step, configs[3] 250.8 -> 241.3 ms per decode
+        const char* e768 = getenv("WB_POST_CLUSTER_768");
+        const int want768 = e768 ? atoi(e768) : 16;
+        c = !wide ? 0 : (want768 == 16 && post_block_cluster_fits<768, 16>()) ? 16 : (post_block_cluster_fits<768, 12>() ? 12 : 0);
+      } break;
       case 1024: c = (wide && post_block_cluster_fits<1024, 16>()) ? 16 : 0; break;
       default: c = (wide >= 2 && post_block_cluster_fits<1280, 10>()) ? 10 : 0; break;
     }
@@ -2649,7 +2655,7 @@ int launch_post_block(const PostBlockDesc& p, cudaStream_t st, int64_t* launches
   if (p.d == 384)
     le = launch_post_block_t<384, 8>(a, n_groups, st);
   else if (p.d == 768)
-    le = launch_post_block_t<768, 12>(a, n_groups, st);
+    le = C == 16 ? launch_post_block_t<768, 16>(a, n_groups, st) : launch_post_block_t<768, 12>(a, n_groups, st);
   else if (p.d == 1024)
     le = launch_post_block_t<1024, 16>(a, n_groups, st);
   else if (p.d == 1280)
