@@ -3185,6 +3185,7 @@ __global__ void __launch_bounds__(256) topk_logprobs_kernel(const float* __restr
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o), os = __shfl_xor_sync(0xffffffffu, bslot, o);
         if (ov > best || (ov == best && oi < bi)) best = ov, bi = oi, bslot = os;
       }
+      __syncwarp();   // every lane's scan of c_val is complete before lane 0 retires the winner (shuffles alone do not order shared memory)
       if (lane == 0) {
         top_lp[(size_t)b * 8 + r] = best - lse;
         top_idx[(size_t)b * 8 + r] = bi;
