@@ -39,9 +39,9 @@ struct OrderedMax<double> {
   }
 };
 
-// One CTA = F consecutive frames of one chunk.  grid = (3000 / F, B).
-template <typename T, int F, int NT>
-__global__ void __launch_bounds__(NT) logmel_kernel(const T* __restrict__ audio, size_t chunk_stride, int chunk_off,
+// One CTA = F consecutive frames of one chunk.  grid = (3000 / F, B).  MINB CTAs per SM bound the registers.
+template <typename T, int F, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) logmel_kernel(const T* __restrict__ audio, size_t chunk_stride, int chunk_off,
                                                     const LogmelTables<T>* __restrict__ gtab, T* __restrict__ logspec,
                                                     typename OrderedMax<T>::U* __restrict__ gmax, long long stream_samples) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -50,16 +50,29 @@ __global__ void __launch_bounds__(NT) logmel_kernel(const T* __restrict__ audio,
   const int tile = blockIdx.x, b = blockIdx.y;
   const T* clip = audio + (size_t)b * chunk_stride + chunk_off;
 
-  // tables -> smem (word copy)
+  // tables -> smem (8-byte copies)
   {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(gtab);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.tab);
-    for (int i = tid; i < (int)(sizeof(LogmelTables<T>) / 4); i += NT) dst[i] = src[i];
+    using Smem = LogmelSmem<T, F>;
+    static_assert(sizeof(LogmelTables<T>) % 8 == 0 && offsetof(Smem, tab) % 8 == 0, "table copy is done in 8-byte words");
+    const uint2* src = reinterpret_cast<const uint2*>(gtab);
+    uint2* dst = reinterpret_cast<uint2*>(&sm.tab);
+    for (int i = tid; i < (int)(sizeof(LogmelTables<T>) / 8); i += NT) dst[i] = __ldg(src + i);
   }
   // samples of this tile, reflection folded into the index map (lib.rs:34-40); padded coordinate p0 + s
   const int p0 = tile * F * WB_HOP;
   if (stream_samples < 0) {
-    for (int s = tid; s < tile_samples<F>(); s += NT) sm.region0[samp_index(s)] = clip[reflect_index(p0 + s)];
+    // a tile that does not touch either reflected end is one contiguous run of the clip: 16-byte loads (float4 / double2),
+    // 16-byte shared-memory stores (a pad group never splits a vector: 160 and 16 are multiples of the vector width)
+    constexpr int VW = 16 / (int)sizeof(T);
+    static_assert(tile_samples<F>() % VW == 0 && kSampGroup % VW == 0 && kSampPad % VW == 0, "vector sample load");
+    const T* run = clip + (p0 - 200);
+    if (p0 >= 200 && p0 - 200 + tile_samples<F>() <= WB_N_SAMPLES && (reinterpret_cast<uintptr_t>(run) & 15) == 0) {
+      const uint4* src = reinterpret_cast<const uint4*>(run);
+      for (int v = tid; v < tile_samples<F>() / VW; v += NT)
+        *reinterpret_cast<uint4*>(&sm.region0[samp_index(v * VW)]) = __ldg(src + v);
+    } else {
+      for (int s = tid; s < tile_samples<F>(); s += NT) sm.region0[samp_index(s)] = clip[reflect_index(p0 + s)];
+    }
   } else {
     // stream mode (upstream whisper/audio.py log_mel_spectrogram on a whole recording followed by 30 s of zeros): item b holds
     // frames [3000 b, 3000 b + 3000) of ONE signal of stream_samples samples; the reflection exists only at the start of the
@@ -180,11 +193,23 @@ template <typename T>
 struct LogmelCfg;
 template <>
 struct LogmelCfg<float> {
-  static constexpr int F = 30, NT = 256;
+  // 15 frames x 256 threads, four CTAs (32 warps) per SM under a 64-register cap (36 bytes of spills): 46 KB of shared memory
+  // per CTA. Measured for 32 chunks, whole front end: 30 frames x 256 threads (two CTAs per SM, 80 registers) 152 us,
+  // 15 x 192 and 24 x 256 (24 warps) 132, 30 x 512 133, this 127 (profiles/r02_logmel_variants.log)
+#ifndef WB_LM_F
+#define WB_LM_F 15
+#endif
+#ifndef WB_LM_NT
+#define WB_LM_NT 256
+#endif
+#ifndef WB_LM_MINB
+#define WB_LM_MINB 4
+#endif
+  static constexpr int F = WB_LM_F, NT = WB_LM_NT, MINB = WB_LM_MINB;
 };
 template <>
 struct LogmelCfg<double> {
-  static constexpr int F = 15, NT = 128;
+  static constexpr int F = 15, NT = 128, MINB = 4;   // 128 registers, two CTAs per SM (92 KB of shared memory)
 };
 
 // Enqueue: logspec/gmax are scratch ([B][80][3000] T and [B] ordered). Returns 0 or -2 (error text recorded).
@@ -196,7 +221,7 @@ int launch_logmel(const T* audio, size_t chunk_stride, int chunk_off, int B, con
   static_assert(WB_N_FRAMES % Cfg::F == 0, "tile must divide 3000 frames");
   static_assert(Cfg::NT >= Cfg::F * 8, "phase A needs 8 threads per frame");
   const size_t smem = sizeof(LogmelSmem<T, Cfg::F>);
-  auto kern = logmel_kernel<T, Cfg::F, Cfg::NT>;
+  auto kern = logmel_kernel<T, Cfg::F, Cfg::NT, Cfg::MINB>;
   WB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fill_kernel<U><<<(B + 127) / 128, 128, 0, st>>>((U*)gmax, (U)0, B);
   kern<<<dim3(WB_N_FRAMES / Cfg::F, B), Cfg::NT, smem, st>>>(audio, chunk_stride, chunk_off, dtab, logspec, (U*)gmax, -1ll);
@@ -217,7 +242,7 @@ int launch_logmel_stream(const float* audio, long long n_samples, int W, const L
   using Cfg = LogmelCfg<float>;
   using U = OrderedMax<float>::U;
   const size_t smem = sizeof(LogmelSmem<float, Cfg::F>);
-  auto kern = logmel_kernel<float, Cfg::F, Cfg::NT>;
+  auto kern = logmel_kernel<float, Cfg::F, Cfg::NT, Cfg::MINB>;
   WB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fill_kernel<U><<<1, 32, 0, st>>>((U*)gmax, (U)0, 1);
   kern<<<dim3(WB_N_FRAMES / Cfg::F, W), Cfg::NT, smem, st>>>(audio, 0, 0, dtab, logspec, (U*)gmax, n_samples);

@@ -63,9 +63,9 @@ template <typename T, int F>
 struct LogmelSmem {
   // region 0: samples during load/phase A, then the power spectrum (phase C)
   static constexpr int kRegion0 = (samp_words<F>() > F * kPFrame ? samp_words<F>() : F * kPFrame);
-  T region0[kRegion0 + 2];
-  Cpx<T> y[F * kYFrame];
-  LogmelTables<T> tab;
+  alignas(16) T region0[kRegion0 + 2];
+  alignas(16) Cpx<T> y[F * kYFrame];
+  alignas(16) LogmelTables<T> tab;
   T red[32];
 };
 
