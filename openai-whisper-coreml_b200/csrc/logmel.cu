@@ -90,15 +90,42 @@ __global__ void __launch_bounds__(NT, MINB) logmel_kernel(const T* __restrict__ 
   __syncthreads();
   for (int task = tid; task < F * 25; task += NT) logmel_phase_b<T, F>(sm, task);
   __syncthreads();
-  for (int task = tid; task < F * 100; task += NT) logmel_phase_c1<T, F>(sm, task);
+  // C1: a thread keeps its bin pair k and walks the frames, so that the slot arithmetic and the twiddle of a bin are computed once
+  {
+    constexpr int FS = NT / 100;                       // frames in flight
+    if (tid < 100 * FS) {
+      const int k = tid % 100 + 1;
+      for (int fl = tid / 100; fl < F; fl += FS) logmel_phase_c1<T, F>(sm, fl, k);
+    }
+  }
   __syncthreads();
 
+  // C2: a thread keeps its mel band and accumulates NF frames at once (one weight load per bin for all of them); the values go
+  // through shared memory (the FFT buffer is free by now) so that the stores run along the frames of a band
   T vmax = (T)-1e30;
+  T* stage = reinterpret_cast<T*>(sm.y);               // [80][F + 1]
+  {
+    constexpr int GF = NT / WB_N_MELS;                 // threads per band
+    constexpr int NF = (F + GF - 1) / GF;              // frames per thread: fl = g + GF * n
+    static_assert(sizeof(sm.y) >= sizeof(T) * WB_N_MELS * (F + 1), "stage fits the FFT buffer");
+    if (tid < WB_N_MELS * GF) {
+      const int i = tid / GF, g = tid - i * GF;
+      T v[NF];
+      logmel_phase_c2<T, F, NF>(sm, i, g, GF, v);
+#pragma unroll
+      for (int n = 0; n < NF; ++n) {
+        const int fl = g + GF * n;
+        if (fl < F) {
+          stage[i * (F + 1) + fl] = v[n];
+          vmax = v[n] > vmax ? v[n] : vmax;
+        }
+      }
+    }
+  }
+  __syncthreads();
   for (int task = tid; task < F * WB_N_MELS; task += NT) {
     const int i = task / F, fl = task - i * F;
-    const T v = logmel_phase_c2<T, F>(sm, fl, i);
-    logspec[((size_t)b * WB_N_MELS + i) * WB_N_FRAMES + tile * F + fl] = v;
-    vmax = v > vmax ? v : vmax;
+    logspec[((size_t)b * WB_N_MELS + i) * WB_N_FRAMES + tile * F + fl] = stage[i * (F + 1) + fl];
   }
   // block max -> one atomic per CTA
 #pragma unroll

@@ -176,9 +176,7 @@ __host__ __device__ __forceinline__ Cpx<T> logmel_z(const LogmelSmem<T, F>& sm, 
 
 // ---- phase C1: split pass + power, bins k and 200-k together (k = 1..100). Bins 0 and 200 carry zero mel weight ---------
 template <typename T, int F>
-__host__ __device__ __forceinline__ void logmel_phase_c1(LogmelSmem<T, F>& sm, int task) {
-  if (task >= F * 100) return;
-  const int fl = task / 100, k = task - fl * 100 + 1;
+__host__ __device__ __forceinline__ void logmel_phase_c1(LogmelSmem<T, F>& sm, int fl, int k) {   // frame fl, bin pair k in [1, 100]
   const Cpx<T> zk = logmel_z(sm, fl, k), zc = logmel_z(sm, fl, 200 - k == 200 ? 0 : 200 - k);
   const Cpx<T> e = {(T)0.5 * (zk.re + zc.re), (T)0.5 * (zk.im - zc.im)};       // (Z[k] + conj Z[200-k]) / 2
   const Cpx<T> d = {(T)0.5 * (zk.re - zc.re), (T)0.5 * (zk.im + zc.im)};       // (Z[k] - conj Z[200-k]) / 2
@@ -197,14 +195,24 @@ __host__ __device__ __forceinline__ float wb_log10<float>(float x) { return log1
 template <>
 __host__ __device__ __forceinline__ double wb_log10<double>(double x) { return log10(x); }
 
-template <typename T, int F>
-__host__ __device__ __forceinline__ T logmel_phase_c2(const LogmelSmem<T, F>& sm, int fl, int i) {
-  const T* P = &sm.region0[fl * kPFrame];
+// Mel band i for the NF frames fl0, fl0 + step, ... (those below F): the weight of a bin is loaded once for all of them, and each
+// frame's sum runs over the band's bins in ascending order, exactly as the dense loop of lib.rs:60-69 does
+template <typename T, int F, int NF>
+__host__ __device__ __forceinline__ void logmel_phase_c2(const LogmelSmem<T, F>& sm, int i, int fl0, int step, T (&out)[NF]) {
   const int lo = sm.tab.mel_lo[i], cnt = sm.tab.mel_cnt[i], off = sm.tab.mel_off[i];
-  T sum = (T)0;
-  for (int c = 0; c < cnt; ++c) sum += P[lo + c] * sm.tab.melw[off + c];
+  const T* P = &sm.region0[fl0 * kPFrame + lo];
+  T sum[NF];
+#pragma unroll
+  for (int n = 0; n < NF; ++n) sum[n] = (T)0;
+  for (int c = 0; c < cnt; ++c) {
+    const T w = sm.tab.melw[off + c];
+#pragma unroll
+    for (int n = 0; n < NF; ++n)
+      if (fl0 + n * step < F) sum[n] += P[n * step * kPFrame + c] * w;
+  }
   const T fl10 = (T)1e-10;
-  return wb_log10<T>(sum > fl10 ? sum : fl10);
+#pragma unroll
+  for (int n = 0; n < NF; ++n) out[n] = wb_log10<T>(sum[n] > fl10 ? sum[n] : fl10);
 }
 
 }  // namespace wb

@@ -19,12 +19,21 @@ void emulate(const T* clip /* unpadded [480000] */, T* out /* [80][3000] */) {
     for (int s = 0; s < wb::tile_samples<F>(); ++s) sm->region0[wb::samp_index(s)] = clip[wb::reflect_index(p0 + s)];
     for (int tid = 0; tid < NT; ++tid) wb::logmel_phase_a<T, F>(*sm, tid);
     for (int task = 0; task < F * 25; ++task) wb::logmel_phase_b<T, F>(*sm, task);
-    for (int task = 0; task < F * 100; ++task) wb::logmel_phase_c1<T, F>(*sm, task);
-    for (int task = 0; task < F * 80; ++task) {
-      const int i = task / F, fl = task - i * F;
-      const T v = wb::logmel_phase_c2<T, F>(*sm, fl, i);
-      logspec[i * 3000 + tile * F + fl] = v;
-      gmax = v > gmax ? v : gmax;
+    // the kernel's thread -> work maps of phases C1 and C2 (a thread keeps its bin pair / its mel band and walks the frames)
+    constexpr int FS = NT / 100;
+    for (int tid = 0; tid < 100 * FS; ++tid)
+      for (int fl = tid / 100; fl < F; fl += FS) wb::logmel_phase_c1<T, F>(*sm, fl, tid % 100 + 1);
+    constexpr int GF = NT / 80, NF = (F + GF - 1) / GF;
+    for (int tid = 0; tid < 80 * GF; ++tid) {
+      const int i = tid / GF, g = tid - i * GF;
+      T v[NF];
+      wb::logmel_phase_c2<T, F, NF>(*sm, i, g, GF, v);
+      for (int n = 0; n < NF; ++n) {
+        const int fl = g + GF * n;
+        if (fl >= F) continue;
+        logspec[i * 3000 + tile * F + fl] = v[n];
+        gmax = v[n] > gmax ? v[n] : gmax;
+      }
     }
   }
   for (int i = 0; i < 80 * 3000; ++i) {

@@ -321,6 +321,36 @@ def test_host_batch_in_slabs_is_bit_identical(wbm):
     w.close()
 
 
+def test_logmel_device_pointer_alignment_does_not_matter(wbm, oracle_logmel):
+    """logmel_kernel loads the samples of an interior tile 16 bytes at a time when the tile's first sample is 16-byte aligned and
+    falls back to the scalar index map otherwise (as the two reflected end tiles always do): a device buffer that starts 4, 8
+    or 12 bytes off a 16-byte boundary gives bit-identical log-mel, and both agree with the f64 oracle."""
+    import ctypes
+    B = 3
+    w = wbm.Whisper("tiny.en", seed=0, max_batch=B)
+    lib = wbm.load_library()
+    g = torch.Generator().manual_seed(11)
+    audio = torch.randn(B, 480000, generator=g) * 0.1
+    dev = torch.device("cuda:0")
+    outs = []
+    for off in (0, 1, 2, 3):
+        buf = torch.zeros(B * 480000 + 4, dtype=torch.float32, device=dev)
+        view = buf[off:off + B * 480000]
+        view.copy_(audio.reshape(-1))
+        assert view.data_ptr() % 16 == (4 * off) % 16
+        out = torch.empty((B, 80, 3000), dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()
+        assert lib.wb_logmel_dev(w.handle, ctypes.c_void_p(view.data_ptr()), B, ctypes.c_void_p(out.data_ptr())) == 0, lib.wb_last_error()
+        w.sync()
+        outs.append(out.cpu().numpy())
+    for o in outs[1:]:
+        assert np.array_equal(outs[0], o)
+    want = oracle_logmel(audio[1].double().numpy())
+    assert np.abs(outs[0][1].astype(np.float64) - want.reshape(80, 3000)).max() <= 2e-4
+    w.close()
+
+
+
 def test_small_at_full_depth_matches_oracle(wbm, ref, oracle_logmel):
     """The model the reference ships (`whisper.load_model("small")`, whisper_to_cml.py:7: d = 768, 12 heads, 12 + 12 layers,
     multilingual vocabulary) at full depth: `Whisper.encode` features, `Whisper.decode`'s language ID, teacher-forced logits
