@@ -144,22 +144,48 @@ __global__ void __launch_bounds__(NT, MINB) logmel_kernel(const T* __restrict__ 
 
 // (max(l, g-8)+4)/4 (lib.rs:96).  One CTA = 120 frames x 80 mels of one chunk.  grid = (25, B).
 // Writes the [80][3000] layout of the reference (optional) and the time-major fp16 layout for conv1 (optional).
-constexpr int kNormFrames = 120;
+#ifndef WB_NORM_FRAMES
+#define WB_NORM_FRAMES 120
+#endif
+constexpr int kNormFrames = WB_NORM_FRAMES;
 template <typename T>
 __global__ void __launch_bounds__(256) logmel_normalize_kernel(const T* __restrict__ logspec,
                                                                const typename OrderedMax<T>::U* __restrict__ gmax,
                                                                T* __restrict__ out, __half* __restrict__ melT) {
-  __shared__ __half tile[kNormFrames][WB_N_MELS + 2];
+  __shared__ __half tile[kNormFrames][WB_N_MELS + 1];   // odd row stride: lanes four frames apart land in 16 different banks
   const int b = blockIdx.y, f0 = blockIdx.x * kNormFrames;
   const T floor_v = OrderedMax<T>::dec(gmax[b]) - (T)8.0;
-  for (int idx = threadIdx.x; idx < WB_N_MELS * kNormFrames; idx += 256) {
-    const int i = idx / kNormFrames, f = idx - i * kNormFrames;
+  // 16 bytes (four floats / two doubles) of a band per thread and iteration: rows of 3000 and tiles of kNormFrames frames keep
+  // every vector aligned
+  constexpr int VW = 16 / (int)sizeof(T), VPR = kNormFrames / VW;
+  static_assert(kNormFrames % VW == 0 && WB_N_FRAMES % VW == 0, "vector width divides the tile and the row");
+  struct alignas(16) Vec {
+    T e[VW];
+  };
+  const bool out_vec = (reinterpret_cast<uintptr_t>(out) & 15) == 0;   // a caller's device buffer may sit at any float boundary
+#pragma unroll 2
+  for (int idx = threadIdx.x; idx < WB_N_MELS * VPR; idx += 256) {
+    const int i = idx / VPR, f = (idx - i * VPR) * VW;
     const size_t g = ((size_t)b * WB_N_MELS + i) * WB_N_FRAMES + f0 + f;
-    T v = logspec[g];
-    v = v > floor_v ? v : floor_v;
-    v = (v + (T)4.0) / (T)4.0;
-    if (out) out[g] = v;
-    if (melT) tile[f][i] = __float2half_rn((float)v);
+    Vec v = *reinterpret_cast<const Vec*>(logspec + g);
+#pragma unroll
+    for (int e = 0; e < VW; ++e) {
+      T x = v.e[e];
+      x = x > floor_v ? x : floor_v;
+      v.e[e] = (x + (T)4.0) / (T)4.0;
+    }
+    if (out) {
+      if (out_vec) {
+        *reinterpret_cast<Vec*>(out + g) = v;
+      } else {
+#pragma unroll
+        for (int e = 0; e < VW; ++e) out[g + e] = v.e[e];
+      }
+    }
+    if (melT) {
+#pragma unroll
+      for (int e = 0; e < VW; ++e) tile[f + e][i] = __float2half_rn((float)v.e[e]);
+    }
   }
   if (melT) {
     __syncthreads();

@@ -324,7 +324,7 @@ def test_host_batch_in_slabs_is_bit_identical(wbm):
 def test_logmel_device_pointer_alignment_does_not_matter(wbm, oracle_logmel):
     """logmel_kernel loads the samples of an interior tile 16 bytes at a time when the tile's first sample is 16-byte aligned and
     falls back to the scalar index map otherwise (as the two reflected end tiles always do): a device buffer that starts 4, 8
-    or 12 bytes off a 16-byte boundary gives bit-identical log-mel, and both agree with the f64 oracle."""
+    or 12 bytes off a 16-byte boundary (input and output alike) gives bit-identical log-mel, and both agree with the f64 oracle."""
     import ctypes
     B = 3
     w = wbm.Whisper("tiny.en", seed=0, max_batch=B)
@@ -338,11 +338,12 @@ def test_logmel_device_pointer_alignment_does_not_matter(wbm, oracle_logmel):
         view = buf[off:off + B * 480000]
         view.copy_(audio.reshape(-1))
         assert view.data_ptr() % 16 == (4 * off) % 16
-        out = torch.empty((B, 80, 3000), dtype=torch.float32, device=dev)
+        obuf = torch.empty(B * 80 * 3000 + 4, dtype=torch.float32, device=dev)
+        out = obuf[off:off + B * 80 * 3000]                       # the output's 16-byte stores have the same fallback
         torch.cuda.synchronize()
         assert lib.wb_logmel_dev(w.handle, ctypes.c_void_p(view.data_ptr()), B, ctypes.c_void_p(out.data_ptr())) == 0, lib.wb_last_error()
         w.sync()
-        outs.append(out.cpu().numpy())
+        outs.append(out.cpu().numpy().reshape(B, 80, 3000))
     for o in outs[1:]:
         assert np.array_equal(outs[0], o)
     want = oracle_logmel(audio[1].double().numpy())
