@@ -37,6 +37,13 @@ def test_python_binding_covers_the_header(wbm):
     assert set(_declared_symbols()) <= bound
 
 
+def test_integration_notes_name_every_entry_point():
+    """INTEGRATION.md is the maintainer's map from the reference's call sites to the C ABI: no declared symbol is left out of it."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [s for s in _declared_symbols() if s not in text]
+    assert not missing, missing
+
+
 def test_library_has_no_libcuda_or_torch_dependency(wbm):
     out = subprocess.run(["ldd", wbm.library_path()], capture_output=True, text=True).stdout
     assert "libcuda.so" not in out and "torch" not in out and "cublas" not in out and "cufft" not in out
