@@ -44,6 +44,19 @@ def test_integration_notes_name_every_entry_point():
     assert not missing, missing
 
 
+def test_swift_mirror_only_uses_declared_names():
+    """The Swift side of the boundary (not compiled here: no toolchain) must at least bind names the header declares."""
+    header = open(os.path.join(ROOT, "include", "whisper_b200.h")).read()
+    declared = set(re.findall(r"\bwb_[a-z0-9_]+\b", header)) | {"generate_spectrogram"}
+    sdir = os.path.join(ROOT, "openai-whisper-coreml_b200", "swift")
+    used = set()
+    for f in os.listdir(sdir):
+        if f.endswith(".swift"):
+            used |= set(re.findall(r"\bwb_[a-z0-9_]+\b", open(os.path.join(sdir, f)).read()))
+    assert used and used <= declared, sorted(used - declared)
+    assert "generate_spectrogram" in open(os.path.join(sdir, "stft.swift")).read()
+
+
 def test_library_has_no_libcuda_or_torch_dependency(wbm):
     out = subprocess.run(["ldd", wbm.library_path()], capture_output=True, text=True).stdout
     assert "libcuda.so" not in out and "torch" not in out and "cublas" not in out and "cufft" not in out
