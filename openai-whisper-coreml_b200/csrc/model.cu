@@ -1624,33 +1624,50 @@ static int decode_beam(wb_handle* h, int32_t B, const wb_decode_opts* opts, int3
     std::vector<float> next_slp;
     std::vector<int32_t> next_src;
     for (int a = 0; a < B; ++a) {
-      // STEP 1: cumulative log-probabilities of the candidates, keyed by sequence (identical prefixes collapse)
-      struct Cand { Seq seq; float score; int source; };
-      std::vector<Cand> cands;
+      // STEP 1: cumulative log-probabilities of the candidates, keyed by sequence (upstream's dict: a sequence reached twice keeps
+      // its first position and takes the later score and source). A candidate is (source beam, token): two of them are the
+      // same sequence iff the tokens agree and the source beams hold equal sequences, so the beams are classed once per step
+      // (at the first step all of them are the prompt) and no candidate sequence is built before it is selected.
+      struct Cand { int source, token, cls; float score; };
+      int cls[8];
+      for (int j = 0; j < beam; ++j) {
+        cls[j] = j;
+        for (int i = 0; i < j; ++i)
+          if (cls[i] == i && seqs[a * beam + i] == seqs[a * beam + j]) {
+            cls[j] = i;
+            break;
+          }
+      }
+      Cand cands[8 * 8];
+      int n_cand = 0;
       for (int j = 0; j < beam; ++j) {
         const int idx = a * beam + j;
         for (int c = 0; c < K; ++c) {
-          Seq sq = seqs[idx];
-          sq.push_back(top_idx[(size_t)idx * 8 + c]);
+          const int tok = top_idx[(size_t)idx * 8 + c];
           const float sc = slp[idx] + top_lp[(size_t)idx * 8 + c];
           bool found = false;
-          for (auto& e : cands)
-            if (e.seq == sq) {
-              e.score = sc, e.source = idx, found = true;
+          for (int e = 0; e < n_cand; ++e)
+            if (cands[e].cls == cls[j] && cands[e].token == tok) {
+              cands[e].score = sc, cands[e].source = idx, found = true;
               break;
             }
-          if (!found) cands.push_back(Cand{sq, sc, idx});
+          if (!found) cands[n_cand++] = Cand{idx, tok, cls[j], sc};
         }
       }
       // STEP 2: rank, keep the best `beam` unfinished sequences; sequences ending in eot are set aside
-      std::stable_sort(cands.begin(), cands.end(), [](const Cand& x, const Cand& y) { return x.score > y.score; });
+      std::stable_sort(cands, cands + n_cand, [](const Cand& x, const Cand& y) { return x.score > y.score; });
       std::vector<std::pair<Seq, float>> newly;
       int saved = 0;
-      for (auto& e : cands) {
-        if (e.seq.back() == eot) {
-          newly.emplace_back(e.seq, e.score);
+      for (int e = 0; e < n_cand; ++e) {
+        const Seq& from = seqs[cands[e].source];
+        Seq sq;
+        sq.reserve(from.size() + 1);
+        sq.insert(sq.end(), from.begin(), from.end());
+        sq.push_back(cands[e].token);
+        if (cands[e].token == eot) {
+          newly.emplace_back(std::move(sq), cands[e].score);
         } else {
-          next_seqs.push_back(e.seq), next_slp.push_back(e.score), next_src.push_back(e.source);
+          next_seqs.push_back(std::move(sq)), next_slp.push_back(cands[e].score), next_src.push_back(cands[e].source);
           if (++saved == beam) break;
         }
       }
